@@ -1,0 +1,709 @@
+// az_engine.cu -- tree-pool engine + C ABI (compiled with -fmad=false: bit-exact f64 PUCT / backup).
+//
+// Replaces, behind include/azb200.h:
+//   MCTS.Env / explore! / policy / reset!                     src/mcts.jl:124-151,239-281
+//   Batchifier inference server + worker tasks                 src/batchifier.jl:47-127, src/simulations.jl:23-155
+//   simulate(): worker loop over games, reset_every            src/simulations.jl:207-244
+// by a per-GPU "tick" scheduler:  select -> leaf batch -> oracle/network -> expand+backup -> per-move kernel.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "az_internal.h"
+#include "az_tree.cuh"
+
+static std::string g_create_err;
+
+#define AZ_TRY(ctx, expr)                 \
+  do {                                    \
+    int s__ = (expr);                     \
+    if (s__ != AZ_OK) return s__;         \
+  } while (0)
+#define AZ_FAIL(ctx, code, msg) \
+  do {                          \
+    (ctx)->err = (msg);         \
+    return (code);              \
+  } while (0)
+
+template <class T>
+static int az_dalloc(az_ctx* ctx, T** p, size_t n, bool zero = true) {
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e != cudaSuccess) {
+    ctx->err = std::string("cudaMalloc ") + std::to_string(n * sizeof(T)) + " B: " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return AZ_ENOMEM;
+  }
+  if (zero) AZ_CUDA(ctx, cudaMemsetAsync(*p, 0, n * sizeof(T), ctx->stream));
+  return AZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// game dispatch
+// ------------------------------------------------------------------------------------------------
+#define AZ_DISPATCH_GAME(game, F, ...)                     \
+  switch (game) {                                          \
+    case 0: return F<GameC4>(__VA_ARGS__);                 \
+    case 1: return F<GameTTT>(__VA_ARGS__);                \
+    case 2: return F<GameMancala>(__VA_ARGS__);            \
+    default: return AZ_EINVAL;                             \
+  }
+
+static const char* AZ_GAME_NAMES[3] = {"connect-four", "tictactoe", "mancala"};
+
+template <class G> static int g_num_actions() { return G::A; }
+template <class G> static int g_state_bytes() { return G::STATE_BYTES; }
+template <class G> static int g_max_plies() { return G::MAX_PLIES; }
+template <class G> static int g_state_dim(int32_t* d) { d[0] = G::XW; d[1] = G::XH; d[2] = G::XC; return AZ_OK; }
+template <class G> static int g_vectorize(const uint8_t* s, float* x) { G::vectorize(G::from_bytes(s), x); return AZ_OK; }
+template <class G> static int g_mask(const uint8_t* s, uint8_t* m) {
+  AzEnv e = G::from_bytes(s);
+  uint32_t l = G::terminated(e) ? G::legal_mask(e) : G::legal_mask(e);
+  for (int i = 0; i < G::A; i++) m[i] = (l >> i) & 1;
+  return AZ_OK;
+}
+template <class G> static int g_play(const uint8_t* s, int a, uint8_t* ns, int32_t* term, double* wr) {
+  AzEnv e = G::from_bytes(s);
+  if (a < 0 || a >= G::A || !((G::legal_mask(e) >> a) & 1) || G::terminated(e)) return AZ_EINVAL;
+  AzEnv n = G::play(e, a);
+  G::to_bytes(n, ns);
+  if (term) *term = G::terminated(n);
+  if (wr) *wr = G::white_reward(n);
+  return AZ_OK;
+}
+template <class G> static int g_init_state(uint8_t* s) { G::to_bytes(G::init(), s); return AZ_OK; }
+template <class G> static int g_random_positions(uint64_t seed, uint64_t first, int n, int max_plies, uint8_t* out) {
+  for (int i = 0; i < n; i++) {
+    for (uint64_t attempt = 0;; attempt++) {
+      uint64_t st = first + (uint64_t)i + (attempt << 32);
+      AzEnv e = G::init();
+      uint32_t o[4];
+      az_philox(seed, 0, AZ_PURPOSE_POSITION, (uint32_t)st, (uint32_t)(st >> 32), o);
+      int k = (int)(o[0] % (uint32_t)(max_plies + 1));
+      bool ok = true;
+      for (int ply = 0; ply < k; ply++) {
+        uint32_t legal = G::legal_mask(e);
+        int acts[AZ_MAX_ACTIONS], na = 0;
+        for (int a = 0; a < G::A; a++) if ((legal >> a) & 1) acts[na++] = a;
+        az_philox(seed, (uint32_t)(ply + 1), AZ_PURPOSE_POSITION, (uint32_t)st, (uint32_t)(st >> 32), o);
+        e = G::play(e, acts[o[0] % (uint32_t)na]);
+        if (G::terminated(e)) { ok = false; break; }
+      }
+      if (ok) { G::to_bytes(e, out + (size_t)i * G::STATE_BYTES); break; }
+    }
+  }
+  return AZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// built-in oracles as networks
+// ------------------------------------------------------------------------------------------------
+template <class G, int KIND>
+struct OracleNet : az_net {
+  int eval(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V) override {
+    az_k_oracle<G, KIND><<<(max_rows + 127) / 128, 128, 0, ctx->stream>>>(envs, n_rows, P, V);
+    ctx->launches++;
+    return AZ_OK;
+  }
+};
+template <class G> static int g_make_oracle(az_ctx* ctx, int kind, az_net** out) {
+  az_net* n = nullptr;
+  if (kind == AZ_NET_UNIFORM) n = new OracleNet<G, 0>();
+  else if (kind == AZ_NET_SYNTH) n = new OracleNet<G, 1>();
+  else AZ_FAIL(ctx, AZ_EINVAL, "az_net_create_oracle: kind must be AZ_NET_UNIFORM or AZ_NET_SYNTH");
+  n->ctx = ctx; n->kind = kind; n->game = G::ID;
+  *out = n;
+  return AZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MCTS pool
+// ------------------------------------------------------------------------------------------------
+struct az_mcts {
+  az_ctx* ctx = nullptr;
+  az_net* net = nullptr;
+  int game = 0;
+  virtual ~az_mcts() {}
+  virtual int set_roots(const uint8_t* states, const double* eta) = 0;
+  virtual int run(int nsims) = 0;
+  virtual int root_stats(int64_t* N, double* W, float* P) = 0;
+  virtual int policy(double* pi) = 0;
+  virtual int reset() = 0;
+  virtual int counters(int64_t* ts, int64_t* tn, int64_t* nn) = 0;
+  double ms_total = 0, ms_net = 0;
+  int64_t ticks = 0, expansions = 0;
+};
+
+template <class G>
+struct Mcts : az_mcts {
+  AzPool p{};
+  az_mcts_params mp{};
+  size_t cap = 0;
+  std::vector<void*> allocs;
+  int64_t* d_N = nullptr; double* d_W = nullptr; float* d_P = nullptr;
+  int32_t* h_pin = nullptr;  // pinned: [0] n_leaves, [1..4] flags
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool profile_net = false;
+
+  template <class T> int alloc(T** ptr, size_t n) {
+    int s = az_dalloc(ctx, ptr, n);
+    if (s == AZ_OK) allocs.push_back(*ptr);
+    return s;
+  }
+  int create(az_ctx* c, az_net* n, const az_mcts_params* params, int S, int cap_nodes) {
+    ctx = c; net = n; game = G::ID; mp = *params;
+    if (S <= 0 || cap_nodes <= 0) AZ_FAIL(ctx, AZ_EINVAL, "az_mcts_create: n_trees and capacity must be positive");
+    if (params->num_iters_per_turn <= 0) AZ_FAIL(ctx, AZ_EINVAL, "MctsPlayer: niters > 0 (src/play.jl:162)");
+    if (n->game != G::ID) AZ_FAIL(ctx, AZ_EINVAL, "az_mcts_create: oracle was built for another game");
+    cap = 64;
+    while (cap < (size_t)cap_nodes + (size_t)cap_nodes / 4 + 8) cap <<= 1;
+    p.S = S; p.cap_mask = (uint32_t)(cap - 1); p.maxd = G::MAX_PLIES + 1;
+    p.c.gamma = params->gamma; p.c.cpuct = params->cpuct; p.c.eps = params->dirichlet_noise_eps;
+    p.c.alpha = params->dirichlet_noise_alpha; p.c.prior_temp = params->prior_temperature;
+    AZ_TRY(ctx, alloc(&p.nodes, (size_t)S * cap * G::LANES));
+    AZ_TRY(ctx, alloc(&p.root, S)); AZ_TRY(ctx, alloc(&p.tag, S)); AZ_TRY(ctx, alloc(&p.node_count, S));
+    AZ_TRY(ctx, alloc(&p.total_sims, S)); AZ_TRY(ctx, alloc(&p.total_nodes, S)); AZ_TRY(ctx, alloc(&p.sims_done, S));
+    AZ_TRY(ctx, alloc(&p.sims_target, S)); AZ_TRY(ctx, alloc(&p.status, S)); AZ_TRY(ctx, alloc(&p.eta, (size_t)S * G::A));
+    AZ_TRY(ctx, alloc(&p.pending, S)); AZ_TRY(ctx, alloc(&p.leaf_pos, S)); AZ_TRY(ctx, alloc(&p.leaf_env, S));
+    AZ_TRY(ctx, alloc(&p.leaf_row, S)); AZ_TRY(ctx, alloc(&p.depth, S));
+    AZ_TRY(ctx, alloc(&p.path_node, (size_t)S * p.maxd)); AZ_TRY(ctx, alloc(&p.path_meta, (size_t)S * p.maxd));
+    AZ_TRY(ctx, alloc(&p.path_r, (size_t)S * p.maxd));
+    AZ_TRY(ctx, alloc(&p.n_leaves, 1)); AZ_TRY(ctx, alloc(&p.batch_env, S));
+    AZ_TRY(ctx, alloc(&p.batch_P, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&p.batch_V, S));
+    AZ_TRY(ctx, alloc(&p.flags, 4)); AZ_TRY(ctx, alloc(&p.expansions, 1));
+    AZ_TRY(ctx, alloc(&d_N, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&d_W, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&d_P, (size_t)S * G::A));
+    std::vector<uint32_t> tags(S, 64u | 1u);
+    AZ_CUDA(ctx, cudaMemcpyAsync(p.tag, tags.data(), S * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    AZ_CUDA(ctx, cudaMallocHost((void**)&h_pin, 64));
+    for (auto& e : ev) AZ_CUDA(ctx, cudaEventCreate(&e));
+    AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AZ_OK;
+  }
+  ~Mcts() override {
+    for (void* q : allocs) cudaFree(q);
+    if (h_pin) cudaFreeHost(h_pin);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+  }
+  int groups_grid() const { return (int)(((size_t)p.S * G::LANES + 127) / 128); }
+
+  int set_roots(const uint8_t* states, const double* eta) override {
+    if (!eta && p.c.eps != 0.0) AZ_FAIL(ctx, AZ_EINVAL, "az_mcts_set_roots: eta is required when dirichlet_noise_eps != 0");
+    std::vector<AzEnv> r(p.S);
+    for (int i = 0; i < p.S; i++) r[i] = G::from_bytes(states + (size_t)i * G::STATE_BYTES);
+    AZ_CUDA(ctx, cudaMemcpyAsync(p.root, r.data(), p.S * sizeof(AzEnv), cudaMemcpyHostToDevice, ctx->stream));
+    if (eta) AZ_CUDA(ctx, cudaMemcpyAsync(p.eta, eta, (size_t)p.S * G::A * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // r is a stack-owned staging buffer
+    return AZ_OK;
+  }
+  // one tick: select -> oracle -> expand+backup
+  int tick(bool time_net) {
+    AZ_CUDA(ctx, cudaMemsetAsync(p.n_leaves, 0, sizeof(int32_t), ctx->stream));
+    az_k_select<G><<<groups_grid(), 128, 0, ctx->stream>>>(p);
+    if (time_net) cudaEventRecord(ev[2], ctx->stream);
+    AZ_TRY(ctx, net->eval(p.batch_env, p.n_leaves, p.S, p.batch_P, p.batch_V));
+    if (time_net) cudaEventRecord(ev[3], ctx->stream);
+    az_k_expand_backup<G><<<groups_grid(), 128, 0, ctx->stream>>>(p);
+    ctx->launches += 2;
+    return AZ_OK;
+  }
+  int check_flags() {
+    AZ_CUDA(ctx, cudaMemcpyAsync(h_pin, p.n_leaves, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AZ_CUDA(ctx, cudaMemcpyAsync(h_pin + 1, p.flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_pin[1]) AZ_FAIL(ctx, AZ_ENOMEM, "MCTS table overflow: raise capacity_nodes_per_tree");
+    if (h_pin[3]) AZ_FAIL(ctx, AZ_ESTATE, "simulation path exceeded the per-game ply bound");
+    if (h_pin[4]) AZ_FAIL(ctx, AZ_ESTATE, "MCTS.policy: explore! must be called before policy (src/mcts.jl:262)");
+    return AZ_OK;
+  }
+  int run(int nsims) override {
+    if (nsims <= 0) AZ_FAIL(ctx, AZ_EINVAL, "az_mcts_run: nsims must be positive");
+    std::vector<int32_t> tgt(p.S, nsims);
+    std::vector<uint8_t> st(p.S, 1);
+    AZ_CUDA(ctx, cudaMemsetAsync(p.sims_done, 0, p.S * sizeof(int32_t), ctx->stream));
+    AZ_CUDA(ctx, cudaMemsetAsync(p.expansions, 0, sizeof(int64_t), ctx->stream));
+    AZ_CUDA(ctx, cudaMemcpyAsync(p.sims_target, tgt.data(), p.S * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    AZ_CUDA(ctx, cudaMemcpyAsync(p.status, st.data(), p.S, cudaMemcpyHostToDevice, ctx->stream));
+    AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    AZ_CUDA(ctx, cudaEventRecord(ev[0], ctx->stream));
+    ticks = 0; ms_net = 0;
+    // every unfinished tree completes >= 1 simulation per tick, so nsims ticks always suffice
+    for (int t = 0; t < nsims; t++) {
+      AZ_TRY(ctx, tick(false));
+      ticks++;
+      if (t + 1 >= nsims / 2 && ((t + 1) % 8 == 0 || t + 1 == nsims)) {
+        AZ_TRY(ctx, check_flags());
+        if (h_pin[0] == 0) break;  // the last select found no leaf: every tree has spent its budget
+      }
+    }
+    AZ_CUDA(ctx, cudaEventRecord(ev[1], ctx->stream));
+    AZ_TRY(ctx, check_flags());
+    int64_t ex = 0;
+    AZ_CUDA(ctx, cudaMemcpy(&ex, p.expansions, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    expansions = ex;
+    float ms = 0;
+    AZ_CUDA(ctx, cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    ms_total = ms;
+    return AZ_OK;
+  }
+  int root_stats(int64_t* N, double* W, float* P) override {
+    az_k_root_stats<G><<<groups_grid(), 128, 0, ctx->stream>>>(p, d_N, d_W, d_P);
+    ctx->launches++;
+    size_t n = (size_t)p.S * G::A;
+    if (N) AZ_CUDA(ctx, cudaMemcpyAsync(N, d_N, n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (W) AZ_CUDA(ctx, cudaMemcpyAsync(W, d_W, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (P) AZ_CUDA(ctx, cudaMemcpyAsync(P, d_P, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AZ_OK;
+  }
+  int policy(double* pi) override {  // src/mcts.jl:255-271 (host arithmetic on the fetched integer counts)
+    std::vector<int64_t> N((size_t)p.S * G::A);
+    AZ_TRY(ctx, root_stats(N.data(), nullptr, nullptr));
+    for (int s = 0; s < p.S; s++) {
+      int64_t ntot = 0;
+      for (int a = 0; a < G::A; a++) ntot += N[(size_t)s * G::A + a];
+      if (ntot == 0) AZ_FAIL(ctx, AZ_ESTATE, "MCTS.explore! must be called before MCTS.policy (src/mcts.jl:262)");
+      double sum = 0.0; bool first = true;
+      for (int a = 0; a < G::A; a++) {
+        double v = (double)N[(size_t)s * G::A + a] / (double)ntot;
+        pi[(size_t)s * G::A + a] = v;
+        if (N[(size_t)s * G::A + a] || true) { sum = first ? v : sum + v; first = false; }
+      }
+      for (int a = 0; a < G::A; a++) pi[(size_t)s * G::A + a] = pi[(size_t)s * G::A + a] / sum;
+    }
+    return AZ_OK;
+  }
+  int reset() override {
+    az_k_reset<G><<<p.S, 128, 0, ctx->stream>>>(p);
+    ctx->launches++;
+    AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AZ_OK;
+  }
+  int counters(int64_t* ts, int64_t* tn, int64_t* nn) override {
+    if (ts) AZ_CUDA(ctx, cudaMemcpy(ts, p.total_sims, p.S * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (tn) AZ_CUDA(ctx, cudaMemcpy(tn, p.total_nodes, p.S * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (nn) {
+      std::vector<int32_t> c(p.S);
+      AZ_CUDA(ctx, cudaMemcpy(c.data(), p.node_count, p.S * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      for (int i = 0; i < p.S; i++) nn[i] = c[i];
+    }
+    return AZ_OK;
+  }
+};
+
+template <class G>
+static int g_make_mcts(az_ctx* ctx, az_net* net, const az_mcts_params* p, int S, int cap, az_mcts** out) {
+  auto* m = new Mcts<G>();
+  int s = m->create(ctx, net, p, S, cap);
+  if (s != AZ_OK) { m->ctx = nullptr; delete m; return s; }
+  *out = m;
+  return AZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// self-play
+// ------------------------------------------------------------------------------------------------
+struct az_selfplay {
+  az_ctx* ctx = nullptr;
+  int game = 0;
+  virtual ~az_selfplay() {}
+  virtual int start(int num_games, int64_t first) = 0;
+  virtual int poll(int32_t* done, int32_t* fin) = 0;
+  virtual int wait() = 0;
+  virtual int counts(int64_t* ns, int64_t* ng) = 0;
+  virtual int fetch(uint8_t* states, float* pi, uint8_t* mask, float* z, float* t, int32_t* gos, double* rew, int32_t* act) = 0;
+  virtual int stats(double* ed, int64_t* nodes, int32_t* moves, double* totals) = 0;
+};
+
+template <class G>
+struct SelfPlay : az_selfplay {
+  std::unique_ptr<Mcts<G>> pool;
+  AzSelfPlay sp{};
+  az_sim_params simp{};
+  std::vector<void*> allocs;
+  int games_cap = 0;
+  std::thread worker;
+  std::atomic<int> a_done{0}, a_finished{1}, a_status{AZ_OK};
+  std::string werr;
+  double seconds = 0;
+  int64_t total_expansions = 0;
+  int32_t* h_pin = nullptr;
+  std::vector<int32_t> h_moves;
+
+  template <class T> int alloc(T** ptr, size_t n) {
+    int s = az_dalloc(ctx, ptr, n);
+    if (s == AZ_OK) allocs.push_back(*ptr);
+    return s;
+  }
+  int create(az_ctx* c, az_net* net, const az_mcts_params* mp, const az_sim_params* s, uint64_t seed) {
+    ctx = c; game = G::ID; simp = *s;
+    if (s->num_workers <= 0) AZ_FAIL(ctx, AZ_EINVAL, "SimParams: num_workers must be positive");
+    if (s->batch_size > s->num_workers) AZ_FAIL(ctx, AZ_EINVAL, "batch_size <= num_workers (src/batchifier.jl:48)");
+    if (s->flip_probability != 0.0) AZ_FAIL(ctx, AZ_EUNSUPPORTED, "flip_probability != 0 is not supported yet");
+    if (mp->temperature_n < 1 || mp->temperature_n > AZ_MAX_SCHEDULE) AZ_FAIL(ctx, AZ_EINVAL, "temperature schedule: 1..8 points");
+    const int S = s->num_workers;
+    int reset = s->reset_every > 0 ? s->reset_every : std::max(1, (s->num_games + S - 1) / S);
+    size_t bound = (size_t)mp->num_iters_per_turn * G::MAX_PLIES * (size_t)reset;
+    size_t budget = (size_t)96 << 30;  // table budget: 96 GB of the 180 GB HBM
+    size_t maxnodes = budget / ((size_t)S * G::LANES * 16) * 3 / 4;
+    int cap_nodes = (int)std::min<size_t>(std::min(bound, maxnodes), (size_t)1 << 28);
+    pool.reset(new Mcts<G>());
+    int st = pool->create(ctx, net, mp, S, cap_nodes);
+    if (st != AZ_OK) { pool.reset(); return st; }
+    sp.seed = seed; sp.nsims = mp->num_iters_per_turn; sp.reset_every = s->reset_every; sp.max_plies = G::MAX_PLIES;
+    sp.sched_n = mp->temperature_n;
+    for (int i = 0; i < mp->temperature_n; i++) { sp.sched_xs[i] = mp->temperature_xs[i]; sp.sched_ys[i] = mp->temperature_ys[i]; }
+    AZ_TRY(ctx, alloc(&sp.game_of_slot, S)); AZ_TRY(ctx, alloc(&sp.move_of_slot, S)); AZ_TRY(ctx, alloc(&sp.games_on_slot, S));
+    AZ_TRY(ctx, alloc(&sp.games_done, 1)); AZ_TRY(ctx, alloc(&sp.active_slots, 1));
+    AZ_CUDA(ctx, cudaMallocHost((void**)&h_pin, 64));
+    return AZ_OK;
+  }
+  ~SelfPlay() override {
+    if (worker.joinable()) worker.join();
+    for (void* q : allocs) cudaFree(q);
+    for (void* q : game_allocs) cudaFree(q);
+    if (h_pin) cudaFreeHost(h_pin);
+  }
+  std::vector<void*> game_allocs;
+  template <class T> int galloc(T** ptr, size_t n) {
+    int s = az_dalloc(ctx, ptr, n);
+    if (s == AZ_OK) game_allocs.push_back(*ptr);
+    return s;
+  }
+  int ensure_game_buffers(int ng) {
+    if (ng <= games_cap) return AZ_OK;
+    for (void* q : game_allocs) cudaFree(q);
+    game_allocs.clear();
+    size_t rows = (size_t)ng * G::MAX_PLIES;
+    AZ_TRY(ctx, galloc(&sp.s_env, rows)); AZ_TRY(ctx, galloc(&sp.s_pi, rows * G::A)); AZ_TRY(ctx, galloc(&sp.s_action, rows));
+    AZ_TRY(ctx, galloc(&sp.s_reward, rows)); AZ_TRY(ctx, galloc(&sp.s_z, rows)); AZ_TRY(ctx, galloc(&sp.s_t, rows));
+    AZ_TRY(ctx, galloc(&sp.g_moves, ng)); AZ_TRY(ctx, galloc(&sp.g_edepth, ng)); AZ_TRY(ctx, galloc(&sp.g_nodes, ng));
+    games_cap = ng;
+    return AZ_OK;
+  }
+  int loop() {
+    auto t0 = std::chrono::steady_clock::now();
+    Mcts<G>& m = *pool;
+    cudaSetDevice(ctx->device);
+    AZ_CUDA(ctx, cudaMemsetAsync(sp.games_done, 0, 4, ctx->stream));
+    AZ_CUDA(ctx, cudaMemsetAsync(sp.active_slots, 0, 4, ctx->stream));
+    AZ_CUDA(ctx, cudaMemsetAsync(m.p.expansions, 0, 8, ctx->stream));
+    AZ_TRY(ctx, m.reset());
+    const int grid1 = (m.p.S + 127) / 128;
+    az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 1);
+    ctx->launches++;
+    int64_t tick = 0;
+    for (;;) {
+      AZ_TRY(ctx, m.tick(false));
+      az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 0);
+      ctx->launches++;
+      tick++;
+      if (tick % 32 == 0) {
+        AZ_CUDA(ctx, cudaMemcpyAsync(h_pin, sp.games_done, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        AZ_CUDA(ctx, cudaMemcpyAsync(h_pin + 1, sp.active_slots, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        AZ_CUDA(ctx, cudaMemcpyAsync(h_pin + 2, m.p.flags, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        a_done.store(h_pin[0]);
+        if (h_pin[2]) AZ_FAIL(ctx, AZ_ENOMEM, "MCTS table overflow during self-play");
+        if (h_pin[4]) AZ_FAIL(ctx, AZ_ESTATE, "simulation path exceeded the per-game ply bound");
+        if (h_pin[5]) AZ_FAIL(ctx, AZ_ESTATE, "root missing at move selection");
+        if (h_pin[0] >= sp.num_games) break;
+      }
+    }
+    AZ_CUDA(ctx, cudaMemcpy(&total_expansions, m.p.expansions, 8, cudaMemcpyDeviceToHost));
+    h_moves.resize(sp.num_games);
+    AZ_CUDA(ctx, cudaMemcpy(h_moves.data(), sp.g_moves, sp.num_games * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return AZ_OK;
+  }
+  int start(int num_games, int64_t first) override {
+    if (!a_finished.load()) AZ_FAIL(ctx, AZ_ESTATE, "az_selfplay_start: a run is already in flight");
+    if (worker.joinable()) worker.join();
+    if (num_games <= 0) AZ_FAIL(ctx, AZ_EINVAL, "num_games must be positive");
+    if (simp.reset_every <= 0) {
+      size_t need = (size_t)sp.nsims * G::MAX_PLIES * (size_t)((num_games + pool->p.S - 1) / pool->p.S);
+      (void)need;  // overflow is detected on device and reported as AZ_ENOMEM
+    }
+    AZ_TRY(ctx, ensure_game_buffers(num_games));
+    sp.num_games = num_games; sp.first_game = first;
+    a_done.store(0); a_finished.store(0); a_status.store(AZ_OK);
+    worker = std::thread([this]() {
+      int s = loop();
+      if (s != AZ_OK) werr = ctx->err;
+      a_status.store(s);
+      a_finished.store(1);
+    });
+    return AZ_OK;
+  }
+  int poll(int32_t* done, int32_t* fin) override {
+    if (done) *done = a_finished.load() && a_status.load() == AZ_OK ? sp.num_games : a_done.load();
+    if (fin) *fin = a_finished.load();
+    return a_status.load();
+  }
+  int wait() override {
+    if (worker.joinable()) worker.join();
+    if (a_status.load() != AZ_OK) ctx->err = werr;
+    return a_status.load();
+  }
+  int counts(int64_t* ns, int64_t* ng) override {
+    AZ_TRY(ctx, wait());
+    int64_t n = 0;
+    for (int v : h_moves) n += v;
+    if (ns) *ns = n;
+    if (ng) *ng = (int64_t)h_moves.size();
+    return AZ_OK;
+  }
+  int fetch(uint8_t* states, float* pi, uint8_t* mask, float* z, float* t, int32_t* gos, double* rew, int32_t* act) override {
+    AZ_TRY(ctx, wait());
+    const int ng = sp.num_games;
+    size_t rows = (size_t)ng * G::MAX_PLIES;
+    std::vector<AzEnv> env(rows);
+    std::vector<float> hpi(rows * G::A), hz(rows), ht(rows);
+    std::vector<int32_t> hact(rows);
+    std::vector<double> hrew(rows);
+    AZ_CUDA(ctx, cudaMemcpy(env.data(), sp.s_env, rows * sizeof(AzEnv), cudaMemcpyDeviceToHost));
+    AZ_CUDA(ctx, cudaMemcpy(hpi.data(), sp.s_pi, rows * G::A * sizeof(float), cudaMemcpyDeviceToHost));
+    AZ_CUDA(ctx, cudaMemcpy(hz.data(), sp.s_z, rows * sizeof(float), cudaMemcpyDeviceToHost));
+    AZ_CUDA(ctx, cudaMemcpy(ht.data(), sp.s_t, rows * sizeof(float), cudaMemcpyDeviceToHost));
+    AZ_CUDA(ctx, cudaMemcpy(hact.data(), sp.s_action, rows * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    AZ_CUDA(ctx, cudaMemcpy(hrew.data(), sp.s_reward, rows * sizeof(double), cudaMemcpyDeviceToHost));
+    size_t k = 0;
+    for (int g = 0; g < ng; g++)
+      for (int i = 0; i < h_moves[g]; i++, k++) {
+        size_t r = (size_t)g * G::MAX_PLIES + i;
+        if (states) G::to_bytes(env[r], states + k * G::STATE_BYTES);
+        uint32_t legal = G::legal_mask(env[r]);
+        for (int a = 0; a < G::A; a++) {
+          if (pi) pi[k * G::A + a] = hpi[r * G::A + a];
+          if (mask) mask[k * G::A + a] = (legal >> a) & 1;
+        }
+        if (z) z[k] = hz[r];
+        if (t) t[k] = ht[r];
+        if (gos) gos[k] = g;
+        if (rew) rew[k] = hrew[r];
+        if (act) act[k] = hact[r];
+      }
+    return AZ_OK;
+  }
+  int stats(double* ed, int64_t* nodes, int32_t* moves, double* totals) override {
+    AZ_TRY(ctx, wait());
+    const int ng = sp.num_games;
+    if (ed) AZ_CUDA(ctx, cudaMemcpy(ed, sp.g_edepth, ng * sizeof(double), cudaMemcpyDeviceToHost));
+    if (nodes) AZ_CUDA(ctx, cudaMemcpy(nodes, sp.g_nodes, ng * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (moves) memcpy(moves, h_moves.data(), ng * sizeof(int32_t));
+    if (totals) {
+      int64_t ns = 0;
+      for (int v : h_moves) ns += v;
+      totals[0] = seconds; totals[1] = (double)ns * sp.nsims; totals[2] = (double)total_expansions; totals[3] = (double)ns;
+    }
+    return AZ_OK;
+  }
+};
+template <class G>
+static int g_make_selfplay(az_ctx* ctx, az_net* net, const az_mcts_params* mp, const az_sim_params* sp, uint64_t seed, az_selfplay** out) {
+  auto* s = new SelfPlay<G>();
+  int st = s->create(ctx, net, mp, sp, seed);
+  if (st != AZ_OK) { delete s; return st; }
+  *out = s;
+  return AZ_OK;
+}
+
+// forward_normalized hook for oracle nets / networks: host states -> device envs -> eval -> host
+template <class G>
+static int g_net_forward(az_net* net, const uint8_t* states, int B, float* P, float* V, float* Pinv) {
+  az_ctx* ctx = net->ctx;
+  std::vector<AzEnv> envs(B);
+  for (int i = 0; i < B; i++) envs[i] = G::from_bytes(states + (size_t)i * G::STATE_BYTES);
+  AzEnv* d_env; int32_t* d_n; float *d_P, *d_V, *d_Pi;
+  AZ_TRY(ctx, az_dalloc(ctx, &d_env, B)); AZ_TRY(ctx, az_dalloc(ctx, &d_n, 1));
+  AZ_TRY(ctx, az_dalloc(ctx, &d_P, (size_t)B * G::A)); AZ_TRY(ctx, az_dalloc(ctx, &d_V, B)); AZ_TRY(ctx, az_dalloc(ctx, &d_Pi, B));
+  int32_t n = B;
+  AZ_CUDA(ctx, cudaMemcpyAsync(d_env, envs.data(), B * sizeof(AzEnv), cudaMemcpyHostToDevice, ctx->stream));
+  AZ_CUDA(ctx, cudaMemcpyAsync(d_n, &n, 4, cudaMemcpyHostToDevice, ctx->stream));
+  int st = net->eval_with_pinv(d_env, d_n, B, d_P, d_V, d_Pi);
+  if (st == AZ_OK) {
+    cudaMemcpyAsync(P, d_P, (size_t)B * G::A * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(V, d_V, B * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (Pinv) cudaMemcpyAsync(Pinv, d_Pi, B * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_env); cudaFree(d_n); cudaFree(d_P); cudaFree(d_V); cudaFree(d_Pi);
+  if (st != AZ_OK) return st;
+  if (e != cudaSuccess) AZ_FAIL(ctx, AZ_ECUDA, std::string("az_net_forward: ") + cudaGetErrorString(e));
+  return AZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+#define AZ_GUARD_BEGIN try {
+#define AZ_GUARD_END(ctx)                                         \
+  } catch (const std::exception& ex) {                            \
+    if (ctx) (ctx)->err = std::string("exception: ") + ex.what(); \
+    return AZ_ESTATE;                                             \
+  } catch (...) {                                                 \
+    if (ctx) (ctx)->err = "unknown exception";                    \
+    return AZ_ESTATE;                                             \
+  }
+
+extern "C" {
+
+int32_t az_version(void) { return AZ_ABI_VERSION; }
+
+int32_t az_ctx_create(int32_t device, az_ctx** out) {
+  if (!out) return AZ_EINVAL;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libazb200 has no CPU fallback)";
+    cudaGetLastError();
+    return AZ_ECUDA;
+  }
+  if (device < 0 || device >= n) { g_create_err = "az_ctx_create: bad device index"; return AZ_EINVAL; }
+  az_ctx* c = new az_ctx();
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_err = "az_ctx_create: cudaSetDevice/cudaStreamCreate failed";
+    delete c;
+    return AZ_ECUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+  *out = c;
+  return AZ_OK;
+}
+int32_t az_ctx_destroy(az_ctx* ctx) {
+  if (!ctx) return AZ_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return AZ_OK;
+}
+const char* az_last_error(az_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+int32_t az_ctx_synchronize(az_ctx* ctx) {
+  if (!ctx) return AZ_EINVAL;
+  AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AZ_OK;
+}
+int64_t az_ctx_num_launches(az_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int32_t az_game_lookup(const char* name) {
+  if (!name) return -1;
+  for (int i = 0; i < 3; i++) if (strcmp(name, AZ_GAME_NAMES[i]) == 0) return i;
+  return -1;
+}
+int32_t az_game_num_actions(int32_t game) { switch (game) { case 0: return GameC4::A; case 1: return GameTTT::A; case 2: return GameMancala::A; } return -1; }
+int32_t az_game_state_bytes(int32_t game) { switch (game) { case 0: return GameC4::STATE_BYTES; case 1: return GameTTT::STATE_BYTES; case 2: return GameMancala::STATE_BYTES; } return -1; }
+int32_t az_game_max_plies(int32_t game) { switch (game) { case 0: return GameC4::MAX_PLIES; case 1: return GameTTT::MAX_PLIES; case 2: return GameMancala::MAX_PLIES; } return -1; }
+int32_t az_game_state_dim(int32_t game, int32_t dim[3]) { if (!dim) return AZ_EINVAL; AZ_DISPATCH_GAME(game, g_state_dim, dim) }
+int32_t az_game_vectorize_state(int32_t game, const uint8_t* s, float* x) { if (!s || !x) return AZ_EINVAL; AZ_DISPATCH_GAME(game, g_vectorize, s, x) }
+int32_t az_game_actions_mask(int32_t game, const uint8_t* s, uint8_t* m) { if (!s || !m) return AZ_EINVAL; AZ_DISPATCH_GAME(game, g_mask, s, m) }
+int32_t az_game_play(int32_t game, const uint8_t* s, int32_t a, uint8_t* ns, int32_t* term, double* wr) {
+  if (!s || !ns) return AZ_EINVAL;
+  AZ_DISPATCH_GAME(game, g_play, s, a, ns, term, wr)
+}
+int32_t az_game_init_state(int32_t game, uint8_t* s) { if (!s) return AZ_EINVAL; AZ_DISPATCH_GAME(game, g_init_state, s) }
+int32_t az_game_random_positions(int32_t game, uint64_t seed, uint64_t first, int32_t n, int32_t max_plies, uint8_t* out) {
+  if (!out || n < 0 || max_plies < 0) return AZ_EINVAL;
+  AZ_DISPATCH_GAME(game, g_random_positions, seed, first, n, max_plies, out)
+}
+
+int32_t az_net_create_oracle(az_ctx* ctx, int32_t kind, int32_t game, az_net** out) {
+  if (!ctx || !out) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  AZ_DISPATCH_GAME(game, g_make_oracle, ctx, kind, out)
+  AZ_GUARD_END(ctx)
+}
+int32_t az_net_create_resnet(az_ctx* ctx, int32_t game, const az_resnet_hp* hp, az_net** out) {
+  if (!ctx || !hp || !out) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  int st = AZ_OK;
+  az_net* n = az_make_resnet(ctx, game, hp, &st);
+  if (st != AZ_OK) return st;
+  *out = n;
+  return AZ_OK;
+  AZ_GUARD_END(ctx)
+}
+int32_t az_net_create_simplenet(az_ctx* ctx, int32_t game, const az_simplenet_hp* hp, az_net** out) {
+  if (!ctx || !hp || !out) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  int st = AZ_OK;
+  az_net* n = az_make_simplenet(ctx, game, hp, &st);
+  if (st != AZ_OK) return st;
+  *out = n;
+  return AZ_OK;
+  AZ_GUARD_END(ctx)
+}
+int32_t az_net_num_params(az_net* net, int64_t* n) { if (!net || !n) return AZ_EINVAL; *n = net->num_params(); return AZ_OK; }
+int32_t az_net_load(az_net* net, const float* blob, int64_t n) {
+  if (!net || !blob) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  cudaSetDevice(net->ctx->device);
+  return net->load(blob, n);
+  AZ_GUARD_END(net->ctx)
+}
+int32_t az_net_forward(az_net* net, const uint8_t* states, int32_t B, float* P, float* V, float* Pinv) {
+  if (!net || !states || !P || !V || B <= 0) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  cudaSetDevice(net->ctx->device);
+  AZ_DISPATCH_GAME(net->game, g_net_forward, net, states, B, P, V, Pinv)
+  AZ_GUARD_END(net->ctx)
+}
+int32_t az_net_destroy(az_net* net) { if (!net) return AZ_EINVAL; cudaSetDevice(net->ctx->device); delete net; return AZ_OK; }
+
+int32_t az_mcts_create(az_ctx* ctx, int32_t game, az_net* oracle, const az_mcts_params* p, int32_t n_trees, int32_t cap, az_mcts** out) {
+  if (!ctx || !oracle || !p || !out) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  cudaSetDevice(ctx->device);
+  AZ_DISPATCH_GAME(game, g_make_mcts, ctx, oracle, p, n_trees, cap, out)
+  AZ_GUARD_END(ctx)
+}
+#define AZ_M(m) if (!(m)) return AZ_EINVAL; cudaSetDevice((m)->ctx->device);
+int32_t az_mcts_set_roots(az_mcts* m, const uint8_t* s, const double* eta) { AZ_M(m) if (!s) return AZ_EINVAL; AZ_GUARD_BEGIN return m->set_roots(s, eta); AZ_GUARD_END(m->ctx) }
+int32_t az_mcts_run(az_mcts* m, int32_t nsims) { AZ_M(m) AZ_GUARD_BEGIN return m->run(nsims); AZ_GUARD_END(m->ctx) }
+int32_t az_mcts_explore(az_mcts* m, const uint8_t* s, const double* eta, int32_t nsims, int64_t* N, double* W, float* P) {
+  AZ_M(m) if (!s) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  AZ_TRY(m->ctx, m->set_roots(s, eta));
+  AZ_TRY(m->ctx, m->run(nsims));
+  return m->root_stats(N, W, P);
+  AZ_GUARD_END(m->ctx)
+}
+int32_t az_mcts_root_stats(az_mcts* m, int64_t* N, double* W, float* P) { AZ_M(m) AZ_GUARD_BEGIN return m->root_stats(N, W, P); AZ_GUARD_END(m->ctx) }
+int32_t az_mcts_policy(az_mcts* m, double* pi) { AZ_M(m) if (!pi) return AZ_EINVAL; AZ_GUARD_BEGIN return m->policy(pi); AZ_GUARD_END(m->ctx) }
+int32_t az_mcts_reset(az_mcts* m) { AZ_M(m) AZ_GUARD_BEGIN return m->reset(); AZ_GUARD_END(m->ctx) }
+int32_t az_mcts_counters(az_mcts* m, int64_t* ts, int64_t* tn, int64_t* nn) { AZ_M(m) AZ_GUARD_BEGIN return m->counters(ts, tn, nn); AZ_GUARD_END(m->ctx) }
+int32_t az_mcts_last_timing(az_mcts* m, double* ms_total, double* ms_net, int64_t* ticks, int64_t* ex) {
+  if (!m) return AZ_EINVAL;
+  if (ms_total) *ms_total = m->ms_total;
+  if (ms_net) *ms_net = m->ms_net;
+  if (ticks) *ticks = m->ticks;
+  if (ex) *ex = m->expansions;
+  return AZ_OK;
+}
+int32_t az_mcts_destroy(az_mcts* m) { AZ_M(m) delete m; return AZ_OK; }
+
+int32_t az_selfplay_create(az_ctx* ctx, int32_t game, az_net* oracle, const az_mcts_params* mp, const az_sim_params* sp, uint64_t seed, az_selfplay** out) {
+  if (!ctx || !oracle || !mp || !sp || !out) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  cudaSetDevice(ctx->device);
+  if (oracle->game != game) AZ_FAIL(ctx, AZ_EINVAL, "az_selfplay_create: oracle was built for another game");
+  if (mp->num_iters_per_turn <= 0) AZ_FAIL(ctx, AZ_EINVAL, "MctsPlayer: niters > 0 (src/play.jl:162)");
+  AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, oracle, mp, sp, seed, out)
+  AZ_GUARD_END(ctx)
+}
+int32_t az_selfplay_start(az_selfplay* s, int32_t ng, int64_t first) { AZ_M(s) AZ_GUARD_BEGIN return s->start(ng, first); AZ_GUARD_END(s->ctx) }
+int32_t az_selfplay_poll(az_selfplay* s, int32_t* done, int32_t* fin) { if (!s) return AZ_EINVAL; return s->poll(done, fin); }
+int32_t az_selfplay_wait(az_selfplay* s) { AZ_M(s) AZ_GUARD_BEGIN return s->wait(); AZ_GUARD_END(s->ctx) }
+int32_t az_selfplay_counts(az_selfplay* s, int64_t* ns, int64_t* ng) { AZ_M(s) AZ_GUARD_BEGIN return s->counts(ns, ng); AZ_GUARD_END(s->ctx) }
+int32_t az_selfplay_fetch(az_selfplay* s, uint8_t* states, float* pi, uint8_t* mask, float* z, float* t, int32_t* gos, double* rew, int32_t* act) {
+  AZ_M(s) AZ_GUARD_BEGIN return s->fetch(states, pi, mask, z, t, gos, rew, act); AZ_GUARD_END(s->ctx)
+}
+int32_t az_selfplay_stats(az_selfplay* s, double* ed, int64_t* nodes, int32_t* moves, double* totals) { AZ_M(s) AZ_GUARD_BEGIN return s->stats(ed, nodes, moves, totals); AZ_GUARD_END(s->ctx) }
+int32_t az_selfplay_destroy(az_selfplay* s) { AZ_M(s) delete s; return AZ_OK; }
+
+}  // extern "C"

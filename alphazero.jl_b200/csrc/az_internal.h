@@ -1,0 +1,46 @@
+// az_internal.h -- host-side types shared by the translation units of libazb200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/azb200.h"
+#include "az_games.cuh"
+
+struct az_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int num_sms = 148;
+};
+
+#define AZ_CUDA(ctx, call)                                                                      \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + __FILE__ + ":" + std::to_string(__LINE__); \
+      return AZ_ECUDA;                                                                          \
+    }                                                                                           \
+  } while (0)
+
+// An oracle in the sense of src/mcts.jl:6-17, evaluated for a whole leaf batch on the context's stream.
+// envs/n_rows/P/V are DEVICE pointers; P is A-wide (masked, renormalised, zero on illegal actions).
+struct az_net {
+  az_ctx* ctx = nullptr;
+  int kind = 0;
+  int game = 0;
+  virtual ~az_net() {}
+  virtual int eval(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V) = 0;
+  virtual int64_t num_params() { return 0; }
+  virtual int load(const float*, int64_t) { return AZ_OK; }
+  // Pinvalid (device, may be null) only for the forward_normalized ABI hook
+  virtual int eval_with_pinv(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V, float* Pinv) {
+    (void)Pinv;
+    return eval(envs, n_rows, max_rows, P, V);
+  }
+};
+
+az_net* az_make_resnet(az_ctx* ctx, int game, const az_resnet_hp* hp, int* status);
+az_net* az_make_simplenet(az_ctx* ctx, int game, const az_simplenet_hp* hp, int* status);

@@ -1,0 +1,553 @@
+// az_tree.cuh -- on-device MCTS: select / expand / backup / per-move kernels over a pool of independent trees.
+//
+// One tree ("slot") = one MCTS.Env of the reference (src/mcts.jl:124-151): a state-keyed transposition table,
+// here an open-addressing hash table in HBM.  A node is one LANES*16-byte line:
+//     lane 0      : key  {a, b | tag<<57}                (16 B)
+//     lane 1 + i  : edge {W f64, P f32, N i32} of action i (16 B)      -> Connect-Four: exactly 128 B
+// A group of LANES threads owns a slot: one coalesced line load fetches key + all edges of a node, the PUCT
+// argmax is a shuffle reduction across the group, and only one writer ever touches a table (no atomics).
+//
+// Numerics follow src/mcts.jl exactly (W, scores, q in f64 with one rounding per operation -- this file is
+// compiled with -fmad=false; P and Vest f32; N integer); see DESIGN.md "bit-exact select".
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "az_games.cuh"
+#include "az_rng.cuh"
+
+union AzLine16 {
+  uint4 u;
+  struct { uint64_t a, b; } key;
+  struct { double W; float P; int32_t N; } e;
+};
+
+struct AzMctsConst {
+  double gamma, cpuct, eps, alpha, prior_temp;
+};
+
+struct AzPool {
+  int S;              // number of trees (slots)
+  uint32_t cap_mask;  // table capacity - 1 (lines per slot)
+  int maxd;           // path capacity
+  uint4* nodes;       // [S][cap][LANES]
+  AzEnv* root;        // [S]
+  uint32_t* tag;      // [S] 7-bit tag: bit6 = occupied, bits0-5 = generation
+  int32_t* node_count;
+  int64_t* total_sims;
+  int64_t* total_nodes;
+  int32_t* sims_done;
+  int32_t* sims_target;
+  uint8_t* status;    // 0 idle, 1 active
+  double* eta;        // [S][A] compact over legal actions
+  int32_t* pending;
+  uint32_t* leaf_pos;
+  AzEnv* leaf_env;
+  int32_t* leaf_row;
+  int32_t* depth;
+  uint32_t* path_node;  // [S][maxd]
+  uint16_t* path_meta;  // [S][maxd]  action | pswitch << 8
+  double* path_r;       // [S][maxd]
+  int32_t* n_leaves;    // [1]
+  AzEnv* batch_env;     // [S]
+  float* batch_P;       // [S][A]
+  float* batch_V;       // [S]
+  int32_t* flags;       // [4]: 0 overflow, 1 active slots not finished (select), 2 path overflow
+  int64_t* expansions;  // [1]
+  AzMctsConst c;
+};
+
+#define AZ_KEYB_MASK ((1ull << 57) - 1)
+
+template <int L>
+__device__ __forceinline__ unsigned az_group_mask() {
+  if (L == 32) return 0xffffffffu;
+  unsigned lane = threadIdx.x & 31u;
+  return ((1u << L) - 1u) << (lane & ~(unsigned)(L - 1));
+}
+__device__ __forceinline__ uint32_t az_hash(uint64_t a, uint64_t b) {
+  uint64_t x = a * 0x9E3779B97F4A7C15ull ^ (b + 0x7F4A7C15F39CC060ull) * 0xC2B2AE3D27D4EB4Full;
+  x ^= x >> 32;
+  x *= 0xD6E8FEB86659FD93ull;
+  x ^= x >> 29;
+  return (uint32_t)x;
+}
+
+// find the line of `env` in the slot's table.  Returns 1 found / 2 empty (h = insert position); ln = the line.
+template <class G>
+__device__ __forceinline__ int az_probe(const uint4* tab, uint32_t cap_mask, uint32_t tag, const AzEnv& env, int lane,
+                                        unsigned gm, uint32_t& h, AzLine16& ln) {
+  constexpr int L = G::LANES;
+  h = az_hash(env.a, env.b) & cap_mask;
+  for (;;) {
+    ln.u = tab[(size_t)h * L + lane];
+    int st = 0;
+    if (lane == 0) {
+      if ((uint32_t)(ln.key.b >> 57) != tag) st = 2;
+      else if (ln.key.a == env.a && (ln.key.b & AZ_KEYB_MASK) == env.b) st = 1;
+    }
+    st = __shfl_sync(gm, st, 0, L);
+    if (st) return st;
+    h = (h + 1) & cap_mask;
+  }
+}
+
+// backup (update_state_info!, src/mcts.jl:190-194,216-221) of the recorded path with leaf value q
+template <class G>
+__device__ __forceinline__ void az_backup(const AzPool& p, int slot, int lane, unsigned gm, uint4* tab, int depth, double q) {
+  constexpr int L = G::LANES;
+  __syncwarp(gm);
+  const uint32_t* pn = p.path_node + (size_t)slot * p.maxd;
+  const uint16_t* pm = p.path_meta + (size_t)slot * p.maxd;
+  const double* pr = p.path_r + (size_t)slot * p.maxd;
+  for (int j = depth - 1; j >= 0; j--) {
+    uint32_t meta = pm[j];
+    if (meta >> 8) q = -q;
+    q = pr[j] + p.c.gamma * q;
+    bool mine = G::ACYCLIC ? ((j % L) == lane) : (lane == 0);
+    if (mine) {
+      uint4* addr = tab + (size_t)pn[j] * L + 1 + (meta & 0xFF);
+      AzLine16 e;
+      e.u = *addr;
+      e.e.W = e.e.W + q;
+      e.e.N += 1;
+      *addr = e.u;
+    }
+  }
+  __syncwarp(gm);
+}
+
+// ---- select: run simulations until a leaf needs the oracle or the budget is spent (src/mcts.jl:199-226,239-245) ----
+template <class G>
+__global__ void __launch_bounds__(128) az_k_select(AzPool p) {
+  constexpr int L = G::LANES;
+  constexpr int A = G::A;
+  int slot = (blockIdx.x * blockDim.x + threadIdx.x) / L;
+  int lane = threadIdx.x % L;
+  if (slot >= p.S) return;
+  unsigned gm = az_group_mask<L>();
+  if (!p.status[slot] || p.pending[slot]) return;
+  int sims_done = p.sims_done[slot];
+  const int target = p.sims_target[slot];
+  if (sims_done >= target) return;
+  const AzEnv root = p.root[slot];
+  const uint32_t tag = p.tag[slot];
+  uint4* tab = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
+  uint32_t* pn = p.path_node + (size_t)slot * p.maxd;
+  uint16_t* pm = p.path_meta + (size_t)slot * p.maxd;
+  double* pr = p.path_r + (size_t)slot * p.maxd;
+  int64_t tsims = 0, tnodes = 0;
+  const int a = lane - 1;
+  while (sims_done < target) {
+    tsims++;
+    AzEnv env = root;
+    int depth = 0;
+    bool isroot = true, need_leaf = false;
+    for (;;) {
+      if (G::terminated(env) || depth >= p.maxd) {
+        if (depth >= p.maxd && lane == 0) p.flags[2] = 1;
+        az_backup<G>(p, slot, lane, gm, tab, depth, 0.0);
+        tnodes += depth;
+        break;
+      }
+      uint32_t h;
+      AzLine16 ln;
+      int st = az_probe<G>(tab, p.cap_mask, tag, env, lane, gm, h, ln);
+      if (st == 2) {  // new node: ask the oracle (state_info, src/mcts.jl:165-174)
+        if (lane == 0) {
+          int row = atomicAdd(p.n_leaves, 1);
+          p.batch_env[row] = env;
+          p.leaf_row[slot] = row;
+          p.leaf_pos[slot] = h;
+          p.leaf_env[slot] = env;
+          p.depth[slot] = depth;
+          p.pending[slot] = 1;
+        }
+        need_leaf = true;
+        break;
+      }
+      // uct_scores (src/mcts.jl:180-188) + argmax (first maximal legal action)
+      const uint32_t legal = G::legal_mask(env);
+      const bool is_edge = (a >= 0) && (a < A) && ((legal >> a) & 1u);
+      int n = is_edge ? ln.e.N : 0;
+      int ntot = n;
+#pragma unroll
+      for (int off = L / 2; off >= 1; off >>= 1) ntot += __shfl_xor_sync(gm, ntot, off, L);
+      double score = __longlong_as_double((long long)0xFFF0000000000000ull);  // -inf
+      if (is_edge) {
+        double Pd = (double)ln.e.P;
+        if (isroot && p.c.eps != 0.0) {
+          int idx = __popc(legal & ((1u << a) - 1u));
+          Pd = (1.0 - p.c.eps) * Pd + p.c.eps * p.eta[(size_t)slot * A + idx];
+        }
+        double sq = sqrt((double)ntot);
+        score = ln.e.W / (double)(n > 1 ? n : 1) + ((p.c.cpuct * Pd) * sq) / (double)(n + 1);
+      }
+      int best = lane;
+#pragma unroll
+      for (int off = L / 2; off >= 1; off >>= 1) {
+        double os = __shfl_xor_sync(gm, score, off, L);
+        int ol = __shfl_xor_sync(gm, best, off, L);
+        if (os > score || (os == score && ol < best)) { score = os; best = ol; }
+      }
+      const int act = best - 1;
+      const bool wp = G::white_playing(env);
+      const AzEnv nx = G::play(env, act);
+      const double wr = G::white_reward(nx);
+      if (lane == 0) {
+        pn[depth] = h;
+        pm[depth] = (uint16_t)(act | ((wp != G::white_playing(nx)) ? 0x100 : 0));
+        pr[depth] = wp ? wr : -wr;
+      }
+      depth++;
+      env = nx;
+      isroot = false;
+    }
+    if (need_leaf) break;
+    sims_done++;
+  }
+  if (lane == 0) {
+    p.sims_done[slot] = sims_done;
+    p.total_sims[slot] += tsims;
+    p.total_nodes[slot] += tnodes;
+  }
+}
+
+// Util.apply_temperature on the prior (src/util.jl:98-110, src/mcts.jl:157-161); sequential like the reference
+template <int A>
+__device__ __forceinline__ void az_prior_temperature(float* P, uint32_t legal, double tau) {
+  if (tau == 1.0) return;
+  if (tau == 0.0) {
+    int k = -1;
+    for (int i = 0; i < A; i++)
+      if ((legal >> i) & 1u) if (k < 0 || P[i] > P[k]) k = i;
+    for (int i = 0; i < A; i++) P[i] = (i == k) ? 1.0f : 0.0f;
+    return;
+  }
+  double r[A], s = 0.0, it = 1.0 / tau;
+  bool first = true;
+  for (int i = 0; i < A; i++) {
+    r[i] = 0.0;
+    if (!((legal >> i) & 1u)) continue;
+    r[i] = (P[i] > 0.0f) ? az_det_exp(it * az_det_log((double)P[i])) : 0.0;
+    s = first ? r[i] : s + r[i];
+    first = false;
+  }
+  for (int i = 0; i < A; i++) P[i] = ((legal >> i) & 1u) ? (float)(r[i] / s) : 0.0f;
+}
+
+// ---- expand + backup: insert the evaluated leaf (init_state_info, src/mcts.jl:157-174) and back its value up ----
+template <class G>
+__global__ void __launch_bounds__(128) az_k_expand_backup(AzPool p) {
+  constexpr int L = G::LANES;
+  constexpr int A = G::A;
+  int slot = (blockIdx.x * blockDim.x + threadIdx.x) / L;
+  int lane = threadIdx.x % L;
+  if (slot >= p.S) return;
+  unsigned gm = az_group_mask<L>();
+  if (!p.pending[slot]) return;
+  const int row = p.leaf_row[slot];
+  const AzEnv env = p.leaf_env[slot];
+  const uint32_t pos = p.leaf_pos[slot];
+  const int depth = p.depth[slot];
+  const uint32_t tag = p.tag[slot];
+  uint4* tab = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
+  const uint32_t legal = G::legal_mask(env);
+  const int a = lane - 1;
+  float P = 0.0f;
+  if (a >= 0 && a < A && ((legal >> a) & 1u)) P = p.batch_P[(size_t)row * A + a];
+  if (p.c.prior_temp != 1.0) {
+    float Pv[A];
+    for (int i = 0; i < A; i++) Pv[i] = __shfl_sync(gm, P, i + 1, L);
+    az_prior_temperature<A>(Pv, legal, p.c.prior_temp);
+    if (a >= 0 && a < A) P = Pv[a];
+  }
+  const float V = p.batch_V[row];
+  AzLine16 ln;
+  ln.u = make_uint4(0, 0, 0, 0);
+  if (lane == 0) { ln.key.a = env.a; ln.key.b = env.b | ((uint64_t)tag << 57); }
+  else if (a < A) { ln.e.W = 0.0; ln.e.P = P; ln.e.N = 0; }
+  tab[(size_t)pos * L + lane] = ln.u;
+  az_backup<G>(p, slot, lane, gm, tab, depth, (double)V);
+  if (lane == 0) {
+    int nc = p.node_count[slot] + 1;
+    p.node_count[slot] = nc;
+    if ((uint64_t)nc * 8 > ((uint64_t)p.cap_mask + 1) * 7) p.flags[0] = 1;
+    p.total_nodes[slot] += depth;
+    p.sims_done[slot] += 1;
+    p.pending[slot] = 0;
+    atomicAdd((unsigned long long*)p.expansions, 1ull);
+  }
+}
+
+// ---- built-in oracles: MCTS.RandomOracle (src/mcts.jl:62-72) and the deterministic hash pseudo-network ----
+template <class G, int KIND>
+__global__ void az_k_oracle(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_rows, float* __restrict__ P,
+                            float* __restrict__ V) {
+  constexpr int A = G::A;
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= *n_rows) return;
+  const AzEnv env = envs[row];
+  const uint32_t legal = G::legal_mask(env);
+  if (KIND == 0) {
+    int n = __popc(legal);
+    float pu = (float)(1.0 / (double)n);
+    for (int i = 0; i < A; i++) P[(size_t)row * A + i] = ((legal >> i) & 1u) ? pu : 0.0f;
+    V[row] = 0.0f;
+  } else {
+    uint64_t h0 = az_splitmix(env.a ^ az_splitmix(env.b));
+    uint32_t raw[A], sum = 0;
+    for (int i = 0; i < A; i++) {
+      raw[i] = 0;
+      if (!((legal >> i) & 1u)) continue;
+      uint64_t hi = az_splitmix(h0 + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ull);
+      raw[i] = 1u + (uint32_t)(hi >> 48);
+      sum += raw[i];
+    }
+    for (int i = 0; i < A; i++) P[(size_t)row * A + i] = ((legal >> i) & 1u) ? (float)raw[i] / (float)sum : 0.0f;
+    V[row] = ((float)(int)(h0 >> 48) - 32768.0f) / 32768.0f;
+  }
+}
+
+// ---- root statistics (action-indexed) -------------------------------------------------------------------
+template <class G>
+__global__ void az_k_root_stats(AzPool p, int64_t* N, double* W, float* P) {
+  constexpr int L = G::LANES;
+  constexpr int A = G::A;
+  int slot = (blockIdx.x * blockDim.x + threadIdx.x) / L;
+  int lane = threadIdx.x % L;
+  if (slot >= p.S) return;
+  unsigned gm = az_group_mask<L>();
+  const AzEnv root = p.root[slot];
+  const uint4* tab = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
+  uint32_t h;
+  AzLine16 ln;
+  int st = G::terminated(root) ? 2 : az_probe<G>(tab, p.cap_mask, p.tag[slot], root, lane, gm, h, ln);
+  int a = lane - 1;
+  if (a >= 0 && a < A) {
+    bool ok = (st == 1) && ((G::legal_mask(root) >> a) & 1u);
+    N[(size_t)slot * A + a] = ok ? (int64_t)ln.e.N : 0;
+    W[(size_t)slot * A + a] = ok ? ln.e.W : 0.0;
+    P[(size_t)slot * A + a] = ok ? ln.e.P : 0.0f;
+  }
+}
+
+// MCTS.reset! (src/mcts.jl:278-281): bump the generation tag; clear the table only when the 6-bit generation wraps
+template <class G>
+__global__ void az_k_reset(AzPool p) {
+  constexpr int L = G::LANES;
+  int slot = blockIdx.x;
+  if (slot >= p.S) return;
+  uint32_t tag = p.tag[slot];
+  uint32_t gen = (tag & 63u) + 1u;
+  if (gen == 64u) {
+    uint4* tab = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
+    size_t n = ((size_t)p.cap_mask + 1) * L;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) tab[i] = make_uint4(0, 0, 0, 0);
+    gen = 1u;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    p.tag[slot] = 64u | gen;
+    p.node_count[slot] = 0;
+    p.pending[slot] = 0;
+  }
+}
+
+// =====================================================================================================
+// Self-play: per-move kernel = MCTS.policy + temperature + categorical sample + play! + trace record
+// (src/play.jl:298-315, src/mcts.jl:255-271, src/util.jl:68-110, src/schedule.jl:64-80) and, at game end,
+// push_trace! (src/memory.jl:74-87), self_play_measurements (src/training.jl:269-273) and the worker's
+// reset_every / next-game logic (src/simulations.jl:221-241).
+// =====================================================================================================
+struct AzSelfPlay {
+  uint64_t seed;
+  int64_t first_game;     // global index of local game 0
+  int32_t num_games;      // local games to play
+  int32_t nsims;
+  int32_t reset_every;
+  int32_t max_plies;
+  int32_t sched_n;
+  int32_t sched_xs[8];
+  double sched_ys[8];
+  // per slot
+  int32_t* game_of_slot;   // local game index or -1
+  int32_t* move_of_slot;
+  int32_t* games_on_slot;
+  // per (game, ply) rows, stride max_plies
+  AzEnv* s_env;
+  float* s_pi;             // [A]
+  int32_t* s_action;
+  double* s_reward;
+  float* s_z;
+  float* s_t;
+  // per game
+  int32_t* g_moves;
+  double* g_edepth;
+  int64_t* g_nodes;
+  int32_t* games_done;     // [1]
+  int32_t* active_slots;   // [1]
+};
+
+__device__ __forceinline__ double az_schedule(const AzSelfPlay& sp, int i) {  // src/schedule.jl:64-80
+  int pt = -1;
+  for (int k = 0; k < sp.sched_n; k++) if (sp.sched_xs[k] <= i) pt = k;
+  if (pt < 0) return sp.sched_ys[0];
+  if (pt == sp.sched_n - 1) return sp.sched_ys[sp.sched_n - 1];
+  double x0 = sp.sched_xs[pt], y0 = sp.sched_ys[pt], x1 = sp.sched_xs[pt + 1], y1 = sp.sched_ys[pt + 1];
+  return y0 + ((y1 - y0) / (x1 - x0)) * ((double)i - x0);
+}
+
+template <class G>
+__device__ void az_begin_move(const AzPool& p, const AzSelfPlay& sp, int slot, const AzEnv& root, int64_t game, int move) {
+  constexpr int A = G::A;
+  p.root[slot] = root;
+  p.sims_done[slot] = 0;
+  p.sims_target[slot] = sp.nsims;
+  double eta[A];
+  int n = __popc(G::legal_mask(root));
+  az_dirichlet(sp.seed, (uint64_t)game, (uint32_t)move, n, p.c.alpha, eta);  // drawn even if eps == 0 (src/mcts.jl:240)
+  for (int i = 0; i < n; i++) p.eta[(size_t)slot * A + i] = eta[i];
+}
+
+// one thread per slot (runs once per move: scalar code, not performance critical)
+template <class G>
+__global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
+  constexpr int L = G::LANES;
+  constexpr int A = G::A;
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= p.S) return;
+  if (start_games) {  // assign the first game of every slot (static round-robin: game = slot + S * k)
+    p.total_sims[slot] = 0;
+    p.total_nodes[slot] = 0;
+    sp.games_on_slot[slot] = 0;
+    if (slot < sp.num_games) {
+      sp.game_of_slot[slot] = slot;
+      sp.move_of_slot[slot] = 0;
+      p.status[slot] = 1;
+      p.pending[slot] = 0;
+      az_begin_move<G>(p, sp, slot, G::init(), sp.first_game + slot, 0);
+      atomicAdd(sp.active_slots, 1);
+    } else {
+      sp.game_of_slot[slot] = -1;
+      p.status[slot] = 0;
+      p.sims_target[slot] = 0;
+    }
+    return;
+  }
+  if (!p.status[slot] || p.pending[slot] || p.sims_done[slot] < p.sims_target[slot]) return;
+  const int g = sp.game_of_slot[slot];
+  const int move = sp.move_of_slot[slot];
+  const int64_t game = sp.first_game + g;
+  const AzEnv root = p.root[slot];
+  const uint32_t legal = G::legal_mask(root);
+  // MCTS.policy (src/mcts.jl:255-271): find the root line (single thread: read the L lanes one by one)
+  const uint4* tab = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
+  uint32_t h = az_hash(root.a, root.b) & p.cap_mask;
+  const uint32_t tag = p.tag[slot];
+  for (;;) {
+    AzLine16 k;
+    k.u = tab[(size_t)h * L];
+    if ((uint32_t)(k.key.b >> 57) == tag && k.key.a == root.a && (k.key.b & AZ_KEYB_MASK) == root.b) break;
+    if ((uint32_t)(k.key.b >> 57) != tag) { p.flags[3] = 1; break; }  // cannot happen after explore!
+    h = (h + 1) & p.cap_mask;
+  }
+  int acts[A];
+  double pi[A], pis[A];
+  float pf[A];
+  int n = 0;
+  int64_t ntot = 0;
+  for (int i = 0; i < A; i++)
+    if ((legal >> i) & 1u) {
+      AzLine16 e;
+      e.u = tab[(size_t)h * L + 1 + i];
+      acts[n] = i;
+      pi[n] = (double)e.e.N;
+      ntot += e.e.N;
+      n++;
+    }
+  double sum = 0.0;
+  for (int i = 0; i < n; i++) { pi[i] = pi[i] / (double)ntot; sum = (i == 0) ? pi[0] : sum + pi[i]; }
+  for (int i = 0; i < n; i++) pi[i] = pi[i] / sum;
+  // temperature (src/play.jl:208-210,309-310; src/util.jl:98-110)
+  const double tau = az_schedule(sp, move);
+  if (tau == 1.0) { for (int i = 0; i < n; i++) pis[i] = pi[i]; }
+  else if (tau == 0.0) {
+    int k = 0;
+    for (int i = 1; i < n; i++) if (pi[i] > pi[k]) k = i;
+    for (int i = 0; i < n; i++) pis[i] = (i == k) ? 1.0 : 0.0;
+  } else {
+    double it = 1.0 / tau, s = 0.0;
+    for (int i = 0; i < n; i++) pis[i] = (pi[i] > 0.0) ? az_det_exp(it * az_det_log(pi[i])) : 0.0;
+    for (int i = 0; i < n; i++) s = (i == 0) ? pis[0] : s + pis[i];
+    for (int i = 0; i < n; i++) pis[i] = pis[i] / s;
+  }
+  // fix_probvec + rand(Categorical) (src/util.jl:68-90)
+  float fs = 0.0f;
+  for (int i = 0; i < n; i++) { pf[i] = (float)pis[i]; fs = (i == 0) ? pf[0] : fs + pf[i]; }
+  {
+    const float rtol = 3.4526698e-4f;
+    float d = fabsf(fs - 1.0f), m = fabsf(fs) > 1.0f ? fabsf(fs) : 1.0f;
+    bool approx = (fs == 1.0f) || (isfinite(fs) && d <= rtol * m);
+    if (!approx) {
+      if (fs == 0.0f) for (int i = 0; i < n; i++) pf[i] = 1.0f / (float)n;
+      else for (int i = 0; i < n; i++) pf[i] = pf[i] / fs;
+    }
+  }
+  const float u = az_uniform_f32(sp.seed, (uint64_t)game, (uint32_t)move, AZ_PURPOSE_CATEGORICAL, 0);
+  float cp = pf[0];
+  int k = 0;
+  while (cp <= u && k < n - 1) { k++; cp = cp + pf[k]; }
+  const int act = acts[k];
+  // record (trace.jl:35-39) and play
+  const size_t rowi = (size_t)g * sp.max_plies + move;
+  sp.s_env[rowi] = root;
+  for (int i = 0; i < A; i++) sp.s_pi[rowi * A + i] = 0.0f;
+  for (int i = 0; i < n; i++) sp.s_pi[rowi * A + acts[i]] = (float)pi[i];
+  sp.s_action[rowi] = act;
+  const AzEnv nx = G::play(root, act);
+  sp.s_reward[rowi] = G::white_reward(nx);
+  const int nm = move + 1;
+  if (G::terminated(nx) || nm >= sp.max_plies) {
+    // push_trace! (src/memory.jl:74-87)
+    double wr = 0.0;
+    for (int i = nm - 1; i >= 0; i--) {
+      const size_t ri = (size_t)g * sp.max_plies + i;
+      wr = p.c.gamma * wr + sp.s_reward[ri];
+      sp.s_z[ri] = (float)(G::white_playing(sp.s_env[ri]) ? wr : -wr);
+      sp.s_t[ri] = (float)(nm - i);
+    }
+    sp.g_moves[g] = nm;
+    sp.g_nodes[g] = p.node_count[slot];
+    const int64_t ts = p.total_sims[slot];
+    sp.g_edepth[g] = ts == 0 ? 0.0 : (double)p.total_nodes[slot] / (double)ts;
+    atomicAdd(sp.games_done, 1);
+    const int gos = sp.games_on_slot[slot] + 1;
+    sp.games_on_slot[slot] = gos;
+    if (sp.reset_every > 0 && gos % sp.reset_every == 0) {  // reset_player! (src/simulations.jl:235-237)
+      uint32_t gen = (p.tag[slot] & 63u) + 1u;
+      if (gen == 64u) {
+        uint4* wt = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
+        size_t cnt = ((size_t)p.cap_mask + 1) * L;
+        for (size_t i = 0; i < cnt; i++) wt[i] = make_uint4(0, 0, 0, 0);
+        gen = 1u;
+      }
+      p.tag[slot] = 64u | gen;
+      p.node_count[slot] = 0;
+    }
+    const int ng = slot + p.S * gos;
+    if (ng < sp.num_games) {
+      sp.game_of_slot[slot] = ng;
+      sp.move_of_slot[slot] = 0;
+      az_begin_move<G>(p, sp, slot, G::init(), sp.first_game + ng, 0);
+    } else {
+      sp.game_of_slot[slot] = -1;
+      p.status[slot] = 0;
+      p.sims_target[slot] = 0;
+      atomicAdd(sp.active_slots, -1);
+    }
+  } else {
+    sp.move_of_slot[slot] = nm;
+    az_begin_move<G>(p, sp, slot, nx, game, nm);
+  }
+}

@@ -1,0 +1,176 @@
+/*
+ * azb200.h -- C ABI of the B200-native self-play engine (libazb200.so).
+ *
+ * Drop-in boundary for the self-play hot path of AlphaZero.jl.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference root);
+ * INTEGRATION.md shows the Julia `ccall` stub for each.  Plain C: opaque handles,
+ * caller-allocated HOST buffers, int32 status codes (0 = OK), no exception crosses.
+ *
+ * State byte formats (what the Julia shim passes; one state = az_game_state_bytes):
+ *   connect-four (43 B): cells[col + 7*row] in {0 empty, 1 white, 2 black}, curplayer {1,2}
+ *                        -- the in-memory layout of (board::SMatrix{7,6,UInt8}, curplayer::UInt8),
+ *                        games/connect-four/game.jl:19-22
+ *   tictactoe    (10 B): cells[pos], pos = (y-1)*3 + (x-1), {0,1 white,2 black}; curplayer {1,2}
+ *                        (games/tictactoe/game.jl:9-14: Bool/Nothing cells mapped to bytes)
+ *   mancala      (15 B): stores[2], houses[(player-1) + 2*(num-1)] (12 B), curplayer {1,2}
+ *                        (games/mancala/game.jl:22-25)
+ * Actions are 0-based here (Julia action a  <->  a-1).
+ */
+#ifndef AZB200_H
+#define AZB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZ_ABI_VERSION 1
+#define AZ_MAX_ACTIONS 9
+#define AZ_MAX_SCHEDULE 8
+
+enum az_status { AZ_OK = 0, AZ_EINVAL = 1, AZ_ECUDA = 2, AZ_ENOMEM = 3, AZ_ESTATE = 4, AZ_EUNSUPPORTED = 5 };
+
+typedef struct az_ctx az_ctx;
+typedef struct az_net az_net;
+typedef struct az_mcts az_mcts;
+typedef struct az_selfplay az_selfplay;
+
+/* ---- library / context ---------------------------------------------------------------- */
+int32_t az_version(void);
+/* one context per GPU per process (the rank-per-GPU analogue of a Distributed worker, src/simulations.jl:268-281) */
+int32_t az_ctx_create(int32_t device, az_ctx** out);
+int32_t az_ctx_destroy(az_ctx* ctx);
+/* message of the last failing call on this context (or of az_ctx_create when ctx == NULL) */
+const char* az_last_error(az_ctx* ctx);
+int32_t az_ctx_synchronize(az_ctx* ctx);
+/* number of kernels launched by this context so far (bench.py's gpu_launches) */
+int64_t az_ctx_num_launches(az_ctx* ctx);
+
+/* ---- games: GI.AbstractGameSpec queries (src/game.jl:34-120; names = src/examples.jl:17-21) ---- */
+int32_t az_game_lookup(const char* name); /* "connect-four" | "tictactoe" | "mancala"; < 0 if unknown */
+int32_t az_game_num_actions(int32_t game);          /* GI.num_actions */
+int32_t az_game_state_bytes(int32_t game);
+int32_t az_game_state_dim(int32_t game, int32_t dim[3]); /* GI.state_dim */
+int32_t az_game_max_plies(int32_t game);
+/* GI.vectorize_state, GI.actions_mask(GI.init(spec, s)), GI.game_terminated, GI.white_reward, GI.play! on host
+   bytes, evaluated by the SAME inline functions the kernels use (host build of csrc/az_games.cuh) */
+int32_t az_game_vectorize_state(int32_t game, const uint8_t* state, float* x);
+int32_t az_game_actions_mask(int32_t game, const uint8_t* state, uint8_t* mask);
+int32_t az_game_play(int32_t game, const uint8_t* state, int32_t action, uint8_t* next_state, int32_t* terminated,
+                     double* white_reward);
+int32_t az_game_init_state(int32_t game, uint8_t* state);
+/* synthetic random positions: k ~ U{0..max_plies} random legal plies, terminal positions rejected */
+int32_t az_game_random_positions(int32_t game, uint64_t seed, uint64_t first_stream, int32_t n, int32_t max_plies,
+                                 uint8_t* states);
+
+/* ---- parameters: MctsParams (src/params.jl:49-57), SimParams (src/params.jl:92-101) ------ */
+typedef struct {
+  double gamma;
+  double cpuct;
+  int32_t num_iters_per_turn;
+  int32_t temperature_n; /* PLSchedule points (ConstSchedule = 1 point), src/schedule.jl:64-80 */
+  double dirichlet_noise_eps;
+  double dirichlet_noise_alpha;
+  double prior_temperature;
+  int32_t temperature_xs[AZ_MAX_SCHEDULE];
+  double temperature_ys[AZ_MAX_SCHEDULE];
+} az_mcts_params;
+
+typedef struct {
+  int32_t num_games;
+  int32_t num_workers; /* concurrent game slots on this GPU (= worker tasks, src/simulations.jl:217) */
+  int32_t batch_size;  /* accepted for API parity; the engine batches every pending leaf of a tick */
+  int32_t fill_batches;
+  int32_t reset_every; /* <= 0: never (Julia `nothing`) */
+  int32_t alternate_colors;
+  double flip_probability; /* must be 0 in this round (self-play configs use 0) */
+} az_sim_params;
+
+/* ---- networks: Network interface (src/networks/network.jl), ResNet (architectures/resnet.jl) ---- */
+enum az_net_kind {
+  AZ_NET_UNIFORM = 0, /* MCTS.RandomOracle, src/mcts.jl:62-72 */
+  AZ_NET_SYNTH = 1,   /* deterministic hash pseudo-network (parity tests: bit-exact on CPU and GPU) */
+  AZ_NET_RESNET = 2,
+  AZ_NET_SIMPLENET = 3
+};
+typedef struct { /* ResNetHP, src/networks/architectures/resnet.jl:30-37 */
+  int32_t num_blocks;
+  int32_t num_filters;
+  int32_t conv_kernel_size[2];
+  int32_t num_policy_head_filters;
+  int32_t num_value_head_filters;
+  float batch_norm_momentum;
+} az_resnet_hp;
+typedef struct { /* SimpleNetHP, src/networks/architectures/simplenet.jl:15-22 */
+  int32_t width;
+  int32_t depth_common;
+  int32_t depth_phead;
+  int32_t depth_vhead;
+  int32_t use_batch_norm;
+  float batch_norm_momentum;
+} az_simplenet_hp;
+
+int32_t az_net_create_oracle(az_ctx* ctx, int32_t kind, int32_t game, az_net** out);
+int32_t az_net_create_resnet(az_ctx* ctx, int32_t game, const az_resnet_hp* hp, az_net** out);
+int32_t az_net_create_simplenet(az_ctx* ctx, int32_t game, const az_simplenet_hp* hp, az_net** out);
+/* number of float32 values of the parameter blob, in Flux order (see DESIGN.md "weight blob"):
+   per Conv: W[kw,kh,cin,cout] (column-major) then b[cout]; per BatchNorm: gamma, beta, mu, sigma2;
+   per Dense: W[out,in] (column-major) then b[out]; layer order = common, vhead, phead */
+int32_t az_net_num_params(az_net* net, int64_t* n);
+/* replaces Network.copy(bestnn; on_gpu=true, test_mode=true) (src/training.jl:278-279): uploads + folds BN */
+int32_t az_net_load(az_net* net, const float* blob, int64_t n);
+/* Network.evaluate_batch / forward_normalized (src/networks/network.jl:264-271,308-315):
+   P is A-wide (masked, renormalised, zero on illegal), V[B], Pinvalid[B] (may be NULL) */
+int32_t az_net_forward(az_net* net, const uint8_t* states, int32_t B, float* P, float* V, float* Pinvalid);
+int32_t az_net_destroy(az_net* net);
+
+/* ---- MCTS.Env pool: n_trees independent MCTS.Env (src/mcts.jl:124-151) on one GPU ---------- */
+int32_t az_mcts_create(az_ctx* ctx, int32_t game, az_net* oracle, const az_mcts_params* p, int32_t n_trees,
+                       int32_t capacity_nodes_per_tree, az_mcts** out);
+/* roots[i] = GI.current_state of tree i's game; eta: n_trees x A doubles, compact over legal actions in ascending
+   order (src/mcts.jl:228-232), or NULL (then dirichlet_noise_eps must be 0) */
+int32_t az_mcts_set_roots(az_mcts* m, const uint8_t* root_states, const double* eta);
+/* MCTS.explore!(env, game, nsims) on every tree (src/mcts.jl:239-245); roots resident on device */
+int32_t az_mcts_run(az_mcts* m, int32_t nsims);
+/* set_roots + run + root_stats in one call with host buffers (the `think` seam, src/play.jl:196-206) */
+int32_t az_mcts_explore(az_mcts* m, const uint8_t* root_states, const double* eta, int32_t nsims, int64_t* N, double* W,
+                        float* P);
+/* per-tree root ActionStats, action-indexed (A wide, zeros on illegal) */
+int32_t az_mcts_root_stats(az_mcts* m, int64_t* N, double* W, float* P);
+/* MCTS.policy (src/mcts.jl:255-271), A-wide float64 */
+int32_t az_mcts_policy(az_mcts* m, double* pi);
+/* MCTS.reset! (src/mcts.jl:278-281) */
+int32_t az_mcts_reset(az_mcts* m);
+/* total_simulations, total_nodes_traversed, length(tree) per tree (src/mcts.jl:142-143,293-321); any may be NULL */
+int32_t az_mcts_counters(az_mcts* m, int64_t* total_simulations, int64_t* total_nodes_traversed, int64_t* num_nodes);
+/* device-side timing of the last az_mcts_run: total ms, ms inside the network forward, ticks, expansions */
+int32_t az_mcts_last_timing(az_mcts* m, double* ms_total, double* ms_network, int64_t* ticks, int64_t* expansions);
+int32_t az_mcts_destroy(az_mcts* m);
+
+/* ---- self-play: simulate(simulator, gspec, SimParams) (src/simulations.jl:207-244) ------------ */
+int32_t az_selfplay_create(az_ctx* ctx, int32_t game, az_net* oracle, const az_mcts_params* mp, const az_sim_params* sp,
+                           uint64_t seed, az_selfplay** out);
+/* plays games first_game_index .. first_game_index + num_games - 1 (global indices key the RNG streams);
+   returns immediately, the engine runs on its own host thread + CUDA stream */
+int32_t az_selfplay_start(az_selfplay* s, int32_t num_games, int64_t first_game_index);
+/* non-blocking progress (drives the `game_simulated` callback, src/simulations.jl:238) */
+int32_t az_selfplay_poll(az_selfplay* s, int32_t* games_done, int32_t* finished);
+int32_t az_selfplay_wait(az_selfplay* s);
+int32_t az_selfplay_counts(az_selfplay* s, int64_t* nsamples, int64_t* ngames);
+/* samples ordered by (game, ply) = Trace rows (src/trace.jl:17-24) + push_trace! targets (src/memory.jl:74-87):
+   states[nsamples*state_bytes], pi[nsamples*A] (zero on illegal), mask[nsamples*A], z, t, game_of_sample,
+   rewards (white_reward after the move), actions; any pointer may be NULL */
+int32_t az_selfplay_fetch(az_selfplay* s, uint8_t* states, float* pi, uint8_t* mask, float* z, float* t,
+                          int32_t* game_of_sample, double* rewards, int32_t* actions);
+/* self_play_measurements (src/training.jl:269-273): per game edepth, node count (mem = nodes x
+   MCTS.memory_footprint_per_node), number of moves; totals[4] = {seconds, simulations, expansions, samples} */
+int32_t az_selfplay_stats(az_selfplay* s, double* edepth_per_game, int64_t* nodes_per_game, int32_t* moves_per_game,
+                          double* totals);
+int32_t az_selfplay_destroy(az_selfplay* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,67 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/azb200.h
+declares, answers the pure-host game queries, and fails loudly (no CPU fallback) without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import _pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def az():
+    _pkg.build()
+    return _pkg.load()
+
+
+def test_library_exports_every_declared_symbol(az):
+    hdr = open(os.path.join(ROOT, "include", "azb200.h")).read()
+    declared = set(re.findall(r"\b(az_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"az_status"}
+    assert declared == set(az.ABI_SYMBOLS), declared ^ set(az.ABI_SYMBOLS)
+    L = az.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert L.az_version() == 1
+
+
+def test_game_queries_match_oracle(az, oz):
+    """The product's host game helpers (same inline code as the kernels) against the CPU oracle on random playouts."""
+    rng = np.random.default_rng(1)
+    for name in ["connect-four", "tictactoe", "mancala"]:
+        gs = az.GameSpec(name)
+        gid = oz.game_id(name)
+        assert gs.num_actions == oz.num_actions(gid) and gs.state_bytes == oz.state_bytes(gid)
+        assert gs.state_dim == oz.state_dim(gid)
+        for _ in range(40):
+            g = oz.GameEnv(gid)
+            s = gs.init_state()
+            assert bytes(s) == g.state()
+            while not g.terminated():
+                m = g.actions_mask()
+                assert (gs.actions_mask(s) == m).all()
+                assert (gs.vectorize_state(s) == oz.vectorize_state(gid, g.state())).all()
+                a = int(rng.choice(np.flatnonzero(m)))
+                g.play(a)
+                s, term, wr = gs.play(s, a)
+                assert bytes(s) == g.state() and term == g.terminated() and wr == g.white_reward()
+
+
+def test_random_positions_match_oracle(az, oz):
+    gs = az.GameSpec("connect-four")
+    a = gs.random_positions(0xA17A2E80, 64, 30)
+    b = oz.random_positions(oz.game_id("connect-four"), 0xA17A2E80, 64, 30)
+    assert (a == b).all()
+
+
+def test_no_cpu_fallback(az):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(az.AzError) as e:
+        az.Context(0)
+    assert "no CPU fallback" in str(e.value)

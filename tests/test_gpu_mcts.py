@@ -1,0 +1,171 @@
+"""GPU parity proper (-m gpu): the CUDA tree kernels, called through the C ABI, against the CPU oracle.
+Bar: visit counts N, accumulated values W (f64), priors P and selected moves BIT-EXACT."""
+import os
+
+import numpy as np
+import pytest
+
+import _pkg
+
+pytestmark = pytest.mark.gpu
+PONS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pons")
+
+
+@pytest.fixture(scope="module")
+def az():
+    return _pkg.load()
+
+
+@pytest.fixture(scope="module")
+def ctx(az):
+    c = az.Context(0)
+    yield c
+    c.close()
+
+
+def _etas(oz, gid, roots, A, seed, alpha=1.0):
+    eta = np.zeros((len(roots), A))
+    for i, r in enumerate(roots):
+        n = int(oz.GameEnv(gid, r).actions_mask().sum())
+        eta[i, :n] = oz.dirichlet(seed, i, 0, n, alpha)
+    return eta
+
+
+def _oracle_explore(oz, gid, kind, roots, eta, nsims, cpuct, eps, rounds=1):
+    out = []
+    for i, r in enumerate(roots):
+        env = oz.Env(gid, kind, cpuct=cpuct, noise_eps=eps)
+        g = oz.GameEnv(gid, r)
+        n = int(g.actions_mask().sum())
+        for _ in range(rounds):
+            env.explore(g, nsims, None if eta is None else eta[i, :n])
+        _, N, W, P, _ = env.root_stats(g)
+        out.append((N, W, P, env.total_simulations, env.total_nodes_traversed, env.num_nodes))
+    return out
+
+
+def _pons_roots(gs, n):
+    roots = []
+    for name in ["Test_L1_R1", "Test_L2_R1", "Test_L3_R1"]:
+        with open(os.path.join(PONS, name)) as f:
+            for ln in list(f)[: n // 3]:
+                s = gs.init_state()
+                for ch in ln.split()[0]:
+                    s, _, _ = gs.play(s, int(ch) - 1)
+                roots.append(s)
+    return np.stack(roots)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "synth"])
+@pytest.mark.parametrize("game,nsims,nroots", [("connect-four", 600, 192), ("tictactoe", 50, 64), ("mancala", 400, 64)])
+def test_explore_bit_exact(az, oz, ctx, game, nsims, nroots, kind):
+    gs = az.GameSpec(game)
+    gid = oz.game_id(game)
+    A = gs.num_actions
+    roots = gs.random_positions(0xA17A2E80, nroots, 30 if game != "tictactoe" else 5)
+    if game == "connect-four":
+        roots = np.concatenate([roots, _pons_roots(gs, 63)])
+        roots[0] = gs.init_state()
+    eta = _etas(oz, gid, roots, A, seed=5)
+    mp = az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, dirichlet_noise_eps=0.25, dirichlet_noise_alpha=1.0)
+    net = az.RandomOracle(ctx, gs) if kind == "uniform" else az.SynthOracle(ctx, gs)
+    env = az.MctsEnv(ctx, gs, net, mp, len(roots), capacity_nodes_per_tree=2 * nsims)
+    N, W, P = env.explore(roots, nsims, eta)
+    ts, tn, nn = env.counters()
+    ref = _oracle_explore(oz, gid, kind, roots, eta, nsims, 2.0, 0.25)
+    for i, (rN, rW, rP, rts, rtn, rnn) in enumerate(ref):
+        assert (N[i] == rN).all(), (i, N[i], rN)
+        assert (W[i] == rW).all(), (i, W[i], rW)          # f64 bit-exact
+        assert (P[i].view(np.uint32) == rP.view(np.uint32)).all()
+        assert (ts[i], tn[i], nn[i]) == (rts, rtn, rnn)
+        assert N[i].sum() == nsims - 1                      # first simulation only expands the root
+    # tree kept across explore! calls (transposition table persists, src/mcts.jl:124-151)
+    env.run(nsims)
+    N2, W2, _ = env.root_stats()
+    ref2 = _oracle_explore(oz, gid, kind, roots[:16], eta[:16], nsims, 2.0, 0.25, rounds=2)
+    for i, (rN, rW, *_r) in enumerate(ref2):
+        assert (N2[i] == rN).all() and (W2[i] == rW).all()
+    pi = env.policy()
+    assert np.allclose(pi.sum(1), 1) and (pi[0] == N2[0] / N2[0].sum() / (N2[0] / N2[0].sum()).sum()).all()
+    env.reset()
+    _, _, nn = env.counters()
+    assert (nn == 0).all()
+    N3, W3, _ = env.explore(roots, nsims, eta)
+    assert (N3 == N).all() and (W3 == W).all()             # reset! really empties the tree
+    env.close()
+    net.close()
+
+
+def test_explore_without_noise_and_gamma(az, oz, ctx):
+    gs = az.GameSpec("connect-four")
+    gid = oz.game_id("connect-four")
+    roots = gs.random_positions(3, 32, 20)
+    mp = az.MctsParams(gamma=0.9, cpuct=1.0, num_iters_per_turn=200, dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0)
+    net = az.SynthOracle(ctx, gs)
+    env = az.MctsEnv(ctx, gs, net, mp, len(roots), 512)
+    N, W, P = env.explore(roots, 200, None)
+    for i, r in enumerate(roots):
+        e = oz.Env(gid, "synth", gamma=0.9, cpuct=1.0)
+        g = oz.GameEnv(gid, r)
+        e.explore(g, 200)
+        _, rN, rW, rP, _ = e.root_stats(g)
+        assert (N[i] == rN).all() and (W[i] == rW).all()
+    env.close()
+    net.close()
+
+
+@pytest.mark.parametrize("game,nsims,temp", [("connect-four", 64, ([0, 20, 30], [1.0, 1.0, 0.3])),
+                                              ("tictactoe", 50, ([0], [1.0])), ("mancala", 32, ([0, 10], [1.0, 0.0]))])
+def test_selfplay_bit_exact(az, oz, ctx, game, nsims, temp):
+    """simulate() with 8 workers, 24 games, reset_every 2 against oracle workers (static game->worker map)."""
+    gs = az.GameSpec(game)
+    gid = oz.game_id(game)
+    S, NG, seed = 8, 24, 77
+    mp = az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, temperature=az.PLSchedule(*temp), dirichlet_noise_eps=0.25,
+                       dirichlet_noise_alpha=1.0)
+    sp = az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=2)
+    net = az.SynthOracle(ctx, gs)
+    called = []
+    out = az.simulate(ctx, gs, net, az.SelfPlayParams(mp, sp), seed=seed, game_simulated=lambda: called.append(1))
+    assert len(called) == NG
+    omp = oz.mcts_params(cpuct=2.0, noise_eps=0.25, noise_alpha=1.0, num_iters_per_turn=nsims, sched_xs=temp[0], sched_ys=temp[1])
+    k = 0
+    for w in range(S):
+        traces = oz.worker_run(gid, "synth", omp, seed, first=w, stride=S, count=NG // S, reset_every=2)
+        for j, tr in enumerate(traces):
+            g = w + S * j
+            rows = np.flatnonzero(out["game"] == g)
+            n = tr["n_moves"]
+            assert len(rows) == n == out["moves"][g], (g, len(rows), n)
+            assert (out["actions"][rows] == tr["action"]).all()
+            assert (out["states"][rows] == tr["states"][:n]).all()
+            assert (out["pi"][rows].view(np.uint32) == tr["pi"].view(np.uint32)).all()
+            assert (out["mask"][rows] == tr["mask"]).all()
+            assert (out["rewards"][rows] == tr["rewards"]).all()
+            assert (out["z"][rows] == tr["z"].astype(np.float32)).all() and (out["t"][rows] == tr["t"]).all()
+            assert out["nodes"][g] == tr["mem_nodes"] and out["edepth"][g] == tr["edepth"]
+            k += n
+    assert k == len(out["game"]) == out["samples"]
+    net.close()
+
+
+def test_full_size_properties(az, ctx):
+    """BASELINE config 1 sizes (4096 trees x 600 sims): size-independent invariants instead of an oracle run."""
+    gs = az.GameSpec("connect-four")
+    S, nsims = 4096, 600
+    roots = gs.random_positions(0xA17A2E80, S, 30)
+    mp = az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0)
+    net = az.SynthOracle(ctx, gs)
+    env = az.MctsEnv(ctx, gs, net, mp, S, capacity_nodes_per_tree=nsims + 8)
+    N, W, P = env.explore(roots, nsims)
+    ts, tn, nn = env.counters()
+    assert (N.sum(1) == nsims - 1).all() and (ts == nsims).all()
+    assert (nn <= nsims).all() and (nn >= 1).all()
+    assert np.allclose(P.sum(1), 1, atol=1e-6)
+    legal = np.stack([gs.actions_mask(r) for r in roots[:256]])
+    assert (N[:256][~legal] == 0).all()
+    assert (np.abs(W) <= N + 1e-9).all()           # |q| <= 1 per visit (gamma = 1, rewards in [-1, 1])
+    t = env.last_timing()
+    assert t["expansions"] == nn.sum()
+    env.close()
+    net.close()

@@ -653,6 +653,12 @@ int32_t az_net_forward(az_net* net, const uint8_t* states, int32_t B, float* P, 
   AZ_DISPATCH_GAME(net->game, g_net_forward, net, states, B, P, V, Pinv)
   AZ_GUARD_END(net->ctx)
 }
+int32_t az_net_set_profiling(az_net* net, int32_t enable) { if (!net) return AZ_EINVAL; cudaSetDevice(net->ctx->device); return net->set_profiling(enable); }
+int32_t az_net_get_profile(az_net* net, double* tower_ms, int64_t* tower_launches, double* total_ms, int64_t* evals) {
+  if (!net) return AZ_EINVAL;
+  cudaSetDevice(net->ctx->device);
+  return net->get_profile(tower_ms, tower_launches, total_ms, evals);
+}
 int32_t az_net_destroy(az_net* net) { if (!net) return AZ_EINVAL; cudaSetDevice(net->ctx->device); delete net; return AZ_OK; }
 
 int32_t az_mcts_create(az_ctx* ctx, int32_t game, az_net* oracle, const az_mcts_params* p, int32_t n_trees, int32_t cap, az_mcts** out) {

@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- MCTS node-expansions/s on Connect-Four (BASELINE.json metric), one rank per GPU.
+
+A "step" = MCTS.explore! (600 simulations) on every one of the rank's 4096 concurrent game trees (fresh trees,
+synthetic random Connect-Four positions), every new node evaluated by the 7-block ResNet: config[1] of BASELINE.json.
+  value : expansions/s with the roots already resident in HBM (az_mcts_set_roots before the timed region)
+  e2e   : the same through the host-buffer seam az_mcts_explore (H2D roots + eta, run, D2H N/W/P inside the timed region)
+Trees are sharded over ranks with no data-path collective (weak scaling: 4096 trees per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  --impl reference : the reference's algorithm on the host CPU cores (oracle port + torch-CPU fp32 network),
+                     rank 0 only, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED_POS = 0xA17A2E80
+TREES_PER_GPU = 4096
+NSIMS = 600
+BLOCKS = 7
+HP = dict(num_blocks=BLOCKS, num_filters=128, conv_kernel_size=(3, 3), num_policy_head_filters=32, num_value_head_filters=32)
+CONV_MFLOP_PER_LEAF = 2 * 42 * 128 * 1152 / 1e6     # one 3x3 conv layer, valid positions only (12.39 MFLOP)
+NET_MFLOP_PER_LEAF = 174.7                           # whole 7-block network
+METRIC = "mcts_node_expansions_per_s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md sustained)"
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.stop, self.th = gpu, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows)
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(r[4 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": reasons, "samples": len(sm)}
+
+
+def make_eta(oz_or_none, roots, A, seed):
+    """Dirichlet(1) root noise per tree; generated with numpy here (bench input, not a parity path)."""
+    rng = np.random.default_rng(seed)
+    eta = np.zeros((len(roots), A))
+    full = np.array([(r[35:42] == 0).sum() for r in roots])  # legal columns = empty top cells
+    for i, n in enumerate(full):
+        e = rng.exponential(size=n)
+        eta[i, :n] = e / e.sum()
+    return eta
+
+
+def cpu_reference_run(n_trees, nsims, threads, seed_offset=0):
+    """The reference's algorithm on host cores: CPU MCTS (oracle port) + batched torch-CPU fp32 7-block ResNet.
+    Returns (expansions, seconds, simulations)."""
+    import torch
+    from oracle import oracle as oz, netref
+    torch.set_num_threads(threads)
+    gid = oz.game_id("connect-four")
+    dim, A = (7, 6, 3), 7
+    blob = netref.make_blob(dim, A, HP, seed=1, randomize=False)
+    roots = oz.random_positions(gid, SEED_POS, n_trees, 30, first_stream=seed_offset)
+    eta = make_eta(None, roots, A, 3)
+    mp = oz.mcts_params(cpuct=2.0, noise_eps=0.25, noise_alpha=1.0, num_iters_per_turn=nsims)
+    b = oz.Batch(gid, n_trees, mp)
+    b.set_roots(roots, eta)
+    t0 = time.perf_counter()
+    while True:
+        ls, _ = b.advance()
+        if len(ls) == 0:
+            break
+        X = np.stack([oz.vectorize_state(gid, bytes(s)) for s in ls])
+        mask = np.stack([X[i, :, 5, 0] > 0 for i in range(len(ls))])  # top row empty -> legal
+        P, V = netref.forward(blob, dim, A, HP, X)
+        Pn, V, _ = netref.forward_normalized(P, V, mask)
+        b.feed(Pn, V)
+    dt = time.perf_counter() - t0
+    return b.expansions, dt, b.simulations
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    n_trees = 256
+    nsims = 150
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference_run(32, 20, threads)
+    ex, dt = 0, 0.0
+    for k in range(args.steps):
+        e, d, _ = cpu_reference_run(n_trees, nsims, threads, seed_offset=1000 * k)
+        ex += e
+        dt += d
+    v = ex / dt
+    sample = "%d trees x %d sims per step (config[1] is 4096 x 600); CPU MCTS (C port of src/mcts.jl) + torch-CPU fp32 7-block ResNet, batch = pending leaves" % (n_trees, nsims)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "expansions/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "connect-four explore: %d trees x %d sims, 7-block ResNet (bounded sample of config[1])" % (n_trees, nsims)},
+            "cpu_baseline": {"value": v, "unit": "expansions/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "expansions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--trees", type=int, default=TREES_PER_GPU)
+    ap.add_argument("--nsims", type=int, default=NSIMS)
+    ap.add_argument("--blocks", type=int, default=BLOCKS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--oracle-net", default=None, choices=[None, "uniform", "synth"], help="tree-only figure: built-in oracle instead of the ResNet")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import _pkg
+    az = _pkg.load()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = az.Context(local)
+    gs = az.GameSpec("connect-four")
+    S, nsims, A = args.trees, args.nsims, 7
+    hp = dict(HP, num_blocks=args.blocks)
+    from tests import netcheck  # blob construction helper only (weights: Glorot-uniform, seed 1, fresh BatchNorm)
+    if args.oracle_net:
+        net = az.RandomOracle(ctx, gs) if args.oracle_net == "uniform" else az.SynthOracle(ctx, gs)
+    else:
+        net, _ = netcheck.make_net(az, ctx, gs, hp, seed=1, randomize=False)
+    mp = az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, dirichlet_noise_eps=0.25, dirichlet_noise_alpha=1.0)
+    env = az.MctsEnv(ctx, gs, net, mp, S, capacity_nodes_per_tree=nsims + 8)
+    roots = gs.random_positions(SEED_POS, S, 30, first_stream=rank * S)
+    eta = make_eta(None, roots, A, 100 + rank)
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def step_resident():
+        env.reset()
+        env.run(nsims)
+        return env.last_timing()
+
+    def step_e2e():
+        env.reset()
+        t0 = time.perf_counter()
+        N, W, P = env.explore(roots, nsims, eta)   # H2D roots+eta, 600 sims, D2H N/W/P
+        dt = time.perf_counter() - t0
+        return dt, env.last_timing()["expansions"], N
+
+    env.set_roots(roots, eta)
+    for _ in range(args.warmup):
+        step_resident()
+    # ---- timed: device-resident ----
+    if not args.oracle_net:
+        net.set_profiling(True)
+    l0 = ctx.num_launches
+    barrier()
+    with ClockSampler(local) as clk:
+        ms, ex, ticks = 0.0, 0, 0
+        t_wall = time.perf_counter()
+        for _ in range(args.steps):
+            t = step_resident()
+            ms += t["ms_total"]
+            ex += t["expansions"]
+            ticks += t["ticks"]
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+    launches = ctx.num_launches - l0
+    prof = net.get_profile() if not args.oracle_net else None
+    if not args.oracle_net:
+        net.set_profiling(False)
+    # ---- timed: end to end through host buffers ----
+    barrier()
+    e_dt, e_ex = 0.0, 0
+    for _ in range(args.steps):
+        d, e, N = step_e2e()
+        e_dt += d
+        e_ex += e
+    barrier()
+    sims = args.steps * S * nsims
+    # ---- reduce over ranks: time = max, work = sum ----
+    if dist is not None:
+        t = torch.tensor([ms, e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        w = torch.tensor([ex, e_ex, sims, launches], device="cuda", dtype=torch.float64)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        ms, e_dt = t.tolist()
+        ex, e_ex, sims, launches = w.tolist()
+    if rank == 0:
+        value = ex / (ms / 1e3)
+        line = {"metric": METRIC, "value": value, "unit": "expansions/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16" if not args.oracle_net else "f64", "data": "synthetic",
+                "config": {"workload": "connect-four: %d concurrent game trees per GPU x %d sims/move, %s, synthetic random positions (0-30 plies), fresh trees per step"
+                           % (S, nsims, ("%d-block ResNet 128 filters" % args.blocks) if not args.oracle_net else args.oracle_net + " oracle"),
+                           "trees_per_gpu": S, "nsims": nsims, "parallelism": "trees sharded over %d rank(s), no data-path collective" % world,
+                           "l2": "inputs larger than L2: tree tables %.0f MB + activations %.0f MB per GPU" % (S * 1024 * 128 / 1e6, 2 * S * 56 * 256 / 1e6)},
+                "simulations_per_s": sims / (ms / 1e3), "expansions_per_simulation": ex / sims, "ticks_per_step": ticks / args.steps,
+                "e2e": {"value": e_ex / e_dt, "unit": "expansions/s",
+                        "h2d_bytes_per_step": int(S * 24 + eta.nbytes),
+                        "d2h_bytes_per_step": int(S * A * (8 + 8 + 4))},
+                "gpu_launches": int(launches), "clocks": clk.summary(), "host_wall_s_resident": t_wall}
+        if prof and prof["evals"]:
+            peak, how = peaks()
+            nconv = 2 * args.blocks
+            achieved = ex / world * CONV_MFLOP_PER_LEAF * nconv / 1e6 / (prof["tower_ms"] / 1e3) if world == 1 else None
+            if world > 1:  # rank 0's own expansions are not separated after the all-reduce; report per-GPU average
+                achieved = (ex / world) * CONV_MFLOP_PER_LEAF * nconv / 1e6 / (prof["tower_ms"] / 1e3)
+            line["roofline"] = {"bound": "tensor", "kernel": "az_k_conv_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                                "frac": achieved / peak, "traffic": None, "peak_source": how,
+                                "avg_launch_us": 1e3 * prof["tower_ms"] / max(1, prof["tower_launches"]),
+                                "network_share_of_step": prof["total_ms"] / (ms / world if dist is None else ms),
+                                "tower_share_of_step": prof["tower_ms"] / ms}
+        if not args.no_cpu_baseline and not args.oracle_net:
+            threads = os.cpu_count() or 1
+            cex, cdt, _ = cpu_reference_run(128, 100, threads)
+            line["cpu_baseline"] = {"value": cex / cdt, "unit": "expansions/s", "cores": threads, "kind": "port",
+                                    "sample": "128 trees x 100 sims of the same workload: CPU MCTS (C port of src/mcts.jl) + torch-CPU fp32 7-block ResNet"}
+        print(json.dumps(line))
+    env.close()
+    net.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

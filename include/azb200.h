@@ -124,6 +124,11 @@ int32_t az_net_load(az_net* net, const float* blob, int64_t n);
 /* Network.evaluate_batch / forward_normalized (src/networks/network.jl:264-271,308-315):
    P is A-wide (masked, renormalised, zero on illegal), V[B], Pinvalid[B] (may be NULL) */
 int32_t az_net_forward(az_net* net, const uint8_t* states, int32_t B, float* P, float* V, float* Pinvalid);
+/* device-side timing (CUDA events on the context's stream) of the network launches, for bench.py's roofline:
+   tower_ms = time inside the conv-tower kernels, tower_launches = number of tower kernel launches,
+   total_ms = stem + tower + heads, evals = number of batched evaluations since profiling was enabled */
+int32_t az_net_set_profiling(az_net* net, int32_t enable);
+int32_t az_net_get_profile(az_net* net, double* tower_ms, int64_t* tower_launches, double* total_ms, int64_t* evals);
 int32_t az_net_destroy(az_net* net);
 
 /* ---- MCTS.Env pool: n_trees independent MCTS.Env (src/mcts.jl:124-151) on one GPU ---------- */

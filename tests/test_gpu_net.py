@@ -1,0 +1,94 @@
+"""GPU parity of the network forward (tcgen05 tower + heads) and of MCTS driven by it."""
+import numpy as np
+import pytest
+
+import _pkg
+from tests import netcheck
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def az():
+    return _pkg.load()
+
+
+@pytest.fixture(scope="module")
+def ctx(az):
+    c = az.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("blocks,batch", [(0, 37), (1, 300), (5, 300), (7, 1000)])
+def test_resnet_forward_matches_fp32_reference(az, oz, ctx, blocks, batch):
+    gs = az.GameSpec("connect-four")
+    hp = netcheck.c4_hp(blocks)
+    net, blob = netcheck.make_net(az, ctx, gs, hp, seed=blocks + 1)
+    states = gs.random_positions(11, batch, 38)
+    states[0] = gs.init_state()
+    r = netcheck.compare(az, oz, gs, net, blob, hp, states)
+    assert r["dP"] < netcheck.TOL and r["dV"] < netcheck.TOL and r["dI"] < netcheck.TOL, (r["dP"], r["dV"], r["dI"])
+    assert (r["P"][~r["mask"]] == 0).all() and np.allclose(r["P"].sum(1), 1, atol=1e-5)
+    # batch invariance: a state's output bits do not depend on its position in the batch
+    P2, V2, _ = net.evaluate_batch(states[::-1].copy())
+    assert (P2[::-1] == r["P"]).all() and (V2[::-1] == r["V"]).all()
+    net.close()
+
+
+def test_fresh_flux_init(az, oz, ctx):
+    """Freshly constructed model (zero biases, identity BatchNorm statistics), 5 blocks as shipped."""
+    gs = az.GameSpec("connect-four")
+    hp = netcheck.c4_hp(5)
+    net, blob = netcheck.make_net(az, ctx, gs, hp, seed=1, randomize=False)
+    r = netcheck.compare(az, oz, gs, net, blob, hp, gs.random_positions(5, 200, 30))
+    assert r["dP"] < netcheck.TOL and r["dV"] < netcheck.TOL
+    net.close()
+
+
+def test_resnet_rejects_bad_blob_and_unsupported(az, ctx):
+    gs = az.GameSpec("connect-four")
+    net = az.ResNet(ctx, gs, az.ResNetHP(1, 128, (3, 3), 32, 32))
+    with pytest.raises(az.AzError):
+        net.load(np.zeros(10, np.float32))
+    with pytest.raises(az.AzError):
+        net.evaluate_batch(gs.random_positions(1, 4, 10))  # not loaded
+    net.close()
+    with pytest.raises(az.AzError) as e:
+        az.ResNet(ctx, gs, az.ResNetHP(1, 64, (3, 3), 32, 32))
+    assert e.value.status == 5
+
+
+def test_mcts_with_network_bit_exact(az, oz, ctx):
+    """Tree logic with a real network: the CPU oracle replays with the network's own (P, V) for every state it
+    asks about (forward is batch invariant), so visit counts and W must match bit for bit."""
+    gs = az.GameSpec("connect-four")
+    gid = oz.game_id("connect-four")
+    hp = netcheck.c4_hp(1)
+    net, _ = netcheck.make_net(az, ctx, gs, hp, seed=3)
+    roots = gs.random_positions(21, 12, 24)
+    nsims = 120
+    eta = np.zeros((len(roots), 7))
+    for i, r in enumerate(roots):
+        n = int(oz.GameEnv(gid, bytes(r)).actions_mask().sum())
+        eta[i, :n] = oz.dirichlet(4, i, 0, n, 1.0)
+    mp = az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, dirichlet_noise_eps=0.25, dirichlet_noise_alpha=1.0)
+    env = az.MctsEnv(ctx, gs, net, mp, len(roots), 2 * nsims)
+    N, W, P = env.explore(roots, nsims, eta)
+    cache = {}
+
+    def oracle(state, n):
+        if state not in cache:
+            p, v, _ = net.evaluate_batch(np.frombuffer(state, np.uint8)[None])
+            m = gs.actions_mask(np.frombuffer(state, np.uint8))
+            cache[state] = (p[0][m].tolist(), float(v[0]))
+        return cache[state]
+
+    for i, r in enumerate(roots):
+        e = oz.Env(gid, oracle, cpuct=2.0, noise_eps=0.25)
+        g = oz.GameEnv(gid, bytes(r))
+        e.explore(g, nsims, eta[i, :int(g.actions_mask().sum())])
+        _, rN, rW, rP, _ = e.root_stats(g)
+        assert (N[i] == rN).all() and (W[i] == rW).all() and (P[i] == rP).all()
+    env.close()
+    net.close()

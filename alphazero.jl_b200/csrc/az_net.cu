@@ -88,20 +88,25 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// tower conv: implicit GEMM, one launch per conv layer
+// tcgen05 implicit-GEMM kernel: tower convs, the heads' 1x1 convs and the value head's dense layer all run here
 // ------------------------------------------------------------------------------------------------
 namespace tc {
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6, F = 128;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int BM = 128, BK = 64, STAGES = 6, F = 128;
+constexpr int A_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 192;
+enum { EPI_CONV1 = 0, EPI_CONV2 = 1, EPI_HEAD = 2, EPI_DENSE = 3 };
+template <int BN>
 struct Smem {
   uint8_t a[STAGES][A_BYTES];
-  uint8_t b[STAGES][B_BYTES];
+  uint8_t b[STAGES][BN * BK * 2];
   uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
   uint32_t tmem_base;
   float bias[BN];
 };
-constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);  // f16 x f16 -> f32, K-major A/B
+template <int BN>
+constexpr uint32_t idesc() {  // f16 x f16 -> f32, K-major A and B, M = 128, N = BN
+  return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 }  // namespace tc
 
 struct ConvGeom {
@@ -109,30 +114,43 @@ struct ConvGeom {
   int board_rows;  // (W+1)*(H+1)
   int valid_rows;  // (W+1)*H
   int wcols;       // W
-  int ntaps;       // 9
   int off[9];
 };
+struct GemmArgs {
+  const int32_t* n_boards;
+  ConvGeom g;
+  int kblocks;       // number of 64-wide K blocks
+  int gemm_k;        // 0: A coords = ((kb&1)*64, row + off[kb>>1]) (shifted-row conv);  1: A coords = (kb*64, row) (plain GEMM)
+  int rows_per_board;  // rows of the M dimension per board: board_rows (conv/head) or 1 (dense)
+  int alloc_rows;
+  const float* bias;
+  const float* resid32;  // EPI_CONV2
+  float* out32;          // EPI_CONV2 (stream), EPI_DENSE (hidden)
+  __half* out16a;        // CONV1: T, CONV2: X16, HEAD: policy features
+  __half* out16b;        // HEAD: value features
+};
 
+template <int BN, int EPI>
 __global__ void __launch_bounds__(tc::NUM_THREADS, 1)
-az_k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __half* __restrict__ resid,
-             __half* __restrict__ out, const float* __restrict__ bias, const int32_t* __restrict__ n_boards, ConvGeom g,
-             int alloc_rows) {
+az_k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmArgs ga) {
   using namespace tc;
+  using SmemT = Smem<BN>;
+  constexpr int B_BYTES = BN * BK * 2;
   extern __shared__ uint8_t smem_raw[];
-  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  SmemT& s = *reinterpret_cast<SmemT*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows_used = (*n_boards) * g.board_rows;
+  const int rows_used = (*ga.n_boards) * ga.rows_per_board;
   const int num_tiles = (rows_used + BM - 1) / BM;
-  const int kblocks = g.ntaps * (F / BK);
+  const int kblocks = ga.kblocks;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x >= 64) s.bias[threadIdx.x - 64] = bias[threadIdx.x - 64];
-  if (warp == 1) {  // TMEM: 2 accumulators x 128 fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(256u) : "memory");
+  if (threadIdx.x >= 64 && threadIdx.x - 64 < BN) s.bias[threadIdx.x - 64] = ga.bias[threadIdx.x - 64];
+  if (warp == 1) {  // TMEM: 2 accumulators x BN fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"((uint32_t)(2 * BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -150,7 +168,8 @@ az_k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = 0; kb < kblocks; kb++) {
           mbar_wait(&s.empty[stage], phase ^ 1);
           mbar_expect_tx(&s.full[stage], A_BYTES + B_BYTES);
-          tma_load_2d(s.a[stage], &tmA, &s.full[stage], (kb & 1) * BK, tile * BM + g.off[kb >> 1]);
+          if (ga.gemm_k) tma_load_2d(s.a[stage], &tmA, &s.full[stage], kb * BK, tile * BM);
+          else tma_load_2d(s.a[stage], &tmA, &s.full[stage], (kb & 1) * BK, tile * BM + ga.g.off[kb >> 1]);
           tma_load_2d(s.b[stage], &tmW, &s.full[stage], kb * BK, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -174,7 +193,7 @@ az_k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[stage]));
 #pragma unroll
           for (int k = 0; k < BK / 16; k++)  // advance 32 B (= 16 fp16) inside the 128-B swizzle row
-            umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
+            umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc<BN>(), (kb | k) ? 1u : 0u);
           umma_commit(&s.empty[stage]);  // frees the smem stage when these MMAs retire
           if (kb == kblocks - 1) umma_commit(&s.tfull[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -190,36 +209,49 @@ az_k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&s.tfull[acc], aphase);
       tcgen05_fence_after();
       const int p = tile * BM + quarter * 32 + lane;
-      const int r = p % g.board_rows;
-      const bool valid = (p < rows_used) && (r < g.valid_rows) && ((r % g.row_stride) != g.wcols);
-      const bool in_alloc = p < alloc_rows;
+      bool valid;
+      if (EPI == EPI_DENSE) valid = p < rows_used;
+      else {
+        const int r = p % ga.g.board_rows;
+        valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
+      }
+      const bool in_alloc = p < ga.alloc_rows;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
         uint32_t v[32];
         tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
-        uint4 rs[4];
-        if (resid != nullptr && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(resid + (size_t)p * F + c * 32);
+        float x[32];
 #pragma unroll
-          for (int j = 0; j < 4; j++) rs[j] = rp[j];
-        } else {
+        for (int j = 0; j < 32; j++) x[j] = __uint_as_float(v[j]) + s.bias[c * 32 + j];
+        if (EPI == EPI_CONV2) {
+          if (valid) {
+            const float4* rp = reinterpret_cast<const float4*>(ga.resid32 + (size_t)p * F + c * 32);
 #pragma unroll
-          for (int j = 0; j < 4; j++) rs[j] = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < 8; j++) {
+              float4 r4 = rp[j];
+              x[4 * j] += r4.x; x[4 * j + 1] += r4.y; x[4 * j + 2] += r4.z; x[4 * j + 3] += r4.w;
+            }
+          }
         }
-        const __half2* rh = reinterpret_cast<const __half2*>(rs);
-        uint4 o[4];
-        __half2* oh = reinterpret_cast<__half2*>(o);
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          float2 rr = __half22float2(rh[j]);
-          float x0 = __uint_as_float(v[2 * j]) + s.bias[c * 32 + 2 * j] + rr.x;
-          float x1 = __uint_as_float(v[2 * j + 1]) + s.bias[c * 32 + 2 * j + 1] + rr.y;
-          x0 = valid ? fmaxf(x0, 0.0f) : 0.0f;
-          x1 = valid ? fmaxf(x1, 0.0f) : 0.0f;
-          oh[j] = __floats2half2_rn(x0, x1);
+        for (int j = 0; j < 32; j++) x[j] = valid ? fmaxf(x[j], 0.0f) : 0.0f;
+        if (!in_alloc) continue;
+        if (EPI == EPI_CONV2 || EPI == EPI_DENSE) {
+          if (EPI == EPI_CONV2 || valid) {
+            float4* op = reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; j++) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          }
         }
-        if (in_alloc) {
-          uint4* op = reinterpret_cast<uint4*>(out + (size_t)p * F + c * 32);
+        if (EPI != EPI_DENSE) {
+          uint4 o[4];
+          __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+          for (int j = 0; j < 16; j++) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+          __half* dst;
+          if (EPI == EPI_HEAD) dst = (c == 0 ? ga.out16a : ga.out16b) + (size_t)p * 32;
+          else dst = ga.out16a + (size_t)p * F + c * 32;
+          uint4* op = reinterpret_cast<uint4*>(dst);
 #pragma unroll
           for (int j = 0; j < 4; j++) op[j] = o[j];
         }
@@ -233,7 +265,7 @@ az_k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
   }
 }
 
@@ -241,27 +273,33 @@ az_k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // stem: leaf states -> first activation (conv 3x3, C_in -> 128, folded BN, ReLU) on CUDA cores.
 // Input planes come straight from the game's vectorize_state (no host round trip; replaces
 // GI.vectorize_state + Flux.batch + convert_input, src/networks/network.jl:310-312).
+// One thread per output channel keeps its 9*C weights in registers; the padded input planes are in smem.
 // ------------------------------------------------------------------------------------------------
 template <class G>
 __global__ void __launch_bounds__(128) az_k_stem(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_boards,
                                                  const float* __restrict__ wstem /* [9][C][128] */, const float* __restrict__ bias,
-                                                 __half* __restrict__ out) {
-  constexpr int W = G::XW, H = G::XH, C = G::XC, RS = W + 1, BS = (W + 1) * (H + 1);
+                                                 float* __restrict__ out32, __half* __restrict__ out16) {
+  constexpr int W = G::XW, H = G::XH, C = G::XC, RS = W + 1, BS = (W + 1) * (H + 1), CP = (C + 3) & ~3;
   __shared__ float x[W * H * C];
-  __shared__ float xp[(H + 2) * (W + 2) * C];
+  __shared__ __align__(16) float xp[(H + 2) * (W + 2) * CP];
   const int b = blockIdx.x;
   if (b >= *n_boards) return;
   if (threadIdx.x == 0) G::vectorize(envs[b], x);
-  for (int i = threadIdx.x; i < (H + 2) * (W + 2) * C; i += blockDim.x) xp[i] = 0.0f;
+  for (int i = threadIdx.x; i < (H + 2) * (W + 2) * CP; i += blockDim.x) xp[i] = 0.0f;
   __syncthreads();
   for (int i = threadIdx.x; i < W * H * C; i += blockDim.x) {
     int c = i / (W * H), rem = i % (W * H), yy = rem / W, xx = rem % W;
-    xp[((yy + 1) * (W + 2) + (xx + 1)) * C + c] = x[i];
+    xp[((yy + 1) * (W + 2) + (xx + 1)) * CP + c] = x[i];
   }
   __syncthreads();
   const int co = threadIdx.x;
+  float w[9][CP];
+#pragma unroll
+  for (int t = 0; t < 9; t++)
+#pragma unroll
+    for (int c = 0; c < CP; c++) w[t][c] = c < C ? wstem[(t * C + c) * 128 + co] : 0.0f;
   const float bs = bias[co];
-  __half* ob = out + (size_t)b * BS * 128;
+  const size_t base = (size_t)b * BS * 128 + co;
   for (int r = 0; r < BS; r++) {
     const int yy = r / RS, xx = r % RS;
     float acc = 0.0f;
@@ -272,116 +310,80 @@ __global__ void __launch_bounds__(128) az_k_stem(const AzEnv* __restrict__ envs,
 #pragma unroll
         for (int kx = 0; kx < 3; kx++) {
           // Flux Conv is a true convolution: tap (kx,ky) reads the input at (x + 1 - kx, y + 1 - ky)
-          const float* px = &xp[((yy + 1 + 1 - ky) * (W + 2) + (xx + 1 + 1 - kx)) * C];
-          const float* pw = &wstem[((ky * 3 + kx) * C) * 128 + co];
+          const float4* px = reinterpret_cast<const float4*>(&xp[((yy + 2 - ky) * (W + 2) + (xx + 2 - kx)) * CP]);
 #pragma unroll
-          for (int c = 0; c < C; c++) acc += px[c] * pw[c * 128];
+          for (int c4 = 0; c4 < CP / 4; c4++) {
+            float4 v = px[c4];
+            acc += v.x * w[ky * 3 + kx][4 * c4] + v.y * w[ky * 3 + kx][4 * c4 + 1] + v.z * w[ky * 3 + kx][4 * c4 + 2] +
+                   v.w * w[ky * 3 + kx][4 * c4 + 3];
+          }
         }
       acc = fmaxf(acc, 0.0f);
     }
-    ob[(size_t)r * 128 + co] = __float2half_rn(acc);
+    out32[base + (size_t)r * 128] = acc;
+    out16[base + (size_t)r * 128] = __float2half_rn(acc);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// heads: 1x1 convs (+BN+ReLU), flatten, dense layers, softmax / tanh, legal-action mask + renormalisation
-// (resnet.jl:79-90, network.jl:264-271).  NB boards per CTA so that dense weights are reused from L1/L2.
+// finalize: policy dense + softmax + legal-action mask + renormalisation (resnet.jl:83-84, network.jl:264-271),
+// value output tanh(w2 . hidden + b2) (resnet.jl:89-90).  One warp per board.
 // ------------------------------------------------------------------------------------------------
-struct HeadParams {
-  const float* wc;    // [128][npf+nvf] folded 1x1 conv weights (policy filters first), fp32
-  const float* bc;    // [npf+nvf]
-  const __half* wv1;  // [in = WH*nvf][128] (transposed: out fastest), fp16
-  const float* bv1;   // [128]
+struct FinalArgs {
+  const __half* hp;   // policy features [rows][32]
+  const float* hid;   // value hidden [boards][128]
+  const float* wp;    // [kp][AP] policy dense weights (AP = A rounded up to 4) in feature order k' = pos'*32 + c (zero for pad positions), fp32
+  const float* bp;    // [A]
   const float* wv2;   // [128]
   const float* bv2;   // [1]
-  const float* wp;    // [in = WH*npf][A] (out fastest), fp32
-  const float* bp;    // [A]
-  int npf, nvf;
+  int kp;             // valid_rows * 32
+  int board_feat;     // board_rows * 32
 };
-
-template <class G, int NB>
-__global__ void __launch_bounds__(256) az_k_heads(const __half* __restrict__ act, const AzEnv* __restrict__ envs,
-                                                  const int32_t* __restrict__ n_boards, HeadParams hp, float* __restrict__ P,
-                                                  float* __restrict__ V, float* __restrict__ Pinv) {
-  constexpr int W = G::XW, H = G::XH, RS = W + 1, BS = (W + 1) * (H + 1), WH = W * H, A = G::A, F = 128;
-  extern __shared__ uint8_t hs_raw[];
-  const int nh = hp.npf + hp.nvf;
-  float* wc = reinterpret_cast<float*>(hs_raw);              // [128][nh]
-  float* hfeat = wc + F * nh;                                // [NB][WH*nh]  (policy block then value block, Flux flatten order)
-  float* hid = hfeat + NB * WH * nh;                         // [NB][128]
-  float* logit = hid + NB * F;                               // [NB][A + 1]
-  __half* xin = reinterpret_cast<__half*>(logit + NB * (A + 1));  // [NB][WH][128]
-  const int b0 = blockIdx.x * NB;
-  const int nb = min(NB, *n_boards - b0);
-  if (nb <= 0) return;
-  for (int i = threadIdx.x; i < F * nh; i += blockDim.x) wc[i] = hp.wc[i];
-  for (int i = threadIdx.x; i < nb * WH * (F / 8); i += blockDim.x) {
-    int bb = i / (WH * (F / 8)), rem = i % (WH * (F / 8)), pos = rem / (F / 8), ch = rem % (F / 8);
-    int yy = pos / W, xx = pos % W;
-    const uint4* src = reinterpret_cast<const uint4*>(act + ((size_t)(b0 + bb) * BS + yy * RS + xx) * F) + ch;
-    reinterpret_cast<uint4*>(xin + ((size_t)bb * WH + pos) * F)[ch] = *src;
-  }
-  __syncthreads();
-  // 1x1 convs: hfeat[bb][pos + WH*c'] (c' within its head), ReLU
-  for (int i = threadIdx.x; i < nb * WH * nh; i += blockDim.x) {
-    int bb = i / (WH * nh), rem = i % (WH * nh), c = rem / WH, pos = rem % WH;
-    const __half2* xr = reinterpret_cast<const __half2*>(xin + ((size_t)bb * WH + pos) * F);
-    float acc = hp.bc[c];
-#pragma unroll 8
-    for (int k = 0; k < F / 2; k++) {
-      float2 xv = __half22float2(xr[k]);
-      acc += xv.x * wc[(2 * k) * nh + c] + xv.y * wc[(2 * k + 1) * nh + c];
-    }
-    hfeat[(size_t)bb * WH * nh + rem] = fmaxf(acc, 0.0f);
-  }
-  __syncthreads();
-  // value dense 1: hid[bb][o] = relu(sum_i wv1[i][o] * hv[bb][i] + b)
-  {
-    const int o = threadIdx.x % F, half_id = threadIdx.x / F;  // 2 halves x 128 outputs
-    float acc[NB / 2];
+template <class G>
+__global__ void __launch_bounds__(256) az_k_finalize(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_boards, FinalArgs fa,
+                                                     float* __restrict__ P, float* __restrict__ V, float* __restrict__ Pinv) {
+  constexpr int A = G::A, AP = (A + 3) & ~3;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= *n_boards) return;
+  float acc[AP];
 #pragma unroll
-    for (int j = 0; j < NB / 2; j++) acc[j] = hp.bv1[o];
-    const int nin = WH * hp.nvf;
-    for (int i = 0; i < nin; i++) {
-      const float w = __half2float(hp.wv1[(size_t)i * F + o]);
+  for (int a = 0; a < AP; a++) acc[a] = 0.0f;
+  const __half2* f = reinterpret_cast<const __half2*>(fa.hp + (size_t)b * fa.board_feat);
+  for (int k2 = lane; k2 < fa.kp / 2; k2 += 32) {
+    const float2 xv = __half22float2(f[k2]);
+    const float4* wr = reinterpret_cast<const float4*>(fa.wp + (size_t)(2 * k2) * AP);
 #pragma unroll
-      for (int j = 0; j < NB / 2; j++) acc[j] += w * hfeat[(size_t)(half_id * (NB / 2) + j) * WH * nh + WH * hp.npf + i];
-    }
-#pragma unroll
-    for (int j = 0; j < NB / 2; j++) hid[(half_id * (NB / 2) + j) * F + o] = fmaxf(acc[j], 0.0f);
-  }
-  __syncthreads();
-  // policy logits (A per board) and value output: one warp per output
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int nin = WH * hp.npf;
-    for (int t = warp; t < nb * (A + 1); t += nwarps) {
-      const int bb = t / (A + 1), o = t % (A + 1);
-      float acc = 0.0f;
-      if (o < A) {
-        for (int i = lane; i < nin; i += 32) acc += hp.wp[(size_t)i * A + o] * hfeat[(size_t)bb * WH * nh + i];
-      } else {
-        for (int i = lane; i < F; i += 32) acc += hp.wv2[i] * hid[bb * F + i];
-      }
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      if (lane == 0) logit[bb * (A + 1) + o] = acc + (o < A ? hp.bp[o] : hp.bv2[0]);
+    for (int q = 0; q < AP / 4; q++) {
+      const float4 wa = wr[q], wb = wr[AP / 4 + q];
+      acc[4 * q] += xv.x * wa.x + xv.y * wb.x;
+      acc[4 * q + 1] += xv.x * wa.y + xv.y * wb.y;
+      acc[4 * q + 2] += xv.x * wa.z + xv.y * wb.z;
+      acc[4 * q + 3] += xv.x * wa.w + xv.y * wb.w;
     }
   }
-  __syncthreads();
-  if (threadIdx.x < nb) {
-    const int bb = threadIdx.x, row = b0 + bb;
-    const float* lg = logit + bb * (A + 1);
-    float m = lg[0];
-    for (int a = 1; a < A; a++) m = fmaxf(m, lg[a]);
-    float e[A], se = 0.0f;
-    for (int a = 0; a < A; a++) { e[a] = expf(lg[a] - m); se += e[a]; }
-    const uint32_t legal = G::legal_mask(envs[row]);
+  float vacc = 0.0f;
+  for (int i = lane; i < 128; i += 32) vacc += fa.wv2[i] * fa.hid[(size_t)b * 128 + i];
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+    for (int a = 0; a < AP; a++) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], off);
+    vacc += __shfl_xor_sync(0xffffffffu, vacc, off);
+  }
+  if (lane == 0) {
+    float lg[A], m = -3.0e38f;
+#pragma unroll
+    for (int a = 0; a < A; a++) { lg[a] = acc[a] + fa.bp[a]; m = fmaxf(m, lg[a]); }
+    float se = 0.0f;
+#pragma unroll
+    for (int a = 0; a < A; a++) { lg[a] = expf(lg[a] - m); se += lg[a]; }
+    const uint32_t legal = G::legal_mask(envs[b]);
     float sp = 0.0f;
-    for (int a = 0; a < A; a++) { e[a] = ((legal >> a) & 1u) ? e[a] / se : 0.0f; sp += e[a]; }
-    for (int a = 0; a < A; a++) P[(size_t)row * A + a] = e[a] / (sp + 1.1920929e-07f);  // eps(Float32), network.jl:268
-    V[row] = tanhf(lg[A]);
-    if (Pinv) Pinv[row] = 1.0f - sp;
+#pragma unroll
+    for (int a = 0; a < A; a++) { lg[a] = ((legal >> a) & 1u) ? lg[a] / se : 0.0f; sp += lg[a]; }
+#pragma unroll
+    for (int a = 0; a < A; a++) P[(size_t)b * A + a] = lg[a] / (sp + 1.1920929e-07f);  // eps(Float32), network.jl:268
+    V[b] = tanhf(vacc + fa.bv2[0]);
+    if (Pinv) Pinv[b] = 1.0f - sp;
   }
 }
 
@@ -401,11 +403,13 @@ static PFN_encodeTiled get_encode_fn() {
   }
   return fn;
 }
-static int make_map_2d(az_ctx* ctx, CUtensorMap* m, void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+// fp16 matrix [outer][inner] with a row pitch in bytes; box = [box_outer][box_inner], SWIZZLE_128B (box_inner = 64 elements)
+static int make_map_2d(az_ctx* ctx, CUtensorMap* m, void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                       uint32_t box_inner, uint32_t box_outer) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) { ctx->err = "cuTensorMapEncodeTiled not available"; return AZ_ECUDA; }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {inner * 2};
+  cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t es[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -417,21 +421,25 @@ static int make_map_2d(az_ctx* ctx, CUtensorMap* m, void* base, uint64_t inner, 
 template <class G>
 struct ResNetImpl : az_net {
   az_resnet_hp hp{};
-  static constexpr int F = 128, W = G::XW, H = G::XH, C = G::XC, A = G::A, BS = (W + 1) * (H + 1), WH = W * H;
-  static constexpr int NB = 8;
+  static constexpr int F = 128, W = G::XW, H = G::XH, C = G::XC, A = G::A, AP = (A + 3) & ~3, BS = (W + 1) * (H + 1), WH = W * H;
+  static constexpr int VR = (W + 1) * H;                       // rows of a board up to (excluding) the pad row
+  static constexpr int KP = VR * 32;                           // policy / value feature length (pad columns carry zero weights)
+  static constexpr int KD = (KP + 63) / 64 * 64;               // value-dense K rounded to the 64-wide K block
   // device weights
   float* d_wstem = nullptr; float* d_bstem = nullptr;
   std::vector<__half*> d_wconv; std::vector<float*> d_bconv;
-  float *d_wc = nullptr, *d_bc = nullptr, *d_bv1 = nullptr, *d_wv2 = nullptr, *d_bv2 = nullptr, *d_wp = nullptr, *d_bp = nullptr;
-  __half* d_wv1 = nullptr;
+  __half *d_wh = nullptr, *d_wd = nullptr;
+  float *d_bh = nullptr, *d_bd = nullptr, *d_wv2 = nullptr, *d_bv2 = nullptr, *d_wp = nullptr, *d_bp = nullptr;
   std::vector<CUtensorMap> mapW;
+  CUtensorMap mapWh{}, mapWd{};
   // activations (allocated for max_rows on first use)
-  int act_boards = 0, alloc_rows = 0;
-  __half *d_x = nullptr, *d_t = nullptr;
-  CUtensorMap mapX{}, mapT{};
+  int act_boards = 0, alloc_rows = 0, alloc_boards = 0;
+  float *d_x32 = nullptr, *d_hid = nullptr;
+  __half *d_x16 = nullptr, *d_t16 = nullptr, *d_hp = nullptr, *d_hv = nullptr;
+  CUtensorMap mapX{}, mapT{}, mapHv{};
   ConvGeom geom{};
   bool loaded = false;
-  size_t conv_smem = 0, head_smem = 0;
+  size_t smem128 = 0, smem64 = 0;
   // profiling: 4 events per evaluation (start, tower begin, tower end, end)
   static constexpr int PROF_SLOTS = 8192;
   bool profiling = false;
@@ -466,26 +474,30 @@ struct ResNetImpl : az_net {
     return AZ_OK;
   }
 
+  template <class K> int set_smem(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e); return AZ_ECUDA; }
+    return AZ_OK;
+  }
   int init() {
     if (hp.num_filters != F || hp.conv_kernel_size[0] != 3 || hp.conv_kernel_size[1] != 3) {
       ctx->err = "ResNet: this build supports num_filters = 128 and conv_kernel_size = (3, 3)";
       return AZ_EUNSUPPORTED;
     }
-    if (hp.num_blocks < 0 || hp.num_policy_head_filters < 1 || hp.num_value_head_filters < 1 ||
-        hp.num_policy_head_filters + hp.num_value_head_filters > 64) {
-      ctx->err = "ResNet: head filters must satisfy 1 <= npf, nvf and npf + nvf <= 64";
-      return AZ_EINVAL;
+    if (hp.num_policy_head_filters != 32 || hp.num_value_head_filters != 32) {
+      ctx->err = "ResNet: this build supports num_policy_head_filters = num_value_head_filters = 32";
+      return AZ_EUNSUPPORTED;
     }
-    geom.row_stride = W + 1; geom.board_rows = BS; geom.valid_rows = (W + 1) * H; geom.wcols = W; geom.ntaps = 9;
+    if (hp.num_blocks < 0) { ctx->err = "ResNet: num_blocks must be >= 0"; return AZ_EINVAL; }
+    geom.row_stride = W + 1; geom.board_rows = BS; geom.valid_rows = VR; geom.wcols = W;
     for (int ky = 0; ky < 3; ky++)
       for (int kx = 0; kx < 3; kx++) geom.off[ky * 3 + kx] = (1 - ky) * (W + 1) + (1 - kx);
-    conv_smem = sizeof(tc::Smem) + 1024;
-    cudaError_t e = cudaFuncSetAttribute(az_k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem);
-    if (e != cudaSuccess) { ctx->err = std::string("conv smem attribute: ") + cudaGetErrorString(e); return AZ_ECUDA; }
-    const int nh = hp.num_policy_head_filters + hp.num_value_head_filters;
-    head_smem = sizeof(float) * ((size_t)F * nh + (size_t)NB * WH * nh + NB * F + NB * (A + 1)) + sizeof(__half) * (size_t)NB * WH * F + 16;
-    e = cudaFuncSetAttribute(az_k_heads<G, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem);
-    if (e != cudaSuccess) { ctx->err = std::string("heads smem attribute: ") + cudaGetErrorString(e); return AZ_ECUDA; }
+    smem128 = sizeof(tc::Smem<128>) + 1024;
+    smem64 = sizeof(tc::Smem<64>) + 1024;
+    AZ_TRY2(set_smem(az_k_gemm_tc<128, tc::EPI_CONV1>, smem128));
+    AZ_TRY2(set_smem(az_k_gemm_tc<128, tc::EPI_CONV2>, smem128));
+    AZ_TRY2(set_smem(az_k_gemm_tc<128, tc::EPI_DENSE>, smem128));
+    AZ_TRY2(set_smem(az_k_gemm_tc<64, tc::EPI_HEAD>, smem64));
     return AZ_OK;
   }
   int64_t num_params() override {
@@ -509,10 +521,14 @@ struct ResNetImpl : az_net {
     for (auto p : d_wconv) cudaFree(p);
     for (auto p : d_bconv) cudaFree(p);
     d_wconv.clear(); d_bconv.clear(); mapW.clear();
-    cudaFree(d_wc); cudaFree(d_bc); cudaFree(d_wv1); cudaFree(d_bv1); cudaFree(d_wv2); cudaFree(d_bv2); cudaFree(d_wp); cudaFree(d_bp);
-    d_wstem = d_bstem = d_wc = d_bc = d_bv1 = d_wv2 = d_bv2 = d_wp = d_bp = nullptr; d_wv1 = nullptr;
+    cudaFree(d_wh); cudaFree(d_wd); cudaFree(d_bh); cudaFree(d_bd); cudaFree(d_wv2); cudaFree(d_bv2); cudaFree(d_wp); cudaFree(d_bp);
+    d_wstem = d_bstem = d_bh = d_bd = d_wv2 = d_bv2 = d_wp = d_bp = nullptr; d_wh = d_wd = nullptr;
   }
-  ~ResNetImpl() override { free_weights(); cudaFree(d_x); cudaFree(d_t); for (auto e : pev) cudaEventDestroy(e); }
+  void free_act() {
+    cudaFree(d_x32); cudaFree(d_hid); cudaFree(d_x16); cudaFree(d_t16); cudaFree(d_hp); cudaFree(d_hv);
+    d_x32 = d_hid = nullptr; d_x16 = d_t16 = d_hp = d_hv = nullptr;
+  }
+  ~ResNetImpl() override { free_weights(); free_act(); for (auto e : pev) cudaEventDestroy(e); }
 
   // blob -> folded device weights.  Flux order: Conv W[kw,kh,cin,cout] (kw fastest), b; BatchNorm gamma, beta, mu, sigma2;
   // Dense W[out,in] (out fastest), b.  Order: common (stem, blocks), vhead, phead.
@@ -520,6 +536,7 @@ struct ResNetImpl : az_net {
     if (n != num_params()) { ctx->err = "az_net_load: blob has " + std::to_string(n) + " floats, expected " + std::to_string(num_params()); return AZ_EINVAL; }
     cudaStreamSynchronize(ctx->stream);
     free_weights();
+    loaded = false;
     const float* q = blob;
     const float eps = 1e-5f;
     auto fold = [&](int cout, const float* b, const float* bn, std::vector<float>& scale, std::vector<float>& shift) {
@@ -553,61 +570,66 @@ struct ResNetImpl : az_net {
       AZ_TRY2(up(&dw, wh)); d_wconv.push_back(dw);
       AZ_TRY2(up(&db, shift)); d_bconv.push_back(db);
       CUtensorMap m;
-      AZ_TRY2(make_map_2d(ctx, &m, dw, 9 * F, F, tc::BK, tc::BN));
+      AZ_TRY2(make_map_2d(ctx, &m, dw, 9 * F, F, 9 * F * 2, tc::BK, 128));
       mapW.push_back(m);
     }
-    const int npf = hp.num_policy_head_filters, nvf = hp.num_value_head_filters, nh = npf + nvf;
-    std::vector<float> wc((size_t)F * nh), bc(nh);
-    {  // vhead: Conv1x1 F->nvf, BN, Dense(WH*nvf -> F), Dense(F -> 1)
-      const float* w = q; q += (int64_t)F * nvf;
-      const float* b = q; q += nvf;
-      const float* bn = q; q += 4 * nvf;
-      fold(nvf, b, bn, scale, shift);
-      for (int c = 0; c < F; c++) for (int o = 0; o < nvf; o++) wc[(size_t)c * nh + npf + o] = w[c + (size_t)F * o] * scale[o];
-      for (int o = 0; o < nvf; o++) bc[npf + o] = shift[o];
-      const float* w1 = q; q += (int64_t)WH * nvf * F;
+    std::vector<__half> whd((size_t)64 * F);   // head 1x1 convs: rows 0..31 policy filters, 32..63 value filters
+    std::vector<float> bh(64);
+    {  // vhead: Conv1x1 F->32, BN, Dense(WH*32 -> F), Dense(F -> 1)
+      const float* w = q; q += (int64_t)F * 32;
+      const float* b = q; q += 32;
+      const float* bn = q; q += 4 * 32;
+      fold(32, b, bn, scale, shift);
+      for (int o = 0; o < 32; o++) { for (int c = 0; c < F; c++) whd[(size_t)(32 + o) * F + c] = __float2half_rn(w[c + (size_t)F * o] * scale[o]); bh[32 + o] = shift[o]; }
+      const float* w1 = q; q += (int64_t)WH * 32 * F;
       const float* b1 = q; q += F;
-      std::vector<__half> wv1((size_t)WH * nvf * F);
-      for (int i = 0; i < WH * nvf; i++) for (int o = 0; o < F; o++) wv1[(size_t)i * F + o] = __float2half_rn(w1[o + (size_t)F * i]);
-      AZ_TRY2(up(&d_wv1, wv1));
-      AZ_TRY2(up(&d_bv1, std::vector<float>(b1, b1 + F)));
+      std::vector<__half> wd((size_t)F * KD, __float2half_rn(0.0f));  // Wd[o][k'], k' = (y*(W+1) + x)*32 + c
+      for (int o = 0; o < F; o++) for (int c = 0; c < 32; c++) for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
+        wd[(size_t)o * KD + (size_t)(y * (W + 1) + x) * 32 + c] = __float2half_rn(w1[o + (size_t)F * ((x + W * y) + (size_t)WH * c)]);
+      AZ_TRY2(up(&d_wd, wd));
+      AZ_TRY2(up(&d_bd, std::vector<float>(b1, b1 + F)));
+      AZ_TRY2(make_map_2d(ctx, &mapWd, d_wd, KD, F, (uint64_t)KD * 2, tc::BK, 128));
       const float* w2 = q; q += F;
       const float* b2 = q; q += 1;
       AZ_TRY2(up(&d_wv2, std::vector<float>(w2, w2 + F)));
       AZ_TRY2(up(&d_bv2, std::vector<float>(b2, b2 + 1)));
     }
-    {  // phead: Conv1x1 F->npf, BN, Dense(WH*npf -> A)
-      const float* w = q; q += (int64_t)F * npf;
-      const float* b = q; q += npf;
-      const float* bn = q; q += 4 * npf;
-      fold(npf, b, bn, scale, shift);
-      for (int c = 0; c < F; c++) for (int o = 0; o < npf; o++) wc[(size_t)c * nh + o] = w[c + (size_t)F * o] * scale[o];
-      for (int o = 0; o < npf; o++) bc[o] = shift[o];
-      const float* w1 = q; q += (int64_t)WH * npf * A;
+    {  // phead: Conv1x1 F->32, BN, Dense(WH*32 -> A)
+      const float* w = q; q += (int64_t)F * 32;
+      const float* b = q; q += 32;
+      const float* bn = q; q += 4 * 32;
+      fold(32, b, bn, scale, shift);
+      for (int o = 0; o < 32; o++) { for (int c = 0; c < F; c++) whd[(size_t)o * F + c] = __float2half_rn(w[c + (size_t)F * o] * scale[o]); bh[o] = shift[o]; }
+      const float* w1 = q; q += (int64_t)WH * 32 * A;
       const float* b1 = q; q += A;
-      std::vector<float> wp((size_t)WH * npf * A);
-      for (int i = 0; i < WH * npf; i++) for (int o = 0; o < A; o++) wp[(size_t)i * A + o] = w1[o + (size_t)A * i];
+      std::vector<float> wp((size_t)KP * AP, 0.0f);  // Wp[k'][a]
+      for (int a = 0; a < A; a++) for (int c = 0; c < 32; c++) for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
+        wp[((size_t)(y * (W + 1) + x) * 32 + c) * AP + a] = w1[a + (size_t)A * ((x + W * y) + (size_t)WH * c)];
       AZ_TRY2(up(&d_wp, wp));
       AZ_TRY2(up(&d_bp, std::vector<float>(b1, b1 + A)));
     }
-    AZ_TRY2(up(&d_wc, wc)); AZ_TRY2(up(&d_bc, bc));
+    AZ_TRY2(up(&d_wh, whd)); AZ_TRY2(up(&d_bh, bh));
+    AZ_TRY2(make_map_2d(ctx, &mapWh, d_wh, F, 64, F * 2, tc::BK, 64));
     loaded = true;
+    return AZ_OK;
+  }
+  template <class T> int dmalloc(T** p, size_t n) {
+    if (cudaMalloc((void**)p, n * sizeof(T)) != cudaSuccess) { ctx->err = "cudaMalloc (activations) failed"; cudaGetLastError(); return AZ_ENOMEM; }
+    cudaMemsetAsync(*p, 0, n * sizeof(T), ctx->stream);
     return AZ_OK;
   }
   int ensure_act(int max_boards) {
     if (max_boards <= act_boards) return AZ_OK;
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_x); cudaFree(d_t);
-    d_x = d_t = nullptr;
+    free_act();
     alloc_rows = ((max_boards * BS + 127) / 128) * 128 + 128;
-    size_t bytes = (size_t)alloc_rows * F * sizeof(__half);
-    if (cudaMalloc((void**)&d_x, bytes) != cudaSuccess || cudaMalloc((void**)&d_t, bytes) != cudaSuccess) {
-      ctx->err = "cudaMalloc (activations) failed"; cudaGetLastError(); return AZ_ENOMEM;
-    }
-    cudaMemsetAsync(d_x, 0, bytes, ctx->stream);
-    cudaMemsetAsync(d_t, 0, bytes, ctx->stream);
-    AZ_TRY2(make_map_2d(ctx, &mapX, d_x, F, alloc_rows, tc::BK, tc::BM));
-    AZ_TRY2(make_map_2d(ctx, &mapT, d_t, F, alloc_rows, tc::BK, tc::BM));
+    alloc_boards = alloc_rows / BS;
+    AZ_TRY2(dmalloc(&d_x32, (size_t)alloc_rows * F)); AZ_TRY2(dmalloc(&d_x16, (size_t)alloc_rows * F));
+    AZ_TRY2(dmalloc(&d_t16, (size_t)alloc_rows * F)); AZ_TRY2(dmalloc(&d_hp, (size_t)alloc_rows * 32));
+    AZ_TRY2(dmalloc(&d_hv, (size_t)alloc_rows * 32)); AZ_TRY2(dmalloc(&d_hid, (size_t)(max_boards + 256) * F));
+    AZ_TRY2(make_map_2d(ctx, &mapX, d_x16, F, alloc_rows, F * 2, tc::BK, tc::BM));
+    AZ_TRY2(make_map_2d(ctx, &mapT, d_t16, F, alloc_rows, F * 2, tc::BK, tc::BM));
+    AZ_TRY2(make_map_2d(ctx, &mapHv, d_hv, (uint64_t)BS * 32, alloc_boards, (uint64_t)BS * 32 * 2, tc::BK, tc::BM));
     act_boards = max_boards;
     return AZ_OK;
   }
@@ -621,19 +643,31 @@ struct ResNetImpl : az_net {
     const bool prof = profiling && prof_evals < PROF_SLOTS;
     cudaEvent_t* pe = prof ? &pev[(size_t)prof_evals * 4] : nullptr;
     if (prof) cudaEventRecord(pe[0], st);
-    az_k_stem<G><<<max_rows, 128, 0, st>>>(envs, n_rows, d_wstem, d_bstem, d_x);
+    az_k_stem<G><<<max_rows, 128, 0, st>>>(envs, n_rows, d_wstem, d_bstem, d_x32, d_x16);
     if (prof) cudaEventRecord(pe[1], st);
-    const int max_tiles = (max_rows * BS + tc::BM - 1) / tc::BM;
-    const int grid = std::min(max_tiles, ctx->num_sms);
+    const int row_tiles = (max_rows * BS + tc::BM - 1) / tc::BM;
+    const int grid = std::min(row_tiles, ctx->num_sms);
+    GemmArgs ga{};
+    ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.gemm_k = 0;
     for (int blk = 0; blk < hp.num_blocks; blk++) {
-      az_k_conv_tc<<<grid, tc::NUM_THREADS, conv_smem, st>>>(mapX, mapW[2 * blk], nullptr, d_t, d_bconv[2 * blk], n_rows, geom, alloc_rows);
-      az_k_conv_tc<<<grid, tc::NUM_THREADS, conv_smem, st>>>(mapT, mapW[2 * blk + 1], d_x, d_x, d_bconv[2 * blk + 1], n_rows, geom, alloc_rows);
+      ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
+      az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
+      ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
+      az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
     }
     if (prof) cudaEventRecord(pe[2], st);
-    HeadParams h{d_wc, d_bc, d_wv1, d_bv1, d_wv2, d_bv2, d_wp, d_bp, hp.num_policy_head_filters, hp.num_value_head_filters};
-    az_k_heads<G, NB><<<(max_rows + NB - 1) / NB, 256, head_smem, st>>>(d_x, envs, n_rows, h, P, V, Pinv);
+    // heads: 1x1 convs (both heads, N = 64), value dense (K = KD), finalize
+    ga.kblocks = 2; ga.bias = d_bh; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_hp; ga.out16b = d_hv;
+    az_k_gemm_tc<64, tc::EPI_HEAD><<<grid, tc::NUM_THREADS, smem64, st>>>(mapX, mapWh, ga);
+    GemmArgs gd{};
+    gd.n_boards = n_rows; gd.g = geom; gd.kblocks = KD / 64; gd.gemm_k = 1; gd.rows_per_board = 1; gd.alloc_rows = max_rows + 256;
+    gd.bias = d_bd; gd.out32 = d_hid;
+    const int board_tiles = (max_rows + tc::BM - 1) / tc::BM;
+    az_k_gemm_tc<128, tc::EPI_DENSE><<<std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem128, st>>>(mapHv, mapWd, gd);
+    FinalArgs fa{d_hp, d_hid, d_wp, d_bp, d_wv2, d_bv2, KP, BS * 32};
+    az_k_finalize<G><<<(max_rows * 32 + 255) / 256, 256, 0, st>>>(envs, n_rows, fa, P, V, Pinv);
     if (prof) { cudaEventRecord(pe[3], st); prof_evals++; }
-    ctx->launches += 2 + 2 * hp.num_blocks;
+    ctx->launches += 4 + 2 * hp.num_blocks;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ctx->err = std::string("network launch: ") + cudaGetErrorString(e); return AZ_ECUDA; }
     return AZ_OK;

@@ -657,6 +657,7 @@ struct ResNetImpl : az_net {
     }
     if (prof) cudaEventRecord(pe[2], st);
     // heads: 1x1 convs (both heads, N = 64), value dense (K = KD), finalize
+    ga.g.off[0] = 0;  // 1x1 conv: single centre tap
     ga.kblocks = 2; ga.bias = d_bh; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_hp; ga.out16b = d_hv;
     az_k_gemm_tc<64, tc::EPI_HEAD><<<grid, tc::NUM_THREADS, smem64, st>>>(mapX, mapWh, ga);
     GemmArgs gd{};

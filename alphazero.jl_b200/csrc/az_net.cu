@@ -15,6 +15,7 @@
 #include <cuda_fp16.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "az_internal.h"
@@ -270,6 +271,163 @@ az_k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------
+// Connect-Four tower kernel (row stride W+1 = 8): the generic kernel above streams 576 KB of TMA traffic per
+// 128x128 tile and is bound by L2->SM bandwidth (profiles/r01_v1_*).  Here each CTA owns HALF of the output
+// channels (64) and keeps that half of the layer's weights resident in shared memory (18 chunks of 64co x 64k,
+// 144 KB), and every A stage is reused by three taps: for each kx the producer loads ONE 144-row copy of the
+// activations shifted by dx = 1-kx; because the row stride is 8, the three dy taps are the same copy at row
+// offsets 16 / 8 / 0 = multiples of the 1024-byte swizzle atom, i.e. just a different descriptor start address.
+// TMA traffic per tile: 6 stages x 18 KB = 108 KB (5.3x less than the generic kernel).
+// ------------------------------------------------------------------------------------------------
+namespace tc2 {
+constexpr int BM = 128, BNH = 64, BK = 64, ASTAGES = 4, AROWS = 144, F = 128;
+constexpr int A_STAGE = AROWS * 128, B_CHUNK = BNH * 128, NCHUNK = 18;
+constexpr int NUM_THREADS = 192;
+struct Smem {
+  uint8_t b[NCHUNK][B_CHUNK];
+  uint8_t a[ASTAGES][A_STAGE];
+  uint64_t full[ASTAGES], empty[ASTAGES], tfull[2], tempty[2], bfull;
+  uint32_t tmem_base;
+  float bias[BNH];
+};
+}  // namespace tc2
+
+template <int EPI>
+__global__ void __launch_bounds__(tc2::NUM_THREADS, 1)
+az_k_conv_c4(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmArgs ga) {
+  using namespace tc2;
+  extern __shared__ uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_used = (*ga.n_boards) * ga.rows_per_board;
+  const int num_tiles = (rows_used + BM - 1) / BM;
+  const int nhalf = blockIdx.x & 1;
+  const int tile0 = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 4); }
+    mbar_init(&s.bfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BNH) s.bias[threadIdx.x - 64] = ga.bias[nhalf * BNH + threadIdx.x - 64];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0 && tile0 < num_tiles) {  // ===== TMA producer =====
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+      mbar_expect_tx(&s.bfull, NCHUNK * B_CHUNK);
+      for (int ch = 0; ch < NCHUNK; ch++) tma_load_2d(s.b[ch], &tmW, &s.bfull, ch * BK, nhalf * BNH);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        for (int st = 0; st < 6; st++) {  // st = kx*2 + channel half
+          mbar_wait(&s.empty[stage], phase ^ 1);
+          mbar_expect_tx(&s.full[stage], A_STAGE);
+          tma_load_2d(s.a[stage], &tmA, &s.full[stage], (st & 1) * BK, tile * BM - 8 + (1 - (st >> 1)));
+          if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && tile0 < num_tiles) {  // ===== MMA issuer =====
+      constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BNH >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      mbar_wait(&s.bfull, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, it++) {
+        const int acc = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&s.tempty[acc], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BNH;
+        for (int st = 0; st < 6; st++) {
+          const int kx = st >> 1, half = st & 1;
+          mbar_wait(&s.full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t abase = smem_u32(s.a[stage]);
+#pragma unroll
+          for (int ky = 0; ky < 3; ky++) {
+            // copy row j <-> activation row tile*128 - 8 + j + (1-kx);  tap (kx,ky) needs j = m + 8 + 8*(1-ky)
+            const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(8 + 8 * (1 - ky)) * 128u);
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++)
+              umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (st | ky | k) ? 1u : 0u);
+          }
+          umma_commit(&s.empty[stage]);
+          if (st == 5) umma_commit(&s.tfull[acc]);
+          if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {  // ===== epilogue warps 2..5 =====
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, it++) {
+      const int acc = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&s.tfull[acc], aphase);
+      tcgen05_fence_after();
+      const int p = tile * BM + quarter * 32 + lane;
+      const int r = p % ga.g.board_rows;
+      const bool valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
+      const bool in_alloc = p < ga.alloc_rows;
+#pragma unroll 1
+      for (int c = 0; c < BNH / 32; c++) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + acc * BNH + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
+        const int col = nhalf * BNH + c * 32;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) x[j] = __uint_as_float(v[j]) + s.bias[c * 32 + j];
+        if (EPI == tc::EPI_CONV2 && valid) {
+          const float4* rp = reinterpret_cast<const float4*>(ga.resid32 + (size_t)p * F + col);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float4 r4 = rp[j];
+            x[4 * j] += r4.x; x[4 * j + 1] += r4.y; x[4 * j + 2] += r4.z; x[4 * j + 3] += r4.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) x[j] = valid ? fmaxf(x[j], 0.0f) : 0.0f;
+        if (!in_alloc) continue;
+        if (EPI == tc::EPI_CONV2) {
+          float4* op = reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + col);
+#pragma unroll
+          for (int j = 0; j < 8; j++) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        }
+        uint4 o[4];
+        __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+        for (int j = 0; j < 16; j++) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+        uint4* op16 = reinterpret_cast<uint4*>(ga.out16a + (size_t)p * F + col);
+#pragma unroll
+        for (int j = 0; j < 4; j++) op16[j] = o[j];
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // stem: leaf states -> first activation (conv 3x3, C_in -> 128, folded BN, ReLU) on CUDA cores.
 // Input planes come straight from the game's vectorize_state (no host round trip; replaces
 // GI.vectorize_state + Flux.batch + convert_input, src/networks/network.jl:310-312).
@@ -437,8 +595,13 @@ struct ResNetImpl : az_net {
   float *d_x32 = nullptr, *d_hid = nullptr;
   __half *d_x16 = nullptr, *d_t16 = nullptr, *d_hp = nullptr, *d_hv = nullptr;
   CUtensorMap mapX{}, mapT{}, mapHv{};
+  CUtensorMap mapX2{}, mapT2{};          // Connect-Four tower kernel: 144-row A boxes
+  std::vector<CUtensorMap> mapW2;        // 64co x 64k weight boxes
+  static constexpr bool C4_TOWER = (W + 1) == 8;
+  size_t smem_c4 = 0;
   ConvGeom geom{};
   bool loaded = false;
+  bool generic_tower = false;  // AZ_GENERIC_TOWER=1: use the generic 9-tap kernel for Connect Four too (A/B comparison)
   size_t smem128 = 0, smem64 = 0;
   // profiling: 4 events per evaluation (start, tower begin, tower end, end)
   static constexpr int PROF_SLOTS = 8192;
@@ -489,6 +652,7 @@ struct ResNetImpl : az_net {
       return AZ_EUNSUPPORTED;
     }
     if (hp.num_blocks < 0) { ctx->err = "ResNet: num_blocks must be >= 0"; return AZ_EINVAL; }
+    { const char* e = getenv("AZ_GENERIC_TOWER"); generic_tower = e && e[0] == '1'; }
     geom.row_stride = W + 1; geom.board_rows = BS; geom.valid_rows = VR; geom.wcols = W;
     for (int ky = 0; ky < 3; ky++)
       for (int kx = 0; kx < 3; kx++) geom.off[ky * 3 + kx] = (1 - ky) * (W + 1) + (1 - kx);
@@ -498,6 +662,9 @@ struct ResNetImpl : az_net {
     AZ_TRY2(set_smem(az_k_gemm_tc<128, tc::EPI_CONV2>, smem128));
     AZ_TRY2(set_smem(az_k_gemm_tc<128, tc::EPI_DENSE>, smem128));
     AZ_TRY2(set_smem(az_k_gemm_tc<64, tc::EPI_HEAD>, smem64));
+    smem_c4 = sizeof(tc2::Smem) + 1024;
+    AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV1>, smem_c4));
+    AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV2>, smem_c4));
     return AZ_OK;
   }
   int64_t num_params() override {
@@ -520,7 +687,7 @@ struct ResNetImpl : az_net {
     cudaFree(d_wstem); cudaFree(d_bstem);
     for (auto p : d_wconv) cudaFree(p);
     for (auto p : d_bconv) cudaFree(p);
-    d_wconv.clear(); d_bconv.clear(); mapW.clear();
+    d_wconv.clear(); d_bconv.clear(); mapW.clear(); mapW2.clear();
     cudaFree(d_wh); cudaFree(d_wd); cudaFree(d_bh); cudaFree(d_bd); cudaFree(d_wv2); cudaFree(d_bv2); cudaFree(d_wp); cudaFree(d_bp);
     d_wstem = d_bstem = d_bh = d_bd = d_wv2 = d_bv2 = d_wp = d_bp = nullptr; d_wh = d_wd = nullptr;
   }
@@ -572,6 +739,8 @@ struct ResNetImpl : az_net {
       CUtensorMap m;
       AZ_TRY2(make_map_2d(ctx, &m, dw, 9 * F, F, 9 * F * 2, tc::BK, 128));
       mapW.push_back(m);
+      AZ_TRY2(make_map_2d(ctx, &m, dw, 9 * F, F, 9 * F * 2, tc2::BK, tc2::BNH));
+      mapW2.push_back(m);
     }
     std::vector<__half> whd((size_t)64 * F);   // head 1x1 convs: rows 0..31 policy filters, 32..63 value filters
     std::vector<float> bh(64);
@@ -629,6 +798,8 @@ struct ResNetImpl : az_net {
     AZ_TRY2(dmalloc(&d_hv, (size_t)alloc_rows * 32)); AZ_TRY2(dmalloc(&d_hid, (size_t)(max_boards + 256) * F));
     AZ_TRY2(make_map_2d(ctx, &mapX, d_x16, F, alloc_rows, F * 2, tc::BK, tc::BM));
     AZ_TRY2(make_map_2d(ctx, &mapT, d_t16, F, alloc_rows, F * 2, tc::BK, tc::BM));
+    AZ_TRY2(make_map_2d(ctx, &mapX2, d_x16, F, alloc_rows, F * 2, tc2::BK, tc2::AROWS));
+    AZ_TRY2(make_map_2d(ctx, &mapT2, d_t16, F, alloc_rows, F * 2, tc2::BK, tc2::AROWS));
     AZ_TRY2(make_map_2d(ctx, &mapHv, d_hv, (uint64_t)BS * 32, alloc_boards, (uint64_t)BS * 32 * 2, tc::BK, tc::BM));
     act_boards = max_boards;
     return AZ_OK;
@@ -649,11 +820,15 @@ struct ResNetImpl : az_net {
     const int grid = std::min(row_tiles, ctx->num_sms);
     GemmArgs ga{};
     ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.gemm_k = 0;
+    const bool c4 = C4_TOWER && !generic_tower;
+    const int grid_c4 = std::max(2, std::min(2 * row_tiles, ctx->num_sms & ~1));
     for (int blk = 0; blk < hp.num_blocks; blk++) {
       ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
-      az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
+      if (c4) az_k_conv_c4<tc::EPI_CONV1><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
+      else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
-      az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
+      if (c4) az_k_conv_c4<tc::EPI_CONV2><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
     }
     if (prof) cudaEventRecord(pe[2], st);
     // heads: 1x1 convs (both heads, N = 64), value dense (K = KD), finalize

@@ -55,6 +55,18 @@ def test_resnet_precision_stress(az, oz, ctx):
         net.close()
 
 
+@pytest.mark.parametrize("game,plies", [("tictactoe", 5), ("mancala", 30)])
+def test_resnet_other_games_generic_tower(az, oz, ctx, game, plies):
+    """Geometries whose row stride is not 8 run the generic 9-tap tcgen05 kernel (3x3 and 14x1 boards)."""
+    gs = az.GameSpec(game)
+    hp = netcheck.c4_hp(2)
+    net, blob = netcheck.make_net(az, ctx, gs, hp, seed=4, randomize=True)
+    states = gs.random_positions(13, 150, plies)
+    r = netcheck.compare(az, oz, gs, net, blob, hp, states)
+    assert r["dP"] < netcheck.TOL and r["dV"] < netcheck.TOL and r["dI"] < netcheck.TOL, (r["dP"], r["dV"], r["dI"])
+    net.close()
+
+
 def test_fresh_flux_init(az, oz, ctx):
     """Freshly constructed model (zero biases, identity BatchNorm statistics), 5 blocks as shipped."""
     gs = az.GameSpec("connect-four")

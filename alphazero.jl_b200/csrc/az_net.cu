@@ -428,6 +428,194 @@ az_k_conv_c4(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------
+// Connect-Four tower kernel, 2-SM version (cta_group::2).  Stall sampling of the 1-SM kernels (profiles/r01_*)
+// shows the tensor pipe starved by SHARED-MEMORY bandwidth, not by L2: an SS-mode M=128,N=128,K=16 MMA reads 8 KB
+// of operands per 64 math cycles, which is all of the 128 B/clk smem port, and the TMA fills share that port.
+// Pairing two CTAs (M = 256 rows per pair) lets each CTA feed its own 128 A rows plus only HALF of B (its resident
+// 64 output channels): 6 KB of operand reads + 1.5 KB of TMA fill per 64 math cycles.
+// Barrier protocol: TMA loads of both CTAs complete on the LEADER's `full` barrier; the leader's single MMA thread
+// issues tcgen05.mma.cta_group::2 and multicasts tcgen05.commit to both CTAs' `empty` / `tfull` barriers; the 8
+// epilogue warps of the pair arrive on the leader's `tempty`.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit cleared), cute::SM100_TMA_2SM_LOAD_2D
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {  // arrive on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc2::NUM_THREADS, 1)
+az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmArgs ga) {
+  using namespace tc2;
+  constexpr int BN = 128;
+  extern __shared__ uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int rows_used = (*ga.n_boards) * ga.rows_per_board;
+  const int num_ptiles = (rows_used + 2 * BM - 1) / (2 * BM);
+  const int pt0 = blockIdx.x >> 1, pt_step = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 8); }
+    mbar_init(&s.bfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // bias for all 128 output channels (the epilogue of each CTA covers full rows); tc2::Smem::bias has 64 floats, so
+  // the second half lives in the tail of the struct's padding-free neighbour: keep a separate static array instead
+  __shared__ float bias_s[BN];
+  if (threadIdx.x >= 64) bias_s[threadIdx.x - 64] = ga.bias[threadIdx.x - 64];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0 && pt0 < num_ptiles) {  // ===== TMA producer (both CTAs) =====
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+      if (leader) mbar_expect_tx(&s.bfull, 2 * NCHUNK * B_CHUNK);
+      for (int ch = 0; ch < NCHUNK; ch++) tma_load_2d_2sm(s.b[ch], &tmW, &s.bfull, ch * BK, (int)rank * BNH);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pt0; pt < num_ptiles; pt += pt_step) {
+        const int row0 = pt * 2 * BM + (int)rank * BM;
+        for (int st = 0; st < 6; st++) {
+          mbar_wait(&s.empty[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&s.full[stage], 2 * A_STAGE);
+          tma_load_2d_2sm(s.a[stage], &tmA, &s.full[stage], (st & 1) * BK, row0 - 8 + (1 - (st >> 1)));
+          if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader && pt0 < num_ptiles) {  // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256, N = 128
+      mbar_wait(&s.bfull, 0);
+      tcgen05_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int pt = pt0; pt < num_ptiles; pt += pt_step, it++) {
+        const int acc = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&s.tempty[acc], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int st = 0; st < 6; st++) {
+          const int kx = st >> 1, half = st & 1;
+          mbar_wait(&s.full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t abase = smem_u32(s.a[stage]);
+#pragma unroll
+          for (int ky = 0; ky < 3; ky++) {
+            const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(8 + 8 * (1 - ky)) * 128u);
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++)
+              umma_f16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (st | ky | k) ? 1u : 0u);
+          }
+          umma_commit_2sm(&s.empty[stage]);
+          if (st == 5) umma_commit_2sm(&s.tfull[acc]);
+          if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {  // ===== epilogue warps 2..5 (both CTAs): own 128 rows x 128 channels =====
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int pt = pt0; pt < num_ptiles; pt += pt_step, it++) {
+      const int acc = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&s.tfull[acc], aphase);
+      tcgen05_fence_after();
+      const int p = pt * 2 * BM + (int)rank * BM + quarter * 32 + lane;
+      const int r = p % ga.g.board_rows;
+      const bool valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
+      const bool in_alloc = p < ga.alloc_rows;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
+        const int col = c * 32;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) x[j] = __uint_as_float(v[j]) + bias_s[col + j];
+        if (EPI == tc::EPI_CONV2 && valid) {
+          const float4* rp = reinterpret_cast<const float4*>(ga.resid32 + (size_t)p * F + col);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float4 r4 = rp[j];
+            x[4 * j] += r4.x; x[4 * j + 1] += r4.y; x[4 * j + 2] += r4.z; x[4 * j + 3] += r4.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) x[j] = valid ? fmaxf(x[j], 0.0f) : 0.0f;
+        if (!in_alloc) continue;
+        if (EPI == tc::EPI_CONV2) {
+          float4* op = reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + col);
+#pragma unroll
+          for (int j = 0; j < 8; j++) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        }
+        uint4 o[4];
+        __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+        for (int j = 0; j < 16; j++) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+        uint4* op16 = reinterpret_cast<uint4*>(ga.out16a + (size_t)p * F + col);
+#pragma unroll
+        for (int j = 0; j < 4; j++) op16[j] = o[j];
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&s.tempty[acc], 0);  // the leader's MMA thread owns the accumulators
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // stem: leaf states -> first activation (conv 3x3, C_in -> 128, folded BN, ReLU) on CUDA cores.
 // Input planes come straight from the game's vectorize_state (no host round trip; replaces
 // GI.vectorize_state + Flux.batch + convert_input, src/networks/network.jl:310-312).
@@ -601,6 +789,7 @@ struct ResNetImpl : az_net {
   size_t smem_c4 = 0;
   ConvGeom geom{};
   bool loaded = false;
+  bool two_sm = true;          // AZ_TOWER_1SM=1: 1-SM Connect-Four kernel instead of the cta_group::2 one
   bool generic_tower = false;  // AZ_GENERIC_TOWER=1: use the generic 9-tap kernel for Connect Four too (A/B comparison)
   size_t smem128 = 0, smem64 = 0;
   // profiling: 4 events per evaluation (start, tower begin, tower end, end)
@@ -653,6 +842,7 @@ struct ResNetImpl : az_net {
     }
     if (hp.num_blocks < 0) { ctx->err = "ResNet: num_blocks must be >= 0"; return AZ_EINVAL; }
     { const char* e = getenv("AZ_GENERIC_TOWER"); generic_tower = e && e[0] == '1'; }
+    { const char* e = getenv("AZ_TOWER_1SM"); two_sm = !(e && e[0] == '1'); }
     geom.row_stride = W + 1; geom.board_rows = BS; geom.valid_rows = VR; geom.wcols = W;
     for (int ky = 0; ky < 3; ky++)
       for (int kx = 0; kx < 3; kx++) geom.off[ky * 3 + kx] = (1 - ky) * (W + 1) + (1 - kx);
@@ -665,6 +855,8 @@ struct ResNetImpl : az_net {
     smem_c4 = sizeof(tc2::Smem) + 1024;
     AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV1>, smem_c4));
     AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV2>, smem_c4));
+    AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV1>, smem_c4));
+    AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV2>, smem_c4));
     return AZ_OK;
   }
   int64_t num_params() override {
@@ -822,12 +1014,15 @@ struct ResNetImpl : az_net {
     ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.gemm_k = 0;
     const bool c4 = C4_TOWER && !generic_tower;
     const int grid_c4 = std::max(2, std::min(2 * row_tiles, ctx->num_sms & ~1));
+    const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
     for (int blk = 0; blk < hp.num_blocks; blk++) {
       ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
-      if (c4) az_k_conv_c4<tc::EPI_CONV1><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
+      if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
+      else if (c4) az_k_conv_c4<tc::EPI_CONV1><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
-      if (c4) az_k_conv_c4<tc::EPI_CONV2><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      else if (c4) az_k_conv_c4<tc::EPI_CONV2><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
     }
     if (prof) cudaEventRecord(pe[2], st);

@@ -563,43 +563,55 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int pt = pt0; pt < num_ptiles; pt += pt_step, it++) {
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&s.tfull[acc], aphase);
-      tcgen05_fence_after();
       const int p = pt * 2 * BM + (int)rank * BM + quarter * 32 + lane;
       const int r = p % ga.g.board_rows;
       const bool valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
       const bool in_alloc = p < ga.alloc_rows;
-#pragma unroll 1
+      // fp32 residual stream: software pipelined one 32-column chunk ahead so that the LDG latency is hidden behind
+      // the accumulator wait / the previous chunk (the first use used to be the top stall of this kernel)
+      float4 res[2][8];
+      const float4* rp = reinterpret_cast<const float4*>(ga.resid32 + (size_t)p * F);
+      if (EPI == tc::EPI_CONV2) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) res[0][j] = valid ? rp[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      mbar_wait(&s.tfull[acc], aphase);
+      tcgen05_fence_after();
+#pragma unroll
       for (int c = 0; c < BN / 32; c++) {
+        if (EPI == tc::EPI_CONV2 && c + 1 < BN / 32) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) res[(c + 1) & 1][j] = valid ? rp[(c + 1) * 8 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         uint32_t v[32];
         tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
         const int col = c * 32;
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) x[j] = __uint_as_float(v[j]) + bias_s[col + j];
-        if (EPI == tc::EPI_CONV2 && valid) {
-          const float4* rp = reinterpret_cast<const float4*>(ga.resid32 + (size_t)p * F + col);
+        if (EPI == tc::EPI_CONV2) {
 #pragma unroll
           for (int j = 0; j < 8; j++) {
-            float4 r4 = rp[j];
+            const float4 r4 = res[c & 1][j];
             x[4 * j] += r4.x; x[4 * j + 1] += r4.y; x[4 * j + 2] += r4.z; x[4 * j + 3] += r4.w;
           }
         }
 #pragma unroll
         for (int j = 0; j < 32; j++) x[j] = valid ? fmaxf(x[j], 0.0f) : 0.0f;
-        if (!in_alloc) continue;
-        if (EPI == tc::EPI_CONV2) {
-          float4* op = reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + col);
+        if (in_alloc) {
+          if (EPI == tc::EPI_CONV2) {
+            float4* op = reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + col);
 #pragma unroll
-          for (int j = 0; j < 8; j++) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            for (int j = 0; j < 8; j++) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          }
+          uint4 o[4];
+          __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+          for (int j = 0; j < 16; j++) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+          uint4* op16 = reinterpret_cast<uint4*>(ga.out16a + (size_t)p * F + col);
+#pragma unroll
+          for (int j = 0; j < 4; j++) op16[j] = o[j];
         }
-        uint4 o[4];
-        __half2* oh = reinterpret_cast<__half2*>(o);
-#pragma unroll
-        for (int j = 0; j < 16; j++) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-        uint4* op16 = reinterpret_cast<uint4*>(ga.out16a + (size_t)p * F + col);
-#pragma unroll
-        for (int j = 0; j < 4; j++) op16[j] = o[j];
       }
       tcgen05_fence_before();
       __syncwarp();

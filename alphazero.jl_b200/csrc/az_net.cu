@@ -573,7 +573,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const float4* rp = reinterpret_cast<const float4*>(ga.resid32 + (size_t)p * F);
       if (EPI == tc::EPI_CONV2) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) res[0][j] = valid ? rp[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 8; j++) res[0][j] = valid ? __ldcs(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       mbar_wait(&s.tfull[acc], aphase);
       tcgen05_fence_after();
@@ -581,7 +581,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = 0; c < BN / 32; c++) {
         if (EPI == tc::EPI_CONV2 && c + 1 < BN / 32) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) res[(c + 1) & 1][j] = valid ? rp[(c + 1) * 8 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 8; j++) res[(c + 1) & 1][j] = valid ? __ldcs(rp + (c + 1) * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         uint32_t v[32];
         tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
@@ -602,7 +602,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (EPI == tc::EPI_CONV2) {
             float4* op = reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + col);
 #pragma unroll
-            for (int j = 0; j < 8; j++) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            for (int j = 0; j < 8; j++) __stcs(op + j, make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
           }
           uint4 o[4];
           __half2* oh = reinterpret_cast<__half2*>(o);
@@ -801,6 +801,7 @@ struct ResNetImpl : az_net {
   size_t smem_c4 = 0;
   ConvGeom geom{};
   bool loaded = false;
+  int tower_debug = 0;         // AZ_TOWER_DEBUG=1: every conv uses the conv1 epilogue (timing experiments only)
   bool two_sm = true;          // AZ_TOWER_1SM=1: 1-SM Connect-Four kernel instead of the cta_group::2 one
   bool generic_tower = false;  // AZ_GENERIC_TOWER=1: use the generic 9-tap kernel for Connect Four too (A/B comparison)
   size_t smem128 = 0, smem64 = 0;
@@ -854,6 +855,7 @@ struct ResNetImpl : az_net {
     }
     if (hp.num_blocks < 0) { ctx->err = "ResNet: num_blocks must be >= 0"; return AZ_EINVAL; }
     { const char* e = getenv("AZ_GENERIC_TOWER"); generic_tower = e && e[0] == '1'; }
+    { const char* e = getenv("AZ_TOWER_DEBUG"); tower_debug = e ? atoi(e) : 0; }
     { const char* e = getenv("AZ_TOWER_1SM"); two_sm = !(e && e[0] == '1'); }
     geom.row_stride = W + 1; geom.board_rows = BS; geom.valid_rows = VR; geom.wcols = W;
     for (int ky = 0; ky < 3; ky++)
@@ -1033,7 +1035,8 @@ struct ResNetImpl : az_net {
       else if (c4) az_k_conv_c4<tc::EPI_CONV1><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
-      if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      if (c4 && two_sm && tower_debug == 1) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else if (c4) az_k_conv_c4<tc::EPI_CONV2><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
     }

@@ -472,13 +472,28 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 
+namespace tc3 {
+constexpr int ASTAGES = 3;
+constexpr int XS = 36;  // staging row pitch in floats (144 B: 16-byte aligned, conflict-free for 128-bit accesses)
+struct Smem {
+  uint8_t b[tc2::NCHUNK][tc2::B_CHUNK];
+  uint8_t a[ASTAGES][tc2::A_STAGE];
+  float stage[4][32 * XS];  // one 32x32 fp32 transpose tile per epilogue warp
+  uint64_t full[ASTAGES], empty[ASTAGES], tfull[2], tempty[2], bfull;
+  uint32_t tmem_base;
+  float bias[128];
+};
+}  // namespace tc3
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc2::NUM_THREADS, 1)
 az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmArgs ga) {
   using namespace tc2;
+  using tc3::XS;
   constexpr int BN = 128;
+  constexpr int ASTAGES = tc3::ASTAGES;
   extern __shared__ uint8_t smem_raw[];
-  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  tc3::Smem& s = *reinterpret_cast<tc3::Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -492,9 +507,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(&s.bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // bias for all 128 output channels (the epilogue of each CTA covers full rows); tc2::Smem::bias has 64 floats, so
-  // the second half lives in the tail of the struct's padding-free neighbour: keep a separate static array instead
-  __shared__ float bias_s[BN];
+  float* bias_s = s.bias;
   if (threadIdx.x >= 64) bias_s[threadIdx.x - 64] = ga.bias[threadIdx.x - 64];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(256u) : "memory");
@@ -558,60 +571,70 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {  // ===== epilogue warps 2..5 (both CTAs): own 128 rows x 128 channels =====
+    // TMEM gives each thread one ROW (32 consecutive columns per tcgen05.ld).  Writing rows straight to global memory
+    // costs 32 distinct 128-B lines per warp instruction and made the LSU tag pipeline the bottleneck of conv2, so each
+    // 32x32 block goes through a per-warp smem tile and leaves as full 128-byte row segments (4 rows per instruction).
     const int quarter = warp & 3;
+    float* stg = s.stage[quarter];
+    const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;  // coalesced phase: 4 rows x (8 lanes x 4 floats)
     int it = 0;
     for (int pt = pt0; pt < num_ptiles; pt += pt_step, it++) {
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int p = pt * 2 * BM + (int)rank * BM + quarter * 32 + lane;
-      const int r = p % ga.g.board_rows;
-      const bool valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
-      const bool in_alloc = p < ga.alloc_rows;
-      // fp32 residual stream: software pipelined one 32-column chunk ahead so that the LDG latency is hidden behind
-      // the accumulator wait / the previous chunk (the first use used to be the top stall of this kernel)
-      float4 res[2][8];
-      const float4* rp = reinterpret_cast<const float4*>(ga.resid32 + (size_t)p * F);
-      if (EPI == tc::EPI_CONV2) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) res[0][j] = valid ? __ldcs(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int prow0 = pt * 2 * BM + (int)rank * BM + quarter * 32;
+      // validity mask of this warp's 32 rows (bit rr = row prow0 + rr is a real board cell inside the used range)
+      uint32_t vmask;
+      {
+        const int p = prow0 + lane;
+        const int r = p % ga.g.board_rows;
+        const bool valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
+        vmask = __ballot_sync(0xffffffffu, valid);
       }
       mbar_wait(&s.tfull[acc], aphase);
       tcgen05_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
-        if (EPI == tc::EPI_CONV2 && c + 1 < BN / 32) {
+        const int col = c * 32;
+        float4 res[8];
+        if (EPI == tc::EPI_CONV2) {  // issue the residual loads first: their latency hides behind the TMEM load + transpose
 #pragma unroll
-          for (int j = 0; j < 8; j++) res[(c + 1) & 1][j] = valid ? __ldcs(rp + (c + 1) * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < 8; q++) {
+            const int rr = q * 4 + sub_row;
+            res[q] = ((vmask >> rr) & 1u) ? __ldcs(reinterpret_cast<const float4*>(ga.resid32 + (size_t)(prow0 + rr) * F + col + sub_col))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         uint32_t v[32];
-        tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
-        const int col = c * 32;
-        float x[32];
+        tmem_ld32(tmem_base + acc * BN + col + ((uint32_t)(quarter * 32) << 16), v);
 #pragma unroll
-        for (int j = 0; j < 32; j++) x[j] = __uint_as_float(v[j]) + bias_s[col + j];
-        if (EPI == tc::EPI_CONV2) {
+        for (int j = 0; j < 8; j++) {
+          float4 t;
+          t.x = __uint_as_float(v[4 * j]) + bias_s[col + 4 * j];
+          t.y = __uint_as_float(v[4 * j + 1]) + bias_s[col + 4 * j + 1];
+          t.z = __uint_as_float(v[4 * j + 2]) + bias_s[col + 4 * j + 2];
+          t.w = __uint_as_float(v[4 * j + 3]) + bias_s[col + 4 * j + 3];
+          *reinterpret_cast<float4*>(stg + lane * XS + 4 * j) = t;
+        }
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const float4 r4 = res[c & 1][j];
-            x[4 * j] += r4.x; x[4 * j + 1] += r4.y; x[4 * j + 2] += r4.z; x[4 * j + 3] += r4.w;
+        for (int q = 0; q < 8; q++) {
+          const int rr = q * 4 + sub_row;
+          const int p = prow0 + rr;
+          float4 y = *reinterpret_cast<const float4*>(stg + rr * XS + sub_col);
+          const bool valid = (vmask >> rr) & 1u;
+          if (EPI == tc::EPI_CONV2) { y.x += res[q].x; y.y += res[q].y; y.z += res[q].z; y.w += res[q].w; }
+          y.x = valid ? fmaxf(y.x, 0.f) : 0.f; y.y = valid ? fmaxf(y.y, 0.f) : 0.f;
+          y.z = valid ? fmaxf(y.z, 0.f) : 0.f; y.w = valid ? fmaxf(y.w, 0.f) : 0.f;
+          if (p < ga.alloc_rows) {
+            if (EPI == tc::EPI_CONV2) __stcs(reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + col + sub_col), y);
+            __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&h0);
+            o.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(ga.out16a + (size_t)p * F + col + sub_col) = o;
           }
         }
-#pragma unroll
-        for (int j = 0; j < 32; j++) x[j] = valid ? fmaxf(x[j], 0.0f) : 0.0f;
-        if (in_alloc) {
-          if (EPI == tc::EPI_CONV2) {
-            float4* op = reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + col);
-#pragma unroll
-            for (int j = 0; j < 8; j++) __stcs(op + j, make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
-          }
-          uint4 o[4];
-          __half2* oh = reinterpret_cast<__half2*>(o);
-#pragma unroll
-          for (int j = 0; j < 16; j++) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-          uint4* op16 = reinterpret_cast<uint4*>(ga.out16a + (size_t)p * F + col);
-#pragma unroll
-          for (int j = 0; j < 4; j++) op16[j] = o[j];
-        }
+        __syncwarp();
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -798,7 +821,7 @@ struct ResNetImpl : az_net {
   CUtensorMap mapX2{}, mapT2{};          // Connect-Four tower kernel: 144-row A boxes
   std::vector<CUtensorMap> mapW2;        // 64co x 64k weight boxes
   static constexpr bool C4_TOWER = (W + 1) == 8;
-  size_t smem_c4 = 0;
+  size_t smem_c4 = 0, smem_2sm = 0;
   ConvGeom geom{};
   bool loaded = false;
   int tower_debug = 0;         // AZ_TOWER_DEBUG=1: every conv uses the conv1 epilogue (timing experiments only)
@@ -869,8 +892,9 @@ struct ResNetImpl : az_net {
     smem_c4 = sizeof(tc2::Smem) + 1024;
     AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV1>, smem_c4));
     AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV2>, smem_c4));
-    AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV1>, smem_c4));
-    AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV2>, smem_c4));
+    smem_2sm = sizeof(tc3::Smem) + 1024;
+    AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV1>, smem_2sm));
+    AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV2>, smem_2sm));
     return AZ_OK;
   }
   int64_t num_params() override {
@@ -1031,12 +1055,12 @@ struct ResNetImpl : az_net {
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
     for (int blk = 0; blk < hp.num_blocks; blk++) {
       ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
-      if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
+      if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc2::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], ga);
       else if (c4) az_k_conv_c4<tc::EPI_CONV1><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
-      if (c4 && two_sm && tower_debug == 1) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
-      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      if (c4 && two_sm && tower_debug == 1) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc2::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc2::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else if (c4) az_k_conv_c4<tc::EPI_CONV2><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
     }

@@ -451,6 +451,9 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* ma
   asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {  // warm L2 only, no smem
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -529,6 +532,11 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int pt = pt0; pt < num_ptiles; pt += pt_step) {
         const int row0 = pt * 2 * BM + (int)rank * BM;
+        if (pt + pt_step < num_ptiles) {  // pull the next tile's activations into L2 while this one is computed
+          const int nrow0 = (pt + pt_step) * 2 * BM + (int)rank * BM;
+          tma_prefetch_2d(&tmA, 0, nrow0 - 8);
+          tma_prefetch_2d(&tmA, BK, nrow0 - 8);
+        }
         for (int st = 0; st < 6; st++) {
           mbar_wait(&s.empty[stage], phase ^ 1);
           if (leader) mbar_expect_tx(&s.full[stage], 2 * A_STAGE);

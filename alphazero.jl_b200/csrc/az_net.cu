@@ -124,6 +124,7 @@ struct GemmArgs {
   int gemm_k;        // 0: A coords = ((kb&1)*64, row + off[kb>>1]) (shifted-row conv);  1: A coords = (kb*64, row) (plain GEMM)
   int rows_per_board;  // rows of the M dimension per board: board_rows (conv/head) or 1 (dense)
   int alloc_rows;
+  int debug;             // timing experiments only (AZ_TOWER_DEBUG bitmask): 2 = no A loads, 4 = no epilogue global I/O
   const float* bias;
   const float* resid32;  // EPI_CONV2
   float* out32;          // EPI_CONV2 (stream), EPI_DENSE (hidden)
@@ -538,6 +539,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_prefetch_2d(&tmA, BK, nrow0 - 8);
         }
         for (int st = 0; st < 6; st++) {
+          if (ga.debug & 2) break;
           mbar_wait(&s.empty[stage], phase ^ 1);
           if (leader) mbar_expect_tx(&s.full[stage], 2 * A_STAGE);
           tma_load_2d_2sm(s.a[stage], &tmA, &s.full[stage], (st & 1) * BK, row0 - 8 + (1 - (st >> 1)));
@@ -561,7 +563,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int st = 0; st < 6; st++) {
           const int kx = st >> 1, half = st & 1;
-          mbar_wait(&s.full[stage], phase);
+          if (!(ga.debug & 2)) mbar_wait(&s.full[stage], phase);
           tcgen05_fence_after();
           const uint32_t abase = smem_u32(s.a[stage]);
 #pragma unroll
@@ -608,7 +610,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int q = 0; q < 8; q++) {
             const int rr = q * 4 + sub_row;
-            res[q] = ((vmask >> rr) & 1u) ? __ldcs(reinterpret_cast<const float4*>(ga.resid32 + (size_t)(prow0 + rr) * F + col + sub_col))
+            res[q] = (((vmask >> rr) & 1u) && !(ga.debug & 4)) ? __ldcs(reinterpret_cast<const float4*>(ga.resid32 + (size_t)(prow0 + rr) * F + col + sub_col))
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
@@ -633,7 +635,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (EPI == tc::EPI_CONV2) { y.x += res[q].x; y.y += res[q].y; y.z += res[q].z; y.w += res[q].w; }
           y.x = valid ? fmaxf(y.x, 0.f) : 0.f; y.y = valid ? fmaxf(y.y, 0.f) : 0.f;
           y.z = valid ? fmaxf(y.z, 0.f) : 0.f; y.w = valid ? fmaxf(y.w, 0.f) : 0.f;
-          if (p < ga.alloc_rows) {
+          if (p < ga.alloc_rows && !(ga.debug & 4)) {
             if (EPI == tc::EPI_CONV2) __stcs(reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + col + sub_col), y);
             __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
             uint2 o;
@@ -1057,7 +1059,7 @@ struct ResNetImpl : az_net {
     const int row_tiles = (max_rows * BS + tc::BM - 1) / tc::BM;
     const int grid = std::min(row_tiles, ctx->num_sms);
     GemmArgs ga{};
-    ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.gemm_k = 0;
+    ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.gemm_k = 0; ga.debug = tower_debug;
     const bool c4 = C4_TOWER && !generic_tower;
     const int grid_c4 = std::max(2, std::min(2 * row_tiles, ctx->num_sms & ~1));
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
@@ -1067,7 +1069,7 @@ struct ResNetImpl : az_net {
       else if (c4) az_k_conv_c4<tc::EPI_CONV1><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
-      if (c4 && two_sm && tower_debug == 1) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc2::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc2::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc2::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else if (c4) az_k_conv_c4<tc::EPI_CONV2><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
@@ -1075,6 +1077,7 @@ struct ResNetImpl : az_net {
     if (prof) cudaEventRecord(pe[2], st);
     // heads: 1x1 convs (both heads, N = 64), value dense (K = KD), finalize
     ga.g.off[0] = 0;  // 1x1 conv: single centre tap
+    ga.debug = 0;
     ga.kblocks = 2; ga.bias = d_bh; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_hp; ga.out16b = d_hv;
     az_k_gemm_tc<64, tc::EPI_HEAD><<<grid, tc::NUM_THREADS, smem64, st>>>(mapX, mapWh, ga);
     GemmArgs gd{};

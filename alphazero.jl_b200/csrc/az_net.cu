@@ -52,6 +52,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// One elected lane of a CONVERGED warp.  The producer / MMA warps run their loops warp-uniformly and predicate only the
+// async instruction with this: inside a divergent `if (lane == 0)` region the compiler has to wrap every UTCHMMA /
+// UTMALDG in an ELECT + R2UR.BROADCAST waterfall (~130 cycles per MMA, measured), because their operands are uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -161,24 +174,25 @@ az_k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = s.tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {  // ===== TMA producer =====
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    {  // ===== TMA producer (warp-uniform; one elected lane issues) =====
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < kblocks; kb++) {
           mbar_wait(&s.empty[stage], phase ^ 1);
-          mbar_expect_tx(&s.full[stage], A_BYTES + B_BYTES);
-          if (ga.gemm_k) tma_load_2d(s.a[stage], &tmA, &s.full[stage], kb * BK, tile * BM);
-          else tma_load_2d(s.a[stage], &tmA, &s.full[stage], (kb & 1) * BK, tile * BM + ga.g.off[kb >> 1]);
-          tma_load_2d(s.b[stage], &tmW, &s.full[stage], kb * BK, 0);
+          if (elect_one()) {
+            mbar_expect_tx(&s.full[stage], A_BYTES + B_BYTES);
+            if (ga.gemm_k) tma_load_2d(s.a[stage], &tmA, &s.full[stage], kb * BK, tile * BM);
+            else tma_load_2d(s.a[stage], &tmA, &s.full[stage], (kb & 1) * BK, tile * BM + ga.g.off[kb >> 1]);
+            tma_load_2d(s.b[stage], &tmW, &s.full[stage], kb * BK, 0);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
+    {  // ===== MMA issuer (warp-uniform; one elected lane issues) =====
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -193,11 +207,14 @@ az_k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tcgen05_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(s.a[stage]));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[stage]));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; k++)  // advance 32 B (= 16 fp16) inside the 128-B swizzle row
-            umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc<BN>(), (kb | k) ? 1u : 0u);
-          umma_commit(&s.empty[stage]);  // frees the smem stage when these MMAs retire
-          if (kb == kblocks - 1) umma_commit(&s.tfull[acc]);
+            for (int k = 0; k < BK / 16; k++)  // advance 32 B (= 16 fp16) inside the 128-B swizzle row
+              umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc<BN>(), (kb | k) ? 1u : 0u);
+            umma_commit(&s.empty[stage]);  // frees the smem stage when these MMAs retire
+            if (kb == kblocks - 1) umma_commit(&s.tfull[acc]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -322,24 +339,28 @@ az_k_conv_c4(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = s.tmem_base;
 
   if (warp == 0) {
-    if (lane == 0 && tile0 < num_tiles) {  // ===== TMA producer =====
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-      mbar_expect_tx(&s.bfull, NCHUNK * B_CHUNK);
-      for (int ch = 0; ch < NCHUNK; ch++) tma_load_2d(s.b[ch], &tmW, &s.bfull, ch * BK, nhalf * BNH);
+    if (tile0 < num_tiles) {  // ===== TMA producer (warp-uniform) =====
+      if (elect_one()) {
+        mbar_expect_tx(&s.bfull, NCHUNK * B_CHUNK);
+        for (int ch = 0; ch < NCHUNK; ch++) tma_load_2d(s.b[ch], &tmW, &s.bfull, ch * BK, nhalf * BNH);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         for (int st = 0; st < 6; st++) {  // st = kx*2 + channel half
           mbar_wait(&s.empty[stage], phase ^ 1);
-          mbar_expect_tx(&s.full[stage], A_STAGE);
-          tma_load_2d(s.a[stage], &tmA, &s.full[stage], (st & 1) * BK, tile * BM - 8 + (1 - (st >> 1)));
+          if (elect_one()) {
+            mbar_expect_tx(&s.full[stage], A_STAGE);
+            tma_load_2d(s.a[stage], &tmA, &s.full[stage], (st & 1) * BK, tile * BM - 8 + (1 - (st >> 1)));
+          }
+          __syncwarp();
           if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && tile0 < num_tiles) {  // ===== MMA issuer =====
+    if (tile0 < num_tiles) {  // ===== MMA issuer (warp-uniform) =====
       constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BNH >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       mbar_wait(&s.bfull, 0);
       int stage = 0;
@@ -356,17 +377,20 @@ az_k_conv_c4(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(&s.full[stage], phase);
           tcgen05_fence_after();
           const uint32_t abase = smem_u32(s.a[stage]);
+          if (elect_one()) {
 #pragma unroll
-          for (int ky = 0; ky < 3; ky++) {
-            // copy row j <-> activation row tile*128 - 8 + j + (1-kx);  tap (kx,ky) needs j = m + 8 + 8*(1-ky)
-            const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(8 + 8 * (1 - ky)) * 128u);
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
+            for (int ky = 0; ky < 3; ky++) {
+              // copy row j <-> activation row tile*128 - 8 + j + (1-kx);  tap (kx,ky) needs j = m + 8 + 8*(1-ky)
+              const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(8 + 8 * (1 - ky)) * 128u);
+              const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
 #pragma unroll
-            for (int k = 0; k < BK / 16; k++)
-              umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (st | ky | k) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; k++)
+                umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (st | ky | k) ? 1u : 0u);
+            }
+            umma_commit(&s.empty[stage]);
+            if (st == 5) umma_commit(&s.tfull[acc]);
           }
-          umma_commit(&s.empty[stage]);
-          if (st == 5) umma_commit(&s.tfull[acc]);
+          __syncwarp();
           if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -524,31 +548,30 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = s.tmem_base;
 
   if (warp == 0) {
-    if (lane == 0 && pt0 < num_ptiles) {  // ===== TMA producer (both CTAs) =====
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-      if (leader) mbar_expect_tx(&s.bfull, 2 * NCHUNK * B_CHUNK);
-      for (int ch = 0; ch < NCHUNK; ch++) tma_load_2d_2sm(s.b[ch], &tmW, &s.bfull, ch * BK, (int)rank * BNH);
+    if (pt0 < num_ptiles) {  // ===== TMA producer (both CTAs; warp-uniform, one elected lane issues) =====
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(&s.bfull, 2 * NCHUNK * B_CHUNK);
+        for (int ch = 0; ch < NCHUNK; ch++) tma_load_2d_2sm(s.b[ch], &tmW, &s.bfull, ch * BK, (int)rank * BNH);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = pt0; pt < num_ptiles; pt += pt_step) {
         const int row0 = pt * 2 * BM + (int)rank * BM;
-        if (pt + pt_step < num_ptiles) {  // pull the next tile's activations into L2 while this one is computed
-          const int nrow0 = (pt + pt_step) * 2 * BM + (int)rank * BM;
-          tma_prefetch_2d(&tmA, 0, nrow0 - 8);
-          tma_prefetch_2d(&tmA, BK, nrow0 - 8);
-        }
         for (int st = 0; st < 6; st++) {
           if (ga.debug & 2) break;
           mbar_wait(&s.empty[stage], phase ^ 1);
-          if (leader) mbar_expect_tx(&s.full[stage], 2 * A_STAGE);
-          tma_load_2d_2sm(s.a[stage], &tmA, &s.full[stage], (st & 1) * BK, row0 - 8 + (1 - (st >> 1)));
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(&s.full[stage], 2 * A_STAGE);
+            tma_load_2d_2sm(s.a[stage], &tmA, &s.full[stage], (st & 1) * BK, row0 - 8 + (1 - (st >> 1)));
+          }
+          __syncwarp();
           if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader && pt0 < num_ptiles) {  // ===== MMA issuer (leader CTA only) =====
+    if (leader && pt0 < num_ptiles) {  // ===== MMA issuer (leader CTA only; warp-uniform, one elected lane issues) =====
       constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256, N = 128
       mbar_wait(&s.bfull, 0);
       tcgen05_fence_after();
@@ -566,16 +589,19 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!(ga.debug & 2)) mbar_wait(&s.full[stage], phase);
           tcgen05_fence_after();
           const uint32_t abase = smem_u32(s.a[stage]);
+          if (elect_one()) {
 #pragma unroll
-          for (int ky = 0; ky < 3; ky++) {
-            const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(8 + 8 * (1 - ky)) * 128u);
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
+            for (int ky = 0; ky < 3; ky++) {
+              const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(8 + 8 * (1 - ky)) * 128u);
+              const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
 #pragma unroll
-            for (int k = 0; k < BK / 16; k++)
-              umma_f16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (st | ky | k) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; k++)
+                umma_f16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (st | ky | k) ? 1u : 0u);
+            }
+            umma_commit_2sm(&s.empty[stage]);
+            if (st == 5) umma_commit_2sm(&s.tfull[acc]);
           }
-          umma_commit_2sm(&s.empty[stage]);
-          if (st == 5) umma_commit_2sm(&s.tfull[acc]);
+          __syncwarp();
           if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
         }
       }

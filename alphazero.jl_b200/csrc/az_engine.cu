@@ -188,7 +188,7 @@ struct Mcts : az_mcts {
     if (h_pin) cudaFreeHost(h_pin);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
   }
-  int groups_grid() const { return (int)(((size_t)p.S * G::LANES + 127) / 128); }
+  int groups_grid() const { return (int)(((size_t)p.S * 32 + 127) / 128); }  // one warp per tree
 
   int set_roots(const uint8_t* states, const double* eta) override {
     if (!eta && p.c.eps != 0.0) AZ_FAIL(ctx, AZ_EINVAL, "az_mcts_set_roots: eta is required when dirichlet_noise_eps != 0");

@@ -60,10 +60,8 @@ struct AzPool {
 #define AZ_KEYB_MASK ((1ull << 57) - 1)
 
 template <int L>
-__device__ __forceinline__ unsigned az_group_mask() {
-  if (L == 32) return 0xffffffffu;
-  unsigned lane = threadIdx.x & 31u;
-  return ((1u << L) - 1u) << (lane & ~(unsigned)(L - 1));
+__device__ __forceinline__ unsigned az_group_mask() {  // the first L lanes of the warp
+  return L == 32 ? 0xffffffffu : ((1u << L) - 1u);
 }
 __device__ __forceinline__ uint32_t az_hash(uint64_t a, uint64_t b) {
   uint64_t x = a * 0x9E3779B97F4A7C15ull ^ (b + 0x7F4A7C15F39CC060ull) * 0xC2B2AE3D27D4EB4Full;
@@ -122,9 +120,11 @@ template <class G>
 __global__ void __launch_bounds__(128) az_k_select(AzPool p) {
   constexpr int L = G::LANES;
   constexpr int A = G::A;
-  int slot = (blockIdx.x * blockDim.x + threadIdx.x) / L;
-  int lane = threadIdx.x % L;
-  if (slot >= p.S) return;
+  // one slot per WARP: slots in the same warp would serialise on their divergent loop trip counts (4 dependent
+  // pointer chains back to back instead of overlapped); lanes >= L of each warp retire immediately
+  int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (slot >= p.S || lane >= L) return;
   unsigned gm = az_group_mask<L>();
   if (!p.status[slot] || p.pending[slot]) return;
   int sims_done = p.sims_done[slot];
@@ -241,9 +241,11 @@ template <class G>
 __global__ void __launch_bounds__(128) az_k_expand_backup(AzPool p) {
   constexpr int L = G::LANES;
   constexpr int A = G::A;
-  int slot = (blockIdx.x * blockDim.x + threadIdx.x) / L;
-  int lane = threadIdx.x % L;
-  if (slot >= p.S) return;
+  // one slot per WARP: slots in the same warp would serialise on their divergent loop trip counts (4 dependent
+  // pointer chains back to back instead of overlapped); lanes >= L of each warp retire immediately
+  int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (slot >= p.S || lane >= L) return;
   unsigned gm = az_group_mask<L>();
   if (!p.pending[slot]) return;
   const int row = p.leaf_row[slot];
@@ -314,9 +316,11 @@ template <class G>
 __global__ void az_k_root_stats(AzPool p, int64_t* N, double* W, float* P) {
   constexpr int L = G::LANES;
   constexpr int A = G::A;
-  int slot = (blockIdx.x * blockDim.x + threadIdx.x) / L;
-  int lane = threadIdx.x % L;
-  if (slot >= p.S) return;
+  // one slot per WARP: slots in the same warp would serialise on their divergent loop trip counts (4 dependent
+  // pointer chains back to back instead of overlapped); lanes >= L of each warp retire immediately
+  int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (slot >= p.S || lane >= L) return;
   unsigned gm = az_group_mask<L>();
   const AzEnv root = p.root[slot];
   const uint4* tab = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;

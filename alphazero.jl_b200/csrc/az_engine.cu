@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -162,6 +163,8 @@ struct Mcts : az_mcts {
     cap = 64;
     while (cap < (size_t)cap_nodes + (size_t)cap_nodes / 4 + 8) cap <<= 1;
     p.S = S; p.cap_mask = (uint32_t)(cap - 1); p.maxd = G::MAX_PLIES + 1;
+    p.max_sims_per_call = 4;
+    if (const char* e = getenv("AZ_MAX_SIMS_PER_CALL")) p.max_sims_per_call = std::max(1, atoi(e));
     p.c.gamma = params->gamma; p.c.cpuct = params->cpuct; p.c.eps = params->dirichlet_noise_eps;
     p.c.alpha = params->dirichlet_noise_alpha; p.c.prior_temp = params->prior_temperature;
     AZ_TRY(ctx, alloc(&p.nodes, (size_t)S * cap * G::LANES));
@@ -172,7 +175,7 @@ struct Mcts : az_mcts {
     AZ_TRY(ctx, alloc(&p.leaf_row, S)); AZ_TRY(ctx, alloc(&p.depth, S));
     AZ_TRY(ctx, alloc(&p.path_node, (size_t)S * p.maxd)); AZ_TRY(ctx, alloc(&p.path_meta, (size_t)S * p.maxd));
     AZ_TRY(ctx, alloc(&p.path_r, (size_t)S * p.maxd));
-    AZ_TRY(ctx, alloc(&p.n_leaves, 1)); AZ_TRY(ctx, alloc(&p.batch_env, S));
+    AZ_TRY(ctx, alloc(&p.n_leaves, 2)); AZ_TRY(ctx, alloc(&p.batch_env, S));
     AZ_TRY(ctx, alloc(&p.batch_P, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&p.batch_V, S));
     AZ_TRY(ctx, alloc(&p.flags, 4)); AZ_TRY(ctx, alloc(&p.expansions, 1));
     AZ_TRY(ctx, alloc(&d_N, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&d_W, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&d_P, (size_t)S * G::A));
@@ -201,7 +204,7 @@ struct Mcts : az_mcts {
   }
   // one tick: select -> oracle -> expand+backup
   int tick(bool time_net) {
-    AZ_CUDA(ctx, cudaMemsetAsync(p.n_leaves, 0, sizeof(int32_t), ctx->stream));
+    AZ_CUDA(ctx, cudaMemsetAsync(p.n_leaves, 0, 2 * sizeof(int32_t), ctx->stream));
     az_k_select<G><<<groups_grid(), 128, 0, ctx->stream>>>(p);
     if (time_net) cudaEventRecord(ev[2], ctx->stream);
     AZ_TRY(ctx, net->eval(p.batch_env, p.n_leaves, p.S, p.batch_P, p.batch_V));
@@ -211,7 +214,7 @@ struct Mcts : az_mcts {
     return AZ_OK;
   }
   int check_flags() {
-    AZ_CUDA(ctx, cudaMemcpyAsync(h_pin, p.n_leaves, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AZ_CUDA(ctx, cudaMemcpyAsync(h_pin + 8, p.n_leaves, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     AZ_CUDA(ctx, cudaMemcpyAsync(h_pin + 1, p.flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (h_pin[1]) AZ_FAIL(ctx, AZ_ENOMEM, "MCTS table overflow: raise capacity_nodes_per_tree");
@@ -231,12 +234,12 @@ struct Mcts : az_mcts {
     AZ_CUDA(ctx, cudaEventRecord(ev[0], ctx->stream));
     ticks = 0; ms_net = 0;
     // every unfinished tree completes >= 1 simulation per tick, so nsims ticks always suffice
-    for (int t = 0; t < nsims; t++) {
+    for (int t = 0; t < nsims + 1; t++) {
       AZ_TRY(ctx, tick(false));
       ticks++;
-      if (t + 1 >= nsims / 2 && ((t + 1) % 8 == 0 || t + 1 == nsims)) {
+      if (t + 1 >= nsims / 2 && ((t + 1) % 8 == 0 || t + 1 >= nsims)) {
         AZ_TRY(ctx, check_flags());
-        if (h_pin[0] == 0) break;  // the last select found no leaf: every tree has spent its budget
+        if (h_pin[8] == 0 && h_pin[9] == 0) break;  // no leaf pending and no tree with simulations left
       }
     }
     AZ_CUDA(ctx, cudaEventRecord(ev[1], ctx->stream));

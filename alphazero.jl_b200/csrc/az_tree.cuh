@@ -48,7 +48,8 @@ struct AzPool {
   uint32_t* path_node;  // [S][maxd]
   uint16_t* path_meta;  // [S][maxd]  action | pswitch << 8
   double* path_r;       // [S][maxd]
-  int32_t* n_leaves;    // [1]
+  int32_t* n_leaves;    // [2]: [0] leaves emitted this tick, [1] trees that still have simulations to run
+  int32_t max_sims_per_call;  // cap on simulations one select call runs for a tree (bounds the kernel's tail)
   AzEnv* batch_env;     // [S]
   float* batch_P;       // [S][A]
   float* batch_V;       // [S]
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(128) az_k_select(AzPool p) {
   double* pr = p.path_r + (size_t)slot * p.maxd;
   int64_t tsims = 0, tnodes = 0;
   const int a = lane - 1;
-  while (sims_done < target) {
+  int budget = p.max_sims_per_call;
+  while (sims_done < target && budget-- > 0) {
     tsims++;
     AzEnv env = root;
     int depth = 0;
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(128) az_k_select(AzPool p) {
     p.sims_done[slot] = sims_done;
     p.total_sims[slot] += tsims;
     p.total_nodes[slot] += tnodes;
+    if (sims_done < target) p.n_leaves[1] = 1;  // this tree is not finished (benign race: everyone writes 1)
   }
 }
 

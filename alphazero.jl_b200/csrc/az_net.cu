@@ -90,6 +90,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
@@ -502,11 +511,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 
 namespace tc3 {
 constexpr int ASTAGES = 3;
-constexpr int XS = 36;  // staging row pitch in floats (144 B: 16-byte aligned, conflict-free for 128-bit accesses)
+constexpr int NUM_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int XS = 20;  // staging row pitch in floats (80 B: 16-byte aligned, conflict-free 128-bit stores)
 struct Smem {
   uint8_t b[tc2::NCHUNK][tc2::B_CHUNK];
   uint8_t a[ASTAGES][tc2::A_STAGE];
-  float stage[4][32 * XS];  // one 32x32 fp32 transpose tile per epilogue warp
+  float stage[8][32 * XS];  // one 32x16 fp32 transpose tile per epilogue warp
   uint64_t full[ASTAGES], empty[ASTAGES], tfull[2], tempty[2], bfull;
   uint32_t tmem_base;
   float bias[128];
@@ -514,7 +524,7 @@ struct Smem {
 }  // namespace tc3
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc2::NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc3::NUM_THREADS, 1)
 az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmArgs ga) {
   using namespace tc2;
   using tc3::XS;
@@ -531,12 +541,12 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 8); }
+    for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 16); }
     mbar_init(&s.bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   float* bias_s = s.bias;
-  if (threadIdx.x >= 64) bias_s[threadIdx.x - 64] = ga.bias[threadIdx.x - 64];
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) bias_s[threadIdx.x - 64] = ga.bias[threadIdx.x - 64];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -606,44 +616,50 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else {  // ===== epilogue warps 2..5 (both CTAs): own 128 rows x 128 channels =====
-    // TMEM gives each thread one ROW (32 consecutive columns per tcgen05.ld).  Writing rows straight to global memory
-    // costs 32 distinct 128-B lines per warp instruction and made the LSU tag pipeline the bottleneck of conv2, so each
-    // 32x32 block goes through a per-warp smem tile and leaves as full 128-byte row segments (4 rows per instruction).
+  } else {  // ===== epilogue warps 2..9 (both CTAs): own 128 rows x 128 channels =====
+    // TMEM gives each thread one ROW.  Writing rows straight to global memory costs 32 distinct 128-B lines per warp
+    // instruction and made the LSU tag pipeline the bottleneck of conv2, so each 32x16 block goes through a per-warp
+    // smem tile and leaves as 64-byte row segments (8 rows per instruction).  Two warps share a TMEM lane quarter
+    // (64 columns each) and the fp32 residual is fetched one 16-column block ahead, so the per-tile latency chain
+    // (load -> add -> store) of the epilogue stays shorter than the tile's MMA time.
     const int quarter = warp & 3;
-    float* stg = s.stage[quarter];
-    const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;  // coalesced phase: 4 rows x (8 lanes x 4 floats)
+    const int colhalf = (warp - 2) >> 2;
+    float* stg = s.stage[warp - 2];
+    const int sub_row = lane >> 2, sub_col = (lane & 3) * 4;  // coalesced phase: 8 rows x (4 lanes x 4 floats)
     int it = 0;
     for (int pt = pt0; pt < num_ptiles; pt += pt_step, it++) {
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int prow0 = pt * 2 * BM + (int)rank * BM + quarter * 32;
-      // validity mask of this warp's 32 rows (bit rr = row prow0 + rr is a real board cell inside the used range)
-      uint32_t vmask;
+      uint32_t vmask;  // bit rr: row prow0 + rr is a real board cell inside the used range
       {
         const int p = prow0 + lane;
         const int r = p % ga.g.board_rows;
         const bool valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
         vmask = __ballot_sync(0xffffffffu, valid);
       }
+      const bool do_io = !(ga.debug & 4);
+      float4 res[2][4];
+      auto load_res = [&](int sc, float4* dst) {
+        const int col = colhalf * 64 + sc * 16 + sub_col;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int rr = q * 8 + sub_row;
+          dst[q] = (((vmask >> rr) & 1u) && do_io) ? __ldcs(reinterpret_cast<const float4*>(ga.resid32 + (size_t)(prow0 + rr) * F + col))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      if (EPI == tc::EPI_CONV2) load_res(0, res[0]);
       mbar_wait(&s.tfull[acc], aphase);
       tcgen05_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
-        const int col = c * 32;
-        float4 res[8];
-        if (EPI == tc::EPI_CONV2) {  // issue the residual loads first: their latency hides behind the TMEM load + transpose
 #pragma unroll
-          for (int q = 0; q < 8; q++) {
-            const int rr = q * 4 + sub_row;
-            res[q] = (((vmask >> rr) & 1u) && !(ga.debug & 4)) ? __ldcs(reinterpret_cast<const float4*>(ga.resid32 + (size_t)(prow0 + rr) * F + col + sub_col))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        uint32_t v[32];
-        tmem_ld32(tmem_base + acc * BN + col + ((uint32_t)(quarter * 32) << 16), v);
+      for (int sc = 0; sc < 4; sc++) {
+        const int col = colhalf * 64 + sc * 16;
+        if (EPI == tc::EPI_CONV2 && sc + 1 < 4) load_res(sc + 1, res[(sc + 1) & 1]);
+        uint32_t v[16];
+        tmem_ld16(tmem_base + acc * BN + col + ((uint32_t)(quarter * 32) << 16), v);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 4; j++) {
           float4 t;
           t.x = __uint_as_float(v[4 * j]) + bias_s[col + 4 * j];
           t.y = __uint_as_float(v[4 * j + 1]) + bias_s[col + 4 * j + 1];
@@ -653,15 +669,15 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const int rr = q * 4 + sub_row;
+        for (int q = 0; q < 4; q++) {
+          const int rr = q * 8 + sub_row;
           const int p = prow0 + rr;
           float4 y = *reinterpret_cast<const float4*>(stg + rr * XS + sub_col);
           const bool valid = (vmask >> rr) & 1u;
-          if (EPI == tc::EPI_CONV2) { y.x += res[q].x; y.y += res[q].y; y.z += res[q].z; y.w += res[q].w; }
+          if (EPI == tc::EPI_CONV2) { const float4 r4 = res[sc & 1][q]; y.x += r4.x; y.y += r4.y; y.z += r4.z; y.w += r4.w; }
           y.x = valid ? fmaxf(y.x, 0.f) : 0.f; y.y = valid ? fmaxf(y.y, 0.f) : 0.f;
           y.z = valid ? fmaxf(y.z, 0.f) : 0.f; y.w = valid ? fmaxf(y.w, 0.f) : 0.f;
-          if (p < ga.alloc_rows && !(ga.debug & 4)) {
+          if (p < ga.alloc_rows && do_io) {
             if (EPI == tc::EPI_CONV2) __stcs(reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + col + sub_col), y);
             __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
             uint2 o;
@@ -1091,12 +1107,12 @@ struct ResNetImpl : az_net {
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
     for (int blk = 0; blk < hp.num_blocks; blk++) {
       ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
-      if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc2::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], ga);
+      if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], ga);
       else if (c4) az_k_conv_c4<tc::EPI_CONV1><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
-      if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc2::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
-      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc2::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else if (c4) az_k_conv_c4<tc::EPI_CONV2><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
     }

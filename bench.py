@@ -125,7 +125,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import torch
-    threads = os.cpu_count() or 1
+    threads = args.cpu_threads or min(os.cpu_count() or 1, 32)
     n_trees = 256
     nsims = 150
     for _ in range(max(1, min(args.warmup, 1))):
@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--nsims", type=int, default=NSIMS)
     ap.add_argument("--blocks", type=int, default=BLOCKS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfplay", action="store_true", help="skip the full self-play leg (games/s)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU reference arm (0 = min(cores, 32))")
     ap.add_argument("--oracle-net", default=None, choices=[None, "uniform", "synth"], help="tree-only figure: built-in oracle instead of the ResNet")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -235,6 +237,31 @@ def main():
         e_ex += e
     barrier()
     sims = args.steps * S * nsims
+    # ---- full self-play (games/s): simulate() with the shipped Connect-Four MctsParams, one game per slot ----
+    sp_out = None
+    if not args.no_selfplay and not args.oracle_net:
+        env.close()
+        env = None
+        import importlib.util
+        spec_d = importlib.util.spec_from_file_location("az_distributed", os.path.join(ROOT, "alphazero.jl_b200", "distributed.py"))
+        azd = importlib.util.module_from_spec(spec_d)
+        spec_d.loader.exec_module(azd)
+        total_games = S * world
+        count, first = azd.split_games(total_games, world, rank)
+        spp = az.SelfPlayParams(
+            az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, temperature=az.PLSchedule([0, 20, 30], [1.0, 1.0, 0.3]),
+                          dirichlet_noise_eps=0.25, dirichlet_noise_alpha=1.0),
+            az.SimParams(num_games=count, num_workers=S, batch_size=S, reset_every=2))
+        barrier()
+        t0 = time.perf_counter()
+        out = az.simulate(ctx, gs, net, spp, seed=1234, first_game_index=first)   # includes the D2H fetch of all samples
+        t_play = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        allg = azd.allgather_samples(out, first, dist, device="cuda" if dist is not None else "cpu")
+        barrier()
+        t_gather = time.perf_counter() - t1
+        sp_out = dict(t=t_play + t_gather, t_gather=t_gather, games=count, samples=int(out["samples"]), expansions=float(out["expansions"]),
+                      total_samples=len(allg["z"]), mean_moves=float(out["moves"].mean()), mean_edepth=float(out["edepth"].mean()))
     # ---- reduce over ranks: time = max, work = sum ----
     if dist is not None:
         t = torch.tensor([ms, e_dt], device="cuda", dtype=torch.float64)
@@ -243,6 +270,13 @@ def main():
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
         ms, e_dt = t.tolist()
         ex, e_ex, sims, launches = w.tolist()
+        if sp_out is not None:
+            tt = torch.tensor([sp_out["t"], sp_out["t_gather"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ww = torch.tensor([sp_out["games"], sp_out["samples"], sp_out["expansions"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+            sp_out["t"], sp_out["t_gather"] = tt.tolist()
+            sp_out["games"], sp_out["samples"], sp_out["expansions"] = ww.tolist()
     if rank == 0:
         value = ex / (ms / 1e3)
         line = {"metric": METRIC, "value": value, "unit": "expansions/s", "n_gpus": world, "steps": args.steps,
@@ -257,6 +291,13 @@ def main():
                         "h2d_bytes_per_step": int(S * 24 + eta.nbytes),
                         "d2h_bytes_per_step": int(S * A * (8 + 8 + 4))},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "host_wall_s_resident": t_wall}
+        if sp_out is not None:
+            line["selfplay"] = {"games_per_s": sp_out["games"] / sp_out["t"], "samples_per_s": sp_out["samples"] / sp_out["t"],
+                                "expansions_per_s": sp_out["expansions"] / sp_out["t"], "seconds": sp_out["t"],
+                                "allgather_seconds": sp_out["t_gather"], "games": int(sp_out["games"]), "samples": int(sp_out["samples"]),
+                                "gathered_samples_on_rank0": sp_out["total_samples"], "mean_moves_per_game": sp_out["mean_moves"],
+                                "mean_exploration_depth": sp_out["mean_edepth"],
+                                "config": "simulate(): %d games per GPU (one per worker slot), 600 sims/move, cpuct 2, eps 0.25, tau PL([0,20,30],[1,1,.3]), reset_every 2; wall clock incl. sample D2H + all-gather" % S}
         if prof and prof["evals"]:
             peak, how = peaks()
             nconv = 2 * args.blocks
@@ -269,12 +310,13 @@ def main():
                                 "network_share_of_step": prof["total_ms"] / (ms / world if dist is None else ms),
                                 "tower_share_of_step": prof["tower_ms"] / ms}
         if not args.no_cpu_baseline and not args.oracle_net:
-            threads = os.cpu_count() or 1
+            threads = args.cpu_threads or min(os.cpu_count() or 1, 32)
             cex, cdt, _ = cpu_reference_run(128, 100, threads)
             line["cpu_baseline"] = {"value": cex / cdt, "unit": "expansions/s", "cores": threads, "kind": "port",
                                     "sample": "128 trees x 100 sims of the same workload: CPU MCTS (C port of src/mcts.jl) + torch-CPU fp32 7-block ResNet"}
         print(json.dumps(line))
-    env.close()
+    if env is not None:
+        env.close()
     net.close()
     ctx.close()
     if dist is not None:

@@ -125,7 +125,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import torch
-    threads = args.cpu_threads or min(os.cpu_count() or 1, 32)
+    threads = args.cpu_threads or min(os.cpu_count() or 1, 16)
     n_trees = 256
     nsims = 150
     for _ in range(max(1, min(args.warmup, 1))):
@@ -157,7 +157,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=BLOCKS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the full self-play leg (games/s)")
-    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU reference arm (0 = min(cores, 32))")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU reference arm (0 = min(cores, 16): torch-CPU conv throughput peaks there on the 128-core box)")
     ap.add_argument("--oracle-net", default=None, choices=[None, "uniform", "synth"], help="tree-only figure: built-in oracle instead of the ResNet")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -310,7 +310,7 @@ def main():
                                 "network_share_of_step": prof["total_ms"] / (ms / world if dist is None else ms),
                                 "tower_share_of_step": prof["tower_ms"] / ms}
         if not args.no_cpu_baseline and not args.oracle_net:
-            threads = args.cpu_threads or min(os.cpu_count() or 1, 32)
+            threads = args.cpu_threads or min(os.cpu_count() or 1, 16)
             cex, cdt, _ = cpu_reference_run(128, 100, threads)
             line["cpu_baseline"] = {"value": cex / cdt, "unit": "expansions/s", "cores": threads, "kind": "port",
                                     "sample": "128 trees x 100 sims of the same workload: CPU MCTS (C port of src/mcts.jl) + torch-CPU fp32 7-block ResNet"}

@@ -123,3 +123,45 @@ def test_mcts_with_network_bit_exact(az, oz, ctx):
         assert (N[i] == rN).all() and (W[i] == rW).all() and (P[i] == rP).all()
     env.close()
     net.close()
+
+
+def test_selfplay_with_network_bit_exact(az, oz, ctx):
+    """simulate() end to end with the ResNet as oracle (4 workers x 8 games x 24 sims, reset_every 2): every oracle worker
+    replays with the network's own (P, V) per state, so traces (states, actions, pi, z, t) must match bit for bit."""
+    import ctypes as C
+    gs = az.GameSpec("connect-four")
+    gid = oz.game_id("connect-four")
+    hp = netcheck.c4_hp(1)
+    net, _ = netcheck.make_net(az, ctx, gs, hp, seed=5)
+    S, NG, nsims, seed = 4, 8, 24, 99
+    mp = az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, temperature=az.PLSchedule([0, 20, 30], [1.0, 1.0, 0.3]),
+                       dirichlet_noise_eps=0.25, dirichlet_noise_alpha=1.0)
+    out = az.simulate(ctx, gs, net, az.SelfPlayParams(mp, az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=2)), seed=seed)
+    cache = {}
+    sb = gs.state_bytes
+
+    def cb(ctxp, g, sp, n, P, V):
+        key = bytes(sp[:sb])
+        if key not in cache:
+            p, v, _ = net.evaluate_batch(np.frombuffer(key, np.uint8)[None])
+            m = gs.actions_mask(np.frombuffer(key, np.uint8))
+            cache[key] = (p[0][m], float(v[0]))
+        p, v = cache[key]
+        for i in range(n):
+            P[i] = p[i]
+        V[0] = v
+
+    fn = oz.ORACLE_FN(cb)
+    omp = oz.mcts_params(cpuct=2.0, noise_eps=0.25, noise_alpha=1.0, num_iters_per_turn=nsims, sched_xs=(0, 20, 30), sched_ys=(1.0, 1.0, 0.3))
+    for w in range(S):
+        traces = oz.worker_run(gid, C.cast(fn, C.c_void_p), omp, seed, first=w, stride=S, count=NG // S, reset_every=2)
+        for j, tr in enumerate(traces):
+            g = w + S * j
+            rows = np.flatnonzero(out["game"] == g)
+            assert len(rows) == tr["n_moves"]
+            assert (out["actions"][rows] == tr["action"]).all()
+            assert (out["states"][rows] == tr["states"][:-1]).all()
+            assert (out["pi"][rows].view(np.uint32) == tr["pi"].view(np.uint32)).all()
+            assert (out["z"][rows] == tr["z"].astype(np.float32)).all()
+            assert out["nodes"][g] == tr["mem_nodes"] and out["edepth"][g] == tr["edepth"]
+    net.close()

@@ -556,6 +556,9 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = s.tmem_base;
+  // Programmatic dependent launch: let the next layer's CTAs be scheduled as SMs drain; everything above and the
+  // weight load below do not depend on the previous layer, activations are only touched after griddepcontrol.wait.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     if (pt0 < num_ptiles) {  // ===== TMA producer (both CTAs; warp-uniform, one elected lane issues) =====
@@ -564,6 +567,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int ch = 0; ch < NCHUNK; ch++) tma_load_2d_2sm(s.b[ch], &tmW, &s.bfull, ch * BK, (int)rank * BNH);
       }
       __syncwarp();
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = pt0; pt < num_ptiles; pt += pt_step) {
@@ -622,6 +626,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // smem tile and leaves as 64-byte row segments (8 rows per instruction).  Two warps share a TMEM lane quarter
     // (64 columns each) and the fp32 residual is fetched one 16-column block ahead, so the per-tile latency chain
     // (load -> add -> store) of the epilogue stays shorter than the tile's MMA time.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int quarter = warp & 3;
     const int colhalf = (warp - 2) >> 2;
     float* stg = s.stage[warp - 2];
@@ -851,6 +856,19 @@ static int make_map_2d(az_ctx* ctx, CUtensorMap* m, void* base, uint64_t inner, 
   return AZ_OK;
 }
 
+// launch with programmatic stream serialization (PDL): the kernel may start while its predecessor in the stream is
+// still draining; it must execute griddepcontrol.wait before touching data the predecessor produces
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <class G>
 struct ResNetImpl : az_net {
   az_resnet_hp hp{};
@@ -877,6 +895,7 @@ struct ResNetImpl : az_net {
   ConvGeom geom{};
   bool loaded = false;
   int tower_debug = 0;         // AZ_TOWER_DEBUG=1: every conv uses the conv1 epilogue (timing experiments only)
+  bool use_pdl = true;         // AZ_NO_PDL=1: plain stream-ordered tower launches
   bool two_sm = true;          // AZ_TOWER_1SM=1: 1-SM Connect-Four kernel instead of the cta_group::2 one
   bool generic_tower = false;  // AZ_GENERIC_TOWER=1: use the generic 9-tap kernel for Connect Four too (A/B comparison)
   size_t smem128 = 0, smem64 = 0;
@@ -931,6 +950,7 @@ struct ResNetImpl : az_net {
     if (hp.num_blocks < 0) { ctx->err = "ResNet: num_blocks must be >= 0"; return AZ_EINVAL; }
     { const char* e = getenv("AZ_GENERIC_TOWER"); generic_tower = e && e[0] == '1'; }
     { const char* e = getenv("AZ_TOWER_DEBUG"); tower_debug = e ? atoi(e) : 0; }
+    { const char* e = getenv("AZ_NO_PDL"); use_pdl = !(e && e[0] == '1'); }
     { const char* e = getenv("AZ_TOWER_1SM"); two_sm = !(e && e[0] == '1'); }
     geom.row_stride = W + 1; geom.board_rows = BS; geom.valid_rows = VR; geom.wcols = W;
     for (int ky = 0; ky < 3; ky++)
@@ -1107,11 +1127,13 @@ struct ResNetImpl : az_net {
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
     for (int blk = 0; blk < hp.num_blocks; blk++) {
       ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
-      if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], ga);
+      if (c4 && two_sm && use_pdl && blk > 0) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV1>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapX2, mapW2[2 * blk], ga);
+      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], ga);
       else if (c4) az_k_conv_c4<tc::EPI_CONV1><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
       if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      else if (c4 && two_sm && use_pdl) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV2>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapT2, mapW2[2 * blk + 1], ga);
       else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else if (c4) az_k_conv_c4<tc::EPI_CONV2><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);

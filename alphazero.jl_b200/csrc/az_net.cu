@@ -149,6 +149,7 @@ struct GemmArgs {
   int debug;             // timing experiments only (AZ_TOWER_DEBUG bitmask): 2 = no A loads, 4 = no epilogue global I/O
   const float* bias;
   const float* resid32;  // EPI_CONV2
+  const __half* resid16; // EPI_CONV2 of block 0 (Connect-Four kernel): residual = fp16 stem output, X32 not yet materialised
   float* out32;          // EPI_CONV2 (stream), EPI_DENSE (hidden)
   __half* out16a;        // CONV1: T, CONV2: X16, HEAD: policy features
   __half* out16b;        // HEAD: value features
@@ -650,8 +651,13 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           const int rr = q * 8 + sub_row;
-          dst[q] = (((vmask >> rr) & 1u) && do_io) ? __ldcs(reinterpret_cast<const float4*>(ga.resid32 + (size_t)(prow0 + rr) * F + col))
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!(((vmask >> rr) & 1u) && do_io)) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          else if (ga.resid16 != nullptr) {
+            const uint2 h = *reinterpret_cast<const uint2*>(ga.resid16 + (size_t)(prow0 + rr) * F + col);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+            dst[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else dst[q] = __ldcs(reinterpret_cast<const float4*>(ga.resid32 + (size_t)(prow0 + rr) * F + col));
         }
       };
       if (EPI == tc::EPI_CONV2) load_res(0, res[0]);
@@ -758,7 +764,7 @@ __global__ void __launch_bounds__(128) az_k_stem(const AzEnv* __restrict__ envs,
         }
       acc = fmaxf(acc, 0.0f);
     }
-    out32[base + (size_t)r * 128] = acc;
+    if (out32 != nullptr) out32[base + (size_t)r * 128] = acc;
     out16[base + (size_t)r * 128] = __float2half_rn(acc);
   }
 }
@@ -780,48 +786,62 @@ struct FinalArgs {
 template <class G>
 __global__ void __launch_bounds__(256) az_k_finalize(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_boards, FinalArgs fa,
                                                      float* __restrict__ P, float* __restrict__ V, float* __restrict__ Pinv) {
-  constexpr int A = G::A, AP = (A + 3) & ~3;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (b >= *n_boards) return;
-  float acc[AP];
+  // 32 boards per block (4 per warp); the policy-dense weights are staged once per block in shared memory with a padded
+  // pitch (2 feature rows = 2*AP floats + 4) so that the 128-bit reads of a quarter warp fall in distinct banks
+  constexpr int A = G::A, AP = (A + 3) & ~3, PITCH = 2 * AP + 4, NBF = 32;
+  extern __shared__ float wps[];
+  const int b0 = blockIdx.x * NBF;
+  if (b0 >= *n_boards) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk2 = fa.kp / 2;
+  for (int i = threadIdx.x; i < nk2 * 2 * AP / 4; i += blockDim.x) {
+    const int k2 = i / (2 * AP / 4), q = i % (2 * AP / 4);
+    reinterpret_cast<float4*>(wps + (size_t)k2 * PITCH)[q] = reinterpret_cast<const float4*>(fa.wp + (size_t)k2 * 2 * AP)[q];
+  }
+  __syncthreads();
+  for (int bb = warp; bb < NBF; bb += 8) {
+    const int b = b0 + bb;
+    if (b >= *n_boards) break;
+    float acc[AP];
 #pragma unroll
-  for (int a = 0; a < AP; a++) acc[a] = 0.0f;
-  const __half2* f = reinterpret_cast<const __half2*>(fa.hp + (size_t)b * fa.board_feat);
-  for (int k2 = lane; k2 < fa.kp / 2; k2 += 32) {
-    const float2 xv = __half22float2(f[k2]);
-    const float4* wr = reinterpret_cast<const float4*>(fa.wp + (size_t)(2 * k2) * AP);
+    for (int a = 0; a < AP; a++) acc[a] = 0.0f;
+    const __half2* f = reinterpret_cast<const __half2*>(fa.hp + (size_t)b * fa.board_feat);
+    for (int k2 = lane; k2 < nk2; k2 += 32) {
+      const float2 xv = __half22float2(f[k2]);
+      const float4* wr = reinterpret_cast<const float4*>(wps + (size_t)k2 * PITCH);
 #pragma unroll
-    for (int q = 0; q < AP / 4; q++) {
-      const float4 wa = wr[q], wb = wr[AP / 4 + q];
-      acc[4 * q] += xv.x * wa.x + xv.y * wb.x;
-      acc[4 * q + 1] += xv.x * wa.y + xv.y * wb.y;
-      acc[4 * q + 2] += xv.x * wa.z + xv.y * wb.z;
-      acc[4 * q + 3] += xv.x * wa.w + xv.y * wb.w;
+      for (int q = 0; q < AP / 4; q++) {
+        const float4 wa = wr[q], wb = wr[AP / 4 + q];
+        acc[4 * q] += xv.x * wa.x + xv.y * wb.x;
+        acc[4 * q + 1] += xv.x * wa.y + xv.y * wb.y;
+        acc[4 * q + 2] += xv.x * wa.z + xv.y * wb.z;
+        acc[4 * q + 3] += xv.x * wa.w + xv.y * wb.w;
+      }
     }
-  }
-  float vacc = 0.0f;
-  for (int i = lane; i < 128; i += 32) vacc += fa.wv2[i] * fa.hid[(size_t)b * 128 + i];
+    float vacc = 0.0f;
+    for (int i = lane; i < 128; i += 32) vacc += fa.wv2[i] * fa.hid[(size_t)b * 128 + i];
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
+    for (int off = 16; off >= 1; off >>= 1) {
 #pragma unroll
-    for (int a = 0; a < AP; a++) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], off);
-    vacc += __shfl_xor_sync(0xffffffffu, vacc, off);
-  }
-  if (lane == 0) {
-    float lg[A], m = -3.0e38f;
+      for (int a = 0; a < AP; a++) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], off);
+      vacc += __shfl_xor_sync(0xffffffffu, vacc, off);
+    }
+    if (lane == 0) {
+      float lg[A], m = -3.0e38f;
 #pragma unroll
-    for (int a = 0; a < A; a++) { lg[a] = acc[a] + fa.bp[a]; m = fmaxf(m, lg[a]); }
-    float se = 0.0f;
+      for (int a = 0; a < A; a++) { lg[a] = acc[a] + fa.bp[a]; m = fmaxf(m, lg[a]); }
+      float se = 0.0f;
 #pragma unroll
-    for (int a = 0; a < A; a++) { lg[a] = expf(lg[a] - m); se += lg[a]; }
-    const uint32_t legal = G::legal_mask(envs[b]);
-    float sp = 0.0f;
+      for (int a = 0; a < A; a++) { lg[a] = expf(lg[a] - m); se += lg[a]; }
+      const uint32_t legal = G::legal_mask(envs[b]);
+      float sp = 0.0f;
 #pragma unroll
-    for (int a = 0; a < A; a++) { lg[a] = ((legal >> a) & 1u) ? lg[a] / se : 0.0f; sp += lg[a]; }
+      for (int a = 0; a < A; a++) { lg[a] = ((legal >> a) & 1u) ? lg[a] / se : 0.0f; sp += lg[a]; }
 #pragma unroll
-    for (int a = 0; a < A; a++) P[(size_t)b * A + a] = lg[a] / (sp + 1.1920929e-07f);  // eps(Float32), network.jl:268
-    V[b] = tanhf(vacc + fa.bv2[0]);
-    if (Pinv) Pinv[b] = 1.0f - sp;
+      for (int a = 0; a < A; a++) P[(size_t)b * A + a] = lg[a] / (sp + 1.1920929e-07f);  // eps(Float32), network.jl:268
+      V[b] = tanhf(vacc + fa.bv2[0]);
+      if (Pinv) Pinv[b] = 1.0f - sp;
+    }
   }
 }
 
@@ -891,7 +911,7 @@ struct ResNetImpl : az_net {
   CUtensorMap mapX2{}, mapT2{};          // Connect-Four tower kernel: 144-row A boxes
   std::vector<CUtensorMap> mapW2;        // 64co x 64k weight boxes
   static constexpr bool C4_TOWER = (W + 1) == 8;
-  size_t smem_c4 = 0, smem_2sm = 0;
+  size_t smem_c4 = 0, smem_2sm = 0, fin_smem = 0;
   ConvGeom geom{};
   bool loaded = false;
   int tower_debug = 0;         // AZ_TOWER_DEBUG=1: every conv uses the conv1 epilogue (timing experiments only)
@@ -964,6 +984,8 @@ struct ResNetImpl : az_net {
     smem_c4 = sizeof(tc2::Smem) + 1024;
     AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV1>, smem_c4));
     AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV2>, smem_c4));
+    fin_smem = (size_t)(KP / 2) * (2 * AP + 4) * sizeof(float);
+    AZ_TRY2(set_smem(az_k_finalize<G>, fin_smem));
     smem_2sm = sizeof(tc3::Smem) + 1024;
     AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV1>, smem_2sm));
     AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV2>, smem_2sm));
@@ -1116,7 +1138,8 @@ struct ResNetImpl : az_net {
     const bool prof = profiling && prof_evals < PROF_SLOTS;
     cudaEvent_t* pe = prof ? &pev[(size_t)prof_evals * 4] : nullptr;
     if (prof) cudaEventRecord(pe[0], st);
-    az_k_stem<G><<<max_rows, 128, 0, st>>>(envs, n_rows, d_wstem, d_bstem, d_x32, d_x16);
+    const bool c4_fast = C4_TOWER && !generic_tower && two_sm && hp.num_blocks > 0;
+    az_k_stem<G><<<max_rows, 128, 0, st>>>(envs, n_rows, d_wstem, d_bstem, c4_fast ? nullptr : d_x32, d_x16);
     if (prof) cudaEventRecord(pe[1], st);
     const int row_tiles = (max_rows * BS + tc::BM - 1) / tc::BM;
     const int grid = std::min(row_tiles, ctx->num_sms);
@@ -1126,12 +1149,13 @@ struct ResNetImpl : az_net {
     const int grid_c4 = std::max(2, std::min(2 * row_tiles, ctx->num_sms & ~1));
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
     for (int blk = 0; blk < hp.num_blocks; blk++) {
-      ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
+      ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.resid16 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
       if (c4 && two_sm && use_pdl && blk > 0) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV1>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapX2, mapW2[2 * blk], ga);
       else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], ga);
       else if (c4) az_k_conv_c4<tc::EPI_CONV1><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
+      ga.resid16 = (c4_fast && blk == 0) ? d_x16 : nullptr;
       if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else if (c4 && two_sm && use_pdl) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV2>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapT2, mapW2[2 * blk + 1], ga);
       else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
@@ -1150,7 +1174,7 @@ struct ResNetImpl : az_net {
     const int board_tiles = (max_rows + tc::BM - 1) / tc::BM;
     az_k_gemm_tc<128, tc::EPI_DENSE><<<std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem128, st>>>(mapHv, mapWd, gd);
     FinalArgs fa{d_hp, d_hid, d_wp, d_bp, d_wv2, d_bv2, KP, BS * 32};
-    az_k_finalize<G><<<(max_rows * 32 + 255) / 256, 256, 0, st>>>(envs, n_rows, fa, P, V, Pinv);
+    az_k_finalize<G><<<(max_rows + 31) / 32, 256, fin_smem, st>>>(envs, n_rows, fa, P, V, Pinv);
     if (prof) { cudaEventRecord(pe[3], st); prof_evals++; }
     ctx->launches += 4 + 2 * hp.num_blocks;
     cudaError_t e = cudaGetLastError();

@@ -146,6 +146,7 @@ struct GemmArgs {
   int gemm_k;        // 0: A coords = ((kb&1)*64, row + off[kb>>1]) (shifted-row conv);  1: A coords = (kb*64, row) (plain GEMM)
   int rows_per_board;  // rows of the M dimension per board: board_rows (conv/head) or 1 (dense)
   int alloc_rows;
+  int no_relu;           // EPI_DENSE: 1 = plain affine output (policy logits)
   int debug;             // timing experiments only (AZ_TOWER_DEBUG bitmask): 2 = no A loads, 4 = no epilogue global I/O
   const float* bias;
   const float* resid32;  // EPI_CONV2
@@ -262,11 +263,12 @@ az_k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
         }
+        const bool relu = !(EPI == EPI_DENSE && ga.no_relu);
 #pragma unroll
-        for (int j = 0; j < 32; j++) x[j] = valid ? fmaxf(x[j], 0.0f) : 0.0f;
+        for (int j = 0; j < 32; j++) x[j] = valid ? (relu ? fmaxf(x[j], 0.0f) : x[j]) : 0.0f;
         if (!in_alloc) continue;
-        if (EPI == EPI_CONV2 || EPI == EPI_DENSE) {
-          if (EPI == EPI_CONV2 || valid) {
+        if (EPI == EPI_CONV2 || EPI == EPI_DENSE || (EPI == EPI_CONV1 && ga.out32 != nullptr)) {
+          if (EPI != EPI_DENSE || valid) {
             float4* op = reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + c * 32);
 #pragma unroll
             for (int j = 0; j < 8; j++) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
@@ -714,58 +716,40 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem: leaf states -> first activation (conv 3x3, C_in -> 128, folded BN, ReLU) on CUDA cores.
-// Input planes come straight from the game's vectorize_state (no host round trip; replaces
-// GI.vectorize_state + Flux.batch + convert_input, src/networks/network.jl:310-312).
-// One thread per output channel keeps its 9*C weights in registers; the padded input planes are in smem.
+// stem: leaf states -> im2col rows -> tcgen05 GEMM.  The first conv (3x3, C_in -> 128, folded BN, ReLU) has K = 9*C_in
+// (27 for Connect Four): az_k_im2col writes, for every padded board row, the 9*C_in input-plane values of its 3x3
+// neighbourhood as one 128-byte fp16 row (K padded to 64), straight from the game's vectorize_state (no host round
+// trip; replaces GI.vectorize_state + Flux.batch + convert_input, src/networks/network.jl:310-312); the conv itself is
+// then one az_k_gemm_tc<128, EPI_CONV1> launch with a single K block.  One warp per board.
 // ------------------------------------------------------------------------------------------------
 template <class G>
-__global__ void __launch_bounds__(128) az_k_stem(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_boards,
-                                                 const float* __restrict__ wstem /* [9][C][128] */, const float* __restrict__ bias,
-                                                 float* __restrict__ out32, __half* __restrict__ out16) {
-  constexpr int W = G::XW, H = G::XH, C = G::XC, RS = W + 1, BS = (W + 1) * (H + 1), CP = (C + 3) & ~3;
-  __shared__ float x[W * H * C];
-  __shared__ __align__(16) float xp[(H + 2) * (W + 2) * CP];
-  const int b = blockIdx.x;
+__global__ void __launch_bounds__(128) az_k_im2col(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_boards,
+                                                   __half* __restrict__ out /* [rows][64] */) {
+  constexpr int W = G::XW, H = G::XH, C = G::XC, RS = W + 1, BS = (W + 1) * (H + 1), NX = W * H * C;
+  __shared__ float xs[4][NX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
   if (b >= *n_boards) return;
-  if (threadIdx.x == 0) G::vectorize(envs[b], x);
-  for (int i = threadIdx.x; i < (H + 2) * (W + 2) * CP; i += blockDim.x) xp[i] = 0.0f;
-  __syncthreads();
-  for (int i = threadIdx.x; i < W * H * C; i += blockDim.x) {
-    int c = i / (W * H), rem = i % (W * H), yy = rem / W, xx = rem % W;
-    xp[((yy + 1) * (W + 2) + (xx + 1)) * CP + c] = x[i];
-  }
-  __syncthreads();
-  const int co = threadIdx.x;
-  float w[9][CP];
+  float* x = xs[warp];
+  if (lane == 0) G::vectorize(envs[b], x);
+  __syncwarp();
+  uint4* ob = reinterpret_cast<uint4*>(out + (size_t)b * BS * 64);
+  for (int i = lane; i < BS * 8; i += 32) {  // 8 x 16-byte chunks per row
+    const int r = i >> 3, q = i & 7, yy = r / RS, xx = r % RS;
+    __align__(16) __half h[8];
 #pragma unroll
-  for (int t = 0; t < 9; t++)
-#pragma unroll
-    for (int c = 0; c < CP; c++) w[t][c] = c < C ? wstem[(t * C + c) * 128 + co] : 0.0f;
-  const float bs = bias[co];
-  const size_t base = (size_t)b * BS * 128 + co;
-  for (int r = 0; r < BS; r++) {
-    const int yy = r / RS, xx = r % RS;
-    float acc = 0.0f;
-    if (yy < H && xx < W) {
-      acc = bs;
-#pragma unroll
-      for (int ky = 0; ky < 3; ky++)
-#pragma unroll
-        for (int kx = 0; kx < 3; kx++) {
-          // Flux Conv is a true convolution: tap (kx,ky) reads the input at (x + 1 - kx, y + 1 - ky)
-          const float4* px = reinterpret_cast<const float4*>(&xp[((yy + 2 - ky) * (W + 2) + (xx + 2 - kx)) * CP]);
-#pragma unroll
-          for (int c4 = 0; c4 < CP / 4; c4++) {
-            float4 v = px[c4];
-            acc += v.x * w[ky * 3 + kx][4 * c4] + v.y * w[ky * 3 + kx][4 * c4 + 1] + v.z * w[ky * 3 + kx][4 * c4 + 2] +
-                   v.w * w[ky * 3 + kx][4 * c4 + 3];
-          }
-        }
-      acc = fmaxf(acc, 0.0f);
+    for (int j = 0; j < 8; j++) {
+      const int k = q * 8 + j;  // k = tap*C + c, tap = ky*3 + kx
+      float v = 0.0f;
+      if (k < 9 * C && yy < H && xx < W) {
+        const int tap = k / C, c = k % C, ky = tap / 3, kx = tap % 3;
+        // Flux Conv is a true convolution: tap (kx,ky) reads the input at (x + 1 - kx, y + 1 - ky)
+        const int ix = xx + 1 - kx, iy = yy + 1 - ky;
+        if (ix >= 0 && ix < W && iy >= 0 && iy < H) v = x[ix + W * iy + W * H * c];
+      }
+      h[j] = __float2half_rn(v);
     }
-    if (out32 != nullptr) out32[base + (size_t)r * 128] = acc;
-    out16[base + (size_t)r * 128] = __float2half_rn(acc);
+    ob[i] = *reinterpret_cast<const uint4*>(h);
   }
 }
 
@@ -774,74 +758,44 @@ __global__ void __launch_bounds__(128) az_k_stem(const AzEnv* __restrict__ envs,
 // value output tanh(w2 . hidden + b2) (resnet.jl:89-90).  One warp per board.
 // ------------------------------------------------------------------------------------------------
 struct FinalArgs {
-  const __half* hp;   // policy features [rows][32]
-  const float* hid;   // value hidden [boards][128]
-  const float* wp;    // [kp][AP] policy dense weights (AP = A rounded up to 4) in feature order k' = pos'*32 + c (zero for pad positions), fp32
-  const float* bp;    // [A]
-  const float* wv2;   // [128]
-  const float* bv2;   // [1]
-  int kp;             // valid_rows * 32
-  int board_feat;     // board_rows * 32
+  const float* logit;  // [boards][128]: policy logits in columns 0..A-1 (bias already added by the GEMM epilogue)
+  const float* hid;    // value hidden [boards][128]
+  const float* wv2;    // [128]
+  const float* bv2;    // [1]
 };
+// softmax + legal-action mask + renormalisation (resnet.jl:84, network.jl:264-271), value = tanh(w2 . hidden + b2)
+// (resnet.jl:89-90).  8 lanes per board.
 template <class G>
 __global__ void __launch_bounds__(256) az_k_finalize(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_boards, FinalArgs fa,
                                                      float* __restrict__ P, float* __restrict__ V, float* __restrict__ Pinv) {
-  // 32 boards per block (4 per warp); the policy-dense weights are staged once per block in shared memory with a padded
-  // pitch (2 feature rows = 2*AP floats + 4) so that the 128-bit reads of a quarter warp fall in distinct banks
-  constexpr int A = G::A, AP = (A + 3) & ~3, PITCH = 2 * AP + 4, NBF = 32;
-  extern __shared__ float wps[];
-  const int b0 = blockIdx.x * NBF;
-  if (b0 >= *n_boards) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nk2 = fa.kp / 2;
-  for (int i = threadIdx.x; i < nk2 * 2 * AP / 4; i += blockDim.x) {
-    const int k2 = i / (2 * AP / 4), q = i % (2 * AP / 4);
-    reinterpret_cast<float4*>(wps + (size_t)k2 * PITCH)[q] = reinterpret_cast<const float4*>(fa.wp + (size_t)k2 * 2 * AP)[q];
+  constexpr int A = G::A;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = gid >> 3, sub = gid & 7;
+  const bool active = b < *n_boards;
+  float vacc = 0.0f;
+  if (active) {
+    const float4* hp = reinterpret_cast<const float4*>(fa.hid + (size_t)b * 128 + sub * 16);
+    const float4* wp = reinterpret_cast<const float4*>(fa.wv2 + sub * 16);
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const float4 h = hp[q], w = wp[q]; vacc += h.x * w.x + h.y * w.y + h.z * w.z + h.w * w.w; }
   }
-  __syncthreads();
-  for (int bb = warp; bb < NBF; bb += 8) {
-    const int b = b0 + bb;
-    if (b >= *n_boards) break;
-    float acc[AP];
 #pragma unroll
-    for (int a = 0; a < AP; a++) acc[a] = 0.0f;
-    const __half2* f = reinterpret_cast<const __half2*>(fa.hp + (size_t)b * fa.board_feat);
-    for (int k2 = lane; k2 < nk2; k2 += 32) {
-      const float2 xv = __half22float2(f[k2]);
-      const float4* wr = reinterpret_cast<const float4*>(wps + (size_t)k2 * PITCH);
+  for (int off = 4; off >= 1; off >>= 1) vacc += __shfl_xor_sync(0xffffffffu, vacc, off);
+  if (active && sub == 0) {
+    float lg[A], m = -3.0e38f;
 #pragma unroll
-      for (int q = 0; q < AP / 4; q++) {
-        const float4 wa = wr[q], wb = wr[AP / 4 + q];
-        acc[4 * q] += xv.x * wa.x + xv.y * wb.x;
-        acc[4 * q + 1] += xv.x * wa.y + xv.y * wb.y;
-        acc[4 * q + 2] += xv.x * wa.z + xv.y * wb.z;
-        acc[4 * q + 3] += xv.x * wa.w + xv.y * wb.w;
-      }
-    }
-    float vacc = 0.0f;
-    for (int i = lane; i < 128; i += 32) vacc += fa.wv2[i] * fa.hid[(size_t)b * 128 + i];
+    for (int a = 0; a < A; a++) { lg[a] = fa.logit[(size_t)b * 128 + a]; m = fmaxf(m, lg[a]); }
+    float se = 0.0f;
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
+    for (int a = 0; a < A; a++) { lg[a] = expf(lg[a] - m); se += lg[a]; }
+    const uint32_t legal = G::legal_mask(envs[b]);
+    float sp = 0.0f;
 #pragma unroll
-      for (int a = 0; a < AP; a++) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], off);
-      vacc += __shfl_xor_sync(0xffffffffu, vacc, off);
-    }
-    if (lane == 0) {
-      float lg[A], m = -3.0e38f;
+    for (int a = 0; a < A; a++) { lg[a] = ((legal >> a) & 1u) ? lg[a] / se : 0.0f; sp += lg[a]; }
 #pragma unroll
-      for (int a = 0; a < A; a++) { lg[a] = acc[a] + fa.bp[a]; m = fmaxf(m, lg[a]); }
-      float se = 0.0f;
-#pragma unroll
-      for (int a = 0; a < A; a++) { lg[a] = expf(lg[a] - m); se += lg[a]; }
-      const uint32_t legal = G::legal_mask(envs[b]);
-      float sp = 0.0f;
-#pragma unroll
-      for (int a = 0; a < A; a++) { lg[a] = ((legal >> a) & 1u) ? lg[a] / se : 0.0f; sp += lg[a]; }
-#pragma unroll
-      for (int a = 0; a < A; a++) P[(size_t)b * A + a] = lg[a] / (sp + 1.1920929e-07f);  // eps(Float32), network.jl:268
-      V[b] = tanhf(vacc + fa.bv2[0]);
-      if (Pinv) Pinv[b] = 1.0f - sp;
-    }
+    for (int a = 0; a < A; a++) P[(size_t)b * A + a] = lg[a] / (sp + 1.1920929e-07f);  // eps(Float32), network.jl:268
+    V[b] = tanhf(vacc + fa.bv2[0]);
+    if (Pinv) Pinv[b] = 1.0f - sp;
   }
 }
 
@@ -897,7 +851,11 @@ struct ResNetImpl : az_net {
   static constexpr int KP = VR * 32;                           // policy / value feature length (pad columns carry zero weights)
   static constexpr int KD = (KP + 63) / 64 * 64;               // value-dense K rounded to the 64-wide K block
   // device weights
-  float* d_wstem = nullptr; float* d_bstem = nullptr;
+  __half* d_wstem = nullptr; float* d_bstem = nullptr;   // stem weights Wt[co][64] (k = tap*C + c, zero padded)
+  __half* d_wpol = nullptr; float* d_bpol = nullptr;     // policy dense as a GEMM: Wt[64 (A used)][KD]
+  CUtensorMap mapWstem{}, mapWpol{}, mapX0{}, mapHp{};
+  __half* d_x0 = nullptr;       // im2col rows [alloc_rows][64]
+  float* d_logit = nullptr;     // [boards][128]
   std::vector<__half*> d_wconv; std::vector<float*> d_bconv;
   __half *d_wh = nullptr, *d_wd = nullptr;
   float *d_bh = nullptr, *d_bd = nullptr, *d_wv2 = nullptr, *d_bv2 = nullptr, *d_wp = nullptr, *d_bp = nullptr;
@@ -984,8 +942,7 @@ struct ResNetImpl : az_net {
     smem_c4 = sizeof(tc2::Smem) + 1024;
     AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV1>, smem_c4));
     AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV2>, smem_c4));
-    fin_smem = (size_t)(KP / 2) * (2 * AP + 4) * sizeof(float);
-    AZ_TRY2(set_smem(az_k_finalize<G>, fin_smem));
+    AZ_TRY2(set_smem(az_k_gemm_tc<64, tc::EPI_DENSE>, smem64));
     smem_2sm = sizeof(tc3::Smem) + 1024;
     AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV1>, smem_2sm));
     AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV2>, smem_2sm));
@@ -1013,11 +970,12 @@ struct ResNetImpl : az_net {
     for (auto p : d_bconv) cudaFree(p);
     d_wconv.clear(); d_bconv.clear(); mapW.clear(); mapW2.clear();
     cudaFree(d_wh); cudaFree(d_wd); cudaFree(d_bh); cudaFree(d_bd); cudaFree(d_wv2); cudaFree(d_bv2); cudaFree(d_wp); cudaFree(d_bp);
-    d_wstem = d_bstem = d_bh = d_bd = d_wv2 = d_bv2 = d_wp = d_bp = nullptr; d_wh = d_wd = nullptr;
+    cudaFree(d_wpol); cudaFree(d_bpol); d_wpol = nullptr; d_bpol = nullptr;
+    d_bstem = d_bh = d_bd = d_wv2 = d_bv2 = d_wp = d_bp = nullptr; d_wh = d_wd = d_wstem = nullptr;
   }
   void free_act() {
-    cudaFree(d_x32); cudaFree(d_hid); cudaFree(d_x16); cudaFree(d_t16); cudaFree(d_hp); cudaFree(d_hv);
-    d_x32 = d_hid = nullptr; d_x16 = d_t16 = d_hp = d_hv = nullptr;
+    cudaFree(d_x32); cudaFree(d_hid); cudaFree(d_x16); cudaFree(d_t16); cudaFree(d_hp); cudaFree(d_hv); cudaFree(d_x0); cudaFree(d_logit);
+    d_x32 = d_hid = d_logit = nullptr; d_x16 = d_t16 = d_hp = d_hv = d_x0 = nullptr;
   }
   ~ResNetImpl() override { free_weights(); free_act(); for (auto e : pev) cudaEventDestroy(e); }
 
@@ -1044,10 +1002,12 @@ struct ResNetImpl : az_net {
       const float* b = q; q += F;
       const float* bn = q; q += 4 * F;
       fold(F, b, bn, scale, shift);
-      std::vector<float> ws((size_t)9 * C * F);
+      static_assert(9 * C <= 64, "stem K must fit one 64-wide K block");
+      std::vector<__half> ws((size_t)F * 64, __float2half_rn(0.0f));
       for (int ky = 0; ky < 3; ky++) for (int kx = 0; kx < 3; kx++) for (int c = 0; c < C; c++) for (int o = 0; o < F; o++)
-        ws[((size_t)(ky * 3 + kx) * C + c) * F + o] = w[kx + 3 * (ky + 3 * (c + (size_t)C * o))] * scale[o];
+        ws[(size_t)o * 64 + (ky * 3 + kx) * C + c] = __float2half_rn(w[kx + 3 * (ky + 3 * (c + (size_t)C * o))] * scale[o]);
       AZ_TRY2(up(&d_wstem, ws)); AZ_TRY2(up(&d_bstem, shift));
+      AZ_TRY2(make_map_2d(ctx, &mapWstem, d_wstem, 64, F, 64 * 2, tc::BK, 128));
     }
     for (int l = 0; l < 2 * hp.num_blocks; l++) {
       const float* w = q; q += 9LL * F * F;
@@ -1095,11 +1055,13 @@ struct ResNetImpl : az_net {
       for (int o = 0; o < 32; o++) { for (int c = 0; c < F; c++) whd[(size_t)o * F + c] = __float2half_rn(w[c + (size_t)F * o] * scale[o]); bh[o] = shift[o]; }
       const float* w1 = q; q += (int64_t)WH * 32 * A;
       const float* b1 = q; q += A;
-      std::vector<float> wp((size_t)KP * AP, 0.0f);  // Wp[k'][a]
+      std::vector<__half> wp((size_t)64 * KD, __float2half_rn(0.0f));  // Wt[a][k'], rows >= A and pad positions zero
       for (int a = 0; a < A; a++) for (int c = 0; c < 32; c++) for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
-        wp[((size_t)(y * (W + 1) + x) * 32 + c) * AP + a] = w1[a + (size_t)A * ((x + W * y) + (size_t)WH * c)];
-      AZ_TRY2(up(&d_wp, wp));
-      AZ_TRY2(up(&d_bp, std::vector<float>(b1, b1 + A)));
+        wp[(size_t)a * KD + (size_t)(y * (W + 1) + x) * 32 + c] = __float2half_rn(w1[a + (size_t)A * ((x + W * y) + (size_t)WH * c)]);
+      std::vector<float> bpol(64, 0.0f);
+      for (int a = 0; a < A; a++) bpol[a] = b1[a];
+      AZ_TRY2(up(&d_wpol, wp)); AZ_TRY2(up(&d_bpol, bpol));
+      AZ_TRY2(make_map_2d(ctx, &mapWpol, d_wpol, KD, 64, (uint64_t)KD * 2, tc::BK, 64));
     }
     AZ_TRY2(up(&d_wh, whd)); AZ_TRY2(up(&d_bh, bh));
     AZ_TRY2(make_map_2d(ctx, &mapWh, d_wh, F, 64, F * 2, tc::BK, 64));
@@ -1120,6 +1082,9 @@ struct ResNetImpl : az_net {
     AZ_TRY2(dmalloc(&d_x32, (size_t)alloc_rows * F)); AZ_TRY2(dmalloc(&d_x16, (size_t)alloc_rows * F));
     AZ_TRY2(dmalloc(&d_t16, (size_t)alloc_rows * F)); AZ_TRY2(dmalloc(&d_hp, (size_t)alloc_rows * 32));
     AZ_TRY2(dmalloc(&d_hv, (size_t)alloc_rows * 32)); AZ_TRY2(dmalloc(&d_hid, (size_t)(max_boards + 256) * F));
+    AZ_TRY2(dmalloc(&d_x0, (size_t)alloc_rows * 64)); AZ_TRY2(dmalloc(&d_logit, (size_t)(max_boards + 256) * F));
+    AZ_TRY2(make_map_2d(ctx, &mapX0, d_x0, 64, alloc_rows, 64 * 2, tc::BK, tc::BM));
+    AZ_TRY2(make_map_2d(ctx, &mapHp, d_hp, (uint64_t)BS * 32, alloc_boards, (uint64_t)BS * 32 * 2, tc::BK, tc::BM));
     AZ_TRY2(make_map_2d(ctx, &mapX, d_x16, F, alloc_rows, F * 2, tc::BK, tc::BM));
     AZ_TRY2(make_map_2d(ctx, &mapT, d_t16, F, alloc_rows, F * 2, tc::BK, tc::BM));
     AZ_TRY2(make_map_2d(ctx, &mapX2, d_x16, F, alloc_rows, F * 2, tc2::BK, tc2::AROWS));
@@ -1139,12 +1104,15 @@ struct ResNetImpl : az_net {
     cudaEvent_t* pe = prof ? &pev[(size_t)prof_evals * 4] : nullptr;
     if (prof) cudaEventRecord(pe[0], st);
     const bool c4_fast = C4_TOWER && !generic_tower && two_sm && hp.num_blocks > 0;
-    az_k_stem<G><<<max_rows, 128, 0, st>>>(envs, n_rows, d_wstem, d_bstem, c4_fast ? nullptr : d_x32, d_x16);
-    if (prof) cudaEventRecord(pe[1], st);
     const int row_tiles = (max_rows * BS + tc::BM - 1) / tc::BM;
     const int grid = std::min(row_tiles, ctx->num_sms);
     GemmArgs ga{};
-    ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.gemm_k = 0; ga.debug = tower_debug;
+    ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.debug = 0;
+    az_k_im2col<G><<<(max_rows + 3) / 4, 128, 0, st>>>(envs, n_rows, d_x0);
+    ga.gemm_k = 1; ga.kblocks = 1; ga.bias = d_bstem; ga.out16a = d_x16; ga.out32 = c4_fast ? nullptr : d_x32;
+    az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX0, mapWstem, ga);
+    ga.gemm_k = 0; ga.out32 = nullptr; ga.debug = tower_debug;
+    if (prof) cudaEventRecord(pe[1], st);
     const bool c4 = C4_TOWER && !generic_tower;
     const int grid_c4 = std::max(2, std::min(2 * row_tiles, ctx->num_sms & ~1));
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
@@ -1173,10 +1141,12 @@ struct ResNetImpl : az_net {
     gd.bias = d_bd; gd.out32 = d_hid;
     const int board_tiles = (max_rows + tc::BM - 1) / tc::BM;
     az_k_gemm_tc<128, tc::EPI_DENSE><<<std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem128, st>>>(mapHv, mapWd, gd);
-    FinalArgs fa{d_hp, d_hid, d_wp, d_bp, d_wv2, d_bv2, KP, BS * 32};
-    az_k_finalize<G><<<(max_rows + 31) / 32, 256, fin_smem, st>>>(envs, n_rows, fa, P, V, Pinv);
+    gd.bias = d_bpol; gd.out32 = d_logit; gd.no_relu = 1;   // policy dense: logits[b][0..A) = Wp . hp + b
+    az_k_gemm_tc<64, tc::EPI_DENSE><<<std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem64, st>>>(mapHp, mapWpol, gd);
+    FinalArgs fa{d_logit, d_hid, d_wv2, d_bv2};
+    az_k_finalize<G><<<(max_rows * 8 + 255) / 256, 256, 0, st>>>(envs, n_rows, fa, P, V, Pinv);
     if (prof) { cudaEventRecord(pe[3], st); prof_evals++; }
-    ctx->launches += 4 + 2 * hp.num_blocks;
+    ctx->launches += 6 + 2 * hp.num_blocks;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ctx->err = std::string("network launch: ") + cudaGetErrorString(e); return AZ_ECUDA; }
     return AZ_OK;

@@ -164,6 +164,7 @@ struct Mcts : az_mcts {
     while (cap < (size_t)cap_nodes + (size_t)cap_nodes / 4 + 8) cap <<= 1;
     p.S = S; p.cap_mask = (uint32_t)(cap - 1); p.maxd = G::MAX_PLIES + 1;
     p.max_sims_per_call = 2;
+    if (const char* e = getenv("AZ_NO_GRAPH")) use_graph = !(e[0] == '1');
     if (const char* e = getenv("AZ_MAX_SIMS_PER_CALL")) p.max_sims_per_call = std::max(1, atoi(e));
     p.c.gamma = params->gamma; p.c.cpuct = params->cpuct; p.c.eps = params->dirichlet_noise_eps;
     p.c.alpha = params->dirichlet_noise_alpha; p.c.prior_temp = params->prior_temperature;
@@ -190,6 +191,7 @@ struct Mcts : az_mcts {
     for (void* q : allocs) cudaFree(q);
     if (h_pin) cudaFreeHost(h_pin);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    drop_graph();
   }
   int groups_grid() const { return (int)(((size_t)p.S * 32 + 127) / 128); }  // one warp per tree
 
@@ -200,6 +202,43 @@ struct Mcts : az_mcts {
     AZ_CUDA(ctx, cudaMemcpyAsync(p.root, r.data(), p.S * sizeof(AzEnv), cudaMemcpyHostToDevice, ctx->stream));
     if (eta) AZ_CUDA(ctx, cudaMemcpyAsync(p.eta, eta, (size_t)p.S * G::A * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // r is a stack-owned staging buffer
+    return AZ_OK;
+  }
+  // ---- CUDA-graph replay of a tick (optionally followed by an extra kernel, e.g. the self-play move kernel) ----
+  cudaGraphExec_t gexec = nullptr;
+  int64_t graph_launches = 0;   // kernels per replay
+  uint64_t graph_net_gen = 0;
+  bool use_graph = true, graph_broken = false;
+  void drop_graph() { if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; } }
+  template <class Extra>
+  int tick_graphed(Extra extra) {
+    if (!use_graph || graph_broken || !net->capturable()) {
+      drop_graph();
+      AZ_TRY(ctx, tick(false));
+      extra();
+      return AZ_OK;
+    }
+    if (gexec && graph_net_gen != net->generation()) drop_graph();  // the network reallocated buffers / reloaded weights
+    if (!gexec) {
+      graph_net_gen = net->generation();
+      const int64_t l0 = ctx->launches;
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { graph_broken = true; cudaGetLastError(); return tick_graphed(extra); }
+      int st = tick(false);
+      extra();
+      cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+      if (st != AZ_OK || e != cudaSuccess || cudaGraphInstantiate(&gexec, g, 0) != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        gexec = nullptr; graph_broken = true; cudaGetLastError();
+        ctx->launches = l0;
+        return tick_graphed(extra);
+      }
+      cudaGraphDestroy(g);
+      graph_launches = ctx->launches - l0;
+      ctx->launches = l0;
+    }
+    AZ_CUDA(ctx, cudaGraphLaunch(gexec, ctx->stream));
+    ctx->launches += graph_launches;
     return AZ_OK;
   }
   // one tick: select -> oracle -> expand+backup
@@ -235,7 +274,7 @@ struct Mcts : az_mcts {
     ticks = 0; ms_net = 0;
     // every unfinished tree completes >= 1 simulation per tick, so nsims ticks always suffice
     for (int t = 0; t < nsims + 1; t++) {
-      AZ_TRY(ctx, tick(false));
+      AZ_TRY(ctx, tick_graphed([] {}));
       ticks++;
       if (t + 1 >= nsims / 2 && ((t + 1) % 8 == 0 || t + 1 >= nsims)) {
         AZ_TRY(ctx, check_flags());
@@ -399,10 +438,12 @@ struct SelfPlay : az_selfplay {
     az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 1);
     ctx->launches++;
     int64_t tick = 0;
+    m.drop_graph();  // `sp` (game range, buffers) is baked into the captured move-kernel launch
     for (;;) {
-      AZ_TRY(ctx, m.tick(false));
-      az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 0);
-      ctx->launches++;
+      AZ_TRY(ctx, m.tick_graphed([&] {
+        az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 0);
+        ctx->launches++;
+      }));
       tick++;
       if (tick % 32 == 0) {
         AZ_CUDA(ctx, cudaMemcpyAsync(h_pin, sp.games_done, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -416,6 +457,7 @@ struct SelfPlay : az_selfplay {
         if (h_pin[0] >= sp.num_games) break;
       }
     }
+    m.drop_graph();
     AZ_CUDA(ctx, cudaMemcpy(&total_expansions, m.p.expansions, 8, cudaMemcpyDeviceToHost));
     h_moves.resize(sp.num_games);
     AZ_CUDA(ctx, cudaMemcpy(h_moves.data(), sp.g_moves, sp.num_games * sizeof(int32_t), cudaMemcpyDeviceToHost));

@@ -35,6 +35,8 @@ struct az_net {
   virtual int eval(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V) = 0;
   virtual int64_t num_params() { return 0; }
   virtual int load(const float*, int64_t) { return AZ_OK; }
+  virtual bool capturable() { return true; }
+  virtual uint64_t generation() { return 0; }  // changes whenever device pointers / weights baked into launches change  // false while per-launch CUDA events are being recorded
   virtual int set_profiling(int) { return AZ_OK; }
   virtual int get_profile(double* tower_ms, int64_t* tower_launches, double* total_ms, int64_t* evals) {
     if (tower_ms) *tower_ms = 0; if (tower_launches) *tower_launches = 0; if (total_ms) *total_ms = 0; if (evals) *evals = 0;

@@ -883,6 +883,9 @@ struct ResNetImpl : az_net {
   std::vector<cudaEvent_t> pev;
   int64_t prof_evals = 0;
 
+  uint64_t gen = 1;
+  uint64_t generation() override { return gen; }
+  bool capturable() override { return !profiling && act_boards > 0; }
   int set_profiling(int enable) override {
     if (enable && pev.empty()) {
       pev.resize((size_t)PROF_SLOTS * 4);
@@ -984,6 +987,7 @@ struct ResNetImpl : az_net {
   int load(const float* blob, int64_t n) override {
     if (n != num_params()) { ctx->err = "az_net_load: blob has " + std::to_string(n) + " floats, expected " + std::to_string(num_params()); return AZ_EINVAL; }
     cudaStreamSynchronize(ctx->stream);
+    gen++;
     free_weights();
     loaded = false;
     const float* q = blob;
@@ -1076,6 +1080,7 @@ struct ResNetImpl : az_net {
   int ensure_act(int max_boards) {
     if (max_boards <= act_boards) return AZ_OK;
     cudaStreamSynchronize(ctx->stream);
+    gen++;
     free_act();
     alloc_rows = ((max_boards * BS + 127) / 128) * 128 + 128;
     alloc_boards = alloc_rows / BS;

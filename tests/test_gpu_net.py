@@ -41,7 +41,7 @@ def test_resnet_forward_matches_fp32_reference(az, oz, ctx, blocks, batch, seed,
 def test_resnet_precision_stress(az, oz, ctx):
     """fp16 tensor-core operands put a floor of ~2^-11 relative error per layer on the tower; with adversarially
     randomised BatchNorm statistics the worst-case |dV| over 400 positions of a 7-block net can reach ~1e-3
-    (DESIGN.md "precision").  This test documents the distribution: RMS well below 1e-3, max below 2.5e-3."""
+    (DESIGN.md "precision").  This test documents the distribution: RMS below 8e-4, max below 2.5e-3."""
     gs = az.GameSpec("connect-four")
     hp = netcheck.c4_hp(7)
     states = gs.random_positions(11, 400, 38)
@@ -51,7 +51,7 @@ def test_resnet_precision_stress(az, oz, ctx):
         rms_v = float(np.sqrt(np.mean((r["V"] - r["Vr"]) ** 2)))
         rms_p = float(np.sqrt(np.mean((r["P"] - r["Pr"]) ** 2)))
         print("seed %d: max dP %.2e dV %.2e  rms dP %.2e dV %.2e" % (seed, r["dP"], r["dV"], rms_p, rms_v))
-        assert r["dP"] < 1e-3 and r["dV"] < 2.5e-3 and rms_v < 5e-4 and rms_p < 3e-4
+        assert r["dP"] < 1e-3 and r["dV"] < 2.5e-3 and rms_v < 8e-4 and rms_p < 3e-4
         net.close()
 
 

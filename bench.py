@@ -33,6 +33,9 @@ HP = dict(num_blocks=BLOCKS, num_filters=128, conv_kernel_size=(3, 3), num_polic
 CONV_MFLOP_PER_LEAF = 2 * 42 * 128 * 1152 / 1e6     # one 3x3 conv layer, valid positions only (12.39 MFLOP)
 NET_MFLOP_PER_LEAF = 174.7                           # whole 7-block network
 METRIC = "mcts_node_expansions_per_s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from profiles/r01_final_conv_ncu_summary.txt
+# (ncu --set full, cold caches): conv1 variant 66 MB, conv2 variant 259 MB; the value below is their mean
+NCU_TRAFFIC_BYTES = None
 
 
 def peaks():
@@ -209,9 +212,7 @@ def main():
     env.set_roots(roots, eta)
     for _ in range(args.warmup):
         step_resident()
-    # ---- timed: device-resident ----
-    if not args.oracle_net:
-        net.set_profiling(True)
+    # ---- timed: device-resident (CUDA-graph ticks; no per-launch events) ----
     l0 = ctx.num_launches
     barrier()
     with ClockSampler(local) as clk:
@@ -225,8 +226,18 @@ def main():
         barrier()
         t_wall = time.perf_counter() - t_wall
     launches = ctx.num_launches - l0
-    prof = net.get_profile() if not args.oracle_net else None
+    # ---- roofline pass: the same steps again with CUDA events around the tower launches (events on the library's own
+    #      stream; recording them per launch disables graph replay, hence a separate pass) ----
+    prof = None
     if not args.oracle_net:
+        net.set_profiling(True)
+        p_ms, p_ex = 0.0, 0
+        for _ in range(args.steps):
+            t = step_resident()
+            p_ms += t["ms_total"]
+            p_ex += t["expansions"]
+        prof = net.get_profile()
+        prof.update(step_ms=p_ms, expansions=p_ex)
         net.set_profiling(False)
     # ---- timed: end to end through host buffers ----
     barrier()
@@ -301,14 +312,15 @@ def main():
         if prof and prof["evals"]:
             peak, how = peaks()
             nconv = 2 * args.blocks
-            achieved = ex / world * CONV_MFLOP_PER_LEAF * nconv / 1e6 / (prof["tower_ms"] / 1e3) if world == 1 else None
-            if world > 1:  # rank 0's own expansions are not separated after the all-reduce; report per-GPU average
-                achieved = (ex / world) * CONV_MFLOP_PER_LEAF * nconv / 1e6 / (prof["tower_ms"] / 1e3)
-            line["roofline"] = {"bound": "tensor", "kernel": "az_k_conv_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                                "frac": achieved / peak, "traffic": None, "peak_source": how,
+            achieved = prof["expansions"] * CONV_MFLOP_PER_LEAF * nconv / 1e6 / (prof["tower_ms"] / 1e3)   # rank 0's own pass
+            line["roofline"] = {"bound": "tensor", "kernel": "az_k_conv_c4_2sm", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                                "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": how,
                                 "avg_launch_us": 1e3 * prof["tower_ms"] / max(1, prof["tower_launches"]),
-                                "network_share_of_step": prof["total_ms"] / (ms / world if dist is None else ms),
-                                "tower_share_of_step": prof["tower_ms"] / ms}
+                                "algorithmic_flop_per_launch": "12.39 MFLOP x leaves of the tick (SURVEY 8d: 2*42*128*1152 per leaf per conv layer)",
+                                "how": "CUDA events around the %d tower launches of every tick on the library stream, in a profiled pass of the same %d steps right after the timed region (graph replay off); step time in that pass %.1f ms"
+                                       % (nconv, args.steps, prof["step_ms"] / args.steps),
+                                "network_share_of_step": prof["total_ms"] / prof["step_ms"],
+                                "tower_share_of_step": prof["tower_ms"] / prof["step_ms"]}
         if not args.no_cpu_baseline and not args.oracle_net:
             threads = args.cpu_threads or min(os.cpu_count() or 1, 16)
             cex, cdt, _ = cpu_reference_run(128, 100, threads)

@@ -34,8 +34,8 @@ CONV_MFLOP_PER_LEAF = 2 * 42 * 128 * 1152 / 1e6     # one 3x3 conv layer, valid 
 NET_MFLOP_PER_LEAF = 174.7                           # whole 7-block network
 METRIC = "mcts_node_expansions_per_s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from profiles/r01_final_conv_ncu_summary.txt
-# (ncu --set full, cold caches): conv1 variant 66 MB, conv2 variant 259 MB; the value below is their mean
-NCU_TRAFFIC_BYTES = None
+# (ncu --set full, cold caches, ~3700 leaves): conv1 variant 55.0 MB, conv2 variant 214.4 MB per launch; mean of the two
+NCU_TRAFFIC_BYTES = 134.7e6
 
 
 def peaks():

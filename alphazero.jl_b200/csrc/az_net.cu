@@ -1177,9 +1177,207 @@ az_net* az_make_resnet(az_ctx* ctx, int game, const az_resnet_hp* hp, int* statu
   return n;
 }
 
+// ------------------------------------------------------------------------------------------------
+// SimpleNet (src/networks/architectures/simplenet.jl:37-64): dense two-head MLP, fp32 on CUDA cores (0.1-0.7 MFLOP per
+// leaf: launch-latency bound, one fused kernel).  BatchNorm (test mode) is folded into the preceding Dense at load.
+// ------------------------------------------------------------------------------------------------
+struct MlpLayer { const float* w; const float* b; int in, out, relu; };
+struct MlpArgs {
+  MlpLayer common[10]; int n_common;
+  MlpLayer vhead[6]; int n_vhead;
+  MlpLayer phead[6]; int n_phead;
+  int width;
+};
+template <int NB>
+__device__ __forceinline__ void mlp_layer(const MlpLayer& L, const float* __restrict__ xin, int xstride, float* __restrict__ xout,
+                                          int ostride, int nb) {
+  for (int o = threadIdx.x; o < L.out; o += blockDim.x) {
+    float acc[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) acc[j] = L.b[o];
+    for (int i = 0; i < L.in; i++) {
+      const float w = L.w[(size_t)o + (size_t)L.out * i];  // Flux Dense W[out,in], column-major: coalesced over o
+#pragma unroll
+      for (int j = 0; j < NB; j++) acc[j] += w * xin[j * xstride + i];
+    }
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+      if (j < nb) xout[j * ostride + o] = L.relu ? fmaxf(acc[j], 0.0f) : acc[j];
+  }
+  __syncthreads();
+}
+template <class G, int NB>
+__global__ void __launch_bounds__(256) az_k_simplenet(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_boards, MlpArgs m,
+                                                      float* __restrict__ P, float* __restrict__ V, float* __restrict__ Pinv) {
+  constexpr int A = G::A, NX = G::XW * G::XH * G::XC, MAXW = 256;
+  __shared__ float x0[NB][NX];
+  __shared__ float ha[NB][MAXW], hb[NB][MAXW], hc[NB][MAXW];
+  __shared__ float outp[NB][A + 1];
+  const int b0 = blockIdx.x * NB;
+  const int nb = min(NB, *n_boards - b0);
+  if (nb <= 0) return;
+  for (int j = 0; j < NB; j++) {
+    if (threadIdx.x == j && j < nb) G::vectorize(envs[b0 + j], x0[j]);
+    if (j >= nb) for (int i = threadIdx.x; i < NX; i += blockDim.x) x0[j][i] = 0.0f;
+  }
+  __syncthreads();
+  // common trunk: ping-pong ha <-> hb
+  float* cur = &ha[0][0];
+  float* nxt = &hb[0][0];
+  mlp_layer<NB>(m.common[0], &x0[0][0], NX, cur, MAXW, NB);
+  for (int l = 1; l < m.n_common; l++) {
+    mlp_layer<NB>(m.common[l], cur, MAXW, nxt, MAXW, NB);
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  float* trunk = cur;           // keep the trunk output; heads use the other two buffers
+  float* s1 = nxt;
+  float* s2 = &hc[0][0];
+  // value head
+  const float* in = trunk;
+  for (int l = 0; l < m.n_vhead - 1; l++) {
+    float* o = (l & 1) ? s2 : s1;
+    mlp_layer<NB>(m.vhead[l], in, MAXW, o, MAXW, NB);
+    in = o;
+  }
+  {
+    const MlpLayer& L = m.vhead[m.n_vhead - 1];  // Dense(width, 1, tanh)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < nb; j += (blockDim.x >> 5)) {
+      float acc = 0.0f;
+      for (int i = lane; i < L.in; i += 32) acc += L.w[i] * in[j * MAXW + i];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane == 0) outp[j][A] = tanhf(acc + L.b[0]);
+    }
+  }
+  __syncthreads();
+  // policy head
+  in = trunk;
+  for (int l = 0; l < m.n_phead - 1; l++) {
+    float* o = (l & 1) ? s2 : s1;
+    mlp_layer<NB>(m.phead[l], in, MAXW, o, MAXW, NB);
+    in = o;
+  }
+  mlp_layer<NB>(m.phead[m.n_phead - 1], in, MAXW, &outp[0][0], A + 1, nb);  // logits (relu = 0), A outputs per board
+  if (threadIdx.x < nb) {
+    const int j = threadIdx.x, row = b0 + j;
+    float lg[A], mx = -3.0e38f;
+#pragma unroll
+    for (int a = 0; a < A; a++) { lg[a] = outp[j][a]; mx = fmaxf(mx, lg[a]); }
+    float se = 0.0f;
+#pragma unroll
+    for (int a = 0; a < A; a++) { lg[a] = expf(lg[a] - mx); se += lg[a]; }
+    const uint32_t legal = G::legal_mask(envs[row]);
+    float sp = 0.0f;
+#pragma unroll
+    for (int a = 0; a < A; a++) { lg[a] = ((legal >> a) & 1u) ? lg[a] / se : 0.0f; sp += lg[a]; }
+#pragma unroll
+    for (int a = 0; a < A; a++) P[(size_t)row * A + a] = lg[a] / (sp + 1.1920929e-07f);
+    V[row] = outp[j][A];
+    if (Pinv) Pinv[row] = 1.0f - sp;
+  }
+}
+
+template <class G>
+struct SimpleNetImpl : az_net {
+  az_simplenet_hp hp{};
+  static constexpr int NX = G::XW * G::XH * G::XC, A = G::A, NB = 4;
+  std::vector<float*> bufs;
+  MlpArgs margs{};
+  bool loaded = false;
+  uint64_t gen = 1;
+  uint64_t generation() override { return gen; }
+  int init() {
+    if (hp.width < 1 || hp.width > 256) { ctx->err = "SimpleNet: this build supports 1 <= width <= 256"; return AZ_EUNSUPPORTED; }
+    if (hp.depth_common < 0 || hp.depth_common > 9 || hp.depth_phead < 0 || hp.depth_phead > 5 || hp.depth_vhead < 0 || hp.depth_vhead > 5) {
+      ctx->err = "SimpleNet: depth_common <= 9, depth_phead/depth_vhead <= 5"; return AZ_EUNSUPPORTED;
+    }
+    return AZ_OK;
+  }
+  int64_t dense_size(int in, int out) const { return (int64_t)in * out + out + (hp.use_batch_norm ? 4 * out : 0); }
+  int64_t num_params() override {
+    const int w = hp.width;
+    int64_t n = dense_size(NX, w) + (int64_t)hp.depth_common * dense_size(w, w);
+    n += (int64_t)hp.depth_vhead * dense_size(w, w) + ((int64_t)w + 1);
+    n += (int64_t)hp.depth_phead * dense_size(w, w) + ((int64_t)w * A + A);
+    return n;
+  }
+  void free_all() { for (auto p : bufs) cudaFree(p); bufs.clear(); }
+  ~SimpleNetImpl() override { free_all(); }
+  int upload(const std::vector<float>& v, const float** out) {
+    float* d = nullptr;
+    if (cudaMalloc((void**)&d, v.size() * sizeof(float)) != cudaSuccess) { ctx->err = "cudaMalloc (weights) failed"; return AZ_ENOMEM; }
+    cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice);
+    bufs.push_back(d);
+    *out = d;
+    return AZ_OK;
+  }
+  // make_dense (simplenet.jl:39-47): Dense(in,out) [+ BatchNorm(out, relu)] or Dense(in,out,relu)
+  int take_dense(const float*& q, int in, int out, bool hidden, MlpLayer* L) {
+    std::vector<float> w(q, q + (size_t)in * out); q += (size_t)in * out;
+    std::vector<float> b(q, q + out); q += out;
+    if (hidden && hp.use_batch_norm) {
+      const float* bn = q; q += 4 * out;
+      for (int o = 0; o < out; o++) {
+        const float sc = bn[o] / std::sqrt(bn[3 * out + o] + 1e-5f);
+        for (int i = 0; i < in; i++) w[(size_t)o + (size_t)out * i] *= sc;
+        b[o] = (b[o] - bn[2 * out + o]) * sc + bn[out + o];
+      }
+    }
+    L->in = in; L->out = out; L->relu = hidden ? 1 : 0;
+    AZ_TRY2(upload(w, &L->w));
+    AZ_TRY2(upload(b, &L->b));
+    return AZ_OK;
+  }
+  int load(const float* blob, int64_t n) override {
+    if (n != num_params()) { ctx->err = "az_net_load: blob has " + std::to_string(n) + " floats, expected " + std::to_string(num_params()); return AZ_EINVAL; }
+    cudaStreamSynchronize(ctx->stream);
+    gen++;
+    free_all();
+    const float* q = blob;
+    const int w = hp.width;
+    margs = MlpArgs{};
+    margs.width = w;
+    AZ_TRY2(take_dense(q, NX, w, true, &margs.common[0]));
+    for (int l = 0; l < hp.depth_common; l++) AZ_TRY2(take_dense(q, w, w, true, &margs.common[1 + l]));
+    margs.n_common = 1 + hp.depth_common;
+    for (int l = 0; l < hp.depth_vhead; l++) AZ_TRY2(take_dense(q, w, w, true, &margs.vhead[l]));
+    AZ_TRY2(take_dense(q, w, 1, false, &margs.vhead[hp.depth_vhead]));
+    margs.n_vhead = hp.depth_vhead + 1;
+    for (int l = 0; l < hp.depth_phead; l++) AZ_TRY2(take_dense(q, w, w, true, &margs.phead[l]));
+    AZ_TRY2(take_dense(q, w, A, false, &margs.phead[hp.depth_phead]));
+    margs.n_phead = hp.depth_phead + 1;
+    loaded = true;
+    return AZ_OK;
+  }
+  int eval(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V) override {
+    return eval_with_pinv(envs, n_rows, max_rows, P, V, nullptr);
+  }
+  int eval_with_pinv(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V, float* Pinv) override {
+    if (!loaded) { ctx->err = "SimpleNet: az_net_load must be called before the network is used"; return AZ_ESTATE; }
+    az_k_simplenet<G, NB><<<(max_rows + NB - 1) / NB, 256, 0, ctx->stream>>>(envs, n_rows, margs, P, V, Pinv);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = std::string("SimpleNet launch: ") + cudaGetErrorString(e); return AZ_ECUDA; }
+    return AZ_OK;
+  }
+};
+
 az_net* az_make_simplenet(az_ctx* ctx, int game, const az_simplenet_hp* hp, int* status) {
-  (void)game; (void)hp;
-  ctx->err = "SimpleNet forward is not built in this round (SURVEY 8f)";
-  *status = AZ_EUNSUPPORTED;
-  return nullptr;
+  az_net* n = nullptr;
+  int st = AZ_OK;
+  auto mk = [&](auto* impl) {
+    impl->ctx = ctx; impl->kind = AZ_NET_SIMPLENET; impl->game = game; impl->hp = *hp;
+    st = impl->init();
+    if (st != AZ_OK) { delete impl; return (az_net*)nullptr; }
+    return (az_net*)impl;
+  };
+  switch (game) {
+    case 0: n = mk(new SimpleNetImpl<GameC4>()); break;
+    case 1: n = mk(new SimpleNetImpl<GameTTT>()); break;
+    case 2: n = mk(new SimpleNetImpl<GameMancala>()); break;
+    default: ctx->err = "az_net_create_simplenet: unknown game"; st = AZ_EINVAL;
+  }
+  *status = st;
+  return n;
 }

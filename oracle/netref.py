@@ -128,3 +128,83 @@ def forward_normalized(P, V, mask):
     sp = P.sum(1, dtype=np.float32)
     Pn = P / (sp[:, None] + np.float32(EPS32))
     return Pn.astype(np.float32), V, (np.float32(1) - sp)
+
+
+# ---- SimpleNet (src/networks/architectures/simplenet.jl:37-64) -------------------------------------------------
+def simplenet_layers(dim, num_actions, hp):
+    """[(kind, ...)] in blob order: common, vhead, phead.  make_dense = Dense [+ BatchNorm(relu)] | Dense(relu)."""
+    indim = dim[0] * dim[1] * dim[2]
+    w, bn = hp["width"], hp.get("use_batch_norm", False)
+
+    def hidden(i, o):
+        return [("dense", o, i, not bn)] + ([("bn", o)] if bn else [])
+    L = hidden(indim, w)
+    for _ in range(hp["depth_common"]):
+        L += hidden(w, w)
+    for _ in range(hp.get("depth_vhead", 1)):
+        L += hidden(w, w)
+    L += [("dense", 1, w, False)]
+    for _ in range(hp.get("depth_phead", 1)):
+        L += hidden(w, w)
+    L += [("dense", num_actions, w, False)]
+    return L
+
+
+def simplenet_make_blob(dim, num_actions, hp, seed=1, randomize=True):
+    rng = np.random.default_rng(seed)
+    parts = []
+    for l in simplenet_layers(dim, num_actions, hp):
+        if l[0] == "dense":
+            out, inn = l[1], l[2]
+            s = np.sqrt(6.0 / (inn + out))
+            parts.append(rng.uniform(-s, s, out * inn))
+            parts.append(rng.normal(0, 0.05, out) if randomize else np.zeros(out))
+        else:
+            n = l[1]
+            if randomize:
+                parts += [rng.uniform(0.7, 1.3, n), rng.normal(0, 0.1, n), rng.normal(0, 0.1, n), rng.uniform(0.6, 1.5, n)]
+            else:
+                parts += [np.ones(n), np.zeros(n), np.zeros(n), np.ones(n)]
+    return np.concatenate(parts).astype(np.float32)
+
+
+def simplenet_forward(blob, dim, num_actions, hp, X):
+    """X: [B, W, H, C]; flatten is column-major over (W,H,C) (Flux.flatten). Returns (P softmax, V)."""
+    blob = np.asarray(blob, np.float32)
+    q = [0]
+
+    def take(n):
+        v = blob[q[0]:q[0] + n]
+        q[0] += n
+        return v
+    B = X.shape[0]
+    x = torch.tensor(np.asarray(X, np.float32).reshape(B, -1, order="F") if False else
+                     np.stack([np.asarray(X[i], np.float32).reshape(-1, order="F") for i in range(B)]))
+    bn_on = hp.get("use_batch_norm", False)
+
+    def dense(x, out, inn, relu):
+        w = take(out * inn).reshape((out, inn), order="F")
+        b = take(out)
+        y = x @ torch.tensor(w).T + torch.tensor(b)
+        return torch.relu(y) if relu else y
+
+    def hidden(x, inn, out):
+        y = dense(x, out, inn, not bn_on)
+        if bn_on:
+            g, be, mu, var = (torch.tensor(take(out)) for _ in range(4))
+            y = torch.relu((y - mu) / torch.sqrt(var + 1e-5) * g + be)
+        return y
+    w = hp["width"]
+    x = hidden(x, x.shape[1], w)
+    for _ in range(hp["depth_common"]):
+        x = hidden(x, w, w)
+    v = x
+    for _ in range(hp.get("depth_vhead", 1)):
+        v = hidden(v, w, w)
+    v = torch.tanh(dense(v, 1, w, False))[:, 0]
+    p = x
+    for _ in range(hp.get("depth_phead", 1)):
+        p = hidden(p, w, w)
+    p = torch.softmax(dense(p, num_actions, w, False), dim=1)
+    assert q[0] == len(blob)
+    return p.numpy().astype(np.float32), v.numpy().astype(np.float32)

@@ -165,3 +165,46 @@ def test_selfplay_with_network_bit_exact(az, oz, ctx):
             assert (out["z"][rows] == tr["z"].astype(np.float32)).all()
             assert out["nodes"][g] == tr["mem_nodes"] and out["edepth"][g] == tr["edepth"]
     net.close()
+
+
+@pytest.mark.parametrize("game,hp", [("tictactoe", dict(width=200, depth_common=6, use_batch_norm=True)),     # games/tictactoe/params.jl:8-12
+                                      ("connect-four", dict(width=100, depth_common=4, use_batch_norm=False)),
+                                      ("mancala", dict(width=64, depth_common=2, depth_phead=2, depth_vhead=0, use_batch_norm=True))])
+def test_simplenet_forward_and_mcts(az, oz, ctx, game, hp):
+    """SimpleNet (fp32 fused MLP) against the torch restatement, and MCTS driven by it (config[0]: 64 trees x 50 sims)."""
+    from oracle import netref
+    gs = az.GameSpec(game)
+    gid = oz.game_id(game)
+    blob = netref.simplenet_make_blob(gs.state_dim, gs.num_actions, hp, seed=7)
+    net = az.SimpleNet(ctx, gs, az.SimpleNetHP(hp["width"], hp["depth_common"], hp.get("depth_phead", 1), hp.get("depth_vhead", 1),
+                                               hp.get("use_batch_norm", False)))
+    assert net.num_params == len(blob)
+    net.load(blob)
+    states = gs.random_positions(3, 64, 5 if game == "tictactoe" else 25)
+    X = np.stack([oz.vectorize_state(gid, bytes(s)) for s in states])
+    mask = np.stack([oz.GameEnv(gid, bytes(s)).actions_mask() for s in states])
+    P0, V0 = netref.simplenet_forward(blob, gs.state_dim, gs.num_actions, hp, X)
+    Pr, Vr, Ir = netref.forward_normalized(P0, V0, mask)
+    P, V, Pinv = net.evaluate_batch(states)
+    assert np.abs(P - Pr).max() < 1e-4 and np.abs(V - Vr).max() < 1e-4 and np.abs(Pinv - Ir).max() < 1e-4
+    # MCTS with the network as oracle, oracle replay with the network's own outputs: bit-exact
+    nsims = 50
+    mp = az.MctsParams(cpuct=1.0, num_iters_per_turn=nsims, dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0)
+    env = az.MctsEnv(ctx, gs, net, mp, len(states), 4 * nsims)
+    N, W, _ = env.explore(states, nsims)
+    cache = {}
+
+    def oracle(state, n):
+        if state not in cache:
+            p, v, _ = net.evaluate_batch(np.frombuffer(state, np.uint8)[None])
+            m = gs.actions_mask(np.frombuffer(state, np.uint8))
+            cache[state] = (p[0][m].tolist(), float(v[0]))
+        return cache[state]
+    for i in range(0, len(states), 8):
+        e = oz.Env(gid, oracle, cpuct=1.0)
+        g = oz.GameEnv(gid, bytes(states[i]))
+        e.explore(g, nsims)
+        _, rN, rW, _, _ = e.root_stats(g)
+        assert (N[i] == rN).all() and (W[i] == rW).all()
+    env.close()
+    net.close()

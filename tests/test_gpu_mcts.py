@@ -169,3 +169,37 @@ def test_full_size_properties(az, ctx):
     assert t["expansions"] == nn.sum()
     env.close()
     net.close()
+
+
+def test_error_paths_mirror_reference_asserts(az, ctx):
+    """Precondition violations return AZ_EINVAL / AZ_ESTATE with a message (no exception crosses the ABI)."""
+    gs = az.GameSpec("connect-four")
+    net = az.SynthOracle(ctx, gs)
+    mp = az.MctsParams(cpuct=1.0, num_iters_per_turn=8, dirichlet_noise_eps=0.25, dirichlet_noise_alpha=1.0)
+    with pytest.raises(az.AzError) as e:   # batch_size <= num_workers (src/batchifier.jl:48)
+        az.SelfPlay(ctx, gs, net, az.SelfPlayParams(mp, az.SimParams(num_games=4, num_workers=4, batch_size=8)))
+    assert e.value.status == 1 and "batch_size" in str(e.value)
+    with pytest.raises(az.AzError) as e:   # niters > 0 (src/play.jl:162)
+        az.MctsEnv(ctx, gs, net, az.MctsParams(cpuct=1.0, num_iters_per_turn=0, dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0), 4)
+    assert e.value.status == 1
+    with pytest.raises(az.AzError) as e:   # flip_probability is not supported yet
+        az.SelfPlay(ctx, gs, net, az.SelfPlayParams(mp, az.SimParams(num_games=4, num_workers=4, batch_size=4, flip_probability=0.5)))
+    assert e.value.status == 5
+    env = az.MctsEnv(ctx, gs, net, mp, 4, 64)
+    with pytest.raises(az.AzError):        # eta required when eps != 0
+        env.set_roots(gs.random_positions(1, 4, 10), None)
+    with pytest.raises(az.AzError) as e:   # MCTS.policy before explore! (src/mcts.jl:262)
+        mp0 = az.MctsParams(cpuct=1.0, num_iters_per_turn=8, dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0)
+        env0 = az.MctsEnv(ctx, gs, net, mp0, 4, 64)
+        env0.set_roots(gs.random_positions(1, 4, 10), None)
+        env0.policy()
+    assert e.value.status == 4
+    ttt = az.GameSpec("tictactoe")
+    with pytest.raises(az.AzError):        # oracle built for another game
+        az.MctsEnv(ctx, ttt, net, mp, 4, 64)
+    # table overflow is detected on device and reported, not silently corrupted
+    small = az.MctsEnv(ctx, gs, net, az.MctsParams(cpuct=1.0, num_iters_per_turn=600, dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0), 4, 16)
+    with pytest.raises(az.AzError) as e:
+        small.explore(gs.random_positions(1, 4, 4), 600)
+    assert e.value.status == 3
+    net.close()

@@ -57,7 +57,7 @@ ABI_SYMBOLS = [
     "az_game_vectorize_state", "az_game_actions_mask", "az_game_play", "az_game_init_state", "az_game_random_positions",
     "az_net_create_oracle", "az_net_create_resnet", "az_net_create_simplenet", "az_net_num_params", "az_net_load",
     "az_net_forward", "az_net_set_profiling", "az_net_get_profile", "az_net_destroy",
-    "az_mcts_create", "az_mcts_set_roots", "az_mcts_run", "az_mcts_explore", "az_mcts_root_stats", "az_mcts_policy",
+    "az_mcts_create", "az_mcts_set_roots", "az_mcts_set_noise", "az_mcts_run", "az_mcts_explore", "az_mcts_root_stats", "az_mcts_policy",
     "az_mcts_reset", "az_mcts_counters", "az_mcts_last_timing", "az_mcts_destroy",
     "az_selfplay_create", "az_selfplay_start", "az_selfplay_poll", "az_selfplay_wait", "az_selfplay_counts",
     "az_selfplay_fetch", "az_selfplay_stats", "az_selfplay_destroy",
@@ -92,7 +92,7 @@ def lib():
             "az_net_forward": [vp, vp, C.c_int32, vp, vp, vp], "az_net_destroy": [vp],
             "az_net_set_profiling": [vp, C.c_int32], "az_net_get_profile": [vp, vp, vp, vp, vp],
             "az_mcts_create": [vp, C.c_int32, vp, C.POINTER(_MctsParams), C.c_int32, C.c_int32, C.POINTER(vp)],
-            "az_mcts_set_roots": [vp, vp, vp], "az_mcts_run": [vp, C.c_int32],
+            "az_mcts_set_roots": [vp, vp, vp], "az_mcts_run": [vp, C.c_int32], "az_mcts_set_noise": [vp, C.c_uint64, vp, vp],
             "az_mcts_explore": [vp, vp, vp, C.c_int32, vp, vp, vp], "az_mcts_root_stats": [vp, vp, vp, vp],
             "az_mcts_policy": [vp, vp], "az_mcts_reset": [vp], "az_mcts_counters": [vp, vp, vp, vp],
             "az_mcts_last_timing": [vp, vp, vp, vp, vp], "az_mcts_destroy": [vp],
@@ -145,7 +145,7 @@ class GameSpec:
         self.name = name
         self.id = lib().az_game_lookup(name.encode())
         if self.id < 0:
-            raise KeyError("unknown game %r (known: connect-four, tictactoe, mancala)" % name)
+            raise KeyError("unknown game %r (known: connect-four, tictactoe, mancala, grid-world)" % name)
         L = lib()
         self.num_actions = L.az_game_num_actions(self.id)
         self.state_bytes = L.az_game_state_bytes(self.id)
@@ -349,6 +349,12 @@ class MctsEnv:
         s = np.ascontiguousarray(states, np.uint8).reshape(self.n, self.gspec.state_bytes)
         e = None if eta is None else np.ascontiguousarray(eta, np.float64).reshape(self.n, self.gspec.num_actions)
         self.ctx.check(lib().az_mcts_set_roots(self.h, s.ctypes.data, _ptr(e)))
+
+    def set_noise(self, seed, games, moves):
+        """Stochastic environments: in-tree noise stream ids per tree (see az_mcts_set_noise)."""
+        g = np.ascontiguousarray(games, np.int64)
+        m = np.ascontiguousarray(moves, np.int32)
+        self.ctx.check(lib().az_mcts_set_noise(self.h, seed, g.ctypes.data, m.ctypes.data))
 
     def run(self, nsims=None):
         self.ctx.check(lib().az_mcts_run(self.h, nsims or self.params.num_iters_per_turn))

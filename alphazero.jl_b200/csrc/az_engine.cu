@@ -51,10 +51,11 @@ static int az_dalloc(az_ctx* ctx, T** p, size_t n, bool zero = true) {
     case 0: return F<GameC4>(__VA_ARGS__);                 \
     case 1: return F<GameTTT>(__VA_ARGS__);                \
     case 2: return F<GameMancala>(__VA_ARGS__);            \
+    case 3: return F<GameGW>(__VA_ARGS__);                 \
     default: return AZ_EINVAL;                             \
   }
 
-static const char* AZ_GAME_NAMES[3] = {"connect-four", "tictactoe", "mancala"};
+static const char* AZ_GAME_NAMES[4] = {"connect-four", "tictactoe", "mancala", "grid-world"};
 
 template <class G> static int g_num_actions() { return G::A; }
 template <class G> static int g_state_bytes() { return G::STATE_BYTES; }
@@ -78,6 +79,14 @@ template <class G> static int g_play(const uint8_t* s, int a, uint8_t* ns, int32
 }
 template <class G> static int g_init_state(uint8_t* s) { G::to_bytes(G::init(), s); return AZ_OK; }
 template <class G> static int g_random_positions(uint64_t seed, uint64_t first, int n, int max_plies, uint8_t* out) {
+  if (G::STOCHASTIC) {  // random non-terminal start cells (RL.reset!, games/grid-world/game.jl:36)
+    for (int i = 0; i < n; i++)
+      for (uint64_t attempt = 0;; attempt++) {
+        AzEnv e = G::init_game(seed, first + (uint64_t)i + (attempt << 32));
+        if (!G::terminated(e)) { G::to_bytes(e, out + (size_t)i * G::STATE_BYTES); break; }
+      }
+    return AZ_OK;
+  }
   for (int i = 0; i < n; i++) {
     for (uint64_t attempt = 0;; attempt++) {
       uint64_t st = first + (uint64_t)i + (attempt << 32);
@@ -135,6 +144,7 @@ struct az_mcts {
   virtual int policy(double* pi) = 0;
   virtual int reset() = 0;
   virtual int counters(int64_t* ts, int64_t* tn, int64_t* nn) = 0;
+  virtual int set_noise(uint64_t seed, const int64_t* games, const int32_t* moves) = 0;
   double ms_total = 0, ms_net = 0;
   int64_t ticks = 0, expansions = 0;
 };
@@ -179,6 +189,7 @@ struct Mcts : az_mcts {
     AZ_TRY(ctx, alloc(&p.n_leaves, 2)); AZ_TRY(ctx, alloc(&p.batch_env, S));
     AZ_TRY(ctx, alloc(&p.batch_P, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&p.batch_V, S));
     AZ_TRY(ctx, alloc(&p.flags, 4)); AZ_TRY(ctx, alloc(&p.expansions, 1));
+    AZ_TRY(ctx, alloc(&p.noise_game, S)); AZ_TRY(ctx, alloc(&p.noise_move, S));
     AZ_TRY(ctx, alloc(&d_N, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&d_W, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&d_P, (size_t)S * G::A));
     std::vector<uint32_t> tags(S, 64u | 1u);
     AZ_CUDA(ctx, cudaMemcpyAsync(p.tag, tags.data(), S * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -324,6 +335,13 @@ struct Mcts : az_mcts {
     AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return AZ_OK;
   }
+  int set_noise(uint64_t seed, const int64_t* games, const int32_t* moves) override {
+    p.noise_seed = seed;
+    drop_graph();  // the seed is a by-value kernel argument
+    AZ_CUDA(ctx, cudaMemcpy(p.noise_game, games, p.S * sizeof(int64_t), cudaMemcpyHostToDevice));
+    AZ_CUDA(ctx, cudaMemcpy(p.noise_move, moves, p.S * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return AZ_OK;
+  }
   int counters(int64_t* ts, int64_t* tn, int64_t* nn) override {
     if (ts) AZ_CUDA(ctx, cudaMemcpy(ts, p.total_sims, p.S * sizeof(int64_t), cudaMemcpyDeviceToHost));
     if (tn) AZ_CUDA(ctx, cudaMemcpy(tn, p.total_nodes, p.S * sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -388,13 +406,14 @@ struct SelfPlay : az_selfplay {
     if (mp->temperature_n < 1 || mp->temperature_n > AZ_MAX_SCHEDULE) AZ_FAIL(ctx, AZ_EINVAL, "temperature schedule: 1..8 points");
     const int S = s->num_workers;
     int reset = s->reset_every > 0 ? s->reset_every : std::max(1, (s->num_games + S - 1) / S);
-    size_t bound = (size_t)mp->num_iters_per_turn * G::MAX_PLIES * (size_t)reset;
+    size_t bound = (size_t)std::min<long long>((long long)mp->num_iters_per_turn * G::MAX_PLIES * (long long)reset, G::MAX_STATES);
     size_t budget = (size_t)96 << 30;  // table budget: 96 GB of the 180 GB HBM
     size_t maxnodes = budget / ((size_t)S * G::LANES * 16) * 3 / 4;
     int cap_nodes = (int)std::min<size_t>(std::min(bound, maxnodes), (size_t)1 << 28);
     pool.reset(new Mcts<G>());
     int st = pool->create(ctx, net, mp, S, cap_nodes);
     if (st != AZ_OK) { pool.reset(); return st; }
+    pool->p.noise_seed = seed;
     sp.seed = seed; sp.nsims = mp->num_iters_per_turn; sp.reset_every = s->reset_every; sp.max_plies = G::MAX_PLIES;
     sp.sched_n = mp->temperature_n;
     for (int i = 0; i < mp->temperature_n; i++) { sp.sched_xs[i] = mp->temperature_xs[i]; sp.sched_ys[i] = mp->temperature_ys[i]; }
@@ -638,12 +657,12 @@ int64_t az_ctx_num_launches(az_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 int32_t az_game_lookup(const char* name) {
   if (!name) return -1;
-  for (int i = 0; i < 3; i++) if (strcmp(name, AZ_GAME_NAMES[i]) == 0) return i;
+  for (int i = 0; i < 4; i++) if (strcmp(name, AZ_GAME_NAMES[i]) == 0) return i;
   return -1;
 }
-int32_t az_game_num_actions(int32_t game) { switch (game) { case 0: return GameC4::A; case 1: return GameTTT::A; case 2: return GameMancala::A; } return -1; }
-int32_t az_game_state_bytes(int32_t game) { switch (game) { case 0: return GameC4::STATE_BYTES; case 1: return GameTTT::STATE_BYTES; case 2: return GameMancala::STATE_BYTES; } return -1; }
-int32_t az_game_max_plies(int32_t game) { switch (game) { case 0: return GameC4::MAX_PLIES; case 1: return GameTTT::MAX_PLIES; case 2: return GameMancala::MAX_PLIES; } return -1; }
+int32_t az_game_num_actions(int32_t game) { switch (game) { case 0: return GameC4::A; case 1: return GameTTT::A; case 2: return GameMancala::A; case 3: return GameGW::A; } return -1; }
+int32_t az_game_state_bytes(int32_t game) { switch (game) { case 0: return GameC4::STATE_BYTES; case 1: return GameTTT::STATE_BYTES; case 2: return GameMancala::STATE_BYTES; case 3: return GameGW::STATE_BYTES; } return -1; }
+int32_t az_game_max_plies(int32_t game) { switch (game) { case 0: return GameC4::MAX_PLIES; case 1: return GameTTT::MAX_PLIES; case 2: return GameMancala::MAX_PLIES; case 3: return GameGW::MAX_PLIES; } return -1; }
 int32_t az_game_state_dim(int32_t game, int32_t dim[3]) { if (!dim) return AZ_EINVAL; AZ_DISPATCH_GAME(game, g_state_dim, dim) }
 int32_t az_game_vectorize_state(int32_t game, const uint8_t* s, float* x) { if (!s || !x) return AZ_EINVAL; AZ_DISPATCH_GAME(game, g_vectorize, s, x) }
 int32_t az_game_actions_mask(int32_t game, const uint8_t* s, uint8_t* m) { if (!s || !m) return AZ_EINVAL; AZ_DISPATCH_GAME(game, g_mask, s, m) }
@@ -728,6 +747,10 @@ int32_t az_mcts_root_stats(az_mcts* m, int64_t* N, double* W, float* P) { AZ_M(m
 int32_t az_mcts_policy(az_mcts* m, double* pi) { AZ_M(m) if (!pi) return AZ_EINVAL; AZ_GUARD_BEGIN return m->policy(pi); AZ_GUARD_END(m->ctx) }
 int32_t az_mcts_reset(az_mcts* m) { AZ_M(m) AZ_GUARD_BEGIN return m->reset(); AZ_GUARD_END(m->ctx) }
 int32_t az_mcts_counters(az_mcts* m, int64_t* ts, int64_t* tn, int64_t* nn) { AZ_M(m) AZ_GUARD_BEGIN return m->counters(ts, tn, nn); AZ_GUARD_END(m->ctx) }
+int32_t az_mcts_set_noise(az_mcts* m, uint64_t seed, const int64_t* games, const int32_t* moves) {
+  AZ_M(m) if (!games || !moves) return AZ_EINVAL;
+  AZ_GUARD_BEGIN return m->set_noise(seed, games, moves); AZ_GUARD_END(m->ctx)
+}
 int32_t az_mcts_last_timing(az_mcts* m, double* ms_total, double* ms_net, int64_t* ticks, int64_t* ex) {
   if (!m) return AZ_EINVAL;
   if (ms_total) *ms_total = m->ms_total;

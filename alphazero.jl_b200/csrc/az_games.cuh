@@ -19,11 +19,15 @@
 #define __forceinline__ inline
 #endif
 #define AZ_HD __host__ __device__ __forceinline__
+#include "az_rng.cuh"
 
 struct AzEnv {
   uint64_t a, b;  // canonical state key (no table tag bits)
   uint32_t aux;   // status outside the state: bit0 finished, bits1-2 winner
 };
+
+// uniform draws consumed by a stochastic environment step (grid-world); ignored by the board games
+struct AzNoise { double u0, u1; };
 
 AZ_HD int az_popc64(uint64_t x) {
 #ifdef __CUDA_ARCH__
@@ -84,6 +88,10 @@ struct GameC4 {
     return n;
   }
   AZ_HD static AzEnv init() { AzEnv e = {0, 0, 0}; return e; }
+  static constexpr bool STOCHASTIC = false;
+  static constexpr long long MAX_STATES = 1ll << 40;  // no useful bound on distinct states
+  AZ_HD static AzEnv play(const AzEnv& e, int a, const AzNoise&) { return play(e, a); }
+  AZ_HD static AzEnv init_game(uint64_t, uint64_t) { return init(); }
   // set_state! (game.jl:50-68): finished if no free column, or if the TOP stone of some column is part of a
   // winning pattern of its colour
   static AzEnv from_bytes(const uint8_t* s) {
@@ -168,6 +176,10 @@ struct GameTTT {
     return n;
   }
   AZ_HD static AzEnv init() { AzEnv e = {0, 0, 0}; return e; }
+  static constexpr bool STOCHASTIC = false;
+  static constexpr long long MAX_STATES = 1ll << 40;  // no useful bound on distinct states
+  AZ_HD static AzEnv play(const AzEnv& e, int a, const AzNoise&) { return play(e, a); }
+  AZ_HD static AzEnv init_game(uint64_t, uint64_t) { return init(); }
   static AzEnv from_bytes(const uint8_t* s) {
     AzEnv e = {0, 0, 0};
     for (int i = 0; i < 9; i++) {
@@ -285,6 +297,10 @@ struct GameMancala {
     e.aux = 0;
     return e;
   }
+  static constexpr bool STOCHASTIC = false;
+  static constexpr long long MAX_STATES = 1ll << 40;  // no useful bound on distinct states
+  AZ_HD static AzEnv play(const AzEnv& e, int a, const AzNoise&) { return play(e, a); }
+  AZ_HD static AzEnv init_game(uint64_t, uint64_t) { return init(); }
   static AzEnv from_bytes(const uint8_t* s) {
     AzEnv e;
     pack(e, s, s[14] == 2);
@@ -309,5 +325,59 @@ struct GameMancala {
       x[i + 42] = (!is_store && player == 2) ? 1.f : 0.f;
       x[i + 56] = (is_store && player == 2) ? 1.f : 0.f;
     }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Grid world (games/grid-world/game.jl through src/common_rl_intf.jl): 10x10 single-player MDP, 4 actions always legal,
+// 40 % chance of a random action, rewards on four terminal cells, episode bound `time > 200` that is NOT part of the
+// state (game.jl:57) but is kept by the cloned environment (:56).  a = x | y << 8; aux = time (bits 0-8) | acted << 16.
+// ------------------------------------------------------------------------------------------------
+struct GameGW {
+  static constexpr int ID = 3;
+  static constexpr int A = 4;
+  static constexpr int LANES = 8;
+  static constexpr int STATE_BYTES = 2;
+  static constexpr int MAX_PLIES = 201;  // time > 200 terminates (game.jl:40-41)
+  static constexpr int XW = 10, XH = 10, XC = 1;
+  static constexpr bool ACYCLIC = false;  // a simulation may revisit a state (time is not in the key)
+  static constexpr bool STOCHASTIC = true;
+  static constexpr long long MAX_STATES = 100;  // 10 x 10 cells: a tree never holds more nodes
+  AZ_HD static int gx(const AzEnv& e) { return (int)(e.a & 0xFF); }
+  AZ_HD static int gy(const AzEnv& e) { return (int)((e.a >> 8) & 0xFF); }
+  AZ_HD static int time(const AzEnv& e) { return (int)(e.aux & 0x1FF); }
+  AZ_HD static double reward_at(int x, int y) {  // game.jl:24-28
+    if (x == 9 && y == 3) return 10.0;
+    if (x == 8 && y == 8) return 3.0;
+    if (x == 4 && y == 3) return -10.0;
+    if (x == 4 && y == 6) return -5.0;
+    return 0.0;
+  }
+  AZ_HD static bool has_reward(int x, int y) { return (x == 9 && y == 3) || (x == 8 && y == 8) || (x == 4 && y == 3) || (x == 4 && y == 6); }
+  AZ_HD static bool terminated(const AzEnv& e) { return has_reward(gx(e), gy(e)) || time(e) > 200; }
+  AZ_HD static bool white_playing(const AzEnv&) { return true; }
+  AZ_HD static uint32_t legal_mask(const AzEnv&) { return 0xFu; }
+  AZ_HD static double white_reward(const AzEnv& e) { return ((e.aux >> 16) & 1u) ? reward_at(gx(e), gy(e)) : 0.0; }  // last_reward
+  AZ_HD static AzEnv play(const AzEnv& e, int a, const AzNoise& nz) {  // act!, game.jl:43-51
+    if (nz.u0 < 0.4) { a = (int)(nz.u1 * 4.0); if (a > 3) a = 3; }
+    int x = gx(e) + (a == 0 ? 1 : (a == 1 ? -1 : 0));
+    int y = gy(e) + (a == 2 ? 1 : (a == 3 ? -1 : 0));
+    x = x < 1 ? 1 : (x > 10 ? 10 : x);
+    y = y < 1 ? 1 : (y > 10 ? 10 : y);
+    AzEnv n;
+    n.a = (uint64_t)x | ((uint64_t)y << 8);
+    n.b = 0;
+    n.aux = (uint32_t)(time(e) + 1) | (1u << 16);
+    return n;
+  }
+  AZ_HD static AzEnv play(const AzEnv& e, int a) { AzNoise nz = {1.0, 0.0}; return play(e, a, nz); }  // noise-free step
+  AZ_HD static AzEnv init() { AzEnv e = {1ull | (1ull << 8), 0, 0}; return e; }
+  AZ_HD static AzEnv from_xy(int x, int y) { AzEnv e = {(uint64_t)x | ((uint64_t)y << 8), 0, 0}; return e; }
+  AZ_HD static AzEnv init_game(uint64_t seed, uint64_t game) { int x, y; az_gw_init_xy(seed, game, &x, &y); return from_xy(x, y); }
+  static AzEnv from_bytes(const uint8_t* s) { return from_xy(s[0], s[1]); }
+  AZ_HD static void to_bytes(const AzEnv& e, uint8_t* s) { s[0] = (uint8_t)gx(e); s[1] = (uint8_t)gy(e); }
+  AZ_HD static void vectorize(const AzEnv& e, float* x) {  // game.jl:86-90
+    for (int i = 0; i < 100; i++) x[i] = 0.0f;
+    x[(gx(e) - 1) + 10 * (gy(e) - 1)] = 1.0f;
   }
 };

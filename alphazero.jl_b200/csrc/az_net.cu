@@ -1171,6 +1171,7 @@ az_net* az_make_resnet(az_ctx* ctx, int game, const az_resnet_hp* hp, int* statu
     case 0: n = mk(new ResNetImpl<GameC4>()); break;
     case 1: n = mk(new ResNetImpl<GameTTT>()); break;
     case 2: n = mk(new ResNetImpl<GameMancala>()); break;
+    case 3: n = mk(new ResNetImpl<GameGW>()); break;
     default: ctx->err = "az_net_create_resnet: unknown game"; st = AZ_EINVAL;
   }
   *status = st;
@@ -1376,6 +1377,7 @@ az_net* az_make_simplenet(az_ctx* ctx, int game, const az_simplenet_hp* hp, int*
     case 0: n = mk(new SimpleNetImpl<GameC4>()); break;
     case 1: n = mk(new SimpleNetImpl<GameTTT>()); break;
     case 2: n = mk(new SimpleNetImpl<GameMancala>()); break;
+    case 3: n = mk(new SimpleNetImpl<GameGW>()); break;
     default: ctx->err = "az_net_create_simplenet: unknown game"; st = AZ_EINVAL;
   }
   *status = st;

@@ -115,3 +115,23 @@ AZ_HD uint64_t az_splitmix(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
+
+// ---- environment noise and random initial states (grid-world) -------------------------------------------------------
+// In-tree noise of simulation `sim` at depth `depth` of move `move` of game `game`; the real move uses sim = AZ_REAL_MOVE.
+#define AZ_REAL_MOVE 0x7FFFFFu
+struct AzNoiseKey { uint64_t seed, game; uint32_t move; };
+template <class Noise>
+AZ_HD Noise az_env_noise(const AzNoiseKey& k, uint32_t sim, uint32_t depth) {
+  const uint32_t idx = (sim * 256u + depth) * 2u;
+  Noise n;
+  n.u0 = az_u01(az_stream_u64(k.seed, k.game, k.move, AZ_PURPOSE_ENV, idx));
+  n.u1 = az_u01(az_stream_u64(k.seed, k.game, k.move, AZ_PURPOSE_ENV, idx + 1u));
+  return n;
+}
+// random initial cell in 1..10 x 1..10 (RL.reset!, games/grid-world/game.jl:36)
+AZ_HD void az_gw_init_xy(uint64_t seed, uint64_t game, int* x, int* y) {
+  uint32_t o[4];
+  az_philox(seed, 0, AZ_PURPOSE_POSITION, (uint32_t)game, (uint32_t)(game >> 32), o);
+  *x = 1 + (int)(o[0] % 10u);
+  *y = 1 + (int)(o[1] % 10u);
+}

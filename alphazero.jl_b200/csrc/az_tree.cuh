@@ -55,6 +55,9 @@ struct AzPool {
   float* batch_V;       // [S]
   int32_t* flags;       // [4]: 0 overflow, 1 active slots not finished (select), 2 path overflow
   int64_t* expansions;  // [1]
+  uint64_t noise_seed;  // stochastic environments: in-tree noise stream = (noise_seed, noise_game[slot], noise_move[slot], sim, depth)
+  int64_t* noise_game;  // [S]
+  int32_t* noise_move;  // [S]
   AzMctsConst c;
 };
 
@@ -139,6 +142,8 @@ __global__ void __launch_bounds__(128) az_k_select(AzPool p) {
   double* pr = p.path_r + (size_t)slot * p.maxd;
   int64_t tsims = 0, tnodes = 0;
   const int a = lane - 1;
+  AzNoiseKey nkey = {0, 0, 0};
+  if (G::STOCHASTIC) { nkey.seed = p.noise_seed; nkey.game = (uint64_t)p.noise_game[slot]; nkey.move = (uint32_t)p.noise_move[slot]; }
   int budget = p.max_sims_per_call;
   while (sims_done < target && budget-- > 0) {
     tsims++;
@@ -194,7 +199,9 @@ __global__ void __launch_bounds__(128) az_k_select(AzPool p) {
       }
       const int act = best - 1;
       const bool wp = G::white_playing(env);
-      const AzEnv nx = G::play(env, act);
+      AzNoise nz = {1.0, 0.0};
+      if (G::STOCHASTIC) nz = az_env_noise<AzNoise>(nkey, (uint32_t)sims_done, (uint32_t)depth);
+      const AzEnv nx = G::play(env, act, nz);
       const double wr = G::white_reward(nx);
       if (lane == 0) {
         pn[depth] = h;
@@ -411,6 +418,7 @@ __device__ void az_begin_move(const AzPool& p, const AzSelfPlay& sp, int slot, c
   p.root[slot] = root;
   p.sims_done[slot] = 0;
   p.sims_target[slot] = sp.nsims;
+  if (G::STOCHASTIC) { p.noise_game[slot] = game; p.noise_move[slot] = move; }
   double eta[A];
   int n = __popc(G::legal_mask(root));
   az_dirichlet(sp.seed, (uint64_t)game, (uint32_t)move, n, p.c.alpha, eta);  // drawn even if eps == 0 (src/mcts.jl:240)
@@ -433,7 +441,7 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
       sp.move_of_slot[slot] = 0;
       p.status[slot] = 1;
       p.pending[slot] = 0;
-      az_begin_move<G>(p, sp, slot, G::init(), sp.first_game + slot, 0);
+      az_begin_move<G>(p, sp, slot, G::init_game(sp.seed, (uint64_t)(sp.first_game + slot)), sp.first_game + slot, 0);
       atomicAdd(sp.active_slots, 1);
     } else {
       sp.game_of_slot[slot] = -1;
@@ -512,7 +520,9 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
   for (int i = 0; i < A; i++) sp.s_pi[rowi * A + i] = 0.0f;
   for (int i = 0; i < n; i++) sp.s_pi[rowi * A + acts[i]] = (float)pi[i];
   sp.s_action[rowi] = act;
-  const AzEnv nx = G::play(root, act);
+  AzNoise rnz = {1.0, 0.0};
+  if (G::STOCHASTIC) { AzNoiseKey rk = {sp.seed, (uint64_t)game, (uint32_t)move}; rnz = az_env_noise<AzNoise>(rk, AZ_REAL_MOVE, 0u); }
+  const AzEnv nx = G::play(root, act, rnz);
   sp.s_reward[rowi] = G::white_reward(nx);
   const int nm = move + 1;
   if (G::terminated(nx) || nm >= sp.max_plies) {
@@ -546,7 +556,7 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
     if (ng < sp.num_games) {
       sp.game_of_slot[slot] = ng;
       sp.move_of_slot[slot] = 0;
-      az_begin_move<G>(p, sp, slot, G::init(), sp.first_game + ng, 0);
+      az_begin_move<G>(p, sp, slot, G::init_game(sp.seed, (uint64_t)(sp.first_game + ng)), sp.first_game + ng, 0);
     } else {
       sp.game_of_slot[slot] = -1;
       p.status[slot] = 0;

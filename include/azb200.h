@@ -14,6 +14,7 @@
  *                        (games/tictactoe/game.jl:9-14: Bool/Nothing cells mapped to bytes)
  *   mancala      (15 B): stores[2], houses[(player-1) + 2*(num-1)] (12 B), curplayer {1,2}
  *                        (games/mancala/game.jl:22-25)
+ *   grid-world   ( 2 B): x, y in 1..10 (games/grid-world/game.jl:20,57; the step counter is not part of the state)
  * Actions are 0-based here (Julia action a  <->  a-1).
  */
 #ifndef AZB200_H
@@ -49,7 +50,7 @@ int32_t az_ctx_synchronize(az_ctx* ctx);
 int64_t az_ctx_num_launches(az_ctx* ctx);
 
 /* ---- games: GI.AbstractGameSpec queries (src/game.jl:34-120; names = src/examples.jl:17-21) ---- */
-int32_t az_game_lookup(const char* name); /* "connect-four" | "tictactoe" | "mancala"; < 0 if unknown */
+int32_t az_game_lookup(const char* name); /* "connect-four" | "tictactoe" | "mancala" | "grid-world"; < 0 if unknown */
 int32_t az_game_num_actions(int32_t game);          /* GI.num_actions */
 int32_t az_game_state_bytes(int32_t game);
 int32_t az_game_state_dim(int32_t game, int32_t dim[3]); /* GI.state_dim */
@@ -137,6 +138,9 @@ int32_t az_mcts_create(az_ctx* ctx, int32_t game, az_net* oracle, const az_mcts_
 /* roots[i] = GI.current_state of tree i's game; eta: n_trees x A doubles, compact over legal actions in ascending
    order (src/mcts.jl:228-232), or NULL (then dirichlet_noise_eps must be 0) */
 int32_t az_mcts_set_roots(az_mcts* m, const uint8_t* root_states, const double* eta);
+/* stochastic environments only (grid-world): the in-tree environment noise of tree i is the stream
+   (seed, games[i], moves[i], simulation index, depth) -- replaces Julia's global rand() in act! (games/grid-world/game.jl:45-46) */
+int32_t az_mcts_set_noise(az_mcts* m, uint64_t seed, const int64_t* games, const int32_t* moves);
 /* MCTS.explore!(env, game, nsims) on every tree (src/mcts.jl:239-245); roots resident on device */
 int32_t az_mcts_run(az_mcts* m, int32_t nsims);
 /* set_roots + run + root_stats in one call with host buffers (the `think` seam, src/play.jl:196-206) */

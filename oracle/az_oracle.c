@@ -492,8 +492,10 @@ struct oz_env { /* :124-151 */
   double gamma, cpuct, noise_eps, noise_alpha, prior_temperature;
   int64_t total_simulations, total_nodes_traversed;
   int game_id;
-  /* stochastic environments: stream position for in-tree env noise (grid-world) */
-  const double* env_u;
+  /* stochastic environments (grid-world): in-tree noise = stream (seed, game, move, ENV, (sim*256 + depth)*2 + {0,1});
+     replaces Julia's global rand() inside act! (games/grid-world/game.jl:45-46) */
+  uint64_t noise_seed, noise_game;
+  uint32_t noise_move, cur_sim;
 };
 
 static uint64_t oz_hash_state(const oz_state* s) {
@@ -514,6 +516,12 @@ void oz_env_reset(oz_env* e) { memset(e->tab, 0, e->cap * sizeof(oz_info)); e->c
 int64_t oz_env_num_nodes(const oz_env* e) { return (int64_t)e->count; }
 int64_t oz_env_total_simulations(const oz_env* e) { return e->total_simulations; }
 int64_t oz_env_total_nodes_traversed(const oz_env* e) { return e->total_nodes_traversed; }
+void oz_env_set_noise(oz_env* e, uint64_t seed, uint64_t game, uint32_t move) { e->noise_seed = seed; e->noise_game = game; e->noise_move = move; }
+static void oz_env_noise(uint64_t seed, uint64_t game, uint32_t move, uint32_t sim, uint32_t depth, double* u) {
+  uint32_t idx = (sim * 256u + depth) * 2u;
+  u[0] = oz_u01(oz_stream_u64(seed, game, move, OZ_PURPOSE_ENV, idx));
+  u[1] = oz_u01(oz_stream_u64(seed, game, move, OZ_PURPOSE_ENV, idx + 1u));
+}
 
 static oz_info* oz_find(const oz_env* e, const oz_state* s) {
   size_t i = oz_hash_state(s) & (e->cap - 1);
@@ -598,7 +606,7 @@ static void oz_uct_scores(const oz_info* info, double cpuct, double eps, const d
 }
 
 /* run_simulation! :199-226 (recursive, exactly as the reference) */
-static double oz_run_simulation(oz_env* e, oz_game* g, const double* eta, int root) {
+static double oz_run_simulation(oz_env* e, oz_game* g, const double* eta, int root, int depth) {
   if (oz_game_terminated(g)) return 0.0;
   oz_state s;
   memset(&s, 0, sizeof(s));
@@ -613,11 +621,14 @@ static double oz_run_simulation(oz_env* e, oz_game* g, const double* eta, int ro
   oz_uct_scores(info, e->cpuct, eps, eta, scores);
   int action_id = oz_argmax_d(scores, n);
   int wp = oz_game_white_playing(g);
-  oz_game_play(g, acts[action_id], e->env_u);
+  double u[2];
+  const double* env_u = NULL;
+  if (e->game_id == OZ_GRID_WORLD) { oz_env_noise(e->noise_seed, e->noise_game, e->noise_move, e->cur_sim, (uint32_t)depth, u); env_u = u; }
+  oz_game_play(g, acts[action_id], env_u);
   double wr = oz_game_white_reward(g);
   double r = wp ? wr : -wr;
   int pswitch = (wp != oz_game_white_playing(g));
-  double qnext = oz_run_simulation(e, g, eta, 0);
+  double qnext = oz_run_simulation(e, g, eta, 0, depth + 1);
   if (pswitch) qnext = -qnext;
   double q = r + e->gamma * qnext;
   info = oz_find(e, &s); /* the table may have been rehashed by the recursive call */
@@ -631,7 +642,8 @@ void oz_explore(oz_env* e, const oz_game* root, int nsims, const double* eta) { 
   for (int i = 0; i < nsims; i++) {
     e->total_simulations += 1;
     oz_game g = *root; /* GI.clone */
-    oz_run_simulation(e, &g, eta, 1);
+    e->cur_sim = (uint32_t)i;
+    oz_run_simulation(e, &g, eta, 1, 0);
   }
 }
 
@@ -713,6 +725,13 @@ int oz_categorical(const float* p, int n, float u) { /* Distributions.jl rand(::
 void oz_play_game(oz_env* env, const oz_mcts_params* mp, uint64_t seed, uint64_t game_idx, oz_trace* tr) {
   oz_game g;
   oz_game_init(&g, env->game_id);
+  if (env->game_id == OZ_GRID_WORLD) { /* RL.reset!: random start cell (games/grid-world/game.jl:36) */
+    uint32_t o[4];
+    uint8_t st[2];
+    oz_philox(seed, 0, OZ_PURPOSE_POSITION, (uint32_t)game_idx, (uint32_t)(game_idx >> 32), o);
+    st[0] = (uint8_t)(1 + o[0] % 10u); st[1] = (uint8_t)(1 + o[1] % 10u);
+    oz_game_set_state(&g, OZ_GRID_WORLD, st);
+  }
   int A = OZ_NACT[env->game_id];
   memset(tr, 0, sizeof(*tr));
   oz_game_get_state(&g, tr->states[0]);
@@ -723,6 +742,7 @@ void oz_play_game(oz_env* env, const oz_mcts_params* mp, uint64_t seed, uint64_t
     float pf[OZ_MAX_ACTIONS];
     int nl = oz_legal_actions(&g, acts);
     oz_dirichlet(seed, game_idx, (uint32_t)n, nl, mp->noise_alpha, eta);  /* drawn even if eps == 0 (mcts.jl:240) */
+    oz_env_set_noise(env, seed, game_idx, (uint32_t)n);
     oz_explore(env, &g, mp->num_iters_per_turn, eta);                      /* think: play.jl:196-206 */
     oz_policy(env, &g, acts, pi);
     double tau = oz_pl_schedule(mp->sched_n, mp->sched_xs, mp->sched_ys, n); /* schedule[length(trace)] */
@@ -733,7 +753,12 @@ void oz_play_game(oz_env* env, const oz_mcts_params* mp, uint64_t seed, uint64_t
     for (int a = 0; a < A; a++) { tr->pi[n][a] = 0.0f; tr->mask[n][a] = 0; }
     for (int i = 0; i < nl; i++) { tr->pi[n][acts[i]] = (float)pi[i]; tr->mask[n][acts[i]] = 1; }
     tr->action[n] = acts[k];
-    oz_game_play(&g, acts[k], NULL);
+    {
+      double u[2];
+      const double* env_u = NULL;
+      if (env->game_id == OZ_GRID_WORLD) { oz_env_noise(seed, game_idx, (uint32_t)n, 0x7FFFFFu, 0u, u); env_u = u; }
+      oz_game_play(&g, acts[k], env_u);
+    }
     tr->rewards[n] = oz_game_white_reward(&g);
     n++;
     oz_game_get_state(&g, tr->states[n]);
@@ -762,6 +787,15 @@ void oz_worker_run(int game_id, oz_oracle_fn oracle, void* octx, const oz_mcts_p
 }
 
 void oz_random_position(int game_id, uint64_t seed, uint64_t stream, int max_plies, uint8_t* state) {
+  if (game_id == OZ_GRID_WORLD) {
+    for (uint64_t attempt = 0;; attempt++) {
+      uint64_t st = stream + (attempt << 32);
+      uint32_t o[4];
+      oz_philox(seed, 0, OZ_PURPOSE_POSITION, (uint32_t)st, (uint32_t)(st >> 32), o);
+      int x = 1 + (int)(o[0] % 10u), y = 1 + (int)(o[1] % 10u);
+      if (!gw_has_reward(x, y)) { state[0] = (uint8_t)x; state[1] = (uint8_t)y; return; }
+    }
+  }
   for (uint64_t attempt = 0;; attempt++) {
     uint64_t st = stream + (attempt << 32);
     oz_game g;

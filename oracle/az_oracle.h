@@ -102,6 +102,8 @@ void oz_env_reset(oz_env*);
 int64_t oz_env_num_nodes(const oz_env*);
 int64_t oz_env_total_simulations(const oz_env*);
 int64_t oz_env_total_nodes_traversed(const oz_env*);
+/* stochastic environments (grid-world): ids of the in-tree environment-noise stream used by the next oz_explore */
+void oz_env_set_noise(oz_env*, uint64_t seed, uint64_t game, uint32_t move);
 /* explore!(env, game, nsims) with an explicit eta (length n_legal; may be NULL iff noise_eps == 0) */
 void oz_explore(oz_env*, const oz_game* root, int nsims, const double* eta);
 /* root statistics in action-indexed form (A wide, zeros on illegal); returns n_legal or -1 if root unknown */

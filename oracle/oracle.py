@@ -76,6 +76,7 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p]
             getattr(L, f).restype = C.c_int64
         L.oz_explore.argtypes = [C.c_void_p, C.POINTER(Game), C.c_int, C.c_void_p]
+        L.oz_env_set_noise.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32]
         L.oz_root_stats.argtypes = [C.c_void_p, C.POINTER(Game)] + [C.c_void_p] * 4
         L.oz_policy.argtypes = [C.c_void_p, C.POINTER(Game), C.c_void_p, C.c_void_p]
         L.oz_game_white_reward.restype = C.c_double
@@ -233,6 +234,9 @@ class Env:
         if getattr(self, "h", None):
             lib().oz_env_destroy(self.h)
             self.h = None
+
+    def set_noise(self, seed, game, move):
+        lib().oz_env_set_noise(self.h, seed, game, move)
 
     def explore(self, game, nsims, eta=None):
         e = None if eta is None else np.ascontiguousarray(eta, np.float64)

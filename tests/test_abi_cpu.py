@@ -65,3 +65,19 @@ def test_no_cpu_fallback(az):
     with pytest.raises(az.AzError) as e:
         az.Context(0)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_grid_world_host_helpers_match_oracle(az, oz):
+    gs = az.GameSpec("grid-world")
+    gid = oz.game_id("grid-world")
+    assert gs.num_actions == 4 and gs.state_bytes == 2 and gs.state_dim == (10, 10, 1) and gs.max_plies == 201
+    a = gs.random_positions(77, 50)
+    b = oz.random_positions(gid, 77, 50)
+    assert (a == b).all()
+    for s in a:
+        assert (gs.vectorize_state(s) == oz.vectorize_state(gid, bytes(s))).all()
+        for act in range(4):                     # az_game_play is the noise-free step
+            g = oz.GameEnv(gid, bytes(s))
+            g.play(act, [0.9, 0.0])
+            ns, term, wr = gs.play(s, act)
+            assert bytes(ns) == g.state() and term == g.terminated() and wr == g.white_reward()

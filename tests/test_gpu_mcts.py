@@ -203,3 +203,72 @@ def test_error_paths_mirror_reference_asserts(az, ctx):
         small.explore(gs.random_positions(1, 4, 4), 600)
     assert e.value.status == 3
     net.close()
+
+
+@pytest.mark.parametrize("kind", ["synth", "simplenet"])
+def test_grid_world_explore_and_selfplay_bit_exact(az, oz, ctx, kind):
+    """Stochastic single-player environment (BASELINE config[4]): in-tree environment noise from the explicit stream,
+    `time` outside the state (revisited states, paths up to 201 deep), intermediate rewards with gamma < 1."""
+    import ctypes as C
+    gs = az.GameSpec("grid-world")
+    gid = oz.game_id("grid-world")
+    if kind == "synth":
+        net = az.SynthOracle(ctx, gs)
+        ofn = "synth"
+    else:
+        from oracle import netref
+        hp = dict(width=100, depth_common=4, use_batch_norm=False)  # games/grid-world/params.jl:5-8
+        blob = netref.simplenet_make_blob(gs.state_dim, 4, hp, seed=2)
+        net = az.SimpleNet(ctx, gs, az.SimpleNetHP(100, 4)).load(blob)
+        cache = {}
+
+        def cb(ctxp, g, sp, n, P, V):
+            key = bytes(sp[:2])
+            if key not in cache:
+                p, v, _ = net.evaluate_batch(np.frombuffer(key, np.uint8)[None])
+                cache[key] = (p[0], float(v[0]))
+            for i in range(n):
+                P[i] = cache[key][0][i]
+            V[0] = cache[key][1]
+        keep = oz.ORACLE_FN(cb)
+        ofn = C.cast(keep, C.c_void_p)
+    # ---- explore!
+    roots = gs.random_positions(9, 48)
+    nsims, seed = 200, 4242
+    mp = az.MctsParams(gamma=0.95, cpuct=1.0, num_iters_per_turn=nsims, dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0)
+    env = az.MctsEnv(ctx, gs, net, mp, len(roots), 256)
+    env.set_noise(seed, np.arange(len(roots)) + 100, np.full(len(roots), 3))
+    N, W, P = env.explore(roots, nsims)
+    ts, tn, nn = env.counters()
+    for i, r in enumerate(roots):
+        e = oz.Env(gid, "synth", gamma=0.95, cpuct=1.0) if kind == "synth" else None
+        if e is None:
+            e = oz.Env.__new__(oz.Env)
+            e.gid, e._fn = gid, ofn
+            e.h = oz.lib().oz_env_create(gid, ofn, None, 0.95, 1.0, 0.0, 1.0, 1.0)
+        e.set_noise(seed, 100 + i, 3)
+        g = oz.GameEnv(gid, bytes(r))
+        e.explore(g, nsims)
+        _, rN, rW, rP, _ = e.root_stats(g)
+        assert (N[i] == rN).all() and (W[i] == rW).all() and (P[i] == rP).all(), i
+        assert (ts[i], tn[i], nn[i]) == (e.total_simulations, e.total_nodes_traversed, e.num_nodes)
+    assert (nn <= 100).all() and tn.max() > nsims       # at most 100 distinct states; deep paths
+    env.close()
+    # ---- simulate(): 8 workers x 16 games, 30 sims, argmax moves (ConstSchedule(0), games/grid-world/params.jl:19), reset_every 4
+    S, NG, ns2 = 8, 16, 30
+    mp2 = az.MctsParams(gamma=0.9, cpuct=1.0, num_iters_per_turn=ns2, temperature=az.ConstSchedule(0.0), dirichlet_noise_eps=0.0,
+                        dirichlet_noise_alpha=1.0)
+    out = az.simulate(ctx, gs, net, az.SelfPlayParams(mp2, az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=4)), seed=31)
+    omp = oz.mcts_params(gamma=0.9, cpuct=1.0, num_iters_per_turn=ns2, sched_xs=(0,), sched_ys=(0.0,))
+    for w in range(S):
+        traces = oz.worker_run(gid, ofn, omp, 31, first=w, stride=S, count=NG // S, reset_every=4)
+        for j, tr in enumerate(traces):
+            g = w + S * j
+            rows = np.flatnonzero(out["game"] == g)
+            assert len(rows) == tr["n_moves"] and 1 <= tr["n_moves"] <= 201
+            assert (out["states"][rows] == tr["states"][:-1]).all() and (out["actions"][rows] == tr["action"]).all()
+            assert (out["rewards"][rows] == tr["rewards"]).all()
+            assert (out["z"][rows] == tr["z"].astype(np.float32)).all() and (out["t"][rows] == tr["t"]).all()
+            assert (out["pi"][rows].view(np.uint32) == tr["pi"].view(np.uint32)).all()
+            assert out["nodes"][g] == tr["mem_nodes"] and out["edepth"][g] == tr["edepth"]
+    net.close()

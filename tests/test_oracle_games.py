@@ -123,3 +123,30 @@ def test_tictactoe_win(oz):
         assert not g.terminated()
         g.play(a)
     assert g.terminated() and g.white_reward() == 1.0
+
+
+def test_grid_world_rules(oz):
+    """games/grid-world/game.jl:14-59 through src/common_rl_intf.jl:118-160."""
+    gid = oz.game_id("grid-world")
+    g = oz.GameEnv(gid, bytes([5, 5]))
+    assert g.white_playing() and g.actions_mask().all() and not g.terminated() and g.white_reward() == 0.0
+    g.play(0, [0.9, 0.0])                      # no noise: action 0 = (+1, 0)
+    assert g.state() == bytes([6, 5]) and g.white_reward() == 0.0
+    g.play(0, [0.1, 0.60])                     # noise: random action floor(4*0.6) = 2 = (0, +1)
+    assert g.state() == bytes([6, 6])
+    g = oz.GameEnv(gid, bytes([10, 10]))
+    g.play(0, [0.9, 0.0])                      # clamped at the border
+    assert g.state() == bytes([10, 10])
+    g = oz.GameEnv(gid, bytes([8, 3]))
+    g.play(0, [0.9, 0.0])                      # (9,3): reward +10, terminal
+    assert g.state() == bytes([9, 3]) and g.white_reward() == 10.0 and g.terminated()
+    g = oz.GameEnv(gid, bytes([4, 5]))
+    g.play(2, [0.9, 0.0])                      # (4,6): reward -5, terminal
+    assert g.white_reward() == -5.0 and g.terminated()
+    g = oz.GameEnv(gid, bytes([1, 1]))         # episode bound: terminal once time > 200 (game.jl:40-41), not part of the state
+    for i in range(201):
+        assert not g.terminated()
+        g.play(1, [0.9, 0.0])
+    assert g.terminated() and g.state() == bytes([1, 1])
+    x = oz.vectorize_state(gid, bytes([3, 7]))
+    assert x.shape == (10, 10, 1) and x[2, 6, 0] == 1 and x.sum() == 1

@@ -279,12 +279,15 @@ __global__ void __launch_bounds__(128) az_k_expand_backup(AzPool p) {
   ln.u = make_uint4(0, 0, 0, 0);
   if (lane == 0) { ln.key.a = env.a; ln.key.b = env.b | ((uint64_t)tag << 57); }
   else if (a < A) { ln.e.W = 0.0; ln.e.P = P; ln.e.N = 0; }
-  tab[(size_t)pos * L + lane] = ln.u;
+  // Never fill the table beyond 7/8: the overflow is reported to the host (AZ_ENOMEM) and the insert is skipped, so that
+  // linear probing always finds an empty line and the kernels cannot spin on a full table.
+  const int nc_new = p.node_count[slot] + 1;
+  const bool room = (uint64_t)nc_new * 8 <= ((uint64_t)p.cap_mask + 1) * 7;
+  if (room) tab[(size_t)pos * L + lane] = ln.u;
   az_backup<G>(p, slot, lane, gm, tab, depth, (double)V);
   if (lane == 0) {
-    int nc = p.node_count[slot] + 1;
-    p.node_count[slot] = nc;
-    if ((uint64_t)nc * 8 > ((uint64_t)p.cap_mask + 1) * 7) p.flags[0] = 1;
+    if (room) p.node_count[slot] = nc_new;
+    else p.flags[0] = 1;
     p.total_nodes[slot] += depth;
     p.sims_done[slot] += 1;
     p.pending[slot] = 0;

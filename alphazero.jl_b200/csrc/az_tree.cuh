@@ -428,6 +428,55 @@ __device__ void az_begin_move(const AzPool& p, const AzSelfPlay& sp, int slot, c
   for (int i = 0; i < n; i++) p.eta[(size_t)slot * A + i] = eta[i];
 }
 
+// Worker loop of simulate() (src/simulations.jl:221-241) for one slot: record the measurements of the game that just
+// ended, apply reset_every, and start the slot's next game (static map: game = slot + S * k).  A game whose initial
+// state is already terminal (possible in grid-world: RL.reset! may pick a reward cell) ends at once with an empty trace,
+// exactly as play_game returns immediately (src/play.jl:301-304).
+template <class G>
+__device__ void az_finish_game_and_start_next(AzPool& p, AzSelfPlay& sp, int slot, int g, int n_moves) {
+  constexpr int L = G::LANES;
+  for (;;) {
+    if (g >= 0) {  // self_play_measurements (src/training.jl:269-273), measured before the reset
+      sp.g_moves[g] = n_moves;
+      sp.g_nodes[g] = p.node_count[slot];
+      const int64_t ts = p.total_sims[slot];
+      sp.g_edepth[g] = ts == 0 ? 0.0 : (double)p.total_nodes[slot] / (double)ts;
+      atomicAdd(sp.games_done, 1);
+      const int gos = sp.games_on_slot[slot] + 1;
+      sp.games_on_slot[slot] = gos;
+      if (sp.reset_every > 0 && gos % sp.reset_every == 0) {  // reset_player! (src/simulations.jl:235-237)
+        uint32_t gen = (p.tag[slot] & 63u) + 1u;
+        if (gen == 64u) {
+          uint4* wt = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
+          size_t cnt = ((size_t)p.cap_mask + 1) * L;
+          for (size_t i = 0; i < cnt; i++) wt[i] = make_uint4(0, 0, 0, 0);
+          gen = 1u;
+        }
+        p.tag[slot] = 64u | gen;
+        p.node_count[slot] = 0;
+      }
+    }
+    const int ng = slot + p.S * sp.games_on_slot[slot];
+    if (ng >= sp.num_games) {
+      sp.game_of_slot[slot] = -1;
+      p.status[slot] = 0;
+      p.sims_target[slot] = 0;
+      return;
+    }
+    const AzEnv first = G::init_game(sp.seed, (uint64_t)(sp.first_game + ng));
+    if (!G::terminated(first)) {
+      sp.game_of_slot[slot] = ng;
+      sp.move_of_slot[slot] = 0;
+      p.status[slot] = 1;
+      p.pending[slot] = 0;
+      az_begin_move<G>(p, sp, slot, first, sp.first_game + ng, 0);
+      return;
+    }
+    g = ng;       // empty game: loop to record it and move on
+    n_moves = 0;
+  }
+}
+
 // one thread per slot (runs once per move: scalar code, not performance critical)
 template <class G>
 __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
@@ -439,18 +488,8 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
     p.total_sims[slot] = 0;
     p.total_nodes[slot] = 0;
     sp.games_on_slot[slot] = 0;
-    if (slot < sp.num_games) {
-      sp.game_of_slot[slot] = slot;
-      sp.move_of_slot[slot] = 0;
-      p.status[slot] = 1;
-      p.pending[slot] = 0;
-      az_begin_move<G>(p, sp, slot, G::init_game(sp.seed, (uint64_t)(sp.first_game + slot)), sp.first_game + slot, 0);
-      atomicAdd(sp.active_slots, 1);
-    } else {
-      sp.game_of_slot[slot] = -1;
-      p.status[slot] = 0;
-      p.sims_target[slot] = 0;
-    }
+    p.status[slot] = 0;
+    az_finish_game_and_start_next<G>(p, sp, slot, -1, 0);
     return;
   }
   if (!p.status[slot] || p.pending[slot] || p.sims_done[slot] < p.sims_target[slot]) return;
@@ -537,35 +576,7 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
       sp.s_z[ri] = (float)(G::white_playing(sp.s_env[ri]) ? wr : -wr);
       sp.s_t[ri] = (float)(nm - i);
     }
-    sp.g_moves[g] = nm;
-    sp.g_nodes[g] = p.node_count[slot];
-    const int64_t ts = p.total_sims[slot];
-    sp.g_edepth[g] = ts == 0 ? 0.0 : (double)p.total_nodes[slot] / (double)ts;
-    atomicAdd(sp.games_done, 1);
-    const int gos = sp.games_on_slot[slot] + 1;
-    sp.games_on_slot[slot] = gos;
-    if (sp.reset_every > 0 && gos % sp.reset_every == 0) {  // reset_player! (src/simulations.jl:235-237)
-      uint32_t gen = (p.tag[slot] & 63u) + 1u;
-      if (gen == 64u) {
-        uint4* wt = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
-        size_t cnt = ((size_t)p.cap_mask + 1) * L;
-        for (size_t i = 0; i < cnt; i++) wt[i] = make_uint4(0, 0, 0, 0);
-        gen = 1u;
-      }
-      p.tag[slot] = 64u | gen;
-      p.node_count[slot] = 0;
-    }
-    const int ng = slot + p.S * gos;
-    if (ng < sp.num_games) {
-      sp.game_of_slot[slot] = ng;
-      sp.move_of_slot[slot] = 0;
-      az_begin_move<G>(p, sp, slot, G::init_game(sp.seed, (uint64_t)(sp.first_game + ng)), sp.first_game + ng, 0);
-    } else {
-      sp.game_of_slot[slot] = -1;
-      p.status[slot] = 0;
-      p.sims_target[slot] = 0;
-      atomicAdd(sp.active_slots, -1);
-    }
+    az_finish_game_and_start_next<G>(p, sp, slot, g, nm);
   } else {
     sp.move_of_slot[slot] = nm;
     az_begin_move<G>(p, sp, slot, nx, game, nm);

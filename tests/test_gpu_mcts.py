@@ -265,7 +265,7 @@ def test_grid_world_explore_and_selfplay_bit_exact(az, oz, ctx, kind):
         for j, tr in enumerate(traces):
             g = w + S * j
             rows = np.flatnonzero(out["game"] == g)
-            assert len(rows) == tr["n_moves"] and 1 <= tr["n_moves"] <= 201
+            assert len(rows) == tr["n_moves"] == out["moves"][g] and 0 <= tr["n_moves"] <= 201  # 0: started on a reward cell
             assert (out["states"][rows] == tr["states"][:-1]).all() and (out["actions"][rows] == tr["action"]).all()
             assert (out["rewards"][rows] == tr["rewards"]).all()
             assert (out["z"][rows] == tr["z"].astype(np.float32)).all() and (out["t"][rows] == tr["t"]).all()

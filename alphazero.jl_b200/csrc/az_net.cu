@@ -147,7 +147,7 @@ struct GemmArgs {
   int rows_per_board;  // rows of the M dimension per board: board_rows (conv/head) or 1 (dense)
   int alloc_rows;
   int no_relu;           // EPI_DENSE: 1 = plain affine output (policy logits)
-  int debug;             // timing experiments only (AZ_TOWER_DEBUG bitmask): 2 = no A loads, 4 = no epilogue global I/O
+  int debug;             // timing experiments only (AZ_TOWER_DEBUG bitmask): 4 = no epilogue global I/O
   const float* bias;
   const float* resid32;  // EPI_CONV2
   const __half* resid16; // EPI_CONV2 of block 0 (Connect-Four kernel): residual = fp16 stem output, X32 not yet materialised
@@ -301,168 +301,18 @@ az_k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------
-// Connect-Four tower kernel (row stride W+1 = 8): the generic kernel above streams 576 KB of TMA traffic per
-// 128x128 tile and is bound by L2->SM bandwidth (profiles/r01_v1_*).  Here each CTA owns HALF of the output
-// channels (64) and keeps that half of the layer's weights resident in shared memory (18 chunks of 64co x 64k,
-// 144 KB), and every A stage is reused by three taps: for each kx the producer loads ONE 144-row copy of the
-// activations shifted by dx = 1-kx; because the row stride is 8, the three dy taps are the same copy at row
-// offsets 16 / 8 / 0 = multiples of the 1024-byte swizzle atom, i.e. just a different descriptor start address.
-// TMA traffic per tile: 6 stages x 18 KB = 108 KB (5.3x less than the generic kernel).
+// Connect-Four tower kernel (row stride W+1 = 8), shared constants.  Each CTA owns HALF of the output channels (64)
+// and keeps that half of the layer's weights resident in shared memory (18 chunks of 64co x 64k, 144 KB); every A
+// stage is reused by three taps: for each kx the producer loads ONE 144-row copy of the activations shifted by
+// dx = 1-kx; because the row stride is 8, the three dy taps are the same copy at row offsets 16 / 8 / 0 = multiples of
+// the 1024-byte swizzle atom, i.e. just a different descriptor start address.  TMA traffic per 128-row tile:
+// 6 stages x 18 KB = 108 KB (5.3x less than the generic kernel).
 // ------------------------------------------------------------------------------------------------
 namespace tc2 {
-constexpr int BM = 128, BNH = 64, BK = 64, ASTAGES = 4, AROWS = 144, F = 128;
+constexpr int BM = 128, BNH = 64, BK = 64, AROWS = 144, F = 128;
 constexpr int A_STAGE = AROWS * 128, B_CHUNK = BNH * 128, NCHUNK = 18;
 constexpr int NUM_THREADS = 192;
-struct Smem {
-  uint8_t b[NCHUNK][B_CHUNK];
-  uint8_t a[ASTAGES][A_STAGE];
-  uint64_t full[ASTAGES], empty[ASTAGES], tfull[2], tempty[2], bfull;
-  uint32_t tmem_base;
-  float bias[BNH];
-};
 }  // namespace tc2
-
-template <int EPI>
-__global__ void __launch_bounds__(tc2::NUM_THREADS, 1)
-az_k_conv_c4(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmArgs ga) {
-  using namespace tc2;
-  extern __shared__ uint8_t smem_raw[];
-  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows_used = (*ga.n_boards) * ga.rows_per_board;
-  const int num_tiles = (rows_used + BM - 1) / BM;
-  const int nhalf = blockIdx.x & 1;
-  const int tile0 = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 4); }
-    mbar_init(&s.bfull, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + BNH) s.bias[threadIdx.x - 64] = ga.bias[nhalf * BNH + threadIdx.x - 64];
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(128u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = s.tmem_base;
-
-  if (warp == 0) {
-    if (tile0 < num_tiles) {  // ===== TMA producer (warp-uniform) =====
-      if (elect_one()) {
-        mbar_expect_tx(&s.bfull, NCHUNK * B_CHUNK);
-        for (int ch = 0; ch < NCHUNK; ch++) tma_load_2d(s.b[ch], &tmW, &s.bfull, ch * BK, nhalf * BNH);
-      }
-      __syncwarp();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        for (int st = 0; st < 6; st++) {  // st = kx*2 + channel half
-          mbar_wait(&s.empty[stage], phase ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&s.full[stage], A_STAGE);
-            tma_load_2d(s.a[stage], &tmA, &s.full[stage], (st & 1) * BK, tile * BM - 8 + (1 - (st >> 1)));
-          }
-          __syncwarp();
-          if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (tile0 < num_tiles) {  // ===== MMA issuer (warp-uniform) =====
-      constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BNH >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      mbar_wait(&s.bfull, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step, it++) {
-        const int acc = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&s.tempty[acc], aphase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BNH;
-        for (int st = 0; st < 6; st++) {
-          const int kx = st >> 1, half = st & 1;
-          mbar_wait(&s.full[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t abase = smem_u32(s.a[stage]);
-          if (elect_one()) {
-#pragma unroll
-            for (int ky = 0; ky < 3; ky++) {
-              // copy row j <-> activation row tile*128 - 8 + j + (1-kx);  tap (kx,ky) needs j = m + 8 + 8*(1-ky)
-              const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(8 + 8 * (1 - ky)) * 128u);
-              const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
-#pragma unroll
-              for (int k = 0; k < BK / 16; k++)
-                umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (st | ky | k) ? 1u : 0u);
-            }
-            umma_commit(&s.empty[stage]);
-            if (st == 5) umma_commit(&s.tfull[acc]);
-          }
-          __syncwarp();
-          if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else {  // ===== epilogue warps 2..5 =====
-    const int quarter = warp & 3;
-    int it = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step, it++) {
-      const int acc = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&s.tfull[acc], aphase);
-      tcgen05_fence_after();
-      const int p = tile * BM + quarter * 32 + lane;
-      const int r = p % ga.g.board_rows;
-      const bool valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
-      const bool in_alloc = p < ga.alloc_rows;
-#pragma unroll 1
-      for (int c = 0; c < BNH / 32; c++) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + acc * BNH + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
-        const int col = nhalf * BNH + c * 32;
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) x[j] = __uint_as_float(v[j]) + s.bias[c * 32 + j];
-        if (EPI == tc::EPI_CONV2 && valid) {
-          const float4* rp = reinterpret_cast<const float4*>(ga.resid32 + (size_t)p * F + col);
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float4 r4 = rp[j];
-            x[4 * j] += r4.x; x[4 * j + 1] += r4.y; x[4 * j + 2] += r4.z; x[4 * j + 3] += r4.w;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j++) x[j] = valid ? fmaxf(x[j], 0.0f) : 0.0f;
-        if (!in_alloc) continue;
-        if (EPI == tc::EPI_CONV2) {
-          float4* op = reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + col);
-#pragma unroll
-          for (int j = 0; j < 8; j++) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-        }
-        uint4 o[4];
-        __half2* oh = reinterpret_cast<__half2*>(o);
-#pragma unroll
-        for (int j = 0; j < 16; j++) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-        uint4* op16 = reinterpret_cast<uint4*>(ga.out16a + (size_t)p * F + col);
-#pragma unroll
-        for (int j = 0; j < 4; j++) op16[j] = o[j];
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tempty[acc]);
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Connect-Four tower kernel, 2-SM version (cta_group::2).  Stall sampling of the 1-SM kernels (profiles/r01_*)
@@ -576,7 +426,6 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int pt = pt0; pt < num_ptiles; pt += pt_step) {
         const int row0 = pt * 2 * BM + (int)rank * BM;
         for (int st = 0; st < 6; st++) {
-          if (ga.debug & 2) break;
           mbar_wait(&s.empty[stage], phase ^ 1);
           if (elect_one()) {
             if (leader) mbar_expect_tx(&s.full[stage], 2 * A_STAGE);
@@ -603,7 +452,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int st = 0; st < 6; st++) {
           const int kx = st >> 1, half = st & 1;
-          if (!(ga.debug & 2)) mbar_wait(&s.full[stage], phase);
+          mbar_wait(&s.full[stage], phase);
           tcgen05_fence_after();
           const uint32_t abase = smem_u32(s.a[stage]);
           if (elect_one()) {
@@ -869,12 +718,12 @@ struct ResNetImpl : az_net {
   CUtensorMap mapX2{}, mapT2{};          // Connect-Four tower kernel: 144-row A boxes
   std::vector<CUtensorMap> mapW2;        // 64co x 64k weight boxes
   static constexpr bool C4_TOWER = (W + 1) == 8;
-  size_t smem_c4 = 0, smem_2sm = 0, fin_smem = 0;
+  size_t smem_2sm = 0;
   ConvGeom geom{};
   bool loaded = false;
   int tower_debug = 0;         // AZ_TOWER_DEBUG=1: every conv uses the conv1 epilogue (timing experiments only)
   bool use_pdl = true;         // AZ_NO_PDL=1: plain stream-ordered tower launches
-  bool two_sm = true;          // AZ_TOWER_1SM=1: 1-SM Connect-Four kernel instead of the cta_group::2 one
+  static constexpr bool two_sm = true;
   bool generic_tower = false;  // AZ_GENERIC_TOWER=1: use the generic 9-tap kernel for Connect Four too (A/B comparison)
   size_t smem128 = 0, smem64 = 0;
   // profiling: 4 events per evaluation (start, tower begin, tower end, end)
@@ -932,7 +781,6 @@ struct ResNetImpl : az_net {
     { const char* e = getenv("AZ_GENERIC_TOWER"); generic_tower = e && e[0] == '1'; }
     { const char* e = getenv("AZ_TOWER_DEBUG"); tower_debug = e ? atoi(e) : 0; }
     { const char* e = getenv("AZ_NO_PDL"); use_pdl = !(e && e[0] == '1'); }
-    { const char* e = getenv("AZ_TOWER_1SM"); two_sm = !(e && e[0] == '1'); }
     geom.row_stride = W + 1; geom.board_rows = BS; geom.valid_rows = VR; geom.wcols = W;
     for (int ky = 0; ky < 3; ky++)
       for (int kx = 0; kx < 3; kx++) geom.off[ky * 3 + kx] = (1 - ky) * (W + 1) + (1 - kx);
@@ -942,9 +790,6 @@ struct ResNetImpl : az_net {
     AZ_TRY2(set_smem(az_k_gemm_tc<128, tc::EPI_CONV2>, smem128));
     AZ_TRY2(set_smem(az_k_gemm_tc<128, tc::EPI_DENSE>, smem128));
     AZ_TRY2(set_smem(az_k_gemm_tc<64, tc::EPI_HEAD>, smem64));
-    smem_c4 = sizeof(tc2::Smem) + 1024;
-    AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV1>, smem_c4));
-    AZ_TRY2(set_smem(az_k_conv_c4<tc::EPI_CONV2>, smem_c4));
     AZ_TRY2(set_smem(az_k_gemm_tc<64, tc::EPI_DENSE>, smem64));
     smem_2sm = sizeof(tc3::Smem) + 1024;
     AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV1>, smem_2sm));
@@ -1118,21 +963,18 @@ struct ResNetImpl : az_net {
     az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX0, mapWstem, ga);
     ga.gemm_k = 0; ga.out32 = nullptr; ga.debug = tower_debug;
     if (prof) cudaEventRecord(pe[1], st);
-    const bool c4 = C4_TOWER && !generic_tower;
-    const int grid_c4 = std::max(2, std::min(2 * row_tiles, ctx->num_sms & ~1));
+    const bool c4 = C4_TOWER && !generic_tower;  // Connect-Four geometry -> cta_group::2 kernel, otherwise the generic 9-tap kernel
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
     for (int blk = 0; blk < hp.num_blocks; blk++) {
       ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.resid16 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
       if (c4 && two_sm && use_pdl && blk > 0) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV1>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapX2, mapW2[2 * blk], ga);
       else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], ga);
-      else if (c4) az_k_conv_c4<tc::EPI_CONV1><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapX2, mapW2[2 * blk], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
       ga.resid16 = (c4_fast && blk == 0) ? d_x16 : nullptr;
       if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else if (c4 && two_sm && use_pdl) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV2>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapT2, mapW2[2 * blk + 1], ga);
       else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
-      else if (c4) az_k_conv_c4<tc::EPI_CONV2><<<grid_c4, tc2::NUM_THREADS, smem_c4, st>>>(mapT2, mapW2[2 * blk + 1], ga);
       else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
     }
     if (prof) cudaEventRecord(pe[2], st);

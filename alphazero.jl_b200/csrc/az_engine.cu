@@ -173,7 +173,7 @@ struct Mcts : az_mcts {
     cap = 64;
     while (cap < (size_t)cap_nodes + (size_t)cap_nodes / 4 + 8) cap <<= 1;
     p.S = S; p.cap_mask = (uint32_t)(cap - 1); p.maxd = G::MAX_PLIES + 1;
-    p.max_sims_per_call = 2;
+    p.max_sims_per_call = 1;
     if (const char* e = getenv("AZ_NO_GRAPH")) use_graph = !(e[0] == '1');
     if (const char* e = getenv("AZ_MAX_SIMS_PER_CALL")) p.max_sims_per_call = std::max(1, atoi(e));
     p.c.gamma = params->gamma; p.c.cpuct = params->cpuct; p.c.eps = params->dirichlet_noise_eps;

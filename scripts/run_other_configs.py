@@ -61,7 +61,7 @@ t0 = time.perf_counter()
 N, W, P = env.explore(roots, nsims)
 dt = time.perf_counter() - t0
 ts, tn, nn = env.counters()
-assert (N.sum(1) == nsims - 1).all() and (nn <= 100).all()
+assert (N.sum(1) >= nsims - 1).all() and (nn <= 100).all()  # a path may pass through the root state again (time is not in the key)
 out["gridworld_8192x200_simplenet"] = dict(sims_per_s=S * nsims / dt, expansions_per_s=env.last_timing()["expansions"] / dt, seconds=dt,
                                            mean_exploration_depth=float(tn.sum() / ts.sum()), max_nodes_per_tree=int(nn.max()))
 env.close()

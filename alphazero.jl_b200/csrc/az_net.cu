@@ -183,6 +183,10 @@ az_k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = s.tmem_base;
+  // programmatic dependent launch: the prologue above overlapped the previous kernel's tail; all global data produced by
+  // earlier kernels (activations, and the leaf count read below) is only touched after griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     {  // ===== TMA producer (warp-uniform; one elected lane issues) =====
@@ -960,7 +964,7 @@ struct ResNetImpl : az_net {
     ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.debug = 0;
     az_k_im2col<G><<<(max_rows + 3) / 4, 128, 0, st>>>(envs, n_rows, d_x0);
     ga.gemm_k = 1; ga.kblocks = 1; ga.bias = d_bstem; ga.out16a = d_x16; ga.out32 = c4_fast ? nullptr : d_x32;
-    az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX0, mapWstem, ga);
+    launch_pdl(az_k_gemm_tc<128, tc::EPI_CONV1>, grid, tc::NUM_THREADS, smem128, st, mapX0, mapWstem, ga);
     ga.gemm_k = 0; ga.out32 = nullptr; ga.debug = tower_debug;
     if (prof) cudaEventRecord(pe[1], st);
     const bool c4 = C4_TOWER && !generic_tower;  // Connect-Four geometry -> cta_group::2 kernel, otherwise the generic 9-tap kernel
@@ -982,14 +986,14 @@ struct ResNetImpl : az_net {
     ga.g.off[0] = 0;  // 1x1 conv: single centre tap
     ga.debug = 0;
     ga.kblocks = 2; ga.bias = d_bh; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_hp; ga.out16b = d_hv;
-    az_k_gemm_tc<64, tc::EPI_HEAD><<<grid, tc::NUM_THREADS, smem64, st>>>(mapX, mapWh, ga);
+    launch_pdl(az_k_gemm_tc<64, tc::EPI_HEAD>, grid, tc::NUM_THREADS, smem64, st, mapX, mapWh, ga);
     GemmArgs gd{};
     gd.n_boards = n_rows; gd.g = geom; gd.kblocks = KD / 64; gd.gemm_k = 1; gd.rows_per_board = 1; gd.alloc_rows = max_rows + 256;
     gd.bias = d_bd; gd.out32 = d_hid;
     const int board_tiles = (max_rows + tc::BM - 1) / tc::BM;
-    az_k_gemm_tc<128, tc::EPI_DENSE><<<std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem128, st>>>(mapHv, mapWd, gd);
+    launch_pdl(az_k_gemm_tc<128, tc::EPI_DENSE>, std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem128, st, mapHv, mapWd, gd);
     gd.bias = d_bpol; gd.out32 = d_logit; gd.no_relu = 1;   // policy dense: logits[b][0..A) = Wp . hp + b
-    az_k_gemm_tc<64, tc::EPI_DENSE><<<std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem64, st>>>(mapHp, mapWpol, gd);
+    launch_pdl(az_k_gemm_tc<64, tc::EPI_DENSE>, std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem64, st, mapHp, mapWpol, gd);
     FinalArgs fa{d_logit, d_hid, d_wv2, d_bv2};
     az_k_finalize<G><<<(max_rows * 8 + 255) / 256, 256, 0, st>>>(envs, n_rows, fa, P, V, Pinv);
     if (prof) { cudaEventRecord(pe[3], st); prof_evals++; }

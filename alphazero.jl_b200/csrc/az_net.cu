@@ -1,16 +1,24 @@
-// az_net.cu -- policy/value ResNet forward on the leaf batch (replaces Network.forward / forward_normalized /
+// az_net.cu -- policy/value network forward on the leaf batch (replaces Network.forward / forward_normalized /
 // evaluate_batch: src/networks/flux.jl:127-132, src/networks/network.jl:264-271,308-315, and the Flux layers of
-// src/networks/architectures/resnet.jl:53-92).
+// src/networks/architectures/resnet.jl:53-92 and simplenet.jl:37-64).
 //
 // Data layout in HBM.  Activations are fp16 "padded NHWC" rows of F=128 channels:
 //     row(board b, col x, row y) = b*BS + y*(W+1) + x,   BS = (W+1)*(H+1)      (Connect-Four: BS = 56)
 // with column x = W and row y = H kept at ZERO, so that the 3x3 "same" convolution becomes nine row-shifted GEMMs
 //     out[p, co] = sum_{tap} sum_{ci} act[p + off(tap), ci] * Wt[co, tap*F + ci],   off = dy*(W+1) + dx
-// and each tap's A operand is ONE TMA box of 128 consecutive rows (out-of-range rows are zero-filled by TMA).
-// The tower kernel is a warp-specialised tcgen05 implicit GEMM: TMA producer warp -> 6-stage smem ring (SWIZZLE_128B)
-// -> single-thread tcgen05.mma (M=128, N=128, K=16, fp16 operands, fp32 accumulators in TMEM, double buffered)
-// -> 4 epilogue warps (tcgen05.ld, folded-BN bias, residual, ReLU, pad-row zeroing, fp16 store).
-// BatchNorm (test mode, eps = 1e-5) is folded into the conv weights/bias when the blob is loaded.
+// and each tap's A operand is ONE TMA box of consecutive rows (out-of-range rows are zero-filled by TMA).
+//
+// Kernels in this file:
+//   az_k_im2col          leaf states -> 64-wide fp16 im2col rows of the first conv (game's vectorize_state on device)
+//   az_k_gemm_tc<BN,EPI> generic warp-specialised tcgen05 implicit GEMM (TMA producer warp -> 6-stage SWIZZLE_128B smem
+//                        ring -> one elected lane issues tcgen05.mma M=128,N=BN,K=16 fp16->fp32 into double-buffered TMEM
+//                        -> 4 epilogue warps).  Used for the stem conv, the towers of non-Connect-Four geometries, the
+//                        heads' 1x1 convs (N=64) and the value / policy dense layers (plain K-major GEMMs).
+//   az_k_conv_c4_2sm<EPI> Connect-Four tower conv: 2-CTA cluster, cta_group::2 MMA, resident half-N weights, 3 dx-shifted
+//                        A copies reused by the dy taps, coalesced epilogue with the fp32 residual stream.
+//   az_k_finalize        softmax + legal-action mask + renormalisation, tanh value.
+//   az_k_simplenet       fused fp32 MLP (SimpleNet).
+// BatchNorm (test mode, eps = 1e-5) is folded into the conv / dense weights and biases when the blob is loaded.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -699,7 +707,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
 template <class G>
 struct ResNetImpl : az_net {
   az_resnet_hp hp{};
-  static constexpr int F = 128, W = G::XW, H = G::XH, C = G::XC, A = G::A, AP = (A + 3) & ~3, BS = (W + 1) * (H + 1), WH = W * H;
+  static constexpr int F = 128, W = G::XW, H = G::XH, C = G::XC, A = G::A, BS = (W + 1) * (H + 1), WH = W * H;
   static constexpr int VR = (W + 1) * H;                       // rows of a board up to (excluding) the pad row
   static constexpr int KP = VR * 32;                           // policy / value feature length (pad columns carry zero weights)
   static constexpr int KD = (KP + 63) / 64 * 64;               // value-dense K rounded to the 64-wide K block
@@ -711,7 +719,7 @@ struct ResNetImpl : az_net {
   float* d_logit = nullptr;     // [boards][128]
   std::vector<__half*> d_wconv; std::vector<float*> d_bconv;
   __half *d_wh = nullptr, *d_wd = nullptr;
-  float *d_bh = nullptr, *d_bd = nullptr, *d_wv2 = nullptr, *d_bv2 = nullptr, *d_wp = nullptr, *d_bp = nullptr;
+  float *d_bh = nullptr, *d_bd = nullptr, *d_wv2 = nullptr, *d_bv2 = nullptr;
   std::vector<CUtensorMap> mapW;
   CUtensorMap mapWh{}, mapWd{};
   // activations (allocated for max_rows on first use)
@@ -821,9 +829,9 @@ struct ResNetImpl : az_net {
     for (auto p : d_wconv) cudaFree(p);
     for (auto p : d_bconv) cudaFree(p);
     d_wconv.clear(); d_bconv.clear(); mapW.clear(); mapW2.clear();
-    cudaFree(d_wh); cudaFree(d_wd); cudaFree(d_bh); cudaFree(d_bd); cudaFree(d_wv2); cudaFree(d_bv2); cudaFree(d_wp); cudaFree(d_bp);
+    cudaFree(d_wh); cudaFree(d_wd); cudaFree(d_bh); cudaFree(d_bd); cudaFree(d_wv2); cudaFree(d_bv2);
     cudaFree(d_wpol); cudaFree(d_bpol); d_wpol = nullptr; d_bpol = nullptr;
-    d_bstem = d_bh = d_bd = d_wv2 = d_bv2 = d_wp = d_bp = nullptr; d_wh = d_wd = d_wstem = nullptr;
+    d_bstem = d_bh = d_bd = d_wv2 = d_bv2 = nullptr; d_wh = d_wd = d_wstem = nullptr;
   }
   void free_act() {
     cudaFree(d_x32); cudaFree(d_hid); cudaFree(d_x16); cudaFree(d_t16); cudaFree(d_hp); cudaFree(d_hv); cudaFree(d_x0); cudaFree(d_logit);

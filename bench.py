@@ -85,7 +85,7 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": reasons, "samples": len(sm)}
 
 
-def make_eta(oz_or_none, roots, A, seed):
+def make_eta(_unused, roots, A, seed):
     """Dirichlet(1) root noise per tree; generated with numpy here (bench input, not a parity path)."""
     rng = np.random.default_rng(seed)
     eta = np.zeros((len(roots), A))

@@ -257,7 +257,7 @@ def main():
         spec_d = importlib.util.spec_from_file_location("az_distributed", os.path.join(ROOT, "alphazero.jl_b200", "distributed.py"))
         azd = importlib.util.module_from_spec(spec_d)
         spec_d.loader.exec_module(azd)
-        total_games = S * world
+        total_games = 2 * S * world   # two games per worker slot, 4096 games in flight per GPU at any time
         count, first = azd.split_games(total_games, world, rank)
         spp = az.SelfPlayParams(
             az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, temperature=az.PLSchedule([0, 20, 30], [1.0, 1.0, 0.3]),
@@ -308,7 +308,7 @@ def main():
                                 "allgather_seconds": sp_out["t_gather"], "games": int(sp_out["games"]), "samples": int(sp_out["samples"]),
                                 "gathered_samples_on_rank0": sp_out["total_samples"], "mean_moves_per_game": sp_out["mean_moves"],
                                 "mean_exploration_depth": sp_out["mean_edepth"],
-                                "config": "simulate(): %d games per GPU (one per worker slot), 600 sims/move, cpuct 2, eps 0.25, tau PL([0,20,30],[1,1,.3]), reset_every 2; wall clock incl. sample D2H + all-gather" % S}
+                                "config": "simulate(): %d games per GPU on 4096 concurrent worker slots (two per slot), 600 sims/move, cpuct 2, eps 0.25, tau PL([0,20,30],[1,1,.3]), reset_every 2; wall clock incl. sample D2H + all-gather" % (2 * S)}
         if prof and prof["evals"]:
             peak, how = peaks()
             nconv = 2 * args.blocks

@@ -419,6 +419,7 @@ struct SelfPlay : az_selfplay {
     for (int i = 0; i < mp->temperature_n; i++) { sp.sched_xs[i] = mp->temperature_xs[i]; sp.sched_ys[i] = mp->temperature_ys[i]; }
     AZ_TRY(ctx, alloc(&sp.game_of_slot, S)); AZ_TRY(ctx, alloc(&sp.move_of_slot, S)); AZ_TRY(ctx, alloc(&sp.games_on_slot, S));
     AZ_TRY(ctx, alloc(&sp.games_done, 1)); AZ_TRY(ctx, alloc(&sp.active_slots, 1));
+    AZ_TRY(ctx, alloc(&sp.next_game, 1)); AZ_TRY(ctx, alloc(&sp.want_game, S));
     AZ_CUDA(ctx, cudaMallocHost((void**)&h_pin, 64));
     return AZ_OK;
   }
@@ -451,17 +452,20 @@ struct SelfPlay : az_selfplay {
     cudaSetDevice(ctx->device);
     AZ_CUDA(ctx, cudaMemsetAsync(sp.games_done, 0, 4, ctx->stream));
     AZ_CUDA(ctx, cudaMemsetAsync(sp.active_slots, 0, 4, ctx->stream));
+    AZ_CUDA(ctx, cudaMemsetAsync(sp.next_game, 0, 4, ctx->stream));
     AZ_CUDA(ctx, cudaMemsetAsync(m.p.expansions, 0, 8, ctx->stream));
     AZ_TRY(ctx, m.reset());
     const int grid1 = (m.p.S + 127) / 128;
     az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 1);
-    ctx->launches++;
+    az_k_assign<G><<<1, 1024, 0, ctx->stream>>>(m.p, sp);
+    ctx->launches += 2;
     int64_t tick = 0;
     m.drop_graph();  // `sp` (game range, buffers) is baked into the captured move-kernel launch
     for (;;) {
       AZ_TRY(ctx, m.tick_graphed([&] {
         az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 0);
-        ctx->launches++;
+        az_k_assign<G><<<1, 1024, 0, ctx->stream>>>(m.p, sp);
+        ctx->launches += 2;
       }));
       tick++;
       if (tick % 32 == 0) {

@@ -403,7 +403,9 @@ struct AzSelfPlay {
   double* g_edepth;
   int64_t* g_nodes;
   int32_t* games_done;     // [1]
-  int32_t* active_slots;   // [1]
+  int32_t* active_slots;   // [1] (unused)
+  int32_t* next_game;      // [1] shared game counter of Util.mapreduce (src/util.jl:172-186)
+  uint8_t* want_game;      // [S] slot finished its game this tick and asks for the next one
 };
 
 __device__ __forceinline__ double az_schedule(const AzSelfPlay& sp, int i) {  // src/schedule.jl:64-80
@@ -428,52 +430,86 @@ __device__ void az_begin_move(const AzPool& p, const AzSelfPlay& sp, int slot, c
   for (int i = 0; i < n; i++) p.eta[(size_t)slot * A + i] = eta[i];
 }
 
-// Worker loop of simulate() (src/simulations.jl:221-241) for one slot: record the measurements of the game that just
-// ended, apply reset_every, and start the slot's next game (static map: game = slot + S * k).  A game whose initial
-// state is already terminal (possible in grid-world: RL.reset! may pick a reward cell) ends at once with an empty trace,
-// exactly as play_game returns immediately (src/play.jl:301-304).
+// End of a game on a slot: self_play_measurements (src/training.jl:269-273, measured before the reset), reset_every
+// (src/simulations.jl:235-237).  The slot then asks az_k_assign for its next game.
 template <class G>
-__device__ void az_finish_game_and_start_next(AzPool& p, AzSelfPlay& sp, int slot, int g, int n_moves) {
+__device__ void az_record_game_end(AzPool& p, AzSelfPlay& sp, int slot, int g, int n_moves) {
   constexpr int L = G::LANES;
+  sp.g_moves[g] = n_moves;
+  sp.g_nodes[g] = p.node_count[slot];
+  const int64_t ts = p.total_sims[slot];
+  sp.g_edepth[g] = ts == 0 ? 0.0 : (double)p.total_nodes[slot] / (double)ts;
+  atomicAdd(sp.games_done, 1);
+  const int gos = sp.games_on_slot[slot] + 1;
+  sp.games_on_slot[slot] = gos;
+  if (sp.reset_every > 0 && gos % sp.reset_every == 0) {
+    uint32_t gen = (p.tag[slot] & 63u) + 1u;
+    if (gen == 64u) {
+      uint4* wt = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
+      size_t cnt = ((size_t)p.cap_mask + 1) * L;
+      for (size_t i = 0; i < cnt; i++) wt[i] = make_uint4(0, 0, 0, 0);
+      gen = 1u;
+    }
+    p.tag[slot] = 64u | gen;
+    p.node_count[slot] = 0;
+  }
+  sp.game_of_slot[slot] = -1;
+  p.status[slot] = 0;
+  p.sims_target[slot] = 0;
+  sp.want_game[slot] = 1;
+}
+
+// Dynamic game assignment = the shared counter of Util.mapreduce (src/util.jl:169-200): a worker that finishes a game
+// takes the next unplayed game index.  Workers that finish in the same tick are served in slot order, which makes the
+// game -> worker map deterministic (every move lasts exactly nsims ticks when select runs one simulation per call).
+// One block; loops because a game whose initial state is already terminal (grid-world: RL.reset! may pick a reward
+// cell) ends at once with an empty trace, exactly as play_game returns immediately (src/play.jl:301-304).
+template <class G>
+__global__ void __launch_bounds__(1024) az_k_assign(AzPool p, AzSelfPlay sp) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_base, s_total, s_again;
   for (;;) {
-    if (g >= 0) {  // self_play_measurements (src/training.jl:269-273), measured before the reset
-      sp.g_moves[g] = n_moves;
-      sp.g_nodes[g] = p.node_count[slot];
-      const int64_t ts = p.total_sims[slot];
-      sp.g_edepth[g] = ts == 0 ? 0.0 : (double)p.total_nodes[slot] / (double)ts;
-      atomicAdd(sp.games_done, 1);
-      const int gos = sp.games_on_slot[slot] + 1;
-      sp.games_on_slot[slot] = gos;
-      if (sp.reset_every > 0 && gos % sp.reset_every == 0) {  // reset_player! (src/simulations.jl:235-237)
-        uint32_t gen = (p.tag[slot] & 63u) + 1u;
-        if (gen == 64u) {
-          uint4* wt = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
-          size_t cnt = ((size_t)p.cap_mask + 1) * L;
-          for (size_t i = 0; i < cnt; i++) wt[i] = make_uint4(0, 0, 0, 0);
-          gen = 1u;
-        }
-        p.tag[slot] = 64u | gen;
-        p.node_count[slot] = 0;
+    if (threadIdx.x == 0) { s_base = *sp.next_game; s_total = 0; s_again = 0; }
+    __syncthreads();
+    for (int start = 0; start < p.S; start += blockDim.x) {
+      const int slot = start + threadIdx.x;
+      const int want = (slot < p.S && sp.want_game[slot]) ? 1 : 0;
+      // inclusive scan of `want` over the block (slot order)
+      s_scan[threadIdx.x] = want;
+      __syncthreads();
+      for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+        int v = threadIdx.x >= (unsigned)off ? s_scan[threadIdx.x - off] : 0;
+        __syncthreads();
+        s_scan[threadIdx.x] += v;
+        __syncthreads();
       }
+      const int rank = s_total + s_scan[threadIdx.x] - want;
+      const int chunk_total = s_scan[blockDim.x - 1];
+      if (want) {
+        const int ng = s_base + rank;
+        sp.want_game[slot] = 0;
+        if (ng < sp.num_games) {
+          const AzEnv first = G::init_game(sp.seed, (uint64_t)(sp.first_game + ng));
+          if (!G::terminated(first)) {
+            sp.game_of_slot[slot] = ng;
+            sp.move_of_slot[slot] = 0;
+            p.status[slot] = 1;
+            p.pending[slot] = 0;
+            az_begin_move<G>(p, sp, slot, first, sp.first_game + ng, 0);
+          } else {
+            az_record_game_end<G>(p, sp, slot, ng, 0);  // empty game; asks again in the next round
+            s_again = 1;
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) s_total += chunk_total;
+      __syncthreads();
     }
-    const int ng = slot + p.S * sp.games_on_slot[slot];
-    if (ng >= sp.num_games) {
-      sp.game_of_slot[slot] = -1;
-      p.status[slot] = 0;
-      p.sims_target[slot] = 0;
-      return;
-    }
-    const AzEnv first = G::init_game(sp.seed, (uint64_t)(sp.first_game + ng));
-    if (!G::terminated(first)) {
-      sp.game_of_slot[slot] = ng;
-      sp.move_of_slot[slot] = 0;
-      p.status[slot] = 1;
-      p.pending[slot] = 0;
-      az_begin_move<G>(p, sp, slot, first, sp.first_game + ng, 0);
-      return;
-    }
-    g = ng;       // empty game: loop to record it and move on
-    n_moves = 0;
+    if (threadIdx.x == 0) *sp.next_game = min(s_base + s_total, sp.num_games);
+    __syncthreads();
+    if (!s_again) break;
+    __syncthreads();
   }
 }
 
@@ -484,12 +520,15 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
   constexpr int A = G::A;
   int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= p.S) return;
-  if (start_games) {  // assign the first game of every slot (static round-robin: game = slot + S * k)
+  if (start_games) {  // every worker starts by asking for a game (az_k_assign serves them in slot order)
     p.total_sims[slot] = 0;
     p.total_nodes[slot] = 0;
     sp.games_on_slot[slot] = 0;
+    sp.game_of_slot[slot] = -1;
     p.status[slot] = 0;
-    az_finish_game_and_start_next<G>(p, sp, slot, -1, 0);
+    p.sims_target[slot] = 0;
+    p.pending[slot] = 0;
+    sp.want_game[slot] = 1;
     return;
   }
   if (!p.status[slot] || p.pending[slot] || p.sims_done[slot] < p.sims_target[slot]) return;
@@ -576,7 +615,7 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
       sp.s_z[ri] = (float)(G::white_playing(sp.s_env[ri]) ? wr : -wr);
       sp.s_t[ri] = (float)(nm - i);
     }
-    az_finish_game_and_start_next<G>(p, sp, slot, g, nm);
+    az_record_game_end<G>(p, sp, slot, g, nm);
   } else {
     sp.move_of_slot[slot] = nm;
     az_begin_move<G>(p, sp, slot, nx, game, nm);

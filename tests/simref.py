@@ -1,0 +1,70 @@
+"""Oracle-side simulate() with the dynamic game assignment of Util.mapreduce (src/util.jl:169-200), emulating the engine's
+lock-step ticks: a move lasts exactly `nsims` ticks (select runs one simulation per call), workers that finish in the
+same tick take the next game indices in slot order, and a game that starts on a terminal state (grid-world) ends at once
+and its worker asks again in the next round of the same tick."""
+import ctypes as C
+
+import numpy as np
+
+
+def oracle_simulate(oz, gid, oracle, omp, seed, S, NG, reset_every):
+    L = oz.lib()
+    fn = oz.builtin_oracle(oracle) if isinstance(oracle, str) else oracle
+    envs = [L.oz_env_create(gid, fn, None, omp.gamma, omp.cpuct, omp.noise_eps, omp.noise_alpha, omp.prior_temperature) for _ in range(S)]
+    A, sb = oz.num_actions(gid), oz.state_bytes(gid)
+    nsims = omp.num_iters_per_turn
+    free_at = {w: 0 for w in range(S)}
+    played = [0] * S
+    traces, slot_of = {}, {}
+    nxt = 0
+    tr = oz.Trace()
+    while nxt < NG:
+        t = min(free_at.values())
+        asking = sorted(w for w, ft in free_at.items() if ft == t)
+        while asking and nxt < NG:
+            again = []
+            for w in asking:
+                if nxt >= NG:
+                    break
+                g = nxt
+                nxt += 1
+                L.oz_play_game(envs[w], C.byref(omp), seed, g, C.byref(tr))
+                n = tr.n_moves
+                traces[g] = dict(n_moves=n, states=np.ctypeslib.as_array(tr.states)[:n + 1, :sb].copy(),
+                                 pi=np.ctypeslib.as_array(tr.pi)[:n, :A].copy(), mask=np.ctypeslib.as_array(tr.mask)[:n, :A].copy(),
+                                 action=np.ctypeslib.as_array(tr.action)[:n].copy(), rewards=np.ctypeslib.as_array(tr.rewards)[:n].copy(),
+                                 z=np.ctypeslib.as_array(tr.z)[:n].copy(), t=np.ctypeslib.as_array(tr.t)[:n].copy(),
+                                 mem_nodes=tr.mem_nodes, edepth=tr.edepth)
+                slot_of[g] = w
+                played[w] += 1
+                if reset_every > 0 and played[w] % reset_every == 0:
+                    L.oz_env_reset(envs[w])
+                free_at[w] = t + n * nsims
+                if n == 0:
+                    again.append(w)
+            asking = again
+        if nxt >= NG:
+            break
+        # workers that did not get a game this tick because the games ran out stay idle
+    for e in envs:
+        L.oz_env_destroy(e)
+    return traces, slot_of
+
+
+def assert_same_samples(out, traces, check_mask=True):
+    k = 0
+    for g in sorted(traces):
+        tr = traces[g]
+        rows = np.flatnonzero(out["game"] == g)
+        n = tr["n_moves"]
+        assert len(rows) == n == out["moves"][g], (g, len(rows), n, out["moves"][g])
+        assert (out["actions"][rows] == tr["action"]).all(), g
+        assert (out["states"][rows] == tr["states"][:n]).all(), g
+        assert (out["pi"][rows].view(np.uint32) == tr["pi"].view(np.uint32)).all(), g
+        if check_mask:
+            assert (out["mask"][rows] == tr["mask"]).all(), g
+        assert (out["rewards"][rows] == tr["rewards"]).all(), g
+        assert (out["z"][rows] == tr["z"].astype(np.float32)).all() and (out["t"][rows] == tr["t"]).all(), g
+        assert out["nodes"][g] == tr["mem_nodes"] and out["edepth"][g] == tr["edepth"], g
+        k += n
+    assert k == len(out["game"]) == out["samples"]

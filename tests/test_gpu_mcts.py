@@ -117,7 +117,7 @@ def test_explore_without_noise_and_gamma(az, oz, ctx):
 @pytest.mark.parametrize("game,nsims,temp", [("connect-four", 64, ([0, 20, 30], [1.0, 1.0, 0.3])),
                                               ("tictactoe", 50, ([0], [1.0])), ("mancala", 32, ([0, 10], [1.0, 0.0]))])
 def test_selfplay_bit_exact(az, oz, ctx, game, nsims, temp):
-    """simulate() with 8 workers, 24 games, reset_every 2 against oracle workers (static game->worker map)."""
+    """simulate() with 8 workers, 24 games, reset_every 2 against the oracle (dynamic game -> worker map of Util.mapreduce)."""
     gs = az.GameSpec(game)
     gid = oz.game_id(game)
     S, NG, seed = 8, 24, 77
@@ -129,23 +129,10 @@ def test_selfplay_bit_exact(az, oz, ctx, game, nsims, temp):
     out = az.simulate(ctx, gs, net, az.SelfPlayParams(mp, sp), seed=seed, game_simulated=lambda: called.append(1))
     assert len(called) == NG
     omp = oz.mcts_params(cpuct=2.0, noise_eps=0.25, noise_alpha=1.0, num_iters_per_turn=nsims, sched_xs=temp[0], sched_ys=temp[1])
-    k = 0
-    for w in range(S):
-        traces = oz.worker_run(gid, "synth", omp, seed, first=w, stride=S, count=NG // S, reset_every=2)
-        for j, tr in enumerate(traces):
-            g = w + S * j
-            rows = np.flatnonzero(out["game"] == g)
-            n = tr["n_moves"]
-            assert len(rows) == n == out["moves"][g], (g, len(rows), n)
-            assert (out["actions"][rows] == tr["action"]).all()
-            assert (out["states"][rows] == tr["states"][:n]).all()
-            assert (out["pi"][rows].view(np.uint32) == tr["pi"].view(np.uint32)).all()
-            assert (out["mask"][rows] == tr["mask"]).all()
-            assert (out["rewards"][rows] == tr["rewards"]).all()
-            assert (out["z"][rows] == tr["z"].astype(np.float32)).all() and (out["t"][rows] == tr["t"]).all()
-            assert out["nodes"][g] == tr["mem_nodes"] and out["edepth"][g] == tr["edepth"]
-            k += n
-    assert k == len(out["game"]) == out["samples"]
+    from tests import simref
+    traces, slot_of = simref.oracle_simulate(oz, gid, "synth", omp, seed, S, NG, 2)
+    assert sorted(traces) == list(range(NG)) and [slot_of[g] for g in range(S)] == list(range(S))
+    simref.assert_same_samples(out, traces)
     net.close()
 
 
@@ -260,15 +247,8 @@ def test_grid_world_explore_and_selfplay_bit_exact(az, oz, ctx, kind):
                         dirichlet_noise_alpha=1.0)
     out = az.simulate(ctx, gs, net, az.SelfPlayParams(mp2, az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=4)), seed=31)
     omp = oz.mcts_params(gamma=0.9, cpuct=1.0, num_iters_per_turn=ns2, sched_xs=(0,), sched_ys=(0.0,))
-    for w in range(S):
-        traces = oz.worker_run(gid, ofn, omp, 31, first=w, stride=S, count=NG // S, reset_every=4)
-        for j, tr in enumerate(traces):
-            g = w + S * j
-            rows = np.flatnonzero(out["game"] == g)
-            assert len(rows) == tr["n_moves"] == out["moves"][g] and 0 <= tr["n_moves"] <= 201  # 0: started on a reward cell
-            assert (out["states"][rows] == tr["states"][:-1]).all() and (out["actions"][rows] == tr["action"]).all()
-            assert (out["rewards"][rows] == tr["rewards"]).all()
-            assert (out["z"][rows] == tr["z"].astype(np.float32)).all() and (out["t"][rows] == tr["t"]).all()
-            assert (out["pi"][rows].view(np.uint32) == tr["pi"].view(np.uint32)).all()
-            assert out["nodes"][g] == tr["mem_nodes"] and out["edepth"][g] == tr["edepth"]
+    from tests import simref
+    traces, _ = simref.oracle_simulate(oz, gid, ofn, omp, 31, S, NG, 4)
+    assert all(0 <= tr["n_moves"] <= 201 for tr in traces.values())  # 0: the game started on a reward cell
+    simref.assert_same_samples(out, traces)
     net.close()

@@ -153,17 +153,9 @@ def test_selfplay_with_network_bit_exact(az, oz, ctx):
 
     fn = oz.ORACLE_FN(cb)
     omp = oz.mcts_params(cpuct=2.0, noise_eps=0.25, noise_alpha=1.0, num_iters_per_turn=nsims, sched_xs=(0, 20, 30), sched_ys=(1.0, 1.0, 0.3))
-    for w in range(S):
-        traces = oz.worker_run(gid, C.cast(fn, C.c_void_p), omp, seed, first=w, stride=S, count=NG // S, reset_every=2)
-        for j, tr in enumerate(traces):
-            g = w + S * j
-            rows = np.flatnonzero(out["game"] == g)
-            assert len(rows) == tr["n_moves"]
-            assert (out["actions"][rows] == tr["action"]).all()
-            assert (out["states"][rows] == tr["states"][:-1]).all()
-            assert (out["pi"][rows].view(np.uint32) == tr["pi"].view(np.uint32)).all()
-            assert (out["z"][rows] == tr["z"].astype(np.float32)).all()
-            assert out["nodes"][g] == tr["mem_nodes"] and out["edepth"][g] == tr["edepth"]
+    from tests import simref
+    traces, _ = simref.oracle_simulate(oz, gid, C.cast(fn, C.c_void_p), omp, seed, S, NG, 2)
+    simref.assert_same_samples(out, traces, check_mask=False)
     net.close()
 
 

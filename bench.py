@@ -38,6 +38,33 @@ METRIC = "mcts_node_expansions_per_s"
 NCU_TRAFFIC_BYTES = 134.7e6
 
 
+def resnet_blob(dim, num_actions, hp, seed=1):
+    """Random-init weights of a freshly constructed Flux ResNet (Glorot-uniform conv/dense weights, zero biases,
+    BatchNorm gamma=1 beta=0 mu=0 sigma2=1) in the blob order az_net_load expects (include/azb200.h).  Kept here so that
+    the product arm of the bench never imports oracle/."""
+    W, H, C = dim
+    nf, nb, npf, nvf = hp["num_filters"], hp["num_blocks"], hp["num_policy_head_filters"], hp["num_value_head_filters"]
+    rng = np.random.default_rng(seed)
+    parts = []
+
+    def conv(k, ci, co):
+        s = np.sqrt(6.0 / (k * k * ci + k * k * co))
+        parts.extend([rng.uniform(-s, s, k * k * ci * co), np.zeros(co)])
+
+    def bn(n):
+        parts.extend([np.ones(n), np.zeros(n), np.zeros(n), np.ones(n)])
+
+    def dense(out, inn):
+        s = np.sqrt(6.0 / (inn + out))
+        parts.extend([rng.uniform(-s, s, out * inn), np.zeros(out)])
+    conv(3, C, nf); bn(nf)
+    for _ in range(nb):
+        conv(3, nf, nf); bn(nf); conv(3, nf, nf); bn(nf)
+    conv(1, nf, nvf); bn(nvf); dense(nf, W * H * nvf); dense(1, nf)
+    conv(1, nf, npf); bn(npf); dense(num_actions, W * H * npf)
+    return np.concatenate(parts).astype(np.float32)
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -181,11 +208,12 @@ def main():
     gs = az.GameSpec("connect-four")
     S, nsims, A = args.trees, args.nsims, 7
     hp = dict(HP, num_blocks=args.blocks)
-    from tests import netcheck  # blob construction helper only (weights: Glorot-uniform, seed 1, fresh BatchNorm)
     if args.oracle_net:
         net = az.RandomOracle(ctx, gs) if args.oracle_net == "uniform" else az.SynthOracle(ctx, gs)
-    else:
-        net, _ = netcheck.make_net(az, ctx, gs, hp, seed=1, randomize=False)
+    else:  # weights: Glorot-uniform, seed 1, fresh BatchNorm statistics (random init of the named architecture)
+        net = az.ResNet(ctx, gs, az.ResNetHP(hp["num_blocks"], hp["num_filters"], hp["conv_kernel_size"],
+                                             hp["num_policy_head_filters"], hp["num_value_head_filters"]))
+        net.load(resnet_blob(gs.state_dim, gs.num_actions, hp, seed=1))
     mp = az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, dirichlet_noise_eps=0.25, dirichlet_noise_alpha=1.0)
     env = az.MctsEnv(ctx, gs, net, mp, S, capacity_nodes_per_tree=nsims + 8)
     roots = gs.random_positions(SEED_POS, S, 30, first_stream=rank * S)

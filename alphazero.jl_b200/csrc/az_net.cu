@@ -73,6 +73,15 @@ __device__ __forceinline__ bool elect_one() {
       "}" : "=r"(pred));
   return pred != 0;
 }
+// TMA bulk-tensor STORE smem -> global (tile written by the threads first, then fence.proxy.async + one issuing lane)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -390,7 +399,8 @@ struct Smem {
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc3::NUM_THREADS, 1)
-az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmArgs ga) {
+az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmO16, GemmArgs ga) {
   using namespace tc2;
   using tc3::XS;
   constexpr int BN = 128;
@@ -494,6 +504,54 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;
     const int colhalf = (warp - 2) >> 2;
     float* stg = s.stage[warp - 2];
+    if (EPI == tc::EPI_CONV1) {
+      // conv1 epilogue: every thread owns one output ROW (TMEM lane).  bias + ReLU + pad-row zeroing + fp16 conversion
+      // happen in registers, the 32 x 16 fp16 block goes to a 1 KB SWIZZLE_32B smem tile (2 conflict-free 16-byte
+      // stores per thread) and leaves through ONE TMA bulk-tensor store: no smem transpose and no per-row STGs in the
+      // L1TEX data pipe that the tensor core's operand reads share.  Two tiles per warp, alternating.
+      uint8_t* tile0 = reinterpret_cast<uint8_t*>(stg);  // 2 x 1024 B inside this warp's 2560-byte staging area
+      int it = 0;
+      for (int pt = pt0; pt < num_ptiles; pt += pt_step, it++) {
+        const int acc = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int prow0 = pt * 2 * BM + (int)rank * BM + quarter * 32;
+        const int p = prow0 + lane;
+        const int r = p % ga.g.board_rows;
+        const bool valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
+        mbar_wait(&s.tfull[acc], aphase);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int sc = 0; sc < 4; sc++) {
+          const int col = colhalf * 64 + sc * 16;
+          uint32_t v[16];
+          tmem_ld16(tmem_base + acc * BN + col + ((uint32_t)(quarter * 32) << 16), v);
+          uint4 o[2];
+          __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float x0 = __uint_as_float(v[2 * j]) + bias_s[col + 2 * j];
+            float x1 = __uint_as_float(v[2 * j + 1]) + bias_s[col + 2 * j + 1];
+            x0 = valid ? fmaxf(x0, 0.f) : 0.f;
+            x1 = valid ? fmaxf(x1, 0.f) : 0.f;
+            oh[j] = __floats2half2_rn(x0, x1);
+          }
+          uint8_t* tile = tile0 + (sc & 1) * 1024;
+          if (lane == 0) tma_store_wait_read<1>();  // the store issued two blocks ago has finished reading this tile
+          __syncwarp();
+          const int sw = (lane >> 2) & 1;  // SWIZZLE_32B: 16-byte chunk index ^= bit 7 of the byte address (row >> 2)
+          *reinterpret_cast<uint4*>(tile + lane * 32 + ((0 ^ sw) << 4)) = o[0];
+          *reinterpret_cast<uint4*>(tile + lane * 32 + ((1 ^ sw) << 4)) = o[1];
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(ga.debug & 4)) { tma_store_2d(&tmO16, tile, col, prow0); tma_store_commit(); }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&s.tempty[acc], 0);
+      }
+      if (lane == 0) tma_store_wait_all();
+      __syncwarp();
+    } else {
     const int sub_row = lane >> 2, sub_col = (lane & 3) * 4;  // coalesced phase: 8 rows x (4 lanes x 4 floats)
     int it = 0;
     for (int pt = pt0; pt < num_ptiles; pt += pt_step, it++) {
@@ -566,6 +624,7 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&s.tempty[acc], 0);  // the leader's MMA thread owns the accumulators
     }
+    }  // EPI_CONV2
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -678,7 +737,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 // fp16 matrix [outer][inner] with a row pitch in bytes; box = [box_outer][box_inner], SWIZZLE_128B (box_inner = 64 elements)
 static int make_map_2d(az_ctx* ctx, CUtensorMap* m, void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
-                       uint32_t box_inner, uint32_t box_outer) {
+                       uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) { ctx->err = "cuTensorMapEncodeTiled not available"; return AZ_ECUDA; }
   cuuint64_t dims[2] = {inner, outer};
@@ -686,7 +745,7 @@ static int make_map_2d(az_ctx* ctx, CUtensorMap* m, void* base, uint64_t inner, 
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t es[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return AZ_ECUDA; }
   return AZ_OK;
 }
@@ -728,6 +787,7 @@ struct ResNetImpl : az_net {
   __half *d_x16 = nullptr, *d_t16 = nullptr, *d_hp = nullptr, *d_hv = nullptr;
   CUtensorMap mapX{}, mapT{}, mapHv{};
   CUtensorMap mapX2{}, mapT2{};          // Connect-Four tower kernel: 144-row A boxes
+  CUtensorMap mapTo{}, mapXo{};          // TMA-store targets: 32-row x 16-column fp16 boxes, SWIZZLE_32B
   std::vector<CUtensorMap> mapW2;        // 64co x 64k weight boxes
   static constexpr bool C4_TOWER = (W + 1) == 8;
   size_t smem_2sm = 0;
@@ -951,6 +1011,8 @@ struct ResNetImpl : az_net {
     AZ_TRY2(make_map_2d(ctx, &mapT, d_t16, F, alloc_rows, F * 2, tc::BK, tc::BM));
     AZ_TRY2(make_map_2d(ctx, &mapX2, d_x16, F, alloc_rows, F * 2, tc2::BK, tc2::AROWS));
     AZ_TRY2(make_map_2d(ctx, &mapT2, d_t16, F, alloc_rows, F * 2, tc2::BK, tc2::AROWS));
+    AZ_TRY2(make_map_2d(ctx, &mapTo, d_t16, F, alloc_rows, F * 2, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
+    AZ_TRY2(make_map_2d(ctx, &mapXo, d_x16, F, alloc_rows, F * 2, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
     AZ_TRY2(make_map_2d(ctx, &mapHv, d_hv, (uint64_t)BS * 32, alloc_boards, (uint64_t)BS * 32 * 2, tc::BK, tc::BM));
     act_boards = max_boards;
     return AZ_OK;
@@ -979,14 +1041,14 @@ struct ResNetImpl : az_net {
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
     for (int blk = 0; blk < hp.num_blocks; blk++) {
       ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.resid16 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
-      if (c4 && two_sm && use_pdl && blk > 0) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV1>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapX2, mapW2[2 * blk], ga);
-      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], ga);
+      if (c4 && two_sm && use_pdl && blk > 0) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV1>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapX2, mapW2[2 * blk], mapTo, ga);
+      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], mapTo, ga);
       else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
       ga.resid16 = (c4_fast && blk == 0) ? d_x16 : nullptr;
-      if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
-      else if (c4 && two_sm && use_pdl) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV2>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapT2, mapW2[2 * blk + 1], ga);
-      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], ga);
+      if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], mapXo, ga);
+      else if (c4 && two_sm && use_pdl) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV2>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapT2, mapW2[2 * blk + 1], mapXo, ga);
+      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], mapXo, ga);
       else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
     }
     if (prof) cudaEventRecord(pe[2], st);

@@ -386,12 +386,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 namespace tc3 {
 constexpr int ASTAGES = 3;
 constexpr int NUM_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
-constexpr int XS = 20;  // staging row pitch in floats (80 B: 16-byte aligned, conflict-free 128-bit stores)
+constexpr int EPI_BYTES = 4 * 7168;  // conv2: 4 warps x (2 x 2 KB residual tiles + 2 KB fp32 out tile + 1 KB fp16 out tile);
+                                     // conv1: 8 warps x 2 x 1 KB fp16 out tiles
 struct Smem {
   uint8_t b[tc2::NCHUNK][tc2::B_CHUNK];
   uint8_t a[ASTAGES][tc2::A_STAGE];
-  float stage[8][32 * XS];  // one 32x16 fp32 transpose tile per epilogue warp
+  uint8_t epi[EPI_BYTES];
   uint64_t full[ASTAGES], empty[ASTAGES], tfull[2], tempty[2], bfull;
+  uint64_t rbar[4][2];  // conv2: residual-tile arrival barriers per epilogue warp
   uint32_t tmem_base;
   float bias[128];
 };
@@ -400,13 +402,15 @@ struct Smem {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc3::NUM_THREADS, 1)
 az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                 const __grid_constant__ CUtensorMap tmO16, GemmArgs ga) {
+                 const __grid_constant__ CUtensorMap tmO16, const __grid_constant__ CUtensorMap tmX32, GemmArgs ga) {
   using namespace tc2;
-  using tc3::XS;
   constexpr int BN = 128;
   constexpr int ASTAGES = tc3::ASTAGES;
-  extern __shared__ uint8_t smem_raw[];
-  tc3::Smem& s = *reinterpret_cast<tc3::Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // every byte of the 227 KB is used, so there is no slack for manual alignment: the dynamic shared memory window starts
+  // 1024-byte aligned (it follows the 1 KB the system reserves per block); trap loudly if that ever stops being true
+  extern __shared__ __align__(1024) uint8_t smem_c4[];
+  if ((smem_u32(smem_c4) & 1023u) != 0u) __trap();
+  tc3::Smem& s = *reinterpret_cast<tc3::Smem*>(smem_c4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -416,7 +420,8 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 16); }
+    for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], EPI == tc::EPI_CONV1 ? 16 : 8); }
+    for (int i = 0; i < 4; i++) { mbar_init(&s.rbar[i][0], 1); mbar_init(&s.rbar[i][1], 1); }
     mbar_init(&s.bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -503,13 +508,12 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int quarter = warp & 3;
     const int colhalf = (warp - 2) >> 2;
-    float* stg = s.stage[warp - 2];
     if (EPI == tc::EPI_CONV1) {
       // conv1 epilogue: every thread owns one output ROW (TMEM lane).  bias + ReLU + pad-row zeroing + fp16 conversion
       // happen in registers, the 32 x 16 fp16 block goes to a 1 KB SWIZZLE_32B smem tile (2 conflict-free 16-byte
       // stores per thread) and leaves through ONE TMA bulk-tensor store: no smem transpose and no per-row STGs in the
       // L1TEX data pipe that the tensor core's operand reads share.  Two tiles per warp, alternating.
-      uint8_t* tile0 = reinterpret_cast<uint8_t*>(stg);  // 2 x 1024 B inside this warp's 2560-byte staging area
+      uint8_t* tile0 = s.epi + (warp - 2) * 2048;  // 2 x 1024 B per warp
       int it = 0;
       for (int pt = pt0; pt < num_ptiles; pt += pt_step, it++) {
         const int acc = it & 1;
@@ -551,79 +555,94 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (lane == 0) tma_store_wait_all();
       __syncwarp();
-    } else {
-    const int sub_row = lane >> 2, sub_col = (lane & 3) * 4;  // coalesced phase: 8 rows x (4 lanes x 4 floats)
-    int it = 0;
-    for (int pt = pt0; pt < num_ptiles; pt += pt_step, it++) {
-      const int acc = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      const int prow0 = pt * 2 * BM + (int)rank * BM + quarter * 32;
-      uint32_t vmask;  // bit rr: row prow0 + rr is a real board cell inside the used range
-      {
+    } else if (warp < 6) {
+      // conv2 epilogue (4 warps, one per TMEM lane quarter, 8 blocks of 16 columns each): every thread owns one output
+      // ROW.  The fp32 residual block arrives by TMA load into a SWIZZLE_64B smem tile (prefetched one block ahead,
+      // two tiles), the thread reads its own row (4 conflict-free LDS.128), adds bias + residual, applies ReLU / pad-row
+      // zeroing and writes the fp32 and fp16 results into two more swizzled tiles that leave through TMA stores.
+      // No per-row LDG/STG and no smem transpose in the L1TEX data pipe that the tensor core's operand reads share.
+      uint8_t* area = s.epi + (warp - 2) * 7168;
+      uint8_t* o32 = area + 4096;
+      uint8_t* o16 = area + 6144;
+      uint64_t* rb = s.rbar[warp - 2];
+      const bool r16 = ga.resid16 != nullptr;  // block 0: residual = fp16 stem output (X32 not materialised yet)
+      uint32_t rph = 0;                        // bit b = phase of rb[b]
+      const int sw64 = (lane >> 1) & 3;        // SWIZZLE_64B: 16-byte chunk ^= address bits 7-8 = (row >> 1) & 3
+      const int sw32 = (lane >> 2) & 1;        // SWIZZLE_32B: 16-byte chunk ^= address bit 7 = (row >> 2) & 1
+      int it = 0;
+      for (int pt = pt0; pt < num_ptiles; pt += pt_step, it++) {
+        const int acc = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int prow0 = pt * 2 * BM + (int)rank * BM + quarter * 32;
         const int p = prow0 + lane;
         const int r = p % ga.g.board_rows;
         const bool valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
-        vmask = __ballot_sync(0xffffffffu, valid);
-      }
-      const bool do_io = !(ga.debug & 4);
-      float4 res[2][4];
-      auto load_res = [&](int sc, float4* dst) {
-        const int col = colhalf * 64 + sc * 16 + sub_col;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int rr = q * 8 + sub_row;
-          if (!(((vmask >> rr) & 1u) && do_io)) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          else if (ga.resid16 != nullptr) {
-            const uint2 h = *reinterpret_cast<const uint2*>(ga.resid16 + (size_t)(prow0 + rr) * F + col);
-            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
-            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
-            dst[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
-          } else dst[q] = __ldcs(reinterpret_cast<const float4*>(ga.resid32 + (size_t)(prow0 + rr) * F + col));
+        if (lane == 0) {
+          mbar_expect_tx(&rb[0], r16 ? 1024u : 2048u);
+          tma_load_2d(area, r16 ? &tmO16 : &tmX32, &rb[0], 0, prow0);
         }
-      };
-      if (EPI == tc::EPI_CONV2) load_res(0, res[0]);
-      mbar_wait(&s.tfull[acc], aphase);
-      tcgen05_fence_after();
+        mbar_wait(&s.tfull[acc], aphase);
+        tcgen05_fence_after();
 #pragma unroll
-      for (int sc = 0; sc < 4; sc++) {
-        const int col = colhalf * 64 + sc * 16;
-        if (EPI == tc::EPI_CONV2 && sc + 1 < 4) load_res(sc + 1, res[(sc + 1) & 1]);
-        uint32_t v[16];
-        tmem_ld16(tmem_base + acc * BN + col + ((uint32_t)(quarter * 32) << 16), v);
+        for (int j = 0; j < 8; j++) {
+          const int col = j * 16;
+          if (j + 1 < 8 && lane == 0) {  // prefetch the next residual block into the other tile
+            mbar_expect_tx(&rb[(j + 1) & 1], r16 ? 1024u : 2048u);
+            tma_load_2d(area + ((j + 1) & 1) * 2048, r16 ? &tmO16 : &tmX32, &rb[(j + 1) & 1], col + 16, prow0);
+          }
+          uint32_t v[16];
+          tmem_ld16(tmem_base + acc * BN + col + ((uint32_t)(quarter * 32) << 16), v);
+          mbar_wait(&rb[j & 1], (rph >> (j & 1)) & 1u);
+          rph ^= 1u << (j & 1);
+          const uint8_t* in = area + (j & 1) * 2048;
+          float x[16];
+          if (r16) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          float4 t;
-          t.x = __uint_as_float(v[4 * j]) + bias_s[col + 4 * j];
-          t.y = __uint_as_float(v[4 * j + 1]) + bias_s[col + 4 * j + 1];
-          t.z = __uint_as_float(v[4 * j + 2]) + bias_s[col + 4 * j + 2];
-          t.w = __uint_as_float(v[4 * j + 3]) + bias_s[col + 4 * j + 3];
-          *reinterpret_cast<float4*>(stg + lane * XS + 4 * j) = t;
-        }
-        __syncwarp();
+            for (int c = 0; c < 2; c++) {
+              const uint4 h = *reinterpret_cast<const uint4*>(in + lane * 32 + ((c ^ sw32) << 4));
+              const __half2* hh = reinterpret_cast<const __half2*>(&h);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int rr = q * 8 + sub_row;
-          const int p = prow0 + rr;
-          float4 y = *reinterpret_cast<const float4*>(stg + rr * XS + sub_col);
-          const bool valid = (vmask >> rr) & 1u;
-          if (EPI == tc::EPI_CONV2) { const float4 r4 = res[sc & 1][q]; y.x += r4.x; y.y += r4.y; y.z += r4.z; y.w += r4.w; }
-          y.x = valid ? fmaxf(y.x, 0.f) : 0.f; y.y = valid ? fmaxf(y.y, 0.f) : 0.f;
-          y.z = valid ? fmaxf(y.z, 0.f) : 0.f; y.w = valid ? fmaxf(y.w, 0.f) : 0.f;
-          if (p < ga.alloc_rows && do_io) {
-            if (EPI == tc::EPI_CONV2) __stcs(reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + col + sub_col), y);
-            __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
-            uint2 o;
-            o.x = *reinterpret_cast<uint32_t*>(&h0);
-            o.y = *reinterpret_cast<uint32_t*>(&h1);
-            *reinterpret_cast<uint2*>(ga.out16a + (size_t)p * F + col + sub_col) = o;
+              for (int q = 0; q < 4; q++) { const float2 f = __half22float2(hh[q]); x[8 * c + 2 * q] = f.x; x[8 * c + 2 * q + 1] = f.y; }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              const float4 f = *reinterpret_cast<const float4*>(in + lane * 64 + ((c ^ sw64) << 4));
+              x[4 * c] = f.x; x[4 * c + 1] = f.y; x[4 * c + 2] = f.z; x[4 * c + 3] = f.w;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 16; q++) {
+            const float y = __uint_as_float(v[q]) + bias_s[col + q] + x[q];
+            x[q] = valid ? fmaxf(y, 0.f) : 0.f;
+          }
+          if (lane == 0) tma_store_wait_read<0>();  // the previous block's stores have finished reading o32 / o16
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+            *reinterpret_cast<float4*>(o32 + lane * 64 + ((c ^ sw64) << 4)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int q = 0; q < 4; q++) oh[q] = __floats2half2_rn(x[8 * c + 2 * q], x[8 * c + 2 * q + 1]);
+            *reinterpret_cast<uint4*>(o16 + lane * 32 + ((c ^ sw32) << 4)) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmX32, o32, col, prow0);
+            tma_store_2d(&tmO16, o16, col, prow0);
+            tma_store_commit();
           }
         }
+        tcgen05_fence_before();
         __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&s.tempty[acc], 0);
       }
-      tcgen05_fence_before();
+      if (lane == 0) tma_store_wait_all();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&s.tempty[acc], 0);  // the leader's MMA thread owns the accumulators
-    }
     }  // EPI_CONV2
   }
   tcgen05_fence_before();
@@ -737,14 +756,15 @@ static PFN_encodeTiled get_encode_fn() {
 }
 // fp16 matrix [outer][inner] with a row pitch in bytes; box = [box_outer][box_inner], SWIZZLE_128B (box_inner = 64 elements)
 static int make_map_2d(az_ctx* ctx, CUtensorMap* m, void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
-                       uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                       uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
+                       CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) { ctx->err = "cuTensorMapEncodeTiled not available"; return AZ_ECUDA; }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(m, dt, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return AZ_ECUDA; }
   return AZ_OK;
@@ -788,6 +808,7 @@ struct ResNetImpl : az_net {
   CUtensorMap mapX{}, mapT{}, mapHv{};
   CUtensorMap mapX2{}, mapT2{};          // Connect-Four tower kernel: 144-row A boxes
   CUtensorMap mapTo{}, mapXo{};          // TMA-store targets: 32-row x 16-column fp16 boxes, SWIZZLE_32B
+  CUtensorMap mapX32{};                  // fp32 residual stream: 32-row x 16-column boxes, SWIZZLE_64B (TMA load + store)
   std::vector<CUtensorMap> mapW2;        // 64co x 64k weight boxes
   static constexpr bool C4_TOWER = (W + 1) == 8;
   size_t smem_2sm = 0;
@@ -863,7 +884,8 @@ struct ResNetImpl : az_net {
     AZ_TRY2(set_smem(az_k_gemm_tc<128, tc::EPI_DENSE>, smem128));
     AZ_TRY2(set_smem(az_k_gemm_tc<64, tc::EPI_HEAD>, smem64));
     AZ_TRY2(set_smem(az_k_gemm_tc<64, tc::EPI_DENSE>, smem64));
-    smem_2sm = sizeof(tc3::Smem) + 1024;
+    smem_2sm = sizeof(tc3::Smem);
+    static_assert(sizeof(tc3::Smem) <= 232448, "Connect-Four tower kernel exceeds the 227 KB shared-memory limit");
     AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV1>, smem_2sm));
     AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV2>, smem_2sm));
     return AZ_OK;
@@ -1013,6 +1035,7 @@ struct ResNetImpl : az_net {
     AZ_TRY2(make_map_2d(ctx, &mapT2, d_t16, F, alloc_rows, F * 2, tc2::BK, tc2::AROWS));
     AZ_TRY2(make_map_2d(ctx, &mapTo, d_t16, F, alloc_rows, F * 2, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
     AZ_TRY2(make_map_2d(ctx, &mapXo, d_x16, F, alloc_rows, F * 2, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
+    AZ_TRY2(make_map_2d(ctx, &mapX32, d_x32, F, alloc_rows, F * 4, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
     AZ_TRY2(make_map_2d(ctx, &mapHv, d_hv, (uint64_t)BS * 32, alloc_boards, (uint64_t)BS * 32 * 2, tc::BK, tc::BM));
     act_boards = max_boards;
     return AZ_OK;
@@ -1041,14 +1064,14 @@ struct ResNetImpl : az_net {
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
     for (int blk = 0; blk < hp.num_blocks; blk++) {
       ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.resid16 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
-      if (c4 && two_sm && use_pdl && blk > 0) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV1>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapX2, mapW2[2 * blk], mapTo, ga);
-      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], mapTo, ga);
+      if (c4 && two_sm && use_pdl && blk > 0) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV1>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapX2, mapW2[2 * blk], mapTo, mapX32, ga);
+      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], mapTo, mapX32, ga);
       else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
       ga.resid16 = (c4_fast && blk == 0) ? d_x16 : nullptr;
-      if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], mapXo, ga);
-      else if (c4 && two_sm && use_pdl) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV2>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapT2, mapW2[2 * blk + 1], mapXo, ga);
-      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], mapXo, ga);
+      if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], mapXo, mapX32, ga);
+      else if (c4 && two_sm && use_pdl) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV2>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapT2, mapW2[2 * blk + 1], mapXo, mapX32, ga);
+      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], mapXo, mapX32, ga);
       else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
     }
     if (prof) cudaEventRecord(pe[2], st);

@@ -164,8 +164,6 @@ struct GemmArgs {
   int rows_per_board;  // rows of the M dimension per board: board_rows (conv/head) or 1 (dense)
   int alloc_rows;
   int no_relu;           // EPI_DENSE: 1 = plain affine output (policy logits)
-  int part;              // -1: whole batch; 0 / 1: first / second part of the board-aligned split (see az_split_boards)
-  int split_pairs;       // CTA pairs of the tower grid (the split keeps the number of tile rounds unchanged)
   int debug;             // timing experiments only (AZ_TOWER_DEBUG bitmask): 4 = no epilogue global I/O
   const float* bias;
   const float* resid32;  // EPI_CONV2
@@ -174,25 +172,6 @@ struct GemmArgs {
   __half* out16a;        // CONV1: T, CONV2: X16, HEAD: policy features
   __half* out16b;        // HEAD: value features
 };
-
-// L2 residency: the fp32 stream + fp16 activations of a whole 4096-tree tick (~157 MB) do not fit the 126 MB L2, which made
-// the conv2 layers HBM-bound.  The Connect-Four network therefore runs as two sequential parts; the split is at a board
-// boundary that is also a 256-row tile boundary (multiples of 32 boards = 7 pair-tiles), so tiles never straddle it and
-// the only rows read across it are zero pad rows; it is placed so that part 0 fills whole tile rounds of the tower grid.
-__device__ __host__ __forceinline__ int az_split_boards(int n_boards, int split_pairs) {
-  const int T = (n_boards * 56 + 255) / 256;
-  const int R = (T + split_pairs - 1) / split_pairs;
-  const int tiles0 = ((R / 2) * split_pairs / 7) * 7;
-  const int s0 = tiles0 / 7 * 32;
-  return s0 < n_boards ? s0 : n_boards;
-}
-__device__ __forceinline__ void az_part_boards(int n_boards, int part, int split_pairs, int* b0, int* b1) {
-  *b0 = 0; *b1 = n_boards;
-  if (part >= 0) {
-    const int s0 = az_split_boards(n_boards, split_pairs);
-    if (part == 0) *b1 = s0; else *b0 = s0;
-  }
-}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(tc::NUM_THREADS, 1)
@@ -204,10 +183,7 @@ az_k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   SmemT& s = *reinterpret_cast<SmemT*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_used = (*ga.n_boards) * ga.rows_per_board;
-  int pb0, pb1;
-  az_part_boards(*ga.n_boards, ga.part, ga.split_pairs, &pb0, &pb1);
-  const int tile_begin = (pb0 * ga.rows_per_board) / BM;                 // part boundaries are tile aligned for the row kernels;
-  const int num_tiles = (pb1 * ga.rows_per_board + BM - 1) / BM;          // the dense kernels may recompute a straddling tile
+  const int num_tiles = (rows_used + BM - 1) / BM;
   const int kblocks = ga.kblocks;
 
   if (threadIdx.x == 0) {
@@ -233,7 +209,7 @@ az_k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     {  // ===== TMA producer (warp-uniform; one elected lane issues) =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile_begin + blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < kblocks; kb++) {
           mbar_wait(&s.empty[stage], phase ^ 1);
           if (elect_one()) {
@@ -252,7 +228,7 @@ az_k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = tile_begin + blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
         const int acc = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&s.tempty[acc], aphase ^ 1);
@@ -278,7 +254,7 @@ az_k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else {  // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
     const int quarter = warp & 3;
     int it = 0;
-    for (int tile = tile_begin + blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&s.tfull[acc], aphase);
@@ -439,10 +415,8 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int rows_used = (*ga.n_boards) * ga.rows_per_board;
-  int pb0, pb1;
-  az_part_boards(*ga.n_boards, ga.part, ga.split_pairs, &pb0, &pb1);
-  const int num_ptiles = (pb1 * ga.rows_per_board + 2 * BM - 1) / (2 * BM);
-  const int pt0 = (pb0 * ga.rows_per_board) / (2 * BM) + (blockIdx.x >> 1), pt_step = gridDim.x >> 1;
+  const int num_ptiles = (rows_used + 2 * BM - 1) / (2 * BM);
+  const int pt0 = blockIdx.x >> 1, pt_step = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
@@ -689,14 +663,12 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 template <class G>
 __global__ void __launch_bounds__(128) az_k_im2col(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_boards,
-                                                   __half* __restrict__ out /* [rows][64] */, int part, int split_pairs) {
+                                                   __half* __restrict__ out /* [rows][64] */) {
   constexpr int W = G::XW, H = G::XH, C = G::XC, RS = W + 1, BS = (W + 1) * (H + 1), NX = W * H * C;
   __shared__ float xs[4][NX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int pb0, pb1;
-  az_part_boards(*n_boards, part, split_pairs, &pb0, &pb1);
-  const int b = pb0 + blockIdx.x * 4 + warp;
-  if (b >= pb1) return;
+  const int b = blockIdx.x * 4 + warp;
+  if (b >= *n_boards) return;
   float* x = xs[warp];
   if (lane == 0) G::vectorize(envs[b], x);
   __syncwarp();
@@ -734,14 +706,11 @@ struct FinalArgs {
 // (resnet.jl:89-90).  8 lanes per board.
 template <class G>
 __global__ void __launch_bounds__(256) az_k_finalize(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_boards, FinalArgs fa,
-                                                     float* __restrict__ P, float* __restrict__ V, float* __restrict__ Pinv,
-                                                     int part, int split_pairs) {
+                                                     float* __restrict__ P, float* __restrict__ V, float* __restrict__ Pinv) {
   constexpr int A = G::A;
-  int pb0, pb1;
-  az_part_boards(*n_boards, part, split_pairs, &pb0, &pb1);
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = pb0 + (gid >> 3), sub = gid & 7;
-  const bool active = b < pb1;
+  const int b = gid >> 3, sub = gid & 7;
+  const bool active = b < *n_boards;
   float vacc = 0.0f;
   if (active) {
     const float4* hp = reinterpret_cast<const float4*>(fa.hid + (size_t)b * 128 + sub * 16);
@@ -846,24 +815,22 @@ struct ResNetImpl : az_net {
   ConvGeom geom{};
   bool loaded = false;
   int tower_debug = 0;         // AZ_TOWER_DEBUG=1: every conv uses the conv1 epilogue (timing experiments only)
-  bool split_batch = true;     // AZ_NO_SPLIT=1: run the network on the whole leaf batch at once (no L2-resident halves)
   bool use_pdl = true;         // AZ_NO_PDL=1: plain stream-ordered tower launches
   static constexpr bool two_sm = true;
   bool generic_tower = false;  // AZ_GENERIC_TOWER=1: use the generic 9-tap kernel for Connect Four too (A/B comparison)
   size_t smem128 = 0, smem64 = 0;
-  // profiling: 6 events per evaluation (start, tower begin/end of part 0, tower begin/end of part 1, end)
+  // profiling: 4 events per evaluation (start, tower begin, tower end, end)
   static constexpr int PROF_SLOTS = 8192;
   bool profiling = false;
   std::vector<cudaEvent_t> pev;
   int64_t prof_evals = 0;
-  int prof_parts = 1;
 
   uint64_t gen = 1;
   uint64_t generation() override { return gen; }
   bool capturable() override { return !profiling && act_boards > 0; }
   int set_profiling(int enable) override {
     if (enable && pev.empty()) {
-      pev.resize((size_t)PROF_SLOTS * 6);
+      pev.resize((size_t)PROF_SLOTS * 4);
       for (auto& e : pev) if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "cudaEventCreate failed"; return AZ_ECUDA; }
     }
     cudaStreamSynchronize(ctx->stream);
@@ -876,14 +843,13 @@ struct ResNetImpl : az_net {
     double tw = 0, tt = 0;
     int64_t n = std::min<int64_t>(prof_evals, PROF_SLOTS);
     for (int64_t i = 0; i < n; i++) {
-      float a = 0, a2 = 0, b = 0;
-      cudaEventElapsedTime(&a, pev[i * 6 + 1], pev[i * 6 + 2]);
-      if (prof_parts == 2) cudaEventElapsedTime(&a2, pev[i * 6 + 3], pev[i * 6 + 4]);
-      cudaEventElapsedTime(&b, pev[i * 6 + 0], pev[i * 6 + 5]);
-      tw += a + a2; tt += b;
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, pev[i * 4 + 1], pev[i * 4 + 2]);
+      cudaEventElapsedTime(&b, pev[i * 4 + 0], pev[i * 4 + 3]);
+      tw += a; tt += b;
     }
     if (tower_ms) *tower_ms = tw;
-    if (tower_launches) *tower_launches = n * 2 * hp.num_blocks;  // per conv layer (both parts of a split batch count as one)
+    if (tower_launches) *tower_launches = n * 2 * hp.num_blocks;
     if (total_ms) *total_ms = tt;
     if (evals) *evals = n;
     prof_evals = 0;
@@ -908,7 +874,6 @@ struct ResNetImpl : az_net {
     { const char* e = getenv("AZ_GENERIC_TOWER"); generic_tower = e && e[0] == '1'; }
     { const char* e = getenv("AZ_TOWER_DEBUG"); tower_debug = e ? atoi(e) : 0; }
     { const char* e = getenv("AZ_NO_PDL"); use_pdl = !(e && e[0] == '1'); }
-    { const char* e = getenv("AZ_NO_SPLIT"); split_batch = !(e && e[0] == '1'); }
     geom.row_stride = W + 1; geom.board_rows = BS; geom.valid_rows = VR; geom.wcols = W;
     for (int ky = 0; ky < 3; ky++)
       for (int kx = 0; kx < 3; kx++) geom.off[ky * 3 + kx] = (1 - ky) * (W + 1) + (1 - kx);
@@ -1083,23 +1048,18 @@ struct ResNetImpl : az_net {
     AZ_TRY2(ensure_act(max_rows));
     cudaStream_t st = ctx->stream;
     const bool prof = profiling && prof_evals < PROF_SLOTS;
-    cudaEvent_t* pe = prof ? &pev[(size_t)prof_evals * 6] : nullptr;
+    cudaEvent_t* pe = prof ? &pev[(size_t)prof_evals * 4] : nullptr;
     if (prof) cudaEventRecord(pe[0], st);
     const bool c4_fast = C4_TOWER && !generic_tower && two_sm && hp.num_blocks > 0;
-    const int split_pairs = std::max(1, (ctx->num_sms & ~1) / 2);
-    const int nparts = (c4_fast && split_batch) ? 2 : 1;
-    for (int pi = 0; pi < nparts; pi++) {
-    const int part = nparts == 2 ? pi : -1;
     const int row_tiles = (max_rows * BS + tc::BM - 1) / tc::BM;
     const int grid = std::min(row_tiles, ctx->num_sms);
     GemmArgs ga{};
     ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.debug = 0;
-    ga.part = part; ga.split_pairs = split_pairs;
-    az_k_im2col<G><<<(max_rows + 3) / 4, 128, 0, st>>>(envs, n_rows, d_x0, part, split_pairs);
+    az_k_im2col<G><<<(max_rows + 3) / 4, 128, 0, st>>>(envs, n_rows, d_x0);
     ga.gemm_k = 1; ga.kblocks = 1; ga.bias = d_bstem; ga.out16a = d_x16; ga.out32 = c4_fast ? nullptr : d_x32;
     launch_pdl(az_k_gemm_tc<128, tc::EPI_CONV1>, grid, tc::NUM_THREADS, smem128, st, mapX0, mapWstem, ga);
     ga.gemm_k = 0; ga.out32 = nullptr; ga.debug = tower_debug;
-    if (prof) cudaEventRecord(pe[part <= 0 ? 1 : 3], st);
+    if (prof) cudaEventRecord(pe[1], st);
     const bool c4 = C4_TOWER && !generic_tower;  // Connect-Four geometry -> cta_group::2 kernel, otherwise the generic 9-tap kernel
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
     for (int blk = 0; blk < hp.num_blocks; blk++) {
@@ -1114,7 +1074,7 @@ struct ResNetImpl : az_net {
       else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], mapXo, mapX32, ga);
       else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
     }
-    if (prof) cudaEventRecord(pe[part <= 0 ? 2 : 4], st);
+    if (prof) cudaEventRecord(pe[2], st);
     // heads: 1x1 convs (both heads, N = 64), value dense (K = KD), finalize
     ga.g.off[0] = 0;  // 1x1 conv: single centre tap
     ga.debug = 0;
@@ -1122,16 +1082,15 @@ struct ResNetImpl : az_net {
     launch_pdl(az_k_gemm_tc<64, tc::EPI_HEAD>, grid, tc::NUM_THREADS, smem64, st, mapX, mapWh, ga);
     GemmArgs gd{};
     gd.n_boards = n_rows; gd.g = geom; gd.kblocks = KD / 64; gd.gemm_k = 1; gd.rows_per_board = 1; gd.alloc_rows = max_rows + 256;
-    gd.bias = d_bd; gd.out32 = d_hid; gd.part = part; gd.split_pairs = split_pairs;
+    gd.bias = d_bd; gd.out32 = d_hid;
     const int board_tiles = (max_rows + tc::BM - 1) / tc::BM;
     launch_pdl(az_k_gemm_tc<128, tc::EPI_DENSE>, std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem128, st, mapHv, mapWd, gd);
     gd.bias = d_bpol; gd.out32 = d_logit; gd.no_relu = 1;   // policy dense: logits[b][0..A) = Wp . hp + b
     launch_pdl(az_k_gemm_tc<64, tc::EPI_DENSE>, std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem64, st, mapHp, mapWpol, gd);
     FinalArgs fa{d_logit, d_hid, d_wv2, d_bv2};
-    az_k_finalize<G><<<(max_rows * 8 + 255) / 256, 256, 0, st>>>(envs, n_rows, fa, P, V, Pinv, part, split_pairs);
-    }  // parts
-    if (prof) { cudaEventRecord(pe[5], st); prof_evals++; prof_parts = nparts; }
-    ctx->launches += nparts * (6 + 2 * hp.num_blocks);
+    az_k_finalize<G><<<(max_rows * 8 + 255) / 256, 256, 0, st>>>(envs, n_rows, fa, P, V, Pinv);
+    if (prof) { cudaEventRecord(pe[3], st); prof_evals++; }
+    ctx->launches += 6 + 2 * hp.num_blocks;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ctx->err = std::string("network launch: ") + cudaGetErrorString(e); return AZ_ECUDA; }
     return AZ_OK;

@@ -577,17 +577,19 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int p = prow0 + lane;
         const int r = p % ga.g.board_rows;
         const bool valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
-        if (lane == 0) {  // both residual tiles are requested before the accumulator wait: two blocks of look-ahead
+        if (lane == 0) {
           mbar_expect_tx(&rb[0], r16 ? 1024u : 2048u);
           tma_load_2d(area, r16 ? &tmO16 : &tmX32, &rb[0], 0, prow0);
-          mbar_expect_tx(&rb[1], r16 ? 1024u : 2048u);
-          tma_load_2d(area + 2048, r16 ? &tmO16 : &tmX32, &rb[1], 16, prow0);
         }
         mbar_wait(&s.tfull[acc], aphase);
         tcgen05_fence_after();
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const int col = j * 16;
+          if (j + 1 < 8 && lane == 0) {  // prefetch the next residual block into the other tile
+            mbar_expect_tx(&rb[(j + 1) & 1], r16 ? 1024u : 2048u);
+            tma_load_2d(area + ((j + 1) & 1) * 2048, r16 ? &tmO16 : &tmX32, &rb[(j + 1) & 1], col + 16, prow0);
+          }
           uint32_t v[16];
           tmem_ld16(tmem_base + acc * BN + col + ((uint32_t)(quarter * 32) << 16), v);
           mbar_wait(&rb[j & 1], (rph >> (j & 1)) & 1u);
@@ -608,11 +610,6 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const float4 f = *reinterpret_cast<const float4*>(in + lane * 64 + ((c ^ sw64) << 4));
               x[4 * c] = f.x; x[4 * c + 1] = f.y; x[4 * c + 2] = f.z; x[4 * c + 3] = f.w;
             }
-          }
-          __syncwarp();  // every lane has read its row: the tile can take the residual of block j + 2 (a look-ahead of one
-          if (j + 2 < 8 && lane == 0) {  // block exposed a full TMA latency per block: 8 x 0.8 us per tile, measured)
-            mbar_expect_tx(&rb[j & 1], r16 ? 1024u : 2048u);
-            tma_load_2d(area + (j & 1) * 2048, r16 ? &tmO16 : &tmX32, &rb[j & 1], col + 32, prow0);
           }
 #pragma unroll
           for (int q = 0; q < 16; q++) {

@@ -60,7 +60,7 @@ ABI_SYMBOLS = [
     "az_mcts_create", "az_mcts_set_roots", "az_mcts_set_noise", "az_mcts_run", "az_mcts_explore", "az_mcts_root_stats", "az_mcts_policy",
     "az_mcts_reset", "az_mcts_counters", "az_mcts_last_timing", "az_mcts_destroy",
     "az_selfplay_create", "az_selfplay_start", "az_selfplay_poll", "az_selfplay_wait", "az_selfplay_counts",
-    "az_selfplay_fetch", "az_selfplay_stats", "az_selfplay_destroy",
+    "az_selfplay_fetch", "az_selfplay_stats", "az_selfplay_destroy", "az_selfplay_create_duel", "az_selfplay_outcomes",
 ]
 
 _lib = None
@@ -100,6 +100,8 @@ def lib():
             "az_selfplay_start": [vp, C.c_int32, C.c_int64], "az_selfplay_poll": [vp, vp, vp], "az_selfplay_wait": [vp],
             "az_selfplay_counts": [vp, vp, vp], "az_selfplay_fetch": [vp] + [vp] * 8, "az_selfplay_stats": [vp, vp, vp, vp, vp],
             "az_selfplay_destroy": [vp],
+            "az_selfplay_create_duel": [vp, C.c_int32, vp, vp, C.POINTER(_MctsParams), C.POINTER(_SimParams), C.c_uint64, C.POINTER(vp)],
+            "az_selfplay_outcomes": [vp, C.c_double, vp, vp, vp, vp],
         }
         for name, args in sigs.items():
             getattr(L, name).argtypes = args
@@ -409,11 +411,16 @@ class MctsEnv:
 class SelfPlay:
     """simulate() for self-play (src/simulations.jl:207-244, src/training.jl:275-300)."""
 
-    def __init__(self, ctx, gspec, oracle, params, seed=0):
+    def __init__(self, ctx, gspec, oracle, params, seed=0, baseline=None):
+        """`baseline` given: a duel TwoPlayers(MctsPlayer(oracle), MctsPlayer(baseline)) (src/training.jl:130-143)."""
         self.ctx, self.gspec, self.params = ctx, gspec, params
         self.h = C.c_void_p()
         mp, sp = params.mcts.c(), params.sim.c()
-        ctx.check(lib().az_selfplay_create(ctx.h, gspec.id, oracle.h, C.byref(mp), C.byref(sp), seed, C.byref(self.h)))
+        if baseline is None:
+            ctx.check(lib().az_selfplay_create(ctx.h, gspec.id, oracle.h, C.byref(mp), C.byref(sp), seed, C.byref(self.h)))
+        else:
+            ctx.check(lib().az_selfplay_create_duel(ctx.h, gspec.id, oracle.h, baseline.h, C.byref(mp), C.byref(sp), seed,
+                                                    C.byref(self.h)))
 
     def start(self, num_games=None, first_game_index=0):
         self.ctx.check(lib().az_selfplay_start(self.h, num_games or self.params.sim.num_games, first_game_index))
@@ -440,16 +447,29 @@ class SelfPlay:
         out.update(edepth=ed, nodes=nodes, moves=moves, seconds=tot[0], simulations=tot[1], expansions=tot[2], samples=tot[3])
         return out
 
+    def outcomes(self, gamma=1.0):
+        """rewards_and_redundancy (src/simulations.jl:292-307): (game_rewards = total reward per game w.r.t. the first player, colors_flipped,
+        final states, redundancy)."""
+        ns, ng = C.c_int64(), C.c_int64()
+        self.ctx.check(lib().az_selfplay_counts(self.h, C.byref(ns), C.byref(ng)))
+        g = ng.value
+        rew, fl = np.zeros(g, np.float64), np.zeros(g, np.int32)
+        fin = np.zeros((g, self.gspec.state_bytes), np.uint8)
+        red = C.c_double()
+        self.ctx.check(lib().az_selfplay_outcomes(self.h, gamma, rew.ctypes.data, fl.ctypes.data, fin.ctypes.data, C.byref(red)))
+        return dict(game_rewards=rew, colors_flipped=fl, final_states=fin, redundancy=red.value)
+
     def close(self):
         if self.h:
             lib().az_selfplay_destroy(self.h)
             self.h = None
 
 
-def simulate(ctx, gspec, oracle, params, seed=0, game_simulated=None, first_game_index=0):
-    """simulate(simulator, gspec, p; game_simulated) for the self-play simulator: returns the fetched samples + measurements."""
+def simulate(ctx, gspec, oracle, params, seed=0, game_simulated=None, first_game_index=0, baseline=None, gamma=None):
+    """simulate(simulator, gspec, p; game_simulated): returns the fetched samples + measurements (self-play simulator,
+    src/training.jl:275-300); with `gamma` also the rewards_and_redundancy outputs of the record_trace simulators."""
     import time
-    sp = SelfPlay(ctx, gspec, oracle, params, seed)
+    sp = SelfPlay(ctx, gspec, oracle, params, seed, baseline=baseline)
     try:
         sp.start(params.sim.num_games, first_game_index)
         seen = 0
@@ -463,6 +483,16 @@ def simulate(ctx, gspec, oracle, params, seed=0, game_simulated=None, first_game
                 break
             time.sleep(0.005)
         sp.wait()
-        return sp.fetch()
+        out = sp.fetch()
+        if gamma is not None:
+            out.update(sp.outcomes(gamma))
+        return out
     finally:
         sp.close()
+
+
+def pit_networks(ctx, gspec, contender, baseline, params, seed=0, game_simulated=None):
+    """pit_networks (src/training.jl:130-143): `params` = ArenaParams-like object with .mcts and .sim; returns
+    (rewards of the contender per game, redundancy)."""
+    out = simulate(ctx, gspec, contender, params, seed, game_simulated, baseline=baseline, gamma=params.mcts.gamma)
+    return out["game_rewards"], out["redundancy"]

@@ -12,6 +12,8 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <string>
+#include <unordered_set>
 #include <thread>
 #include <vector>
 
@@ -136,6 +138,7 @@ template <class G> static int g_make_oracle(az_ctx* ctx, int kind, az_net** out)
 struct az_mcts {
   az_ctx* ctx = nullptr;
   az_net* net = nullptr;
+  az_net* net2 = nullptr;  // duel mode: oracle of the odd trees (player 1)
   int game = 0;
   virtual ~az_mcts() {}
   virtual int set_roots(const uint8_t* states, const double* eta) = 0;
@@ -165,8 +168,11 @@ struct Mcts : az_mcts {
     if (s == AZ_OK) allocs.push_back(*ptr);
     return s;
   }
-  int create(az_ctx* c, az_net* n, const az_mcts_params* params, int S, int cap_nodes) {
-    ctx = c; net = n; game = G::ID; mp = *params;
+  int create(az_ctx* c, az_net* n, const az_mcts_params* params, int S, int cap_nodes, az_net* n2 = nullptr) {
+    ctx = c; net = n; net2 = n2; game = G::ID; mp = *params;
+    if (n2 && (S & 1)) AZ_FAIL(ctx, AZ_EINVAL, "duel pool: the number of trees must be even");
+    if (n2 && n2->game != G::ID) AZ_FAIL(ctx, AZ_EINVAL, "az_mcts_create: second oracle was built for another game");
+    p.duel = n2 ? 1 : 0; p.row_base1 = n2 ? S / 2 : 0;
     if (S <= 0 || cap_nodes <= 0) AZ_FAIL(ctx, AZ_EINVAL, "az_mcts_create: n_trees and capacity must be positive");
     if (params->num_iters_per_turn <= 0) AZ_FAIL(ctx, AZ_EINVAL, "MctsPlayer: niters > 0 (src/play.jl:162)");
     if (n->game != G::ID) AZ_FAIL(ctx, AZ_EINVAL, "az_mcts_create: oracle was built for another game");
@@ -186,7 +192,7 @@ struct Mcts : az_mcts {
     AZ_TRY(ctx, alloc(&p.leaf_row, S)); AZ_TRY(ctx, alloc(&p.depth, S));
     AZ_TRY(ctx, alloc(&p.path_node, (size_t)S * p.maxd)); AZ_TRY(ctx, alloc(&p.path_meta, (size_t)S * p.maxd));
     AZ_TRY(ctx, alloc(&p.path_r, (size_t)S * p.maxd));
-    AZ_TRY(ctx, alloc(&p.n_leaves, 2)); AZ_TRY(ctx, alloc(&p.batch_env, S));
+    AZ_TRY(ctx, alloc(&p.n_leaves, 4)); AZ_TRY(ctx, alloc(&p.batch_env, S));
     AZ_TRY(ctx, alloc(&p.batch_P, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&p.batch_V, S));
     AZ_TRY(ctx, alloc(&p.flags, 4)); AZ_TRY(ctx, alloc(&p.expansions, 1));
     AZ_TRY(ctx, alloc(&p.noise_game, S)); AZ_TRY(ctx, alloc(&p.noise_move, S));
@@ -223,15 +229,16 @@ struct Mcts : az_mcts {
   void drop_graph() { if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; } }
   template <class Extra>
   int tick_graphed(Extra extra) {
-    if (!use_graph || graph_broken || !net->capturable()) {
+    if (!use_graph || graph_broken || !net->capturable() || (net2 && !net2->capturable())) {
       drop_graph();
       AZ_TRY(ctx, tick(false));
       extra();
       return AZ_OK;
     }
-    if (gexec && graph_net_gen != net->generation()) drop_graph();  // the network reallocated buffers / reloaded weights
+    const uint64_t gen_now = net->generation() + (net2 ? 0x100000000ull * net2->generation() : 0);
+    if (gexec && graph_net_gen != gen_now) drop_graph();  // a network reallocated buffers / reloaded weights
     if (!gexec) {
-      graph_net_gen = net->generation();
+      graph_net_gen = gen_now;
       const int64_t l0 = ctx->launches;
       cudaGraph_t g = nullptr;
       if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { graph_broken = true; cudaGetLastError(); return tick_graphed(extra); }
@@ -254,17 +261,23 @@ struct Mcts : az_mcts {
   }
   // one tick: select -> oracle -> expand+backup
   int tick(bool time_net) {
-    AZ_CUDA(ctx, cudaMemsetAsync(p.n_leaves, 0, 2 * sizeof(int32_t), ctx->stream));
+    AZ_CUDA(ctx, cudaMemsetAsync(p.n_leaves, 0, 4 * sizeof(int32_t), ctx->stream));
     az_k_select<G><<<groups_grid(), 128, 0, ctx->stream>>>(p);
     if (time_net) cudaEventRecord(ev[2], ctx->stream);
-    AZ_TRY(ctx, net->eval(p.batch_env, p.n_leaves, p.S, p.batch_P, p.batch_V));
+    if (!net2) {
+      AZ_TRY(ctx, net->eval(p.batch_env, p.n_leaves, p.S, p.batch_P, p.batch_V));
+    } else {  // one leaf queue per player's oracle (at most one tree per worker is thinking)
+      const int b1 = p.row_base1;
+      AZ_TRY(ctx, net->eval(p.batch_env, p.n_leaves, b1, p.batch_P, p.batch_V));
+      AZ_TRY(ctx, net2->eval(p.batch_env + b1, p.n_leaves + 2, b1, p.batch_P + (size_t)b1 * G::A, p.batch_V + b1));
+    }
     if (time_net) cudaEventRecord(ev[3], ctx->stream);
     az_k_expand_backup<G><<<groups_grid(), 128, 0, ctx->stream>>>(p);
     ctx->launches += 2;
     return AZ_OK;
   }
   int check_flags() {
-    AZ_CUDA(ctx, cudaMemcpyAsync(h_pin + 8, p.n_leaves, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AZ_CUDA(ctx, cudaMemcpyAsync(h_pin + 8, p.n_leaves, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     AZ_CUDA(ctx, cudaMemcpyAsync(h_pin + 1, p.flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (h_pin[1]) AZ_FAIL(ctx, AZ_ENOMEM, "MCTS table overflow: raise capacity_nodes_per_tree");
@@ -289,7 +302,7 @@ struct Mcts : az_mcts {
       ticks++;
       if (t + 1 >= nsims / 2 && ((t + 1) % 8 == 0 || t + 1 >= nsims)) {
         AZ_TRY(ctx, check_flags());
-        if (h_pin[8] == 0 && h_pin[9] == 0) break;  // no leaf pending and no tree with simulations left
+        if (h_pin[8] == 0 && h_pin[9] == 0 && h_pin[10] == 0) break;  // no leaf pending and no tree with simulations left
       }
     }
     AZ_CUDA(ctx, cudaEventRecord(ev[1], ctx->stream));
@@ -376,6 +389,7 @@ struct az_selfplay {
   virtual int counts(int64_t* ns, int64_t* ng) = 0;
   virtual int fetch(uint8_t* states, float* pi, uint8_t* mask, float* z, float* t, int32_t* gos, double* rew, int32_t* act) = 0;
   virtual int stats(double* ed, int64_t* nodes, int32_t* moves, double* totals) = 0;
+  virtual int outcomes(double gamma, double* rewards, int32_t* colors_flipped, uint8_t* final_states, double* redundancy) = 0;
 };
 
 template <class G>
@@ -398,28 +412,32 @@ struct SelfPlay : az_selfplay {
     if (s == AZ_OK) allocs.push_back(*ptr);
     return s;
   }
-  int create(az_ctx* c, az_net* net, const az_mcts_params* mp, const az_sim_params* s, uint64_t seed) {
+  int create(az_ctx* c, az_net* net, az_net* net2, const az_mcts_params* mp, const az_sim_params* s, uint64_t seed) {
     ctx = c; game = G::ID; simp = *s;
     if (s->num_workers <= 0) AZ_FAIL(ctx, AZ_EINVAL, "SimParams: num_workers must be positive");
     if (s->batch_size > s->num_workers) AZ_FAIL(ctx, AZ_EINVAL, "batch_size <= num_workers (src/batchifier.jl:48)");
-    if (s->flip_probability != 0.0) AZ_FAIL(ctx, AZ_EUNSUPPORTED, "flip_probability != 0 is not supported yet");
+    if (s->flip_probability != 0.0 && G::NSYM == 0)
+      AZ_FAIL(ctx, AZ_EINVAL, "You must specify some game symmetries to use flip_probability>0. (src/params.jl:377-381)");
+    if (!(s->flip_probability >= 0.0 && s->flip_probability <= 1.0)) AZ_FAIL(ctx, AZ_EINVAL, "flip_probability must be in [0, 1]");
     if (mp->temperature_n < 1 || mp->temperature_n > AZ_MAX_SCHEDULE) AZ_FAIL(ctx, AZ_EINVAL, "temperature schedule: 1..8 points");
-    const int S = s->num_workers;
-    int reset = s->reset_every > 0 ? s->reset_every : std::max(1, (s->num_games + S - 1) / S);
+    const int W = s->num_workers;
+    const int S = net2 ? 2 * W : W;  // duel: one tree per player per worker (TwoPlayers, src/play.jl:248-252)
+    int reset = s->reset_every > 0 ? s->reset_every : std::max(1, (s->num_games + W - 1) / W);
     size_t bound = (size_t)std::min<long long>((long long)mp->num_iters_per_turn * G::MAX_PLIES * (long long)reset, G::MAX_STATES);
     size_t budget = (size_t)96 << 30;  // table budget: 96 GB of the 180 GB HBM
     size_t maxnodes = budget / ((size_t)S * G::LANES * 16) * 3 / 4;
     int cap_nodes = (int)std::min<size_t>(std::min(bound, maxnodes), (size_t)1 << 28);
     pool.reset(new Mcts<G>());
-    int st = pool->create(ctx, net, mp, S, cap_nodes);
+    int st = pool->create(ctx, net, mp, S, cap_nodes, net2);
     if (st != AZ_OK) { pool.reset(); return st; }
     pool->p.noise_seed = seed;
+    sp.W = W; sp.duel = net2 ? 1 : 0; sp.alternate = s->alternate_colors ? 1 : 0; sp.flip_p = s->flip_probability;
     sp.seed = seed; sp.nsims = mp->num_iters_per_turn; sp.reset_every = s->reset_every; sp.max_plies = G::MAX_PLIES;
     sp.sched_n = mp->temperature_n;
     for (int i = 0; i < mp->temperature_n; i++) { sp.sched_xs[i] = mp->temperature_xs[i]; sp.sched_ys[i] = mp->temperature_ys[i]; }
-    AZ_TRY(ctx, alloc(&sp.game_of_slot, S)); AZ_TRY(ctx, alloc(&sp.move_of_slot, S)); AZ_TRY(ctx, alloc(&sp.games_on_slot, S));
+    AZ_TRY(ctx, alloc(&sp.game_of_slot, W)); AZ_TRY(ctx, alloc(&sp.move_of_slot, W)); AZ_TRY(ctx, alloc(&sp.games_on_slot, W));
     AZ_TRY(ctx, alloc(&sp.games_done, 1)); AZ_TRY(ctx, alloc(&sp.active_slots, 1));
-    AZ_TRY(ctx, alloc(&sp.next_game, 1)); AZ_TRY(ctx, alloc(&sp.want_game, S));
+    AZ_TRY(ctx, alloc(&sp.next_game, 1)); AZ_TRY(ctx, alloc(&sp.want_game, W));
     AZ_CUDA(ctx, cudaMallocHost((void**)&h_pin, 64));
     return AZ_OK;
   }
@@ -440,7 +458,8 @@ struct SelfPlay : az_selfplay {
     for (void* q : game_allocs) cudaFree(q);
     game_allocs.clear();
     size_t rows = (size_t)ng * G::MAX_PLIES;
-    AZ_TRY(ctx, galloc(&sp.s_env, rows)); AZ_TRY(ctx, galloc(&sp.s_pi, rows * G::A)); AZ_TRY(ctx, galloc(&sp.s_action, rows));
+    AZ_TRY(ctx, galloc(&sp.s_env, rows)); AZ_TRY(ctx, galloc(&sp.s_root, rows)); AZ_TRY(ctx, galloc(&sp.g_final, ng));
+    AZ_TRY(ctx, galloc(&sp.s_pi, rows * G::A)); AZ_TRY(ctx, galloc(&sp.s_action, rows));
     AZ_TRY(ctx, galloc(&sp.s_reward, rows)); AZ_TRY(ctx, galloc(&sp.s_z, rows)); AZ_TRY(ctx, galloc(&sp.s_t, rows));
     AZ_TRY(ctx, galloc(&sp.g_moves, ng)); AZ_TRY(ctx, galloc(&sp.g_edepth, ng)); AZ_TRY(ctx, galloc(&sp.g_nodes, ng));
     games_cap = ng;
@@ -492,7 +511,7 @@ struct SelfPlay : az_selfplay {
     if (worker.joinable()) worker.join();
     if (num_games <= 0) AZ_FAIL(ctx, AZ_EINVAL, "num_games must be positive");
     if (simp.reset_every <= 0) {
-      size_t need = (size_t)sp.nsims * G::MAX_PLIES * (size_t)((num_games + pool->p.S - 1) / pool->p.S);
+      size_t need = (size_t)sp.nsims * G::MAX_PLIES * (size_t)((num_games + sp.W - 1) / sp.W);
       (void)need;  // overflow is detected on device and reported as AZ_ENOMEM
     }
     AZ_TRY(ctx, ensure_game_buffers(num_games));
@@ -528,11 +547,12 @@ struct SelfPlay : az_selfplay {
     AZ_TRY(ctx, wait());
     const int ng = sp.num_games;
     size_t rows = (size_t)ng * G::MAX_PLIES;
-    std::vector<AzEnv> env(rows);
+    std::vector<AzEnv> env(rows), think(rows);
     std::vector<float> hpi(rows * G::A), hz(rows), ht(rows);
     std::vector<int32_t> hact(rows);
     std::vector<double> hrew(rows);
     AZ_CUDA(ctx, cudaMemcpy(env.data(), sp.s_env, rows * sizeof(AzEnv), cudaMemcpyDeviceToHost));
+    AZ_CUDA(ctx, cudaMemcpy(think.data(), sp.s_root, rows * sizeof(AzEnv), cudaMemcpyDeviceToHost));
     AZ_CUDA(ctx, cudaMemcpy(hpi.data(), sp.s_pi, rows * G::A * sizeof(float), cudaMemcpyDeviceToHost));
     AZ_CUDA(ctx, cudaMemcpy(hz.data(), sp.s_z, rows * sizeof(float), cudaMemcpyDeviceToHost));
     AZ_CUDA(ctx, cudaMemcpy(ht.data(), sp.s_t, rows * sizeof(float), cudaMemcpyDeviceToHost));
@@ -543,7 +563,7 @@ struct SelfPlay : az_selfplay {
       for (int i = 0; i < h_moves[g]; i++, k++) {
         size_t r = (size_t)g * G::MAX_PLIES + i;
         if (states) G::to_bytes(env[r], states + k * G::STATE_BYTES);
-        uint32_t legal = G::legal_mask(env[r]);
+        uint32_t legal = G::legal_mask(think[r]);  // pi and the mask are in the frame the player thought in
         for (int a = 0; a < G::A; a++) {
           if (pi) pi[k * G::A + a] = hpi[r * G::A + a];
           if (mask) mask[k * G::A + a] = (legal >> a) & 1;
@@ -569,11 +589,46 @@ struct SelfPlay : az_selfplay {
     }
     return AZ_OK;
   }
+  // rewards_and_redundancy (src/simulations.jl:292-307): per game total_reward(trace, gamma) (src/trace.jl:45-47), negated
+  // when the colours were flipped; redundancy = 1 - |unique states| / |states| over every trace state (final ones included)
+  int outcomes(double gamma, double* rewards, int32_t* flipped, uint8_t* finals, double* redundancy) override {
+    AZ_TRY(ctx, wait());
+    const int ng = sp.num_games;
+    size_t rows = (size_t)ng * G::MAX_PLIES;
+    std::vector<AzEnv> env(rows), fin(ng);
+    std::vector<double> hrew(rows);
+    AZ_CUDA(ctx, cudaMemcpy(env.data(), sp.s_env, rows * sizeof(AzEnv), cudaMemcpyDeviceToHost));
+    AZ_CUDA(ctx, cudaMemcpy(fin.data(), sp.g_final, (size_t)ng * sizeof(AzEnv), cudaMemcpyDeviceToHost));
+    AZ_CUDA(ctx, cudaMemcpy(hrew.data(), sp.s_reward, rows * sizeof(double), cudaMemcpyDeviceToHost));
+    std::unordered_set<std::string> uniq;
+    size_t total = 0;
+    uint8_t buf[G::STATE_BYTES];
+    for (int g = 0; g < ng; g++) {
+      const bool fl = sp.duel && sp.alternate && (((sp.first_game + g + 1) & 1) == 1);
+      double s = 0.0, gp = 1.0;
+      for (int i = 0; i < h_moves[g]; i++) {
+        const size_t r = (size_t)g * G::MAX_PLIES + i;
+        s = (i == 0) ? gp * hrew[r] : s + gp * hrew[r];
+        gp = gp * gamma;
+        G::to_bytes(env[r], buf);
+        uniq.emplace((const char*)buf, (size_t)G::STATE_BYTES);
+        total++;
+      }
+      G::to_bytes(fin[g], buf);
+      uniq.emplace((const char*)buf, (size_t)G::STATE_BYTES);
+      total++;
+      if (finals) memcpy(finals + (size_t)g * G::STATE_BYTES, buf, G::STATE_BYTES);
+      if (rewards) rewards[g] = fl ? -s : s;
+      if (flipped) flipped[g] = fl ? 1 : 0;
+    }
+    if (redundancy) *redundancy = 1.0 - (double)uniq.size() / (double)total;
+    return AZ_OK;
+  }
 };
 template <class G>
-static int g_make_selfplay(az_ctx* ctx, az_net* net, const az_mcts_params* mp, const az_sim_params* sp, uint64_t seed, az_selfplay** out) {
+static int g_make_selfplay(az_ctx* ctx, az_net* net, az_net* net2, const az_mcts_params* mp, const az_sim_params* sp, uint64_t seed, az_selfplay** out) {
   auto* s = new SelfPlay<G>();
-  int st = s->create(ctx, net, mp, sp, seed);
+  int st = s->create(ctx, net, net2, mp, sp, seed);
   if (st != AZ_OK) { delete s; return st; }
   *out = s;
   return AZ_OK;
@@ -771,8 +826,21 @@ int32_t az_selfplay_create(az_ctx* ctx, int32_t game, az_net* oracle, const az_m
   cudaSetDevice(ctx->device);
   if (oracle->game != game) AZ_FAIL(ctx, AZ_EINVAL, "az_selfplay_create: oracle was built for another game");
   if (mp->num_iters_per_turn <= 0) AZ_FAIL(ctx, AZ_EINVAL, "MctsPlayer: niters > 0 (src/play.jl:162)");
-  AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, oracle, mp, sp, seed, out)
+  AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, oracle, nullptr, mp, sp, seed, out)
   AZ_GUARD_END(ctx)
+}
+int32_t az_selfplay_create_duel(az_ctx* ctx, int32_t game, az_net* white, az_net* black, const az_mcts_params* mp, const az_sim_params* sp,
+                                uint64_t seed, az_selfplay** out) {
+  if (!ctx || !white || !black || !mp || !sp || !out) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  cudaSetDevice(ctx->device);
+  if (white->game != game || black->game != game) AZ_FAIL(ctx, AZ_EINVAL, "az_selfplay_create_duel: oracle was built for another game");
+  if (mp->num_iters_per_turn <= 0) AZ_FAIL(ctx, AZ_EINVAL, "MctsPlayer: niters > 0 (src/play.jl:162)");
+  AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, white, black, mp, sp, seed, out)
+  AZ_GUARD_END(ctx)
+}
+int32_t az_selfplay_outcomes(az_selfplay* s, double gamma, double* rewards, int32_t* flipped, uint8_t* finals, double* red) {
+  AZ_M(s) AZ_GUARD_BEGIN return s->outcomes(gamma, rewards, flipped, finals, red); AZ_GUARD_END(s->ctx)
 }
 int32_t az_selfplay_start(az_selfplay* s, int32_t ng, int64_t first) { AZ_M(s) AZ_GUARD_BEGIN return s->start(ng, first); AZ_GUARD_END(s->ctx) }
 int32_t az_selfplay_poll(az_selfplay* s, int32_t* done, int32_t* fin) { if (!s) return AZ_EINVAL; return s->poll(done, fin); }

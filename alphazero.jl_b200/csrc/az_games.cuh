@@ -92,6 +92,17 @@ struct GameC4 {
   static constexpr long long MAX_STATES = 1ll << 40;  // no useful bound on distinct states
   AZ_HD static AzEnv play(const AzEnv& e, int a, const AzNoise&) { return play(e, a); }
   AZ_HD static AzEnv init_game(uint64_t, uint64_t) { return init(); }
+  // GI.symmetries (game.jl:247-257): the column mirror.  Only applied to non-terminal states (src/play.jl:302-307), whose
+  // status bits are symmetric.
+  static constexpr int NSYM = 1;
+  AZ_HD static AzEnv symmetry(const AzEnv& e, int) {
+    AzEnv n = {0, e.b & PLAYER, e.aux};
+    for (int col = 0; col < 7; col++) {
+      n.a |= ((e.a >> (7 * col)) & 0x7Full) << (7 * (6 - col));
+      n.b |= ((e.b >> (7 * col)) & 0x7Full) << (7 * (6 - col));
+    }
+    return n;
+  }
   // set_state! (game.jl:50-68): finished if no free column, or if the TOP stone of some column is part of a
   // winning pattern of its colour
   static AzEnv from_bytes(const uint8_t* s) {
@@ -180,6 +191,22 @@ struct GameTTT {
   static constexpr long long MAX_STATES = 1ll << 40;  // no useful bound on distinct states
   AZ_HD static AzEnv play(const AzEnv& e, int a, const AzNoise&) { return play(e, a); }
   AZ_HD static AzEnv init_game(uint64_t, uint64_t) { return init(); }
+  // GI.symmetries (game.jl:149-168): rot, rot2, rot3, flip, flip.rot, flip.rot2, flip.rot3 with rot(x,y) = (y, N-x+1),
+  // flip(x,y) = (x, N-y+1); the image board is board'[p] = board[sym[p]]
+  static constexpr int NSYM = 7;
+  AZ_HD static AzEnv symmetry(const AzEnv& e, int j) {
+    AzEnv n = {e.a & PLAYER, 0, e.aux};
+    const int nrot = j < 3 ? j + 1 : j - 3;
+    for (int p = 0; p < 9; p++) {
+      int x = p % 3, y = p / 3;
+      for (int k = 0; k < nrot; k++) { int nx = y, ny = 2 - x; x = nx; y = ny; }
+      if (j >= 3) y = 2 - y;
+      const int src = y * 3 + x;
+      n.a |= ((e.a >> src) & 1ull) << p;
+      n.a |= ((e.a >> (16 + src)) & 1ull) << (16 + p);
+    }
+    return n;
+  }
   static AzEnv from_bytes(const uint8_t* s) {
     AzEnv e = {0, 0, 0};
     for (int i = 0; i < 9; i++) {
@@ -298,6 +325,8 @@ struct GameMancala {
     return e;
   }
   static constexpr bool STOCHASTIC = false;
+  static constexpr int NSYM = 0;  // no GI.symmetries declared for this game
+  AZ_HD static AzEnv symmetry(const AzEnv& e, int) { return e; }
   static constexpr long long MAX_STATES = 1ll << 40;  // no useful bound on distinct states
   AZ_HD static AzEnv play(const AzEnv& e, int a, const AzNoise&) { return play(e, a); }
   AZ_HD static AzEnv init_game(uint64_t, uint64_t) { return init(); }
@@ -342,6 +371,8 @@ struct GameGW {
   static constexpr int XW = 10, XH = 10, XC = 1;
   static constexpr bool ACYCLIC = false;  // a simulation may revisit a state (time is not in the key)
   static constexpr bool STOCHASTIC = true;
+  static constexpr int NSYM = 0;  // no GI.symmetries declared for this game
+  AZ_HD static AzEnv symmetry(const AzEnv& e, int) { return e; }
   static constexpr long long MAX_STATES = 100;  // 10 x 10 cells: a tree never holds more nodes
   AZ_HD static int gx(const AzEnv& e) { return (int)(e.a & 0xFF); }
   AZ_HD static int gy(const AzEnv& e) { return (int)((e.a >> 8) & 0xFF); }

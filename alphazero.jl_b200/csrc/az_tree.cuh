@@ -48,7 +48,11 @@ struct AzPool {
   uint32_t* path_node;  // [S][maxd]
   uint16_t* path_meta;  // [S][maxd]  action | pswitch << 8
   double* path_r;       // [S][maxd]
-  int32_t* n_leaves;    // [2]: [0] leaves emitted this tick, [1] trees that still have simulations to run
+  int32_t* n_leaves;    // [4]: [0] leaves emitted this tick, [1] trees that still have simulations to run,
+                        //      [2] leaves of the second oracle's queue (duel mode)
+  int32_t duel;         // duel mode (TwoPlayers, src/play.jl:248-282): tree 2*w + k belongs to player k of worker w and its
+                        // leaves go to oracle k; queue k starts at row k * row_base1 of the batch arrays
+  int32_t row_base1;
   int32_t max_sims_per_call;  // cap on simulations one select call runs for a tree (bounds the kernel's tail)
   AzEnv* batch_env;     // [S]
   float* batch_P;       // [S][A]
@@ -162,7 +166,8 @@ __global__ void __launch_bounds__(128) az_k_select(AzPool p) {
       int st = az_probe<G>(tab, p.cap_mask, tag, env, lane, gm, h, ln);
       if (st == 2) {  // new node: ask the oracle (state_info, src/mcts.jl:165-174)
         if (lane == 0) {
-          int row = atomicAdd(p.n_leaves, 1);
+          const int q = p.duel ? (slot & 1) : 0;
+          int row = atomicAdd(p.n_leaves + 2 * q, 1) + q * p.row_base1;
           p.batch_env[row] = env;
           p.leaf_row[slot] = row;
           p.leaf_pos[slot] = h;
@@ -387,12 +392,18 @@ struct AzSelfPlay {
   int32_t sched_n;
   int32_t sched_xs[8];
   double sched_ys[8];
-  // per slot
+  double flip_p;          // SimParams.flip_probability (src/play.jl:305-307)
+  int32_t duel;           // TwoPlayers: two trees per worker (player 0 = `white` argument of TwoPlayers, 1 = `black`)
+  int32_t alternate;      // SimParams.alternate_colors (src/simulations.jl:224-230)
+  int32_t W;              // number of workers (game slots); trees = W * (duel ? 2 : 1)
+  // per worker
   int32_t* game_of_slot;   // local game index or -1
   int32_t* move_of_slot;
   int32_t* games_on_slot;
   // per (game, ply) rows, stride max_plies
-  AzEnv* s_env;
+  AzEnv* s_env;            // trace.states[i] (before the optional symmetry of move i)
+  AzEnv* s_root;           // the state the player thought on (s_pi and the mask are in its frame)
+  AzEnv* g_final;          // per game: last state of the trace
   float* s_pi;             // [A]
   int32_t* s_action;
   double* s_reward;
@@ -417,12 +428,39 @@ __device__ __forceinline__ double az_schedule(const AzSelfPlay& sp, int i) {  //
   return y0 + ((y1 - y0) / (x1 - x0)) * ((double)i - x0);
 }
 
+// colors_flipped of game `game` (0-based global index; sim_id = game + 1): src/simulations.jl:224-226
+__device__ __forceinline__ bool az_colors_flipped(const AzSelfPlay& sp, int64_t game) {
+  return sp.duel && sp.alternate && (((game + 1) & 1) == 1);
+}
+// the tree that thinks on `e` for worker w (think(::TwoPlayers), src/play.jl:258-264; flipped_colors :256)
 template <class G>
-__device__ void az_begin_move(const AzPool& p, const AzSelfPlay& sp, int slot, const AzEnv& root, int64_t game, int move) {
+__device__ __forceinline__ int az_tree_of(const AzSelfPlay& sp, int w, const AzEnv& e, int64_t game) {
+  if (!sp.duel) return w;
+  const bool white = G::white_playing(e);
+  const bool fl = az_colors_flipped(sp, game);
+  return 2 * w + ((white != fl) ? 0 : 1);
+}
+
+// Start of a turn of play_game (src/play.jl:301-308): record the trace state, apply the optional random symmetry
+// (GI.apply_random_symmetry!, src/game.jl:329-336), pick the thinking player's tree and set up explore!.
+template <class G>
+__device__ void az_begin_move(const AzPool& p, const AzSelfPlay& sp, int w, const AzEnv& state, int g, int64_t game, int move) {
   constexpr int A = G::A;
+  sp.s_env[(size_t)g * sp.max_plies + move] = state;
+  AzEnv root = state;
+  if (G::NSYM > 0 && sp.flip_p != 0.0) {
+    const double u = az_u01(az_stream_u64(sp.seed, (uint64_t)game, (uint32_t)move, AZ_PURPOSE_SYMMETRY, 0));
+    if (u < sp.flip_p) {
+      const int j = (int)(az_stream_u64(sp.seed, (uint64_t)game, (uint32_t)move, AZ_PURPOSE_SYMMETRY, 1) % (uint64_t)(G::NSYM > 0 ? G::NSYM : 1));
+      root = G::symmetry(state, j);
+    }
+  }
+  const int slot = az_tree_of<G>(sp, w, root, game);
   p.root[slot] = root;
   p.sims_done[slot] = 0;
   p.sims_target[slot] = sp.nsims;
+  p.status[slot] = 1;
+  p.pending[slot] = 0;
   if (G::STOCHASTIC) { p.noise_game[slot] = game; p.noise_move[slot] = move; }
   double eta[A];
   int n = __popc(G::legal_mask(root));
@@ -430,33 +468,40 @@ __device__ void az_begin_move(const AzPool& p, const AzSelfPlay& sp, int slot, c
   for (int i = 0; i < n; i++) p.eta[(size_t)slot * A + i] = eta[i];
 }
 
-// End of a game on a slot: self_play_measurements (src/training.jl:269-273, measured before the reset), reset_every
-// (src/simulations.jl:235-237).  The slot then asks az_k_assign for its next game.
+// End of a game on a worker: self_play_measurements (src/training.jl:269-273, measured before the reset), reset_every
+// (src/simulations.jl:235-237; reset!(::TwoPlayers) resets both trees, src/play.jl:274-277).  The worker then asks
+// az_k_assign for its next game.
 template <class G>
-__device__ void az_record_game_end(AzPool& p, AzSelfPlay& sp, int slot, int g, int n_moves) {
+__device__ void az_record_game_end(AzPool& p, AzSelfPlay& sp, int w, int g, int n_moves, const AzEnv& last) {
   constexpr int L = G::LANES;
+  const int nt = sp.duel ? 2 : 1, t0 = sp.duel ? 2 * w : w;
   sp.g_moves[g] = n_moves;
-  sp.g_nodes[g] = p.node_count[slot];
-  const int64_t ts = p.total_sims[slot];
-  sp.g_edepth[g] = ts == 0 ? 0.0 : (double)p.total_nodes[slot] / (double)ts;
+  sp.g_final[g] = last;
+  int64_t nodes = 0, ts = 0, tn = 0;
+  for (int k = 0; k < nt; k++) { nodes += p.node_count[t0 + k]; ts += p.total_sims[t0 + k]; tn += p.total_nodes[t0 + k]; }
+  sp.g_nodes[g] = nodes;
+  sp.g_edepth[g] = ts == 0 ? 0.0 : (double)tn / (double)ts;
   atomicAdd(sp.games_done, 1);
-  const int gos = sp.games_on_slot[slot] + 1;
-  sp.games_on_slot[slot] = gos;
-  if (sp.reset_every > 0 && gos % sp.reset_every == 0) {
-    uint32_t gen = (p.tag[slot] & 63u) + 1u;
-    if (gen == 64u) {
-      uint4* wt = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
-      size_t cnt = ((size_t)p.cap_mask + 1) * L;
-      for (size_t i = 0; i < cnt; i++) wt[i] = make_uint4(0, 0, 0, 0);
-      gen = 1u;
+  const int gos = sp.games_on_slot[w] + 1;
+  sp.games_on_slot[w] = gos;
+  for (int k = 0; k < nt; k++) {
+    const int slot = t0 + k;
+    if (sp.reset_every > 0 && gos % sp.reset_every == 0) {
+      uint32_t gen = (p.tag[slot] & 63u) + 1u;
+      if (gen == 64u) {
+        uint4* wt = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
+        size_t cnt = ((size_t)p.cap_mask + 1) * L;
+        for (size_t i = 0; i < cnt; i++) wt[i] = make_uint4(0, 0, 0, 0);
+        gen = 1u;
+      }
+      p.tag[slot] = 64u | gen;
+      p.node_count[slot] = 0;
     }
-    p.tag[slot] = 64u | gen;
-    p.node_count[slot] = 0;
+    p.status[slot] = 0;
+    p.sims_target[slot] = 0;
   }
-  sp.game_of_slot[slot] = -1;
-  p.status[slot] = 0;
-  p.sims_target[slot] = 0;
-  sp.want_game[slot] = 1;
+  sp.game_of_slot[w] = -1;
+  sp.want_game[w] = 1;
 }
 
 // Dynamic game assignment = the shared counter of Util.mapreduce (src/util.jl:169-200): a worker that finishes a game
@@ -471,9 +516,9 @@ __global__ void __launch_bounds__(1024) az_k_assign(AzPool p, AzSelfPlay sp) {
   for (;;) {
     if (threadIdx.x == 0) { s_base = *sp.next_game; s_total = 0; s_again = 0; }
     __syncthreads();
-    for (int start = 0; start < p.S; start += blockDim.x) {
-      const int slot = start + threadIdx.x;
-      const int want = (slot < p.S && sp.want_game[slot]) ? 1 : 0;
+    for (int start = 0; start < sp.W; start += blockDim.x) {
+      const int slot = start + threadIdx.x;  // worker index
+      const int want = (slot < sp.W && sp.want_game[slot]) ? 1 : 0;
       // inclusive scan of `want` over the block (slot order)
       s_scan[threadIdx.x] = want;
       __syncthreads();
@@ -493,11 +538,9 @@ __global__ void __launch_bounds__(1024) az_k_assign(AzPool p, AzSelfPlay sp) {
           if (!G::terminated(first)) {
             sp.game_of_slot[slot] = ng;
             sp.move_of_slot[slot] = 0;
-            p.status[slot] = 1;
-            p.pending[slot] = 0;
-            az_begin_move<G>(p, sp, slot, first, sp.first_game + ng, 0);
+            az_begin_move<G>(p, sp, slot, first, ng, sp.first_game + ng, 0);
           } else {
-            az_record_game_end<G>(p, sp, slot, ng, 0);  // empty game; asks again in the next round
+            az_record_game_end<G>(p, sp, slot, ng, 0, first);  // empty game; asks again in the next round
             s_again = 1;
           }
         }
@@ -518,22 +561,29 @@ template <class G>
 __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
   constexpr int L = G::LANES;
   constexpr int A = G::A;
-  int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= p.S) return;
-  if (start_games) {  // every worker starts by asking for a game (az_k_assign serves them in slot order)
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;  // tree index; the thread of the tree that just finished thinking acts
+  const int w = sp.duel ? (slot >> 1) : slot;        // worker
+  if (start_games) {
+    if (slot >= p.S) return;  // every worker starts by asking for a game (az_k_assign serves them in slot order)
     p.total_sims[slot] = 0;
     p.total_nodes[slot] = 0;
-    sp.games_on_slot[slot] = 0;
-    sp.game_of_slot[slot] = -1;
     p.status[slot] = 0;
     p.sims_target[slot] = 0;
     p.pending[slot] = 0;
-    sp.want_game[slot] = 1;
+    if (!sp.duel || (slot & 1) == 0) {
+      sp.games_on_slot[w] = 0;
+      sp.game_of_slot[w] = -1;
+      sp.want_game[w] = 1;
+    }
     return;
   }
-  if (!p.status[slot] || p.pending[slot] || p.sims_done[slot] < p.sims_target[slot]) return;
-  const int g = sp.game_of_slot[slot];
-  const int move = sp.move_of_slot[slot];
+  // In a duel the acting thread hands the turn to the sibling tree (lane ^ 1 of the same warp): every lane takes its
+  // decision before any lane writes.
+  const bool my_turn = slot < p.S && p.status[slot] && !p.pending[slot] && p.sims_done[slot] >= p.sims_target[slot];
+  __syncwarp();
+  if (!my_turn) return;
+  const int g = sp.game_of_slot[w];
+  const int move = sp.move_of_slot[w];
   const int64_t game = sp.first_game + g;
   const AzEnv root = p.root[slot];
   const uint32_t legal = G::legal_mask(root);
@@ -597,7 +647,7 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
   const int act = acts[k];
   // record (trace.jl:35-39) and play
   const size_t rowi = (size_t)g * sp.max_plies + move;
-  sp.s_env[rowi] = root;
+  sp.s_root[rowi] = root;
   for (int i = 0; i < A; i++) sp.s_pi[rowi * A + i] = 0.0f;
   for (int i = 0; i < n; i++) sp.s_pi[rowi * A + acts[i]] = (float)pi[i];
   sp.s_action[rowi] = act;
@@ -615,9 +665,11 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
       sp.s_z[ri] = (float)(G::white_playing(sp.s_env[ri]) ? wr : -wr);
       sp.s_t[ri] = (float)(nm - i);
     }
-    az_record_game_end<G>(p, sp, slot, g, nm);
+    az_record_game_end<G>(p, sp, w, g, nm, nx);
   } else {
-    sp.move_of_slot[slot] = nm;
-    az_begin_move<G>(p, sp, slot, nx, game, nm);
+    sp.move_of_slot[w] = nm;
+    p.status[slot] = 0;       // this player's turn is over; az_begin_move activates the tree of the player to move
+    p.sims_target[slot] = 0;
+    az_begin_move<G>(p, sp, w, nx, g, game, nm);
   }
 }

@@ -85,8 +85,9 @@ typedef struct {
   int32_t batch_size;  /* accepted for API parity; the engine batches every pending leaf of a tick */
   int32_t fill_batches;
   int32_t reset_every; /* <= 0: never (Julia `nothing`) */
-  int32_t alternate_colors;
-  double flip_probability; /* must be 0 in this round (self-play configs use 0) */
+  int32_t alternate_colors; /* duels only: odd sim_id (1-based game index) swaps the players' colours (src/simulations.jl:224-230) */
+  double flip_probability;  /* random GI.symmetries image before each turn (src/play.jl:305-307); needs a game that declares
+                               symmetries (connect-four, tictactoe), else AZ_EINVAL (src/params.jl:377-381) */
 } az_sim_params;
 
 /* ---- networks: Network interface (src/networks/network.jl), ResNet (architectures/resnet.jl) ---- */
@@ -161,6 +162,12 @@ int32_t az_mcts_destroy(az_mcts* m);
 /* ---- self-play: simulate(simulator, gspec, SimParams) (src/simulations.jl:207-244) ------------ */
 int32_t az_selfplay_create(az_ctx* ctx, int32_t game, az_net* oracle, const az_mcts_params* mp, const az_sim_params* sp,
                            uint64_t seed, az_selfplay** out);
+/* pit_networks / Benchmark duels: simulate() with TwoPlayers(MctsPlayer(white_oracle), MctsPlayer(black_oracle))
+   (src/training.jl:130-143, src/benchmark.jl:78-99, src/play.jl:248-282).  Each worker owns one tree per player; both
+   players use `mp`; leaves of the two players are evaluated by their own oracle each tick.  With alternate_colors,
+   `white_oracle`'s player takes black in every game whose 1-based index is odd. */
+int32_t az_selfplay_create_duel(az_ctx* ctx, int32_t game, az_net* white_oracle, az_net* black_oracle, const az_mcts_params* mp,
+                                const az_sim_params* sp, uint64_t seed, az_selfplay** out);
 /* plays games first_game_index .. first_game_index + num_games - 1 (global indices key the RNG streams);
    returns immediately, the engine runs on its own host thread + CUDA stream */
 int32_t az_selfplay_start(az_selfplay* s, int32_t num_games, int64_t first_game_index);
@@ -170,13 +177,20 @@ int32_t az_selfplay_wait(az_selfplay* s);
 int32_t az_selfplay_counts(az_selfplay* s, int64_t* nsamples, int64_t* ngames);
 /* samples ordered by (game, ply) = Trace rows (src/trace.jl:17-24) + push_trace! targets (src/memory.jl:74-87):
    states[nsamples*state_bytes], pi[nsamples*A] (zero on illegal), mask[nsamples*A], z, t, game_of_sample,
-   rewards (white_reward after the move), actions; any pointer may be NULL */
+   rewards (white_reward after the move), actions; any pointer may be NULL.  With flip_probability > 0 `states` holds
+   trace.states[i] (the state before the symmetry of turn i, as the reference records it) while pi, mask and actions
+   are in the frame the player thought in (the image state), so that policies[i] == pi[mask] exactly as in the reference. */
 int32_t az_selfplay_fetch(az_selfplay* s, uint8_t* states, float* pi, uint8_t* mask, float* z, float* t,
                           int32_t* game_of_sample, double* rewards, int32_t* actions);
 /* self_play_measurements (src/training.jl:269-273): per game edepth, node count (mem = nodes x
    MCTS.memory_footprint_per_node), number of moves; totals[4] = {seconds, simulations, expansions, samples} */
 int32_t az_selfplay_stats(az_selfplay* s, double* edepth_per_game, int64_t* nodes_per_game, int32_t* moves_per_game,
                           double* totals);
+/* rewards_and_redundancy (src/simulations.jl:292-307): rewards[ngames] = total_reward(trace, gamma) (src/trace.jl:45-47)
+   negated when colors_flipped; colors_flipped[ngames]; final_states[ngames*state_bytes] = last state of each trace;
+   *redundancy = 1 - |unique states| / |states| over all trace states; any pointer may be NULL */
+int32_t az_selfplay_outcomes(az_selfplay* s, double gamma, double* rewards, int32_t* colors_flipped, uint8_t* final_states,
+                             double* redundancy);
 int32_t az_selfplay_destroy(az_selfplay* s);
 
 #ifdef __cplusplus

@@ -722,17 +722,43 @@ int oz_categorical(const float* p, int n, float u) { /* Distributions.jl rand(::
 /* ------------------------------------------------------------------------- */
 /* Self-play (src/play.jl:298-315, src/memory.jl:74-87, src/simulations.jl:221-241) */
 /* ------------------------------------------------------------------------- */
-void oz_play_game(oz_env* env, const oz_mcts_params* mp, uint64_t seed, uint64_t game_idx, oz_trace* tr) {
+/* GI.symmetries: connect-four = the column mirror (games/connect-four/game.jl:247-257); tic-tac-toe = the 7 non-trivial
+   dihedral maps in the order rot, rot2, rot3, flip, flip.rot, flip.rot2, flip.rot3 where board'[p] = board[sym[p]]
+   (games/tictactoe/game.jl:149-168); mancala and grid-world declare none. */
+int oz_num_symmetries(int game_id) { return game_id == OZ_CONNECT_FOUR ? 1 : (game_id == OZ_TICTACTOE ? 7 : 0); }
+static void ttt_sym_xy(int j, int* x, int* y) { /* 0-based: rot(x,y) = (y, 2-x); flip(x,y) = (x, 2-y) */
+  int nrot = (j < 3) ? j + 1 : j - 3;
+  for (int k = 0; k < nrot; k++) { int nx = *y, ny = 2 - *x; *x = nx; *y = ny; }
+  if (j >= 3) *y = 2 - *y;
+}
+void oz_apply_symmetry(int game_id, int sym, const uint8_t* in, uint8_t* out) {
+  int sb = OZ_SBYTES[game_id];
+  memcpy(out, in, (size_t)sb);
+  if (game_id == OZ_CONNECT_FOUR) {
+    for (int col = 0; col < 7; col++)
+      for (int row = 0; row < 6; row++) out[col + 7 * row] = in[(6 - col) + 7 * row];
+  } else if (game_id == OZ_TICTACTOE) {
+    for (int p = 0; p < 9; p++) {
+      int x = p % 3, y = p / 3;
+      ttt_sym_xy(sym, &x, &y);
+      out[p] = in[y * 3 + x];
+    }
+  }
+}
+
+void oz_play_game2(oz_env* white, oz_env* black, const oz_mcts_params* mp, double flip_p, uint64_t seed, uint64_t game_idx,
+                   oz_trace* tr) {
+  const int gid = white->game_id;
   oz_game g;
-  oz_game_init(&g, env->game_id);
-  if (env->game_id == OZ_GRID_WORLD) { /* RL.reset!: random start cell (games/grid-world/game.jl:36) */
+  oz_game_init(&g, gid);
+  if (gid == OZ_GRID_WORLD) { /* RL.reset!: random start cell (games/grid-world/game.jl:36) */
     uint32_t o[4];
     uint8_t st[2];
     oz_philox(seed, 0, OZ_PURPOSE_POSITION, (uint32_t)game_idx, (uint32_t)(game_idx >> 32), o);
     st[0] = (uint8_t)(1 + o[0] % 10u); st[1] = (uint8_t)(1 + o[1] % 10u);
     oz_game_set_state(&g, OZ_GRID_WORLD, st);
   }
-  int A = OZ_NACT[env->game_id];
+  int A = OZ_NACT[gid];
   memset(tr, 0, sizeof(*tr));
   oz_game_get_state(&g, tr->states[0]);
   int n = 0;
@@ -740,6 +766,20 @@ void oz_play_game(oz_env* env, const oz_mcts_params* mp, uint64_t seed, uint64_t
     int acts[OZ_MAX_ACTIONS];
     double eta[OZ_MAX_ACTIONS], pi[OZ_MAX_ACTIONS], pis[OZ_MAX_ACTIONS];
     float pf[OZ_MAX_ACTIONS];
+    if (flip_p != 0.0) { /* play.jl:305-307; game.jl:329-336 */
+      int ns = oz_num_symmetries(gid);
+      double u = oz_u01(oz_stream_u64(seed, game_idx, (uint32_t)n, OZ_PURPOSE_SYMMETRY, 0));
+      if (ns > 0 && u < flip_p) {
+        int j = (int)(oz_stream_u64(seed, game_idx, (uint32_t)n, OZ_PURPOSE_SYMMETRY, 1) % (uint64_t)ns);
+        uint8_t cur[OZ_STATE_BYTES] = {0}, img[OZ_STATE_BYTES] = {0};
+        oz_game_get_state(&g, cur);
+        oz_apply_symmetry(gid, j, cur, img);
+        oz_game_set_state(&g, gid, img);
+        tr->sym[n] = j + 1;
+      }
+    }
+    oz_game_get_state(&g, tr->think_states[n]);
+    oz_env* env = oz_game_white_playing(&g) ? white : black;              /* think(::TwoPlayers): play.jl:258-264 */
     int nl = oz_legal_actions(&g, acts);
     oz_dirichlet(seed, game_idx, (uint32_t)n, nl, mp->noise_alpha, eta);  /* drawn even if eps == 0 (mcts.jl:240) */
     oz_env_set_noise(env, seed, game_idx, (uint32_t)n);
@@ -756,7 +796,7 @@ void oz_play_game(oz_env* env, const oz_mcts_params* mp, uint64_t seed, uint64_t
     {
       double u[2];
       const double* env_u = NULL;
-      if (env->game_id == OZ_GRID_WORLD) { oz_env_noise(seed, game_idx, (uint32_t)n, 0x7FFFFFu, 0u, u); env_u = u; }
+      if (gid == OZ_GRID_WORLD) { oz_env_noise(seed, game_idx, (uint32_t)n, 0x7FFFFFu, 0u, u); env_u = u; }
       oz_game_play(&g, acts[k], env_u);
     }
     tr->rewards[n] = oz_game_white_reward(&g);
@@ -766,14 +806,28 @@ void oz_play_game(oz_env* env, const oz_mcts_params* mp, uint64_t seed, uint64_t
   tr->n_moves = n;
   double wr = 0.0; /* push_trace! */
   for (int i = n - 1; i >= 0; i--) {
-    wr = env->gamma * wr + tr->rewards[i];
+    wr = white->gamma * wr + tr->rewards[i];
     oz_game gi;
-    oz_game_set_state(&gi, env->game_id, tr->states[i]);
+    oz_game_set_state(&gi, gid, tr->states[i]);
     tr->z[i] = oz_game_white_playing(&gi) ? wr : -wr;
     tr->t[i] = (double)(n - i);
   }
-  tr->mem_nodes = (int64_t)env->count;
-  tr->edepth = env->total_simulations == 0 ? 0.0 : (double)env->total_nodes_traversed / (double)env->total_simulations;
+  if (white == black) {
+    tr->mem_nodes = (int64_t)white->count;
+    tr->edepth = white->total_simulations == 0 ? 0.0 : (double)white->total_nodes_traversed / (double)white->total_simulations;
+  } else {
+    int64_t ts = white->total_simulations + black->total_simulations;
+    tr->mem_nodes = (int64_t)white->count + (int64_t)black->count;
+    tr->edepth = ts == 0 ? 0.0 : (double)(white->total_nodes_traversed + black->total_nodes_traversed) / (double)ts;
+  }
+}
+void oz_play_game(oz_env* env, const oz_mcts_params* mp, uint64_t seed, uint64_t game_idx, oz_trace* tr) {
+  oz_play_game2(env, env, mp, 0.0, seed, game_idx, tr);
+}
+double oz_total_reward(const oz_trace* tr, double gamma) { /* sum(gamma^(i-1) * r_i), left to right */
+  double s = 0.0, gp = 1.0;
+  for (int i = 0; i < tr->n_moves; i++) { s = (i == 0) ? gp * tr->rewards[0] : s + gp * tr->rewards[i]; gp = gp * gamma; }
+  return s;
 }
 
 void oz_worker_run(int game_id, oz_oracle_fn oracle, void* octx, const oz_mcts_params* mp, uint64_t seed, uint64_t first,

@@ -135,12 +135,26 @@ typedef struct {
   double rewards[OZ_MAX_PLIES];
   double z[OZ_MAX_PLIES];
   double t[OZ_MAX_PLIES];
-  int64_t mem_nodes;                           /* length(env.tree) when measured */
-  double edepth;                               /* average_exploration_depth */
+  int64_t mem_nodes;                           /* length(env.tree) when measured (both players' trees in a duel) */
+  double edepth;                               /* average_exploration_depth (both players pooled in a duel) */
+  int32_t sym[OZ_MAX_PLIES];                   /* 0, or 1 + index of the symmetry applied before thinking (play.jl:305-307) */
+  uint8_t think_states[OZ_MAX_PLIES][OZ_STATE_BYTES]; /* the state the player thought on (pi and mask are in its frame) */
 } oz_trace;
 
 /* play_game (src/play.jl:298-315) for game index `game` on worker env `env` */
 void oz_play_game(oz_env* env, const oz_mcts_params* mp, uint64_t seed, uint64_t game, oz_trace* out);
+/* GI.symmetries (games/connect-four/game.jl:247-257, games/tictactoe/game.jl:149-168): number of declared symmetries
+   (0: none -> flip_probability > 0 is a parameter error, src/params.jl:377-381) and the image of a state */
+int oz_num_symmetries(int game_id);
+void oz_apply_symmetry(int game_id, int sym, const uint8_t* state_in, uint8_t* state_out);
+/* play_game with TwoPlayers(white, black) (src/play.jl:248-282) and flip_probability (src/play.jl:305-307).
+   `white` thinks when white is to play, `black` otherwise (the same env twice = a single MctsPlayer).  The flip
+   decision of move m is u01(stream(seed, game, m, SYMMETRY, 0)) < flip_probability and the symmetry index is
+   stream(seed, game, m, SYMMETRY, 1) mod num_symmetries. */
+void oz_play_game2(oz_env* white, oz_env* black, const oz_mcts_params* mp, double flip_probability, uint64_t seed,
+                   uint64_t game, oz_trace* out);
+/* total_reward(trace, gamma) (src/trace.jl:45-47) */
+double oz_total_reward(const oz_trace* tr, double gamma);
 /* one worker of simulate() (src/simulations.jl:207-244): plays games first, first+stride, ... (count games),
    measures before reset, resets every reset_every games (<=0: never) */
 void oz_worker_run(int game_id, oz_oracle_fn oracle, void* octx, const oz_mcts_params* mp, uint64_t seed,

@@ -54,7 +54,8 @@ class Trace(C.Structure):
     _fields_ = [("n_moves", C.c_int), ("states", (C.c_uint8 * STATE_BYTES) * (MAX_PLIES + 1)),
                 ("pi", (C.c_float * MAX_ACTIONS) * MAX_PLIES), ("mask", (C.c_uint8 * MAX_ACTIONS) * MAX_PLIES),
                 ("action", C.c_int32 * MAX_PLIES), ("rewards", C.c_double * MAX_PLIES), ("z", C.c_double * MAX_PLIES),
-                ("t", C.c_double * MAX_PLIES), ("mem_nodes", C.c_int64), ("edepth", C.c_double)]
+                ("t", C.c_double * MAX_PLIES), ("mem_nodes", C.c_int64), ("edepth", C.c_double), ("sym", C.c_int32 * MAX_PLIES),
+                ("think_states", (C.c_uint8 * STATE_BYTES) * MAX_PLIES)]
 
 
 ORACLE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float))
@@ -93,6 +94,10 @@ def lib():
         L.oz_apply_temperature.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         L.oz_fix_probvec.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oz_play_game.argtypes = [C.c_void_p, C.POINTER(MctsParams), C.c_uint64, C.c_uint64, C.POINTER(Trace)]
+        L.oz_play_game2.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(MctsParams), C.c_double, C.c_uint64, C.c_uint64, C.POINTER(Trace)]
+        L.oz_apply_symmetry.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.oz_total_reward.restype = C.c_double
+        L.oz_total_reward.argtypes = [C.POINTER(Trace), C.c_double]
         L.oz_worker_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(MctsParams), C.c_uint64, C.c_uint64,
                                     C.c_uint64, C.c_int, C.c_int, C.POINTER(Trace)]
         L.oz_random_position.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]

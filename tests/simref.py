@@ -7,10 +7,12 @@ import ctypes as C
 import numpy as np
 
 
-def oracle_simulate(oz, gid, oracle, omp, seed, S, NG, reset_every):
+def oracle_simulate(oz, gid, oracle, omp, seed, S, NG, reset_every, baseline=None, alternate_colors=False, flip_probability=0.0):
+    """`baseline` given: every worker is TwoPlayers(MctsPlayer(oracle), MctsPlayer(baseline)) (src/training.jl:130-143)."""
     L = oz.lib()
-    fn = oz.builtin_oracle(oracle) if isinstance(oracle, str) else oracle
-    envs = [L.oz_env_create(gid, fn, None, omp.gamma, omp.cpuct, omp.noise_eps, omp.noise_alpha, omp.prior_temperature) for _ in range(S)]
+    fns = [oz.builtin_oracle(o) if isinstance(o, str) else o for o in ([oracle] if baseline is None else [oracle, baseline])]
+    mk = lambda fn: L.oz_env_create(gid, fn, None, omp.gamma, omp.cpuct, omp.noise_eps, omp.noise_alpha, omp.prior_temperature)
+    envs = [[mk(fn) for fn in fns] for _ in range(S)]
     A, sb = oz.num_actions(gid), oz.state_bytes(gid)
     nsims = omp.num_iters_per_turn
     free_at = {w: 0 for w in range(S)}
@@ -28,17 +30,22 @@ def oracle_simulate(oz, gid, oracle, omp, seed, S, NG, reset_every):
                     break
                 g = nxt
                 nxt += 1
-                L.oz_play_game(envs[w], C.byref(omp), seed, g, C.byref(tr))
+                flipped = baseline is not None and alternate_colors and (g + 1) % 2 == 1   # src/simulations.jl:224-226
+                white, black = (envs[w][0], envs[w][-1]) if not flipped else (envs[w][-1], envs[w][0])
+                L.oz_play_game2(white, black, C.byref(omp), flip_probability, seed, g, C.byref(tr))
                 n = tr.n_moves
                 traces[g] = dict(n_moves=n, states=np.ctypeslib.as_array(tr.states)[:n + 1, :sb].copy(),
                                  pi=np.ctypeslib.as_array(tr.pi)[:n, :A].copy(), mask=np.ctypeslib.as_array(tr.mask)[:n, :A].copy(),
                                  action=np.ctypeslib.as_array(tr.action)[:n].copy(), rewards=np.ctypeslib.as_array(tr.rewards)[:n].copy(),
                                  z=np.ctypeslib.as_array(tr.z)[:n].copy(), t=np.ctypeslib.as_array(tr.t)[:n].copy(),
-                                 mem_nodes=tr.mem_nodes, edepth=tr.edepth)
+                                 mem_nodes=tr.mem_nodes, edepth=tr.edepth, sym=np.ctypeslib.as_array(tr.sym)[:n].copy(),
+                                 think_states=np.ctypeslib.as_array(tr.think_states)[:n, :sb].copy(), colors_flipped=flipped,
+                                 total_reward=L.oz_total_reward(C.byref(tr), omp.gamma))
                 slot_of[g] = w
                 played[w] += 1
                 if reset_every > 0 and played[w] % reset_every == 0:
-                    L.oz_env_reset(envs[w])
+                    for e in envs[w]:
+                        L.oz_env_reset(e)
                 free_at[w] = t + n * nsims
                 if n == 0:
                     again.append(w)
@@ -46,9 +53,17 @@ def oracle_simulate(oz, gid, oracle, omp, seed, S, NG, reset_every):
         if nxt >= NG:
             break
         # workers that did not get a game this tick because the games ran out stay idle
-    for e in envs:
-        L.oz_env_destroy(e)
+    for ee in envs:
+        for e in ee:
+            L.oz_env_destroy(e)
     return traces, slot_of
+
+
+def rewards_and_redundancy(traces):
+    """src/simulations.jl:292-307 over the oracle traces."""
+    rewards = np.array([(-t["total_reward"] if t["colors_flipped"] else t["total_reward"]) for _, t in sorted(traces.items())])
+    states = [bytes(s) for _, t in sorted(traces.items()) for s in t["states"]]
+    return rewards, 1.0 - len(set(states)) / len(states)
 
 
 def assert_same_samples(out, traces, check_mask=True):
@@ -68,3 +83,13 @@ def assert_same_samples(out, traces, check_mask=True):
         assert out["nodes"][g] == tr["mem_nodes"] and out["edepth"][g] == tr["edepth"], g
         k += n
     assert k == len(out["game"]) == out["samples"]
+
+
+def assert_same_outcomes(out, traces):
+    """rewards_and_redundancy + the final state of every trace."""
+    rewards, red = rewards_and_redundancy(traces)
+    assert (out["game_rewards"] == rewards).all()
+    assert out["redundancy"] == red
+    for g, t in sorted(traces.items()):
+        assert bytes(out["final_states"][g]) == bytes(t["states"][t["n_moves"]]), g
+        assert bool(out["colors_flipped"][g]) == bool(t["colors_flipped"]), g

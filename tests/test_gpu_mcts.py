@@ -136,6 +136,54 @@ def test_selfplay_bit_exact(az, oz, ctx, game, nsims, temp):
     net.close()
 
 
+@pytest.mark.parametrize("game,nsims", [("connect-four", 48), ("tictactoe", 40)])
+def test_selfplay_flip_probability_bit_exact(az, oz, ctx, game, nsims):
+    """play_game(flip_probability = 0.5) (src/play.jl:305-307): trace states before the symmetry, pi / mask / actions in the
+    image frame, exactly as the oracle records them."""
+    from tests import simref
+    gs, gid = az.GameSpec(game), oz.game_id(game)
+    S, NG, seed = 8, 20, 31
+    mp = az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, temperature=az.PLSchedule([0, 4], [1.0, 0.5]), dirichlet_noise_eps=0.25,
+                       dirichlet_noise_alpha=1.0)
+    net = az.SynthOracle(ctx, gs)
+    out = az.simulate(ctx, gs, net, az.SelfPlayParams(mp, az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=2,
+                                                                        flip_probability=0.5)), seed=seed, gamma=1.0)
+    omp = oz.mcts_params(cpuct=2.0, noise_eps=0.25, noise_alpha=1.0, num_iters_per_turn=nsims, sched_xs=(0, 4), sched_ys=(1.0, 0.5))
+    traces, _ = simref.oracle_simulate(oz, gid, "synth", omp, seed, S, NG, 2, flip_probability=0.5)
+    assert sum(int((t["sym"] != 0).sum()) for t in traces.values()) > NG  # the case is exercised
+    simref.assert_same_samples(out, traces)
+    simref.assert_same_outcomes(out, traces)
+    net.close()
+
+
+@pytest.mark.parametrize("game,nsims,alt,flip,reset", [("connect-four", 48, True, 0.5, 2), ("tictactoe", 40, True, 0.0, 1),
+                                                       ("mancala", 24, False, 0.0, 3), ("connect-four", 32, False, 0.0, 0)])
+def test_duel_bit_exact(az, oz, ctx, game, nsims, alt, flip, reset):
+    """pit_networks-style simulate() with TwoPlayers (src/training.jl:130-143, src/play.jl:248-282): one tree per player per
+    worker, per-player oracle, alternate_colors (src/simulations.jl:224-230), rewards_and_redundancy (:292-307)."""
+    from tests import simref
+    gs, gid = az.GameSpec(game), oz.game_id(game)
+    S, NG, seed = 6, 17, 1234
+    mp = az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, temperature=az.PLSchedule([0], [0.8]), dirichlet_noise_eps=0.1,
+                       dirichlet_noise_alpha=1.0)
+    contender, baseline = az.SynthOracle(ctx, gs), az.RandomOracle(ctx, gs)
+    sim = az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=reset, flip_probability=flip, alternate_colors=alt)
+    called = []
+    out = az.simulate(ctx, gs, contender, az.SelfPlayParams(mp, sim), seed=seed, baseline=baseline, gamma=1.0,
+                      game_simulated=lambda: called.append(1))
+    assert len(called) == NG
+    omp = oz.mcts_params(cpuct=2.0, noise_eps=0.1, noise_alpha=1.0, num_iters_per_turn=nsims, sched_xs=(0,), sched_ys=(0.8,))
+    traces, _ = simref.oracle_simulate(oz, gid, "synth", omp, seed, S, NG, reset, baseline="uniform", alternate_colors=alt,
+                                       flip_probability=flip)
+    simref.assert_same_samples(out, traces)
+    simref.assert_same_outcomes(out, traces)
+    assert (out["colors_flipped"] == [1 if alt and (g + 1) % 2 == 1 else 0 for g in range(NG)]).all()
+    rewards, red = az.pit_networks(ctx, gs, contender, baseline, az.SelfPlayParams(mp, sim), seed=seed)
+    assert (rewards == out["game_rewards"]).all() and red == out["redundancy"]
+    contender.close()
+    baseline.close()
+
+
 def test_full_size_properties(az, ctx):
     """BASELINE config 1 sizes (4096 trees x 600 sims): size-independent invariants instead of an oracle run."""
     gs = az.GameSpec("connect-four")
@@ -169,9 +217,14 @@ def test_error_paths_mirror_reference_asserts(az, ctx):
     with pytest.raises(az.AzError) as e:   # niters > 0 (src/play.jl:162)
         az.MctsEnv(ctx, gs, net, az.MctsParams(cpuct=1.0, num_iters_per_turn=0, dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0), 4)
     assert e.value.status == 1
-    with pytest.raises(az.AzError) as e:   # flip_probability is not supported yet
-        az.SelfPlay(ctx, gs, net, az.SelfPlayParams(mp, az.SimParams(num_games=4, num_workers=4, batch_size=4, flip_probability=0.5)))
-    assert e.value.status == 5
+    man = az.GameSpec("mancala")
+    mnet = az.SynthOracle(ctx, man)
+    with pytest.raises(az.AzError) as e:   # flip_probability needs declared symmetries (src/params.jl:377-381)
+        az.SelfPlay(ctx, man, mnet, az.SelfPlayParams(mp, az.SimParams(num_games=4, num_workers=4, batch_size=4, flip_probability=0.5)))
+    assert e.value.status == 1 and "symmetries" in str(e.value)
+    with pytest.raises(az.AzError):        # duel oracles must belong to the game
+        az.SelfPlay(ctx, gs, net, az.SelfPlayParams(mp, az.SimParams(num_games=4, num_workers=4, batch_size=4)), baseline=mnet)
+    mnet.close()
     env = az.MctsEnv(ctx, gs, net, mp, 4, 64)
     with pytest.raises(az.AzError):        # eta required when eps != 0
         env.set_roots(gs.random_positions(1, 4, 10), None)

@@ -159,6 +159,43 @@ def test_selfplay_with_network_bit_exact(az, oz, ctx):
     net.close()
 
 
+def test_duel_of_two_networks_bit_exact(az, oz, ctx):
+    """pit_networks (src/training.jl:130-143) with two different ResNets, alternate_colors and flip_probability = 0.5 (the
+    shipped connect-four ArenaParams, games/connect-four/params.jl:32-45, at a small size): each oracle-side player replays
+    with its own network's (P, V), so traces and rewards must match bit for bit."""
+    import ctypes as C
+    from tests import simref
+    gs = az.GameSpec("connect-four")
+    gid = oz.game_id("connect-four")
+    nets = [netcheck.make_net(az, ctx, gs, netcheck.c4_hp(1), seed=5)[0], netcheck.make_net(az, ctx, gs, netcheck.c4_hp(2), seed=6)[0]]
+    S, NG, nsims, seed = 4, 10, 24, 4242
+    mp = az.MctsParams(cpuct=1.0, num_iters_per_turn=nsims, temperature=az.PLSchedule([0], [0.2]), dirichlet_noise_eps=0.05,
+                       dirichlet_noise_alpha=1.0)
+    sim = az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=2, flip_probability=0.5, alternate_colors=True)
+    out = az.simulate(ctx, gs, nets[0], az.SelfPlayParams(mp, sim), seed=seed, baseline=nets[1], gamma=1.0)
+    sb = gs.state_bytes
+    fns = []
+    for net in nets:
+        def cb(ctxp, g, sp, n, P, V, net=net, cache={}):
+            key = bytes(sp[:sb])
+            if key not in cache:
+                p, v, _ = net.evaluate_batch(np.frombuffer(key, np.uint8)[None])
+                m = gs.actions_mask(np.frombuffer(key, np.uint8))
+                cache[key] = (p[0][m], float(v[0]))
+            p, v = cache[key]
+            for i in range(n):
+                P[i] = p[i]
+            V[0] = v
+        fns.append(oz.ORACLE_FN(cb))
+    omp = oz.mcts_params(cpuct=1.0, noise_eps=0.05, noise_alpha=1.0, num_iters_per_turn=nsims, sched_xs=(0,), sched_ys=(0.2,))
+    traces, _ = simref.oracle_simulate(oz, gid, C.cast(fns[0], C.c_void_p), omp, seed, S, NG, 2, baseline=C.cast(fns[1], C.c_void_p),
+                                       alternate_colors=True, flip_probability=0.5)
+    simref.assert_same_samples(out, traces, check_mask=False)
+    simref.assert_same_outcomes(out, traces)
+    for n in nets:
+        n.close()
+
+
 @pytest.mark.parametrize("game,hp", [("tictactoe", dict(width=200, depth_common=6, use_batch_norm=True)),     # games/tictactoe/params.jl:8-12
                                       ("connect-four", dict(width=100, depth_common=4, use_batch_norm=False)),
                                       ("mancala", dict(width=64, depth_common=2, depth_phead=2, depth_vhead=0, use_batch_norm=True))])

@@ -157,3 +157,113 @@ def test_fix_probvec_and_categorical(oz):
     assert t.tolist() == [0, 0, 1]
     L.oz_apply_temperature(pi.ctypes.data, 3, 0.5, t.ctypes.data)
     assert np.allclose(t, pi ** 2 / (pi ** 2).sum(), rtol=1e-14)
+
+
+# ---- symmetries, flip_probability, TwoPlayers ------------------------------------------------------
+
+def _sym(oz, gid, j, state):
+    sb = oz.state_bytes(gid)
+    src = np.zeros(oz.STATE_BYTES, np.uint8)
+    src[:sb] = state[:sb]
+    out = np.zeros(oz.STATE_BYTES, np.uint8)
+    oz.lib().oz_apply_symmetry(gid, j, src.ctypes.data, out.ctypes.data)
+    return out[:sb].copy()
+
+
+def test_symmetry_tables(oz):
+    """GI.symmetries: connect-four mirror (games/connect-four/game.jl:247-257); tic-tac-toe dihedral group
+    (games/tictactoe/game.jl:149-168); checks of src/scripts/test_game.jl:81-96 (same player, image is a valid state,
+    legal actions are permuted)."""
+    L = oz.lib()
+    assert [L.oz_num_symmetries(oz.game_id(n)) for n in ("connect-four", "tictactoe", "mancala", "grid-world")] == [1, 7, 0, 0]
+    c4, ttt = oz.game_id("connect-four"), oz.game_id("tictactoe")
+    for s in oz.random_positions(c4, 5, 64):
+        m = _sym(oz, c4, 0, s)
+        assert (m[:42].reshape(6, 7) == s[:42].reshape(6, 7)[:, ::-1]).all() and m[42] == s[42]
+        assert (_sym(oz, c4, 0, m) == s).all()  # involution
+        assert (oz.GameEnv(c4, m).actions_mask() == oz.GameEnv(c4, s).actions_mask()[::-1]).all()
+    # tic-tac-toe: hand-derived tables. rot (x,y)->(y,N-x+1): sym[p] = pos(rot(xy(p)))
+    rot = [6, 3, 0, 7, 4, 1, 8, 5, 2]      # p=0 (x=1,y=1) -> (1,3) -> pos 6 (0-based) ...
+    flip = [6, 7, 8, 3, 4, 5, 0, 1, 2]     # (x,y) -> (x, N-y+1)
+    comp = lambda f, g: [f[g[p]] for p in range(9)]  # (f . g)(p) = f(g(p))
+    rot2, rot3 = comp(rot, rot), comp(rot, comp(rot, rot))
+    tables = [rot, rot2, rot3, flip, comp(flip, rot), comp(flip, rot2), comp(flip, rot3)]
+    base = np.array([1, 2, 0, 0, 1, 0, 2, 0, 0, 2], np.uint8)
+    images = set()
+    for j, tab in enumerate(tables):
+        img = _sym(oz, ttt, j, base)
+        assert (img[:9] == base[:9][tab]).all() and img[9] == base[9], j
+        images.add(bytes(img))
+        # the image is a state with the same number of stones and the same outcome status
+        ga, gb = oz.GameEnv(ttt, base), oz.GameEnv(ttt, img)
+        assert ga.terminated() == gb.terminated() and ga.actions_mask().sum() == gb.actions_mask().sum()
+    assert len(images) == 7 and bytes(base) not in images
+
+
+@pytest.mark.parametrize("name", ["connect-four", "tictactoe"])
+def test_play_game_with_flips(oz, name):
+    """play_game(flip_probability=p) (src/play.jl:298-315): the trace keeps the pre-symmetry state, the player thinks on the
+    image, and the game continues from the image."""
+    gid = oz.game_id(name)
+    L = oz.lib()
+    mp = oz.mcts_params(num_iters_per_turn=24, cpuct=2.0, noise_eps=0.25, noise_alpha=1.0, sched_xs=(0,), sched_ys=(1.0,))
+    tr, tr0 = oz.Trace(), oz.Trace()
+    sb = oz.state_bytes(gid)
+    nflips = 0
+    for game in range(6):
+        env = oz.Env(gid, "synth", cpuct=2.0, noise_eps=0.25)
+        L.oz_play_game2(env.h, env.h, C.byref(mp), 0.5, 77, game, C.byref(tr))
+        n = tr.n_moves
+        assert n > 0
+        states = np.ctypeslib.as_array(tr.states)[:n + 1, :sb]
+        think = np.ctypeslib.as_array(tr.think_states)[:n, :sb]
+        sym = np.ctypeslib.as_array(tr.sym)[:n]
+        acts = np.ctypeslib.as_array(tr.action)[:n]
+        mask = np.ctypeslib.as_array(tr.mask)[:n, :oz.num_actions(gid)]
+        for i in range(n):
+            if sym[i]:
+                nflips += 1
+                assert (think[i] == _sym(oz, gid, int(sym[i]) - 1, states[i])).all()
+            else:
+                assert (think[i] == states[i]).all()
+            g = oz.GameEnv(gid, think[i])
+            assert (g.actions_mask() == mask[i]).all() and mask[i][acts[i]]
+            g.play(int(acts[i]))
+            assert bytes(g.state()[:sb]) == bytes(states[i + 1])
+        # flip_probability = 0 reproduces oz_play_game
+        env1, env2 = oz.Env(gid, "synth", cpuct=2.0, noise_eps=0.25), oz.Env(gid, "synth", cpuct=2.0, noise_eps=0.25)
+        L.oz_play_game2(env1.h, env1.h, C.byref(mp), 0.0, 77, game, C.byref(tr))
+        L.oz_play_game(env2.h, C.byref(mp), 77, game, C.byref(tr0))
+        assert bytes(tr) == bytes(tr0)
+    assert nflips > 5
+
+
+def test_two_players_duel(oz):
+    """TwoPlayers (src/play.jl:248-282): white's tree only grows on white's turns, black's on black's; with both players
+    equal to one env the duel degenerates to a single MctsPlayer."""
+    gid = oz.game_id("connect-four")
+    L = oz.lib()
+    mp = oz.mcts_params(num_iters_per_turn=20, cpuct=2.0, noise_eps=0.25, noise_alpha=1.0, sched_xs=(0,), sched_ys=(1.0,))
+    w, b = oz.Env(gid, "synth", cpuct=2.0, noise_eps=0.25), oz.Env(gid, "uniform", cpuct=2.0, noise_eps=0.25)
+    tr = oz.Trace()
+    L.oz_play_game2(w.h, b.h, C.byref(mp), 0.0, 3, 0, C.byref(tr))
+    n = tr.n_moves
+    nw, nb = (n + 1) // 2, n // 2  # white moves first and colours alternate in connect-four
+    assert w.total_simulations == 20 * nw and b.total_simulations == 20 * nb
+    assert tr.mem_nodes == w.num_nodes + b.num_nodes
+    assert tr.edepth == (w.total_nodes_traversed + b.total_nodes_traversed) / (w.total_simulations + b.total_simulations)
+    tot = L.oz_total_reward(C.byref(tr), 1.0)
+    assert tot == sum(np.ctypeslib.as_array(tr.rewards)[:n]) and tot in (-1.0, 0.0, 1.0)
+
+
+def test_simulate_duel_alternate_colors(oz):
+    """simulate() with TwoPlayers and alternate_colors (src/simulations.jl:221-241) + rewards_and_redundancy (:292-307)."""
+    from tests import simref
+    gid = oz.game_id("tictactoe")
+    mp = oz.mcts_params(num_iters_per_turn=16, cpuct=1.0, noise_eps=0.25, noise_alpha=1.0, sched_xs=(0,), sched_ys=(1.0,))
+    traces, _ = simref.oracle_simulate(oz, gid, "synth", mp, 9, 4, 12, 2, baseline="uniform", alternate_colors=True, flip_probability=0.5)
+    assert [traces[g]["colors_flipped"] for g in range(4)] == [True, False, True, False]
+    rewards, red = simref.rewards_and_redundancy(traces)
+    assert len(rewards) == 12 and set(rewards) <= {-1.0, 0.0, 1.0} and 0.0 < red < 1.0
+    for g, t in traces.items():
+        assert rewards[g] == (-1 if t["colors_flipped"] else 1) * t["rewards"].sum()

@@ -127,6 +127,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return d;
 }
 
+// K-major, SWIZZLE_NONE descriptor for one 8-row x 16-element fp16 slice (two 8x8 core matrices of 128 B each, the second
+// K half `lbo` bytes after the first): cute canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units
+__device__ __forceinline__ uint64_t umma_desc_interleave(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;  // layout type 0 = SWIZZLE_NONE
+}
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 implicit-GEMM kernel: tower convs, the heads' 1x1 convs and the value head's dense layer all run here
 // ------------------------------------------------------------------------------------------------
@@ -167,7 +178,7 @@ struct GemmArgs {
   int debug;             // timing experiments only (AZ_TOWER_DEBUG bitmask): 4 = no epilogue global I/O
   const float* bias;
   const float* resid32;  // EPI_CONV2
-  const __half* resid16; // EPI_CONV2 of block 0 (Connect-Four kernel): residual = fp16 stem output, X32 not yet materialised
+  int res_lo;            // Connect-Four kernel, EPI_CONV2: 1 = the residual has a low-order part (blocks >= 1), 0 = fp16 only (block 0)
   float* out32;          // EPI_CONV2 (stream), EPI_DENSE (hidden)
   __half* out16a;        // CONV1: T, CONV2: X16, HEAD: policy features
   __half* out16b;        // HEAD: value features
@@ -386,14 +397,15 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 namespace tc3 {
 constexpr int ASTAGES = 3;
 constexpr int NUM_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
-constexpr int EPI_BYTES = 4 * 7168;  // conv2: 4 warps x (2 x 2 KB residual tiles + 2 KB fp32 out tile + 1 KB fp16 out tile);
+constexpr int EPI_BYTES = 8 * 3072;  // conv2: 8 warps x 3 x 1 KB fp16 out tiles (ring shared by the hi and lo streams);
                                      // conv1: 8 warps x 2 x 1 KB fp16 out tiles
+constexpr int RES_BYTES = tc2::BM * 128;  // one residual A stage: 128 rows x 64 channels fp16
 struct Smem {
   uint8_t b[tc2::NCHUNK][tc2::B_CHUNK];
   uint8_t a[ASTAGES][tc2::A_STAGE];
+  uint8_t ident[1024];  // conv2: this CTA's 8 x 16 slice of the 16 x 16 identity (B operand of the residual MMAs)
   uint8_t epi[EPI_BYTES];
   uint64_t full[ASTAGES], empty[ASTAGES], tfull[2], tempty[2], bfull;
-  uint64_t rbar[4][2];  // conv2: residual-tile arrival barriers per epilogue warp
   uint32_t tmem_base;
   float bias[128];
 };
@@ -402,7 +414,8 @@ struct Smem {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc3::NUM_THREADS, 1)
 az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                 const __grid_constant__ CUtensorMap tmO16, const __grid_constant__ CUtensorMap tmX32, GemmArgs ga) {
+                 const __grid_constant__ CUtensorMap tmO16, const __grid_constant__ CUtensorMap tmOlo,
+                 const __grid_constant__ CUtensorMap tmRhi, const __grid_constant__ CUtensorMap tmRlo, GemmArgs ga) {
   using namespace tc2;
   constexpr int BN = 128;
   constexpr int ASTAGES = tc3::ASTAGES;
@@ -420,13 +433,22 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], EPI == tc::EPI_CONV1 ? 16 : 8); }
-    for (int i = 0; i < 4; i++) { mbar_init(&s.rbar[i][0], 1); mbar_init(&s.rbar[i][1], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 16); }
     mbar_init(&s.bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   float* bias_s = s.bias;
   if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) bias_s[threadIdx.x - 64] = ga.bias[threadIdx.x - 64];
+  if (EPI == tc::EPI_CONV2 && threadIdx.x >= 192 && threadIdx.x < 192 + 64) {
+    // identity slice: the residual MMAs are M = 256, N = 16, K = 16 with D columns [c, c+16) += A[:, c..c+15] . I16; this
+    // CTA supplies output columns rank*8 .. rank*8+7, i.e. B[n'][k] = (k == rank*8 + n'), un-swizzled K-major core matrices
+    const int i = threadIdx.x - 192;  // 64 x 4 bytes = the 256-byte slice
+    const int n = (i & 31) >> 2, khalf = i >> 5, kk = (i & 3) * 2;  // 16 B per row: 4 words of 2 halves
+    const int k0 = khalf * 8 + kk, kone = (int)rank * 8 + n;
+    const uint32_t w = (k0 == kone ? 0x3C00u : 0u) | (k0 + 1 == kone ? 0x3C000000u : 0u);
+    *reinterpret_cast<uint32_t*>(s.ident + khalf * 128 + n * 16 + (i & 3) * 4) = w;
+    fence_proxy_async();
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -452,6 +474,19 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int pt = pt0; pt < num_ptiles; pt += pt_step) {
         const int row0 = pt * 2 * BM + (int)rank * BM;
+        if (EPI == tc::EPI_CONV2) {
+          // residual stages first: this CTA's 128 rows of the block input, 64 channels at a time, hi then lo part
+          const int nres = ga.res_lo ? 4 : 2;
+          for (int rs = 0; rs < nres; rs++) {
+            mbar_wait(&s.empty[stage], phase ^ 1);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(&s.full[stage], 2 * tc3::RES_BYTES);
+              tma_load_2d_2sm(s.a[stage], (rs >> 1) ? &tmRlo : &tmRhi, &s.full[stage], (rs & 1) * BK, row0);
+            }
+            __syncwarp();
+            if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+          }
+        }
         for (int st = 0; st < 6; st++) {
           mbar_wait(&s.empty[stage], phase ^ 1);
           if (elect_one()) {
@@ -477,6 +512,26 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&s.tempty[acc], aphase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        if (EPI == tc::EPI_CONV2) {
+          // skip connection on the tensor core: the accumulator starts as x = hi (+ lo), added by 16-column identity MMAs
+          // (resnet.jl:55-62: relu(x + conv2(...))), so the epilogue never reads the residual
+          constexpr uint32_t IDESC_R = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256, N = 16
+          const uint64_t idsc = umma_desc_interleave(smem_u32(s.ident), 128u, 256u);
+          const int nres = ga.res_lo ? 4 : 2;
+          for (int rs = 0; rs < nres; rs++) {
+            mbar_wait(&s.full[stage], phase);
+            tcgen05_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(s.a[stage]));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; k++)
+                umma_f16_2sm(tmem_d + (uint32_t)((rs & 1) * BK + k * 16), adesc + (uint64_t)(k * 2), idsc, IDESC_R, (rs >> 1) ? 1u : 0u);
+              umma_commit_2sm(&s.empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+          }
+        }
         for (int st = 0; st < 6; st++) {
           const int kx = st >> 1, half = st & 1;
           mbar_wait(&s.full[stage], phase);
@@ -489,7 +544,8 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
 #pragma unroll
               for (int k = 0; k < BK / 16; k++)
-                umma_f16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (st | ky | k) ? 1u : 0u);
+                umma_f16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC,
+                             (EPI == tc::EPI_CONV2 || (st | ky | k)) ? 1u : 0u);
             }
             umma_commit_2sm(&s.empty[stage]);
             if (st == 5) umma_commit_2sm(&s.tfull[acc]);
@@ -555,20 +611,14 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (lane == 0) tma_store_wait_all();
       __syncwarp();
-    } else if (warp < 6) {
-      // conv2 epilogue (4 warps, one per TMEM lane quarter, 8 blocks of 16 columns each): every thread owns one output
-      // ROW.  The fp32 residual block arrives by TMA load into a SWIZZLE_64B smem tile (prefetched one block ahead,
-      // two tiles), the thread reads its own row (4 conflict-free LDS.128), adds bias + residual, applies ReLU / pad-row
-      // zeroing and writes the fp32 and fp16 results into two more swizzled tiles that leave through TMA stores.
-      // No per-row LDG/STG and no smem transpose in the L1TEX data pipe that the tensor core's operand reads share.
-      uint8_t* area = s.epi + (warp - 2) * 7168;
-      uint8_t* o32 = area + 4096;
-      uint8_t* o16 = area + 6144;
-      uint64_t* rb = s.rbar[warp - 2];
-      const bool r16 = ga.resid16 != nullptr;  // block 0: residual = fp16 stem output (X32 not materialised yet)
-      uint32_t rph = 0;                        // bit b = phase of rb[b]
-      const int sw64 = (lane >> 1) & 3;        // SWIZZLE_64B: 16-byte chunk ^= address bits 7-8 = (row >> 1) & 3
-      const int sw32 = (lane >> 2) & 1;        // SWIZZLE_32B: 16-byte chunk ^= address bit 7 = (row >> 2) & 1
+    } else {
+      // conv2 epilogue: the accumulator already holds x + conv2 (identity MMAs above), so this is the conv1 epilogue plus
+      // the split of the fp32 result y = relu(acc + bias) into hi = fp16(y) (the next conv's input) and lo = fp16(y - hi)
+      // (the rest of the skip path's precision: hi + lo carries ~22 mantissa bits).  Both leave through TMA stores from a
+      // ring of three 1 KB SWIZZLE_32B tiles per warp, one bulk group per store.
+      uint8_t* tiles = s.epi + (warp - 2) * 3072;
+      int ring = 0;
+      const int sw = (lane >> 2) & 1;  // SWIZZLE_32B: 16-byte chunk index ^= bit 7 of the byte address (row >> 2)
       int it = 0;
       for (int pt = pt0; pt < num_ptiles; pt += pt_step, it++) {
         const int acc = it & 1;
@@ -577,64 +627,39 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int p = prow0 + lane;
         const int r = p % ga.g.board_rows;
         const bool valid = (p < rows_used) && (r < ga.g.valid_rows) && ((r % ga.g.row_stride) != ga.g.wcols);
-        if (lane == 0) {
-          mbar_expect_tx(&rb[0], r16 ? 1024u : 2048u);
-          tma_load_2d(area, r16 ? &tmO16 : &tmX32, &rb[0], 0, prow0);
-        }
         mbar_wait(&s.tfull[acc], aphase);
         tcgen05_fence_after();
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int col = j * 16;
-          if (j + 1 < 8 && lane == 0) {  // prefetch the next residual block into the other tile
-            mbar_expect_tx(&rb[(j + 1) & 1], r16 ? 1024u : 2048u);
-            tma_load_2d(area + ((j + 1) & 1) * 2048, r16 ? &tmO16 : &tmX32, &rb[(j + 1) & 1], col + 16, prow0);
-          }
+        for (int sc = 0; sc < 4; sc++) {
+          const int col = colhalf * 64 + sc * 16;
           uint32_t v[16];
           tmem_ld16(tmem_base + acc * BN + col + ((uint32_t)(quarter * 32) << 16), v);
-          mbar_wait(&rb[j & 1], (rph >> (j & 1)) & 1u);
-          rph ^= 1u << (j & 1);
-          const uint8_t* in = area + (j & 1) * 2048;
-          float x[16];
-          if (r16) {
+          uint4 oh4[2], ol4[2];
+          __half2* oh = reinterpret_cast<__half2*>(oh4);
+          __half2* ol = reinterpret_cast<__half2*>(ol4);
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-              const uint4 h = *reinterpret_cast<const uint4*>(in + lane * 32 + ((c ^ sw32) << 4));
-              const __half2* hh = reinterpret_cast<const __half2*>(&h);
-#pragma unroll
-              for (int q = 0; q < 4; q++) { const float2 f = __half22float2(hh[q]); x[8 * c + 2 * q] = f.x; x[8 * c + 2 * q + 1] = f.y; }
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-              const float4 f = *reinterpret_cast<const float4*>(in + lane * 64 + ((c ^ sw64) << 4));
-              x[4 * c] = f.x; x[4 * c + 1] = f.y; x[4 * c + 2] = f.z; x[4 * c + 3] = f.w;
-            }
+          for (int j = 0; j < 8; j++) {
+            float x0 = __uint_as_float(v[2 * j]) + bias_s[col + 2 * j];
+            float x1 = __uint_as_float(v[2 * j + 1]) + bias_s[col + 2 * j + 1];
+            x0 = valid ? fmaxf(x0, 0.f) : 0.f;
+            x1 = valid ? fmaxf(x1, 0.f) : 0.f;
+            const __half2 h = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h);
+            oh[j] = h;
+            ol[j] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
           }
 #pragma unroll
-          for (int q = 0; q < 16; q++) {
-            const float y = __uint_as_float(v[q]) + bias_s[col + q] + x[q];
-            x[q] = valid ? fmaxf(y, 0.f) : 0.f;
-          }
-          if (lane == 0) tma_store_wait_read<0>();  // the previous block's stores have finished reading o32 / o16
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 4; c++)
-            *reinterpret_cast<float4*>(o32 + lane * 64 + ((c ^ sw64) << 4)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
-#pragma unroll
-          for (int c = 0; c < 2; c++) {
-            uint4 o;
-            __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-            for (int q = 0; q < 4; q++) oh[q] = __floats2half2_rn(x[8 * c + 2 * q], x[8 * c + 2 * q + 1]);
-            *reinterpret_cast<uint4*>(o16 + lane * 32 + ((c ^ sw32) << 4)) = o;
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmX32, o32, col, prow0);
-            tma_store_2d(&tmO16, o16, col, prow0);
-            tma_store_commit();
+          for (int part = 0; part < 2; part++) {
+            uint8_t* tile = tiles + ring * 1024;
+            if (++ring == 3) ring = 0;
+            if (lane == 0) tma_store_wait_read<2>();  // the store issued three stores ago has finished reading this tile
+            __syncwarp();
+            const uint4* o = part ? ol4 : oh4;
+            *reinterpret_cast<uint4*>(tile + lane * 32 + ((0 ^ sw) << 4)) = o[0];
+            *reinterpret_cast<uint4*>(tile + lane * 32 + ((1 ^ sw) << 4)) = o[1];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(part ? &tmOlo : &tmO16, tile, col, prow0); tma_store_commit(); }
           }
         }
         tcgen05_fence_before();
@@ -808,7 +833,10 @@ struct ResNetImpl : az_net {
   CUtensorMap mapX{}, mapT{}, mapHv{};
   CUtensorMap mapX2{}, mapT2{};          // Connect-Four tower kernel: 144-row A boxes
   CUtensorMap mapTo{}, mapXo{};          // TMA-store targets: 32-row x 16-column fp16 boxes, SWIZZLE_32B
-  CUtensorMap mapX32{};                  // fp32 residual stream: 32-row x 16-column boxes, SWIZZLE_64B (TMA load + store)
+  CUtensorMap mapX32{};                  // (generic tower only) fp32 residual stream
+  __half* d_xl16 = nullptr;              // Connect-Four tower: low-order part of the block outputs (x = X16 + XL16)
+  CUtensorMap mapXr{}, mapXLr{};         // residual A stages: 128-row x 64-channel boxes of X16 / XL16
+  CUtensorMap mapXLo{};                  // TMA-store target for XL16
   std::vector<CUtensorMap> mapW2;        // 64co x 64k weight boxes
   static constexpr bool C4_TOWER = (W + 1) == 8;
   size_t smem_2sm = 0;
@@ -917,7 +945,8 @@ struct ResNetImpl : az_net {
   }
   void free_act() {
     cudaFree(d_x32); cudaFree(d_hid); cudaFree(d_x16); cudaFree(d_t16); cudaFree(d_hp); cudaFree(d_hv); cudaFree(d_x0); cudaFree(d_logit);
-    d_x32 = d_hid = d_logit = nullptr; d_x16 = d_t16 = d_hp = d_hv = d_x0 = nullptr;
+    cudaFree(d_xl16);
+    d_x32 = d_hid = d_logit = nullptr; d_x16 = d_t16 = d_hp = d_hv = d_x0 = d_xl16 = nullptr;
   }
   ~ResNetImpl() override { free_weights(); free_act(); for (auto e : pev) cudaEventDestroy(e); }
 
@@ -1023,7 +1052,10 @@ struct ResNetImpl : az_net {
     free_act();
     alloc_rows = ((max_boards * BS + 127) / 128) * 128 + 128;
     alloc_boards = alloc_rows / BS;
-    AZ_TRY2(dmalloc(&d_x32, (size_t)alloc_rows * F)); AZ_TRY2(dmalloc(&d_x16, (size_t)alloc_rows * F));
+    const bool need_x32 = !(C4_TOWER && !generic_tower && hp.num_blocks > 0);
+    if (need_x32) AZ_TRY2(dmalloc(&d_x32, (size_t)alloc_rows * F));
+    else AZ_TRY2(dmalloc(&d_xl16, (size_t)alloc_rows * F));
+    AZ_TRY2(dmalloc(&d_x16, (size_t)alloc_rows * F));
     AZ_TRY2(dmalloc(&d_t16, (size_t)alloc_rows * F)); AZ_TRY2(dmalloc(&d_hp, (size_t)alloc_rows * 32));
     AZ_TRY2(dmalloc(&d_hv, (size_t)alloc_rows * 32)); AZ_TRY2(dmalloc(&d_hid, (size_t)(max_boards + 256) * F));
     AZ_TRY2(dmalloc(&d_x0, (size_t)alloc_rows * 64)); AZ_TRY2(dmalloc(&d_logit, (size_t)(max_boards + 256) * F));
@@ -1035,7 +1067,11 @@ struct ResNetImpl : az_net {
     AZ_TRY2(make_map_2d(ctx, &mapT2, d_t16, F, alloc_rows, F * 2, tc2::BK, tc2::AROWS));
     AZ_TRY2(make_map_2d(ctx, &mapTo, d_t16, F, alloc_rows, F * 2, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
     AZ_TRY2(make_map_2d(ctx, &mapXo, d_x16, F, alloc_rows, F * 2, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
-    AZ_TRY2(make_map_2d(ctx, &mapX32, d_x32, F, alloc_rows, F * 4, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
+    if (!need_x32) {
+      AZ_TRY2(make_map_2d(ctx, &mapXr, d_x16, F, alloc_rows, F * 2, tc2::BK, tc2::BM));
+      AZ_TRY2(make_map_2d(ctx, &mapXLr, d_xl16, F, alloc_rows, F * 2, tc2::BK, tc2::BM));
+      AZ_TRY2(make_map_2d(ctx, &mapXLo, d_xl16, F, alloc_rows, F * 2, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
+    }
     AZ_TRY2(make_map_2d(ctx, &mapHv, d_hv, (uint64_t)BS * 32, alloc_boards, (uint64_t)BS * 32 * 2, tc::BK, tc::BM));
     act_boards = max_boards;
     return AZ_OK;
@@ -1063,15 +1099,15 @@ struct ResNetImpl : az_net {
     const bool c4 = C4_TOWER && !generic_tower;  // Connect-Four geometry -> cta_group::2 kernel, otherwise the generic 9-tap kernel
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
     for (int blk = 0; blk < hp.num_blocks; blk++) {
-      ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.resid16 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
-      if (c4 && two_sm && use_pdl && blk > 0) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV1>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapX2, mapW2[2 * blk], mapTo, mapX32, ga);
-      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], mapTo, mapX32, ga);
+      ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
+      if (c4 && two_sm && use_pdl && blk > 0) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV1>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapX2, mapW2[2 * blk], mapTo, mapXLo, mapXr, mapXLr, ga);
+      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], mapTo, mapXLo, mapXr, mapXLr, ga);
       else az_k_gemm_tc<128, tc::EPI_CONV1><<<grid, tc::NUM_THREADS, smem128, st>>>(mapX, mapW[2 * blk], ga);
       ga.bias = d_bconv[2 * blk + 1]; ga.resid32 = d_x32; ga.out32 = d_x32; ga.out16a = d_x16;
-      ga.resid16 = (c4_fast && blk == 0) ? d_x16 : nullptr;
-      if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], mapXo, mapX32, ga);
-      else if (c4 && two_sm && use_pdl) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV2>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapT2, mapW2[2 * blk + 1], mapXo, mapX32, ga);
-      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], mapXo, mapX32, ga);
+      ga.res_lo = blk > 0 ? 1 : 0;  // block 0: the residual is the fp16 stem output, no low-order part yet
+      if (c4 && two_sm && (tower_debug & 1)) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], mapXo, mapXLo, mapXr, mapXLr, ga);
+      else if (c4 && two_sm && use_pdl) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV2>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapT2, mapW2[2 * blk + 1], mapXo, mapXLo, mapXr, mapXLr, ga);
+      else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV2><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapT2, mapW2[2 * blk + 1], mapXo, mapXLo, mapXr, mapXLr, ga);
       else az_k_gemm_tc<128, tc::EPI_CONV2><<<grid, tc::NUM_THREADS, smem128, st>>>(mapT, mapW[2 * blk + 1], ga);
     }
     if (prof) cudaEventRecord(pe[2], st);

@@ -474,24 +474,22 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int pt = pt0; pt < num_ptiles; pt += pt_step) {
         const int row0 = pt * 2 * BM + (int)rank * BM;
-        if (EPI == tc::EPI_CONV2) {
-          // residual stages first: this CTA's 128 rows of the block input, 64 channels at a time, hi then lo part
-          const int nres = ga.res_lo ? 4 : 2;
-          for (int rs = 0; rs < nres; rs++) {
-            mbar_wait(&s.empty[stage], phase ^ 1);
-            if (elect_one()) {
-              if (leader) mbar_expect_tx(&s.full[stage], 2 * tc3::RES_BYTES);
-              tma_load_2d_2sm(s.a[stage], (rs >> 1) ? &tmRlo : &tmRhi, &s.full[stage], (rs & 1) * BK, row0);
-            }
-            __syncwarp();
-            if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-        for (int st = 0; st < 6; st++) {
+        // conv2 interleaves its residual stages (this CTA's 128 rows of the block input, 64 channels at a time, hi then lo
+        // part) with the first conv stages: C0 R0 C1 R1 C2 [R2 C3 R3] C.. -- a residual stage is consumed ~6x faster than
+        // a conv stage, and four in a row would leave the 3-slot ring only ~0.2 us of prefetch distance
+        const int nres = (EPI == tc::EPI_CONV2) ? (ga.res_lo ? 4 : 2) : 0;
+        for (int q = 0; q < 6 + nres; q++) {
+          const bool isres = q < 2 * nres && (q & 1);
+          const int st = q < 2 * nres ? (q >> 1) : q - nres;  // residual stage index or conv stage index
           mbar_wait(&s.empty[stage], phase ^ 1);
           if (elect_one()) {
-            if (leader) mbar_expect_tx(&s.full[stage], 2 * A_STAGE);
-            tma_load_2d_2sm(s.a[stage], &tmA, &s.full[stage], (st & 1) * BK, row0 - 8 + (1 - (st >> 1)));
+            if (isres) {
+              if (leader) mbar_expect_tx(&s.full[stage], 2 * tc3::RES_BYTES);
+              tma_load_2d_2sm(s.a[stage], (st >> 1) ? &tmRlo : &tmRhi, &s.full[stage], (st & 1) * BK, row0);
+            } else {
+              if (leader) mbar_expect_tx(&s.full[stage], 2 * A_STAGE);
+              tma_load_2d_2sm(s.a[stage], &tmA, &s.full[stage], (st & 1) * BK, row0 - 8 + (1 - (st >> 1)));
+            }
           }
           __syncwarp();
           if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
@@ -512,43 +510,36 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&s.tempty[acc], aphase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        if (EPI == tc::EPI_CONV2) {
-          // skip connection on the tensor core: the accumulator starts as x = hi (+ lo), added by 16-column identity MMAs
-          // (resnet.jl:55-62: relu(x + conv2(...))), so the epilogue never reads the residual
-          constexpr uint32_t IDESC_R = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256, N = 16
-          const uint64_t idsc = umma_desc_interleave(smem_u32(s.ident), 128u, 256u);
-          const int nres = ga.res_lo ? 4 : 2;
-          for (int rs = 0; rs < nres; rs++) {
-            mbar_wait(&s.full[stage], phase);
-            tcgen05_fence_after();
-            const uint64_t adesc = umma_desc_sw128(smem_u32(s.a[stage]));
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < BK / 16; k++)
-                umma_f16_2sm(tmem_d + (uint32_t)((rs & 1) * BK + k * 16), adesc + (uint64_t)(k * 2), idsc, IDESC_R, (rs >> 1) ? 1u : 0u);
-              umma_commit_2sm(&s.empty[stage]);
-            }
-            __syncwarp();
-            if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-        for (int st = 0; st < 6; st++) {
+        // skip connection on the tensor core (conv2): x = hi (+ lo) is added to the accumulator by 16-column identity MMAs
+        // (resnet.jl:55-62: relu(x + conv2(...))), so the epilogue never reads the residual
+        constexpr uint32_t IDESC_R = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256, N = 16
+        const uint64_t idsc = umma_desc_interleave(smem_u32(s.ident), 128u, 256u);
+        const int nres = (EPI == tc::EPI_CONV2) ? (ga.res_lo ? 4 : 2) : 0;
+        for (int q = 0; q < 6 + nres; q++) {
+          const bool isres = q < 2 * nres && (q & 1);
+          const int st = q < 2 * nres ? (q >> 1) : q - nres;
           const int kx = st >> 1, half = st & 1;
           mbar_wait(&s.full[stage], phase);
           tcgen05_fence_after();
           const uint32_t abase = smem_u32(s.a[stage]);
           if (elect_one()) {
-#pragma unroll
-            for (int ky = 0; ky < 3; ky++) {
-              const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(8 + 8 * (1 - ky)) * 128u);
-              const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
+            if (isres) {
+              const uint64_t adesc = umma_desc_sw128(abase);
 #pragma unroll
               for (int k = 0; k < BK / 16; k++)
-                umma_f16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC,
-                             (EPI == tc::EPI_CONV2 || (st | ky | k)) ? 1u : 0u);
+                umma_f16_2sm(tmem_d + (uint32_t)(half * BK + k * 16), adesc + (uint64_t)(k * 2), idsc, IDESC_R, 1u);
+            } else {
+#pragma unroll
+              for (int ky = 0; ky < 3; ky++) {
+                const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(8 + 8 * (1 - ky)) * 128u);
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++)
+                  umma_f16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (st | ky | k) ? 1u : 0u);
+              }
             }
             umma_commit_2sm(&s.empty[stage]);
-            if (st == 5) umma_commit_2sm(&s.tfull[acc]);
+            if (q == 5 + nres) umma_commit_2sm(&s.tfull[acc]);
           }
           __syncwarp();
           if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
@@ -557,10 +548,8 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {  // ===== epilogue warps 2..9 (both CTAs): own 128 rows x 128 channels =====
     // TMEM gives each thread one ROW.  Writing rows straight to global memory costs 32 distinct 128-B lines per warp
-    // instruction and made the LSU tag pipeline the bottleneck of conv2, so each 32x16 block goes through a per-warp
-    // smem tile and leaves as 64-byte row segments (8 rows per instruction).  Two warps share a TMEM lane quarter
-    // (64 columns each) and the fp32 residual is fetched one 16-column block ahead, so the per-tile latency chain
-    // (load -> add -> store) of the epilogue stays shorter than the tile's MMA time.
+    // instruction (the LSU tag pipeline became the bottleneck), so each 32x16 block goes through a per-warp swizzled smem
+    // tile and leaves by a TMA bulk-tensor store.  Two warps share a TMEM lane quarter (64 columns each).
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int quarter = warp & 3;
     const int colhalf = (warp - 2) >> 2;

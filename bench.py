@@ -301,8 +301,35 @@ def main():
         t_gather = time.perf_counter() - t1
         sp_out = dict(t=t_play + t_gather, t_gather=t_gather, games=count, samples=int(out["samples"]), expansions=float(out["expansions"]),
                       total_samples=len(allg["z"]), mean_moves=float(out["moves"].mean()), mean_edepth=float(out["edepth"].mean()))
+    # ---- arena: pit_networks of two 7-block nets with the shipped Connect-Four ArenaParams
+    # (games/connect-four/params.jl:32-45: 600 sims, cpuct 2, eps 0.05, tau 0.2, flip_probability 0.5, alternate_colors,
+    # reset_every 2), one game per worker; every rank plays its own share, no collective ----
+    ar_out = None
+    if not args.no_selfplay and not args.oracle_net:
+        net_b = az.ResNet(ctx, gs, az.ResNetHP(hp["num_blocks"], hp["num_filters"], hp["conv_kernel_size"],
+                                               hp["num_policy_head_filters"], hp["num_value_head_filters"]))
+        net_b.load(resnet_blob(gs.state_dim, gs.num_actions, hp, seed=2))
+        AW = max(2, S // 2)
+        app = az.SelfPlayParams(
+            az.MctsParams(cpuct=2.0, num_iters_per_turn=nsims, temperature=az.ConstSchedule(0.2), dirichlet_noise_eps=0.05,
+                          dirichlet_noise_alpha=1.0),
+            az.SimParams(num_games=AW, num_workers=AW, batch_size=AW, reset_every=2, flip_probability=0.5, alternate_colors=True))
+        barrier()
+        t0 = time.perf_counter()
+        ao = az.simulate(ctx, gs, net, app, seed=4321, first_game_index=rank * AW, baseline=net_b, gamma=1.0)
+        barrier()
+        ar_out = dict(t=time.perf_counter() - t0, games=AW, expansions=float(ao["expansions"]), avgr=float(ao["game_rewards"].mean()),
+                      redundancy=float(ao["redundancy"]), mean_moves=float(ao["moves"].mean()))
+        net_b.close()
     # ---- reduce over ranks: time = max, work = sum ----
     if dist is not None:
+        if ar_out is not None:
+            ta = torch.tensor([ar_out["t"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+            wa = torch.tensor([ar_out["games"], ar_out["expansions"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(wa, op=dist.ReduceOp.SUM)
+            ar_out["t"] = ta.item()
+            ar_out["games"], ar_out["expansions"] = wa.tolist()
         t = torch.tensor([ms, e_dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         w = torch.tensor([ex, e_ex, sims, launches], device="cuda", dtype=torch.float64)
@@ -337,6 +364,11 @@ def main():
                                 "gathered_samples_on_rank0": sp_out["total_samples"], "mean_moves_per_game": sp_out["mean_moves"],
                                 "mean_exploration_depth": sp_out["mean_edepth"],
                                 "config": "simulate(): %d games per GPU on 4096 concurrent worker slots (two per slot), 600 sims/move, cpuct 2, eps 0.25, tau PL([0,20,30],[1,1,.3]), reset_every 2; wall clock incl. sample D2H + all-gather" % (2 * S)}
+        if ar_out is not None:
+            line["arena"] = {"games_per_s": ar_out["games"] / ar_out["t"], "expansions_per_s": ar_out["expansions"] / ar_out["t"],
+                             "seconds": ar_out["t"], "games": int(ar_out["games"]), "mean_moves_per_game": ar_out["mean_moves"],
+                             "avg_reward_rank0": ar_out["avgr"], "redundancy_rank0": ar_out["redundancy"],
+                             "config": "pit_networks(): two random-init 7-block ResNets, %d games per GPU on %d workers (two trees + two oracles per worker), 600 sims/move, cpuct 2, eps 0.05, tau 0.2, flip_probability 0.5, alternate_colors, reset_every 2" % (max(2, S // 2), max(2, S // 2))}
         if prof and prof["evals"]:
             peak, how = peaks()
             nconv = 2 * args.blocks

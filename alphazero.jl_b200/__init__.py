@@ -61,6 +61,8 @@ ABI_SYMBOLS = [
     "az_mcts_reset", "az_mcts_counters", "az_mcts_last_timing", "az_mcts_destroy",
     "az_selfplay_create", "az_selfplay_start", "az_selfplay_poll", "az_selfplay_wait", "az_selfplay_counts",
     "az_selfplay_fetch", "az_selfplay_stats", "az_selfplay_destroy", "az_selfplay_create_duel", "az_selfplay_outcomes",
+    "az_selfplay_export_samples", "az_samples_from_host", "az_samples_count", "az_samples_concat", "az_samples_merge_by_state",
+    "az_samples_augment_with_symmetries", "az_samples_convert", "az_samples_fetch", "az_samples_destroy",
 ]
 
 _lib = None
@@ -102,6 +104,12 @@ def lib():
             "az_selfplay_destroy": [vp],
             "az_selfplay_create_duel": [vp, C.c_int32, vp, vp, C.POINTER(_MctsParams), C.POINTER(_SimParams), C.c_uint64, C.POINTER(vp)],
             "az_selfplay_outcomes": [vp, C.c_double, vp, vp, vp, vp],
+            "az_selfplay_export_samples": [vp, C.POINTER(vp)],
+            "az_samples_from_host": [vp, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, C.POINTER(vp)],
+            "az_samples_count": [vp, C.POINTER(C.c_int64)], "az_samples_concat": [vp, vp, C.POINTER(vp)],
+            "az_samples_merge_by_state": [vp, C.POINTER(vp)], "az_samples_augment_with_symmetries": [vp, C.POINTER(vp)],
+            "az_samples_convert": [vp, C.c_int32, vp, vp, vp, vp, vp], "az_samples_fetch": [vp, vp, vp, vp, vp, vp],
+            "az_samples_destroy": [vp],
         }
         for name, args in sigs.items():
             getattr(L, name).argtypes = args
@@ -462,6 +470,76 @@ class SelfPlay:
     def close(self):
         if self.h:
             lib().az_selfplay_destroy(self.h)
+            self.h = None
+
+
+CONSTANT_WEIGHT, LOG_WEIGHT, LINEAR_WEIGHT = 0, 1, 2  # SamplesWeighingPolicy, src/params.jl:104-108
+
+
+class Samples:
+    """A device-resident Vector{TrainingSample} (src/memory.jl:20-26): the replay-buffer side of the wire.  Every operation
+    returns a new set; `close()` frees the device memory."""
+
+    def __init__(self, ctx, gspec, handle):
+        self.ctx, self.gspec, self.h = ctx, gspec, handle
+
+    @classmethod
+    def from_selfplay(cls, sp):
+        """push_trace! rows of a finished SelfPlay run, ordered by (game, ply), no host round trip (src/memory.jl:74-87)."""
+        h = C.c_void_p()
+        sp.ctx.check(lib().az_selfplay_export_samples(sp.h, C.byref(h)))
+        return cls(sp.ctx, sp.gspec, h)
+
+    @classmethod
+    def from_host(cls, ctx, gspec, states, pi, z, t, n=None):
+        s = np.ascontiguousarray(states, np.uint8).reshape(-1, gspec.state_bytes)
+        k = s.shape[0]
+        pi = np.ascontiguousarray(pi, np.float64).reshape(k, gspec.num_actions)
+        z, t = np.ascontiguousarray(z, np.float64), np.ascontiguousarray(t, np.float64)
+        nn = None if n is None else np.ascontiguousarray(n, np.int32)
+        h = C.c_void_p()
+        ctx.check(lib().az_samples_from_host(ctx.h, gspec.id, k, s.ctypes.data, pi.ctypes.data, z.ctypes.data, t.ctypes.data,
+                                             None if nn is None else nn.ctypes.data, C.byref(h)))
+        return cls(ctx, gspec, h)
+
+    def __len__(self):
+        n = C.c_int64()
+        self.ctx.check(lib().az_samples_count(self.h, C.byref(n)))
+        return n.value
+
+    def _new(self, fn, *args):
+        h = C.c_void_p()
+        self.ctx.check(fn(self.h, *args, C.byref(h)))
+        return Samples(self.ctx, self.gspec, h)
+
+    def concat(self, other):
+        return self._new(lib().az_samples_concat, other.h)
+
+    def merge_by_state(self):  # src/memory.jl:98-110 (groups in order of first occurrence)
+        return self._new(lib().az_samples_merge_by_state)
+
+    def augment_with_symmetries(self):  # src/memory.jl:126-130
+        return self._new(lib().az_samples_augment_with_symmetries)
+
+    def convert(self, weighing=LOG_WEIGHT):
+        """convert_samples (src/learning.jl:38-51): dict of Float32 arrays W [n], X [n, state_dim], A [n, a], P [n, a], V [n]."""
+        n, a = len(self), self.gspec.num_actions
+        xd = int(np.prod(self.gspec.state_dim))
+        out = dict(W=np.zeros(n, np.float32), X=np.zeros((n, xd), np.float32), A=np.zeros((n, a), np.float32),
+                   P=np.zeros((n, a), np.float32), V=np.zeros(n, np.float32))
+        self.ctx.check(lib().az_samples_convert(self.h, weighing, *[out[k].ctypes.data for k in ("W", "X", "A", "P", "V")]))
+        return out
+
+    def fetch(self):
+        n, a = len(self), self.gspec.num_actions
+        out = dict(states=np.zeros((n, self.gspec.state_bytes), np.uint8), pi=np.zeros((n, a), np.float64), z=np.zeros(n, np.float64),
+                   t=np.zeros(n, np.float64), n=np.zeros(n, np.int32))
+        self.ctx.check(lib().az_samples_fetch(self.h, *[out[k].ctypes.data for k in ("states", "pi", "z", "t", "n")]))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().az_samples_destroy(self.h)
             self.h = None
 
 

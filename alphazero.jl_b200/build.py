@@ -13,6 +13,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = {
     "az_engine.cu": ["-fmad=false"],
     "az_net.cu": [],
+    "az_samples.cu": ["-fmad=false"],
 }
 
 

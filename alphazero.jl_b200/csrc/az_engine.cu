@@ -390,6 +390,7 @@ struct az_selfplay {
   virtual int fetch(uint8_t* states, float* pi, uint8_t* mask, float* z, float* t, int32_t* gos, double* rew, int32_t* act) = 0;
   virtual int stats(double* ed, int64_t* nodes, int32_t* moves, double* totals) = 0;
   virtual int outcomes(double gamma, double* rewards, int32_t* colors_flipped, uint8_t* final_states, double* redundancy) = 0;
+  virtual int export_samples(az_samples** out) = 0;
 };
 
 template <class G>
@@ -548,13 +549,14 @@ struct SelfPlay : az_selfplay {
     const int ng = sp.num_games;
     size_t rows = (size_t)ng * G::MAX_PLIES;
     std::vector<AzEnv> env(rows), think(rows);
-    std::vector<float> hpi(rows * G::A), hz(rows), ht(rows);
+    std::vector<double> hpi(rows * G::A), hz(rows);
+    std::vector<float> ht(rows);
     std::vector<int32_t> hact(rows);
     std::vector<double> hrew(rows);
     AZ_CUDA(ctx, cudaMemcpy(env.data(), sp.s_env, rows * sizeof(AzEnv), cudaMemcpyDeviceToHost));
     AZ_CUDA(ctx, cudaMemcpy(think.data(), sp.s_root, rows * sizeof(AzEnv), cudaMemcpyDeviceToHost));
-    AZ_CUDA(ctx, cudaMemcpy(hpi.data(), sp.s_pi, rows * G::A * sizeof(float), cudaMemcpyDeviceToHost));
-    AZ_CUDA(ctx, cudaMemcpy(hz.data(), sp.s_z, rows * sizeof(float), cudaMemcpyDeviceToHost));
+    AZ_CUDA(ctx, cudaMemcpy(hpi.data(), sp.s_pi, rows * G::A * sizeof(double), cudaMemcpyDeviceToHost));
+    AZ_CUDA(ctx, cudaMemcpy(hz.data(), sp.s_z, rows * sizeof(double), cudaMemcpyDeviceToHost));
     AZ_CUDA(ctx, cudaMemcpy(ht.data(), sp.s_t, rows * sizeof(float), cudaMemcpyDeviceToHost));
     AZ_CUDA(ctx, cudaMemcpy(hact.data(), sp.s_action, rows * sizeof(int32_t), cudaMemcpyDeviceToHost));
     AZ_CUDA(ctx, cudaMemcpy(hrew.data(), sp.s_reward, rows * sizeof(double), cudaMemcpyDeviceToHost));
@@ -565,10 +567,10 @@ struct SelfPlay : az_selfplay {
         if (states) G::to_bytes(env[r], states + k * G::STATE_BYTES);
         uint32_t legal = G::legal_mask(think[r]);  // pi and the mask are in the frame the player thought in
         for (int a = 0; a < G::A; a++) {
-          if (pi) pi[k * G::A + a] = hpi[r * G::A + a];
+          if (pi) pi[k * G::A + a] = (float)hpi[r * G::A + a];
           if (mask) mask[k * G::A + a] = (legal >> a) & 1;
         }
-        if (z) z[k] = hz[r];
+        if (z) z[k] = (float)hz[r];
         if (t) t[k] = ht[r];
         if (gos) gos[k] = g;
         if (rew) rew[k] = hrew[r];
@@ -587,6 +589,27 @@ struct SelfPlay : az_selfplay {
       for (int v : h_moves) ns += v;
       totals[0] = seconds; totals[1] = (double)ns * sp.nsims; totals[2] = (double)total_expansions; totals[3] = (double)ns;
     }
+    return AZ_OK;
+  }
+  // the finished run's samples as a device-resident set (no host round trip): feeds az_samples_* (merge / augment / convert)
+  int export_samples(az_samples** out) override {
+    AZ_TRY(ctx, wait());
+    const int ng = sp.num_games;
+    std::vector<int64_t> off((size_t)ng + 1, 0);
+    for (int g = 0; g < ng; g++) off[g + 1] = off[g] + h_moves[g];
+    az_samples* o = nullptr;
+    AZ_TRY(ctx, az_samples_alloc(ctx, G::ID, off[ng], &o));
+    int64_t* d_off = nullptr;
+    if (cudaMalloc((void**)&d_off, off.size() * 8) != cudaSuccess) { az_samples_destroy(o); AZ_FAIL(ctx, AZ_ENOMEM, "export_samples: cudaMalloc failed"); }
+    cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+    const int64_t rows = (int64_t)ng * G::MAX_PLIES;
+    az_k_export_samples<G><<<(int)((rows + 255) / 256), 256, 0, ctx->stream>>>(sp, ng, d_off, az_samples_env(o), az_samples_pi(o), az_samples_z(o),
+                                                                            az_samples_t(o), az_samples_cnt(o));
+    ctx->launches += 1;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_off);
+    if (e != cudaSuccess) { az_samples_destroy(o); AZ_FAIL(ctx, AZ_ECUDA, std::string("export_samples: ") + cudaGetErrorString(e)); }
+    *out = o;
     return AZ_OK;
   }
   // rewards_and_redundancy (src/simulations.jl:292-307): per game total_reward(trace, gamma) (src/trace.jl:45-47), negated
@@ -838,6 +861,10 @@ int32_t az_selfplay_create_duel(az_ctx* ctx, int32_t game, az_net* white, az_net
   if (mp->num_iters_per_turn <= 0) AZ_FAIL(ctx, AZ_EINVAL, "MctsPlayer: niters > 0 (src/play.jl:162)");
   AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, white, black, mp, sp, seed, out)
   AZ_GUARD_END(ctx)
+}
+int32_t az_selfplay_export_samples(az_selfplay* s, az_samples** out) {
+  AZ_M(s) if (!out) return AZ_EINVAL;
+  AZ_GUARD_BEGIN cudaSetDevice(s->ctx->device); return s->export_samples(out); AZ_GUARD_END(s->ctx)
 }
 int32_t az_selfplay_outcomes(az_selfplay* s, double gamma, double* rewards, int32_t* flipped, uint8_t* finals, double* red) {
   AZ_M(s) AZ_GUARD_BEGIN return s->outcomes(gamma, rewards, flipped, finals, red); AZ_GUARD_END(s->ctx)

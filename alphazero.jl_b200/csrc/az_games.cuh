@@ -95,6 +95,8 @@ struct GameC4 {
   // GI.symmetries (game.jl:247-257): the column mirror.  Only applied to non-terminal states (src/play.jl:302-307), whose
   // status bits are symmetric.
   static constexpr int NSYM = 1;
+  // action permutation of the symmetry (the sigma of GI.symmetries): pi'[p] = pi[sym_source(j, p)] (src/memory.jl:112-124)
+  AZ_HD static int sym_source(int, int p) { return 6 - p; }
   AZ_HD static AzEnv symmetry(const AzEnv& e, int) {
     AzEnv n = {0, e.b & PLAYER, e.aux};
     for (int col = 0; col < 7; col++) {
@@ -194,14 +196,17 @@ struct GameTTT {
   // GI.symmetries (game.jl:149-168): rot, rot2, rot3, flip, flip.rot, flip.rot2, flip.rot3 with rot(x,y) = (y, N-x+1),
   // flip(x,y) = (x, N-y+1); the image board is board'[p] = board[sym[p]]
   static constexpr int NSYM = 7;
+  AZ_HD static int sym_source(int j, int p) {  // sym[p] of SYMMETRIES[j]: board'[p] = board[sym[p]], pi'[p] = pi[sym[p]]
+    const int nrot = j < 3 ? j + 1 : j - 3;
+    int x = p % 3, y = p / 3;
+    for (int k = 0; k < nrot; k++) { int nx = y, ny = 2 - x; x = nx; y = ny; }
+    if (j >= 3) y = 2 - y;
+    return y * 3 + x;
+  }
   AZ_HD static AzEnv symmetry(const AzEnv& e, int j) {
     AzEnv n = {e.a & PLAYER, 0, e.aux};
-    const int nrot = j < 3 ? j + 1 : j - 3;
     for (int p = 0; p < 9; p++) {
-      int x = p % 3, y = p / 3;
-      for (int k = 0; k < nrot; k++) { int nx = y, ny = 2 - x; x = nx; y = ny; }
-      if (j >= 3) y = 2 - y;
-      const int src = y * 3 + x;
+      const int src = sym_source(j, p);
       n.a |= ((e.a >> src) & 1ull) << p;
       n.a |= ((e.a >> (16 + src)) & 1ull) << (16 + p);
     }
@@ -327,6 +332,7 @@ struct GameMancala {
   static constexpr bool STOCHASTIC = false;
   static constexpr int NSYM = 0;  // no GI.symmetries declared for this game
   AZ_HD static AzEnv symmetry(const AzEnv& e, int) { return e; }
+  AZ_HD static int sym_source(int, int p) { return p; }
   static constexpr long long MAX_STATES = 1ll << 40;  // no useful bound on distinct states
   AZ_HD static AzEnv play(const AzEnv& e, int a, const AzNoise&) { return play(e, a); }
   AZ_HD static AzEnv init_game(uint64_t, uint64_t) { return init(); }
@@ -373,6 +379,7 @@ struct GameGW {
   static constexpr bool STOCHASTIC = true;
   static constexpr int NSYM = 0;  // no GI.symmetries declared for this game
   AZ_HD static AzEnv symmetry(const AzEnv& e, int) { return e; }
+  AZ_HD static int sym_source(int, int p) { return p; }
   static constexpr long long MAX_STATES = 100;  // 10 x 10 cells: a tree never holds more nodes
   AZ_HD static int gx(const AzEnv& e) { return (int)(e.a & 0xFF); }
   AZ_HD static int gy(const AzEnv& e) { return (int)((e.a >> 8) & 0xFF); }

@@ -51,3 +51,13 @@ struct az_net {
 
 az_net* az_make_resnet(az_ctx* ctx, int game, const az_resnet_hp* hp, int* status);
 az_net* az_make_simplenet(az_ctx* ctx, int game, const az_simplenet_hp* hp, int* status);
+
+// device-resident training samples (az_samples.cu)
+struct az_samples;
+int az_samples_alloc(az_ctx* ctx, int game, int64_t n, az_samples** out);
+AzEnv* az_samples_env(az_samples* s);
+double* az_samples_pi(az_samples* s);
+double* az_samples_z(az_samples* s);
+double* az_samples_t(az_samples* s);
+int32_t* az_samples_cnt(az_samples* s);
+extern "C" int32_t az_samples_destroy(az_samples* s);

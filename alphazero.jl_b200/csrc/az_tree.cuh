@@ -404,10 +404,10 @@ struct AzSelfPlay {
   AzEnv* s_env;            // trace.states[i] (before the optional symmetry of move i)
   AzEnv* s_root;           // the state the player thought on (s_pi and the mask are in its frame)
   AzEnv* g_final;          // per game: last state of the trace
-  float* s_pi;             // [A]
+  double* s_pi;            // [A] MCTS.policy output (Float64 in the reference Trace), zero on illegal actions
   int32_t* s_action;
   double* s_reward;
-  float* s_z;
+  double* s_z;
   float* s_t;
   // per game
   int32_t* g_moves;
@@ -648,8 +648,8 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
   // record (trace.jl:35-39) and play
   const size_t rowi = (size_t)g * sp.max_plies + move;
   sp.s_root[rowi] = root;
-  for (int i = 0; i < A; i++) sp.s_pi[rowi * A + i] = 0.0f;
-  for (int i = 0; i < n; i++) sp.s_pi[rowi * A + acts[i]] = (float)pi[i];
+  for (int i = 0; i < A; i++) sp.s_pi[rowi * A + i] = 0.0;
+  for (int i = 0; i < n; i++) sp.s_pi[rowi * A + acts[i]] = pi[i];
   sp.s_action[rowi] = act;
   AzNoise rnz = {1.0, 0.0};
   if (G::STOCHASTIC) { AzNoiseKey rk = {sp.seed, (uint64_t)game, (uint32_t)move}; rnz = az_env_noise<AzNoise>(rk, AZ_REAL_MOVE, 0u); }
@@ -662,7 +662,7 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
     for (int i = nm - 1; i >= 0; i--) {
       const size_t ri = (size_t)g * sp.max_plies + i;
       wr = p.c.gamma * wr + sp.s_reward[ri];
-      sp.s_z[ri] = (float)(G::white_playing(sp.s_env[ri]) ? wr : -wr);
+      sp.s_z[ri] = G::white_playing(sp.s_env[ri]) ? wr : -wr;
       sp.s_t[ri] = (float)(nm - i);
     }
     az_record_game_end<G>(p, sp, w, g, nm, nx);
@@ -672,4 +672,30 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
     p.sims_target[slot] = 0;
     az_begin_move<G>(p, sp, w, nx, g, game, nm);
   }
+}
+
+// push_trace! rows of a finished run -> device-resident TrainingSamples (src/memory.jl:74-87), ordered by (game, ply).
+// The reference pairs trace.states[i] with trace.policies[i], a vector over the legal actions of the state the player
+// THOUGHT on; convert_sample later scatters it over the mask of trace.states[i] (src/learning.jl:31-34).  With
+// flip_probability > 0 the two frames differ, so the compact policy is re-scattered here the same way.
+template <class G>
+__global__ void az_k_export_samples(AzSelfPlay sp, int num_games, const int64_t* __restrict__ goff, AzEnv* oenv, double* opi, double* oz,
+                                    double* ot, int32_t* ocnt) {
+  constexpr int A = G::A;
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (int64_t)num_games * sp.max_plies) return;
+  const int g = (int)(r / sp.max_plies), i = (int)(r % sp.max_plies);
+  if (i >= sp.g_moves[g]) return;
+  const int64_t k = goff[g] + i;
+  const AzEnv st = sp.s_env[r], th = sp.s_root[r];
+  double c[A];
+  int n = 0;
+  const uint32_t lt = G::legal_mask(th), ls = G::legal_mask(st);
+  for (int a = 0; a < A; a++) if ((lt >> a) & 1u) c[n++] = sp.s_pi[r * A + a];
+  int m = 0;
+  for (int a = 0; a < A; a++) opi[k * A + a] = ((ls >> a) & 1u) && m < n ? c[m++] : 0.0;
+  oenv[k] = st;
+  oz[k] = sp.s_z[r];
+  ot[k] = (double)sp.s_t[r];
+  ocnt[k] = 1;
 }

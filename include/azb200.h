@@ -37,6 +37,7 @@ typedef struct az_ctx az_ctx;
 typedef struct az_net az_net;
 typedef struct az_mcts az_mcts;
 typedef struct az_selfplay az_selfplay;
+typedef struct az_samples az_samples;
 
 /* ---- library / context ---------------------------------------------------------------- */
 int32_t az_version(void);
@@ -192,6 +193,30 @@ int32_t az_selfplay_stats(az_selfplay* s, double* edepth_per_game, int64_t* node
 int32_t az_selfplay_outcomes(az_selfplay* s, double gamma, double* rewards, int32_t* colors_flipped, uint8_t* final_states,
                              double* redundancy);
 int32_t az_selfplay_destroy(az_selfplay* s);
+
+/* ---- replay-buffer side (src/memory.jl:20-130, src/learning.jl:17-51): device-resident TrainingSamples -------------
+   A sample set is a device-side struct of arrays (state, pi[A] Float64 zero on illegal actions, z, t Float64, n Int32)
+   = Vector{TrainingSample}; every operation returns a NEW set (inputs stay valid until destroyed). */
+/* push_trace! rows of the finished run, ordered by (game, ply), without a host round trip (src/memory.jl:74-87) */
+int32_t az_selfplay_export_samples(az_selfplay* s, az_samples** out);
+/* samples from host arrays (e.g. the Julia MemoryBuffer): states[n*state_bytes], pi[n*A], z[n], t[n], n_rec[n] or NULL (=1) */
+int32_t az_samples_from_host(az_ctx* ctx, int32_t game, int64_t n, const uint8_t* states, const double* pi, const double* z,
+                             const double* t, const int32_t* n_rec, az_samples** out);
+int32_t az_samples_count(az_samples* s, int64_t* n);
+/* [a ; b] (append!(buf, experience), src/memory.jl:41) */
+int32_t az_samples_concat(az_samples* a, az_samples* b, az_samples** out);
+/* merge_by_state (src/memory.jl:98-110): one sample per distinct state, pi / z / t = mean in original order (left-to-right
+   Float64 sum / count), n = sum.  The reference returns the groups in Dict iteration order (unspecified); here they come
+   in the order of each state's first occurrence. */
+int32_t az_samples_merge_by_state(az_samples* in, az_samples** out);
+/* augment_with_symmetries (src/memory.jl:112-130): [samples ; apply_symmetry(s, sym) for s in samples for sym in symmetries(s)] */
+int32_t az_samples_augment_with_symmetries(az_samples* in, az_samples** out);
+/* convert_samples (src/learning.jl:17-51): Float32 tensors with the sample index as the slowest dimension (= Julia's last):
+   W[n] (weighing: 0 CONSTANT_WEIGHT, 1 LOG_WEIGHT = log2(n)+1, 2 LINEAR_WEIGHT), X[n*state_dim], A[n*num_actions] (mask),
+   P[n*num_actions], V[n]; computed on the GPU, written to host buffers; any pointer may be NULL */
+int32_t az_samples_convert(az_samples* s, int32_t weighing, float* W, float* X, float* A, float* P, float* V);
+int32_t az_samples_fetch(az_samples* s, uint8_t* states, double* pi, double* z, double* t, int32_t* n_rec);
+int32_t az_samples_destroy(az_samples* s);
 
 #ifdef __cplusplus
 }

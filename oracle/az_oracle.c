@@ -790,8 +790,8 @@ void oz_play_game2(oz_env* white, oz_env* black, const oz_mcts_params* mp, doubl
     oz_fix_probvec(pis, nl, pf);
     float u = oz_uniform_f32(seed, game_idx, (uint32_t)n, OZ_PURPOSE_CATEGORICAL, 0);
     int k = oz_categorical(pf, nl, u);
-    for (int a = 0; a < A; a++) { tr->pi[n][a] = 0.0f; tr->mask[n][a] = 0; }
-    for (int i = 0; i < nl; i++) { tr->pi[n][acts[i]] = (float)pi[i]; tr->mask[n][acts[i]] = 1; }
+    for (int a = 0; a < A; a++) { tr->pi[n][a] = 0.0f; tr->pi64[n][a] = 0.0; tr->mask[n][a] = 0; }
+    for (int i = 0; i < nl; i++) { tr->pi[n][acts[i]] = (float)pi[i]; tr->pi64[n][acts[i]] = pi[i]; tr->mask[n][acts[i]] = 1; }
     tr->action[n] = acts[k];
     {
       double u[2];

@@ -139,6 +139,7 @@ typedef struct {
   double edepth;                               /* average_exploration_depth (both players pooled in a duel) */
   int32_t sym[OZ_MAX_PLIES];                   /* 0, or 1 + index of the symmetry applied before thinking (play.jl:305-307) */
   uint8_t think_states[OZ_MAX_PLIES][OZ_STATE_BYTES]; /* the state the player thought on (pi and mask are in its frame) */
+  double pi64[OZ_MAX_PLIES][OZ_MAX_ACTIONS];   /* trace.policies[i] as the reference holds it (Float64), A-wide */
 } oz_trace;
 
 /* play_game (src/play.jl:298-315) for game index `game` on worker env `env` */

@@ -55,7 +55,7 @@ class Trace(C.Structure):
                 ("pi", (C.c_float * MAX_ACTIONS) * MAX_PLIES), ("mask", (C.c_uint8 * MAX_ACTIONS) * MAX_PLIES),
                 ("action", C.c_int32 * MAX_PLIES), ("rewards", C.c_double * MAX_PLIES), ("z", C.c_double * MAX_PLIES),
                 ("t", C.c_double * MAX_PLIES), ("mem_nodes", C.c_int64), ("edepth", C.c_double), ("sym", C.c_int32 * MAX_PLIES),
-                ("think_states", (C.c_uint8 * STATE_BYTES) * MAX_PLIES)]
+                ("think_states", (C.c_uint8 * STATE_BYTES) * MAX_PLIES), ("pi64", (C.c_double * MAX_ACTIONS) * MAX_PLIES)]
 
 
 ORACLE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float))

@@ -35,7 +35,7 @@ def oracle_simulate(oz, gid, oracle, omp, seed, S, NG, reset_every, baseline=Non
                 L.oz_play_game2(white, black, C.byref(omp), flip_probability, seed, g, C.byref(tr))
                 n = tr.n_moves
                 traces[g] = dict(n_moves=n, states=np.ctypeslib.as_array(tr.states)[:n + 1, :sb].copy(),
-                                 pi=np.ctypeslib.as_array(tr.pi)[:n, :A].copy(), mask=np.ctypeslib.as_array(tr.mask)[:n, :A].copy(),
+                                 pi=np.ctypeslib.as_array(tr.pi)[:n, :A].copy(), pi64=np.ctypeslib.as_array(tr.pi64)[:n, :A].copy(), mask=np.ctypeslib.as_array(tr.mask)[:n, :A].copy(),
                                  action=np.ctypeslib.as_array(tr.action)[:n].copy(), rewards=np.ctypeslib.as_array(tr.rewards)[:n].copy(),
                                  z=np.ctypeslib.as_array(tr.z)[:n].copy(), t=np.ctypeslib.as_array(tr.t)[:n].copy(),
                                  mem_nodes=tr.mem_nodes, edepth=tr.edepth, sym=np.ctypeslib.as_array(tr.sym)[:n].copy(),

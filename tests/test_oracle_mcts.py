@@ -267,3 +267,39 @@ def test_simulate_duel_alternate_colors(oz):
     assert len(rewards) == 12 and set(rewards) <= {-1.0, 0.0, 1.0} and 0.0 < red < 1.0
     for g, t in traces.items():
         assert rewards[g] == (-1 if t["colors_flipped"] else 1) * t["rewards"].sum()
+
+
+# ---- replay-buffer side: oracle restatement sanity -------------------------------------------------
+
+def test_samples_ref_merge_augment_convert(oz):
+    """merge_by_state / augment_with_symmetries / convert_samples restatement (src/memory.jl:89-130, src/learning.jl:17-51):
+    hand-checked small case + invariants of src/scripts/test_game.jl:81-96 for the action permutations."""
+    from oracle import samples_ref as sr
+    from tests import simref
+    gid = oz.game_id("connect-four")
+    s0 = bytes(oz.GameEnv(gid).state()[:oz.state_bytes(gid)])
+    g = oz.GameEnv(gid); g.play(2)
+    s1 = bytes(g.state()[:oz.state_bytes(gid)])
+    u = [1 / 7] * 7
+    es = [dict(s=s0, pi=[0.1, 0.2, 0.3, 0.4, 0.0, 0.0, 0.0], z=1.0, t=9.0, n=1), dict(s=s1, pi=u, z=-1.0, t=8.0, n=1),
+          dict(s=s0, pi=[0.3, 0.2, 0.1, 0.4, 0.0, 0.0, 0.0], z=-1.0, t=5.0, n=3)]
+    m = sr.merge_by_state(es)
+    assert [e["s"] for e in m] == [s0, s1] and m[0]["n"] == 4 and m[0]["z"] == 0.0 and m[0]["t"] == 7.0
+    assert m[0]["pi"] == [(0.1 + 0.3) / 2, (0.2 + 0.2) / 2, (0.3 + 0.1) / 2, 0.4, 0.0, 0.0, 0.0] and m[1] == es[1]
+    a = sr.augment_with_symmetries(gid, es[:2])
+    assert len(a) == 4 and a[:2] == es[:2]
+    assert a[2]["s"] == s0 and a[2]["pi"] == es[0]["pi"][::-1]           # the empty board is its own mirror
+    assert a[3]["s"] != s1 and a[3]["z"] == -1.0
+    c = sr.convert_samples(gid, 1, m)
+    assert c["W"].tolist() == [3.0, 1.0] and c["X"].shape == (2, 126) and c["A"].sum() == 14 and c["V"].tolist() == [0.0, -1.0]
+    # tic-tac-toe action permutations are the board permutations of games/tictactoe/game.jl:149-160
+    ttt = oz.game_id("tictactoe")
+    assert sr._aperm(ttt, 0) == [6, 3, 0, 7, 4, 1, 8, 5, 2] and sr._aperm(ttt, 3) == [6, 7, 8, 3, 4, 5, 0, 1, 2]
+    # augment on real traces: image policies are still distributions over the image's legal actions
+    mp = oz.mcts_params(num_iters_per_turn=16, cpuct=1.0, noise_eps=0.25, noise_alpha=1.0)
+    traces, _ = simref.oracle_simulate(oz, ttt, "synth", mp, 5, 2, 4, 1)
+    smp = sr.samples_from_traces(traces)
+    aug = sr.augment_with_symmetries(ttt, smp)
+    assert len(aug) == 8 * len(smp) and all(abs(sum(e["pi"]) - 1) < 1e-12 for e in aug)
+    mg = sr.merge_by_state(aug)
+    assert sum(e["n"] for e in mg) == len(aug) and len({e["s"] for e in mg}) == len(mg) < len(aug)

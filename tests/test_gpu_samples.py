@@ -5,7 +5,21 @@ from a finished self-play run on the device, merge_by_state, augment_with_symmet
 import numpy as np
 import pytest
 
+import _pkg
+
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def az():
+    return _pkg.load()
+
+
+@pytest.fixture(scope="module")
+def ctx(az):
+    c = az.Context(0)
+    yield c
+    c.close()
 
 
 def _same(gid, oz, got, want):

@@ -50,6 +50,7 @@ function state_from_bytes(::Val{Symbol("connect-four")}, b::AbstractVector{UInt8
   (board = reshape(copy(b[1:42]), 7, 6) |> x -> typeof(GI.current_state(GI.init(Examples.games["connect-four"]))[:board])(x),
    curplayer = b[43])
 end
+state_to_bytes(::Val{Symbol("connect-four")}, s) = vcat(vec(Array(s.board)), s.curplayer)
 # (tictactoe / mancala converters are the same two lines with their cell encodings)
 
 # ---- network upload: Flux parameters in blob order (DESIGN.md "weight blob") --------------------------------
@@ -66,9 +67,11 @@ end
 mutable struct Engine
   ctx::Ptr{Cvoid}; game::Int32; net::Ptr{Cvoid}
 end
-function Engine(gspec, nn; device = 0)
-  ctx = Ref{Ptr{Cvoid}}()
-  st = ccall((:az_ctx_create, LIB), Int32, (Int32, Ptr{Ptr{Cvoid}}), device, ctx); check(C_NULL, st)
+function Engine(gspec, nn; device = 0, ctx = nothing)   # pass `ctx = other.ctx` to put a second network on the same GPU context
+  ctx = Ref{Ptr{Cvoid}}(ctx === nothing ? C_NULL : ctx)
+  if ctx[] == C_NULL
+    st = ccall((:az_ctx_create, LIB), Int32, (Int32, Ptr{Ptr{Cvoid}}), device, ctx); check(C_NULL, st)
+  end
   game = ccall((:az_game_lookup, LIB), Int32, (Cstring,), game_name(gspec))
   hp = Network.hyperparams(nn)
   chp = CResNetHP(hp.num_blocks, hp.num_filters, Int32.(hp.conv_kernel_size), hp.num_policy_head_filters,
@@ -120,6 +123,59 @@ function simulate_selfplay(e::Engine, gspec, params::SelfPlayParams; game_simula
     k += n
   end
   results
+end
+
+# pit_networks (src/training.jl:130-143) on the engine: a duel of two networks with the ArenaParams' mcts / sim settings.
+# `contender` and `baseline` are Engines sharing one az_ctx (build the second with Engine(gspec, nn; ctx = first.ctx)).
+function pit_networks(contender::Engine, baseline::Engine, gspec, params; game_simulated, seed = rand(UInt64))
+  mp, sp = c_mcts_params(params.mcts), c_sim_params(params.sim)
+  h = Ref{Ptr{Cvoid}}()
+  check(contender.ctx, ccall((:az_selfplay_create_duel, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ref{CMctsParams}, Ref{CSimParams}, UInt64, Ptr{Ptr{Cvoid}}),
+        contender.ctx, contender.game, contender.net, baseline.net, mp, sp, seed, h))
+  check(contender.ctx, ccall((:az_selfplay_start, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), h[], sp.num_games, 0))
+  done, fin, seen = Ref{Int32}(0), Ref{Int32}(0), 0
+  while fin[] == 0
+    check(contender.ctx, ccall((:az_selfplay_poll, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), h[], done, fin))
+    for _ in seen+1:done[]; game_simulated(); end
+    seen = max(seen, done[]); sleep(0.01)
+  end
+  rewards = Vector{Float64}(undef, sp.num_games); red = Ref{Float64}(0)
+  GC.@preserve rewards check(contender.ctx, ccall((:az_selfplay_outcomes, LIB), Int32,
+        (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Int32}, Ptr{UInt8}, Ptr{Float64}), h[], params.mcts.gamma, rewards, C_NULL, C_NULL, red))
+  ccall((:az_selfplay_destroy, LIB), Int32, (Ptr{Cvoid},), h[])
+  return rewards, red[]                        # = rewards_and_redundancy(samples, gamma=params.mcts.gamma)
+end
+
+# Learning-side sample preparation on the GPU (src/learning.jl:38-51 after src/memory.jl:98-130): `samples` is the
+# Vector{TrainingSample} of get_experience(env); returns the (W, X, A, P, V) Float32 tensors of convert_samples.
+function prepare_samples(e::Engine, gspec, samples, wp::Int32; use_symmetries::Bool, merge::Bool = true)
+  n, A = length(samples), GI.num_actions(gspec)
+  SB = ccall((:az_game_state_bytes, LIB), Int32, (Int32,), e.game)
+  states = Matrix{UInt8}(undef, SB, n); pi = zeros(Float64, A, n)
+  for (i, s) in enumerate(samples)
+    states[:, i] = state_to_bytes(Val(Symbol(game_name(gspec))), s.s)
+    pi[GI.actions_mask(GI.init(gspec, s.s)), i] = s.π
+  end
+  z = Float64[s.z for s in samples]; t = Float64[s.t for s in samples]; cnt = Int32[s.n for s in samples]
+  cur = Ref{Ptr{Cvoid}}()
+  GC.@preserve states pi z t cnt check(e.ctx, ccall((:az_samples_from_host, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Int64, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Ptr{Cvoid}}),
+        e.ctx, e.game, n, states, pi, z, t, cnt, cur))
+  for (on, f) in ((use_symmetries, :az_samples_augment_with_symmetries), (merge, :az_samples_merge_by_state))
+    on || continue
+    nxt = Ref{Ptr{Cvoid}}()
+    check(e.ctx, ccall((f, LIB), Int32, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), cur[], nxt))
+    ccall((:az_samples_destroy, LIB), Int32, (Ptr{Cvoid},), cur[]); cur = nxt
+  end
+  m = Ref{Int64}(0); check(e.ctx, ccall((:az_samples_count, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}), cur[], m))
+  xdim = GI.state_dim(gspec)
+  W = Matrix{Float32}(undef, 1, m[]); X = Array{Float32}(undef, xdim..., m[]); Am = Matrix{Float32}(undef, A, m[])
+  P = similar(Am); V = Matrix{Float32}(undef, 1, m[])
+  GC.@preserve W X Am P V check(e.ctx, ccall((:az_samples_convert, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}), cur[], wp, W, X, Am, P, V))
+  ccall((:az_samples_destroy, LIB), Int32, (Ptr{Cvoid},), cur[])
+  return (; W, X, A = Am, P, V)
 end
 
 end # module

@@ -293,8 +293,28 @@ def main():
             az.SimParams(num_games=count, num_workers=S, batch_size=S, reset_every=2))
         barrier()
         t0 = time.perf_counter()
-        out = az.simulate(ctx, gs, net, spp, seed=1234, first_game_index=first)   # includes the D2H fetch of all samples
+        sp_h = az.SelfPlay(ctx, gs, net, spp, seed=1234)
+        sp_h.start(count, first)
+        sp_h.wait()
+        out = sp_h.fetch()                                                        # includes the D2H fetch of all samples
         t_play = time.perf_counter() - t0
+        # replay-buffer side on this rank's samples, device resident: export -> augment -> merge -> convert
+        rp = {}
+        tr0 = time.perf_counter()
+        smp = az.Samples.from_selfplay(sp_h)
+        rp["export_ms"] = 1e3 * (time.perf_counter() - tr0); tr0 = time.perf_counter()
+        aug = smp.augment_with_symmetries()
+        rp["augment_ms"] = 1e3 * (time.perf_counter() - tr0); tr0 = time.perf_counter()
+        mrg = aug.merge_by_state()
+        rp["merge_ms"] = 1e3 * (time.perf_counter() - tr0); tr0 = time.perf_counter()
+        cv = mrg.convert(az.LOG_WEIGHT)
+        rp["convert_to_host_ms"] = 1e3 * (time.perf_counter() - tr0)
+        rp.update(samples=len(smp), augmented=len(aug), merged=len(mrg), bytes_per_sample=24 + 8 * 7 + 8 + 8 + 4,
+                  note="host wall clock per call incl. cudaMalloc of outputs and stream sync; rank 0's share")
+        for x in (smp, aug, mrg):
+            x.close()
+        del cv
+        sp_h.close()
         t1 = time.perf_counter()
         allg = azd.allgather_samples(out, first, dist, device="cuda" if dist is not None else "cpu")
         barrier()
@@ -364,6 +384,8 @@ def main():
                                 "gathered_samples_on_rank0": sp_out["total_samples"], "mean_moves_per_game": sp_out["mean_moves"],
                                 "mean_exploration_depth": sp_out["mean_edepth"],
                                 "config": "simulate(): %d games per GPU on 4096 concurrent worker slots (two per slot), 600 sims/move, cpuct 2, eps 0.25, tau PL([0,20,30],[1,1,.3]), reset_every 2; wall clock incl. sample D2H + all-gather" % (2 * S)}
+        if sp_out is not None:
+            line["replay"] = rp
         if ar_out is not None:
             line["arena"] = {"games_per_s": ar_out["games"] / ar_out["t"], "expansions_per_s": ar_out["expansions"] / ar_out["t"],
                              "seconds": ar_out["t"], "games": int(ar_out["games"]), "mean_moves_per_game": ar_out["mean_moves"],

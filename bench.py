@@ -35,7 +35,7 @@ NET_MFLOP_PER_LEAF = 174.7                           # whole 7-block network (SU
 METRIC = "mcts_node_expansions_per_s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from profiles/r01_final_conv_ncu_summary.txt
 # (ncu --set full, cold caches, ~3700 leaves): conv1 variant 55.0 MB, conv2 variant 214.4 MB per launch; mean of the two
-NCU_TRAFFIC_BYTES = 134.7e6
+NCU_TRAFFIC_BYTES = 114.4e6  # profiles/r01_final2_conv_ncu_summary.txt: (conv1 54.2 MB + conv2 174.6 MB) / 2 per launch, cold caches
 
 
 def resnet_blob(dim, num_actions, hp, seed=1):

@@ -237,3 +237,38 @@ def test_simplenet_forward_and_mcts(az, oz, ctx, game, hp):
         assert (N[i] == rN).all() and (W[i] == rW).all()
     env.close()
     net.close()
+
+
+def test_learning_step_hands_weights_to_engine(az, ctx):
+    """a few optimiser steps in torch on the GPU (alphazero.jl_b200/learning.py), then the trained blob goes
+    straight into the engine's network; the engine's forward_normalized must agree with the torch model in test mode."""
+    import torch
+    import alphazero_jl_b200.learning as lrn
+    gs = az.GameSpec("connect-four")
+    hp = az.ResNetHP(1, 128, (3, 3), 32, 32, batch_norm_momentum=0.6)
+    torch.manual_seed(0)
+    net_t = lrn.ResNetTorch(gs.state_dim, gs.num_actions, hp)
+    states = gs.random_positions(11, 512, 30)
+    X = np.stack([gs.vectorize_state(s).reshape(-1, order="F") for s in states]).astype(np.float32)
+    Am = np.stack([gs.actions_mask(s) for s in states]).astype(np.float32)
+    rng = np.random.default_rng(0)
+    P = rng.random(Am.shape).astype(np.float32) * Am
+    P /= P.sum(1, keepdims=True)
+    data = dict(W=np.ones(len(states), np.float32), X=X, A=Am, P=P, V=rng.choice([-1.0, 0.0, 1.0], len(states)).astype(np.float32))
+    params = lrn.LearningParams(lrn.Adam(1e-3), l2_regularization=1e-4, batch_size=128, loss_computation_batch_size=256)
+    tr = lrn.Trainer(net_t, data, params, device="cuda", seed=1)
+    before = tr.learning_status()
+    tr.batch_updates(12)
+    after = tr.learning_status()
+    assert after["L"] < before["L"]
+    blob = tr.get_trained_network_blob()
+    net = az.ResNet(ctx, gs, hp)
+    assert net.num_params == len(blob)
+    net.load(blob)
+    Pe, Ve, Pinv = net.evaluate_batch(states)
+    net_t.eval()
+    with torch.no_grad():
+        Pt, Vt, pinv_t = lrn.forward_normalized(net_t, torch.from_numpy(X).cuda(), torch.from_numpy(Am).cuda())
+    assert np.abs(Pe - Pt.cpu().numpy()).max() < 1e-3 and np.abs(Ve - Vt.cpu().numpy()).max() < 1e-3
+    assert np.abs(Pinv - pinv_t.cpu().numpy()).max() < 1e-3
+    net.close()

@@ -178,4 +178,56 @@ function prepare_samples(e::Engine, gspec, samples, wp::Int32; use_symmetries::B
   return (; W, X, A = Am, P, V)
 end
 
+# ---- checkpoint interop (alphazero.jl_b200/checkpoint.py documents the format) --------------------------------------------
+# Written next to the Serialization files of save_env (src/ui/session.jl:92-108) so the engine side can resume from a
+# Julia session and vice versa.  JSON headers are hand-assembled to avoid a dependency beyond JSON3 (already a dependency).
+function write_azb(path, gspec, nn)
+  blob = flux_blob(Network.to_cpu(nn))
+  header = JSON3.write((kind = "resnet", game = game_name(gspec), hyperparams = Network.hyperparams(nn),
+                        num_params = length(blob), dtype = "float32", order = "flux"))
+  open(path, "w") do io
+    write(io, "AZB1"); write(io, htol(UInt32(sizeof(header)))); write(io, header); write(io, htol.(blob))
+  end
+end
+function read_azb_blob(path)
+  open(path, "r") do io
+    String(read(io, 4)) == "AZB1" || error("not an AZB1 file: $path")
+    n = ltoh(read(io, UInt32)); skip(io, n)
+    return ltoh.(reinterpret(Float32, read(io)))
+  end
+end
+# load a blob back into a Flux model (inverse of flux_blob): same traversal order
+function import_weights!(nn, path)
+  blob, q = read_azb_blob(path), 0
+  take!(dst) = (copyto!(dst, reshape(view(blob, q+1:q+length(dst)), size(dst))); q += length(dst))
+  for chain in (nn.common, nn.vhead, nn.phead), l in Flux.modules(chain)
+    l isa Flux.Conv && (take!(l.weight); take!(l.bias))
+    l isa Flux.BatchNorm && (take!(l.γ); take!(l.β); take!(l.μ); take!(l.σ²))
+    l isa Flux.Dense && (take!(l.weight); take!(l.bias))
+  end
+  q == length(blob) || error("blob size mismatch")
+  return nn
+end
+function write_azs(path, gspec, samples)   # get_experience(env) -> mem.azs
+  n, A = length(samples), GI.num_actions(gspec)
+  g = game_name(gspec)
+  SB = ccall((:az_game_state_bytes, LIB), Int32, (Int32,), ccall((:az_game_lookup, LIB), Int32, (Cstring,), g))
+  states = Matrix{UInt8}(undef, SB, n); pi = zeros(Float64, A, n)
+  for (i, s) in enumerate(samples)
+    states[:, i] = state_to_bytes(Val(Symbol(g)), s.s)
+    pi[GI.actions_mask(GI.init(gspec, s.s)), i] = s.π
+  end
+  header = JSON3.write((game = g, num_samples = n, state_bytes = Int(SB), num_actions = A))
+  open(path, "w") do io
+    write(io, "AZS1"); write(io, htol(UInt32(sizeof(header)))); write(io, header)
+    write(io, states); write(io, htol.(pi)); write(io, htol.(Float64[s.z for s in samples]))
+    write(io, htol.(Float64[s.t for s in samples])); write(io, htol.(Int32[s.n for s in samples]))
+  end
+end
+function export_session(env, dir)          # next to save_env(env, dir)
+  write_azb(joinpath(dir, "bestnn.azb"), env.gspec, env.bestnn)
+  write_azb(joinpath(dir, "curnn.azb"), env.gspec, env.curnn)
+  write_azs(joinpath(dir, "mem.azs"), env.gspec, AlphaZero.get_experience(env))
+end
+
 end # module

@@ -18,29 +18,54 @@ def split_games(num_games, world, rank):
     return count, first
 
 
+def _single(dist):
+    return dist is None or not dist.is_initialized() or dist.get_world_size() == 1
+
+
+def allgather_counts(n, dist, device="cpu"):
+    import torch
+    cnt = torch.tensor([n], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(cnt) for _ in range(dist.get_world_size())]
+    dist.all_gather(counts, cnt)
+    return [int(c.item()) for c in counts]
+
+
+def allgather_rows(a, dist, device="cpu", counts=None):
+    """Concatenate the per-rank arrays `a` (rows differ per rank) in rank order on every rank: counts first (unless the
+    caller already has them), then ONE all_gather of rows padded to the maximum count."""
+    import torch
+    a = np.ascontiguousarray(a)
+    if _single(dist):
+        return a
+    world = dist.get_world_size()
+    if counts is None:
+        counts = allgather_counts(len(a), dist, device)
+    pad = np.zeros((max(counts),) + a.shape[1:], a.dtype)
+    pad[:len(a)] = a
+    t = torch.from_numpy(pad).to(device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    return np.concatenate([p[:c].cpu().numpy() for p, c in zip(parts, counts)])
+
+
 def allgather_samples(samples, first_game, dist=None, device="cpu"):
     """All-gather the per-rank sample rows (dict of numpy arrays as returned by SelfPlay.fetch) so that every rank holds
-    the whole iteration's samples in rank order.  Row counts differ per rank: counts are gathered first, rows are padded
-    to the maximum, gathered with one all_gather per field group, then trimmed."""
-    import torch
-    n = len(samples["z"])
+    the whole iteration's samples in rank order (reduce(vcat, results), src/simulations.jl:289)."""
     local = {k: np.ascontiguousarray(samples[k]) for k in SAMPLE_KEYS}
     local["game"] = local["game"] + np.int32(first_game)  # local game index -> global game index
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+    if _single(dist):
         return local
-    world = dist.get_world_size()
-    cnt = torch.tensor([n], dtype=torch.int64, device=device)
-    counts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(counts, cnt)
-    counts = [int(c.item()) for c in counts]
-    m = max(counts)
-    out = {}
-    for k in SAMPLE_KEYS:
-        a = local[k]
-        pad = np.zeros((m,) + a.shape[1:], a.dtype)
-        pad[:n] = a
-        t = torch.from_numpy(pad).to(device)
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t)
-        out[k] = np.concatenate([p[:c].cpu().numpy() for p, c in zip(parts, counts)])
-    return out
+    counts = allgather_counts(len(local["z"]), dist, device)
+    return {k: allgather_rows(local[k], dist, device, counts) for k in SAMPLE_KEYS}
+
+
+def allgather_outcomes(samples, outcomes, dist=None, device="cpu"):
+    """rewards_and_redundancy over the games of ALL ranks (src/simulations.jl:282-307): per-game rewards and colors_flipped
+    concatenated in rank order; redundancy = 1 - |unique states| / |states| over every trace state of every rank (the
+    per-rank value az_selfplay_outcomes returns only sees its own games).  `samples` = SelfPlay.fetch(), `outcomes` =
+    SelfPlay.outcomes()."""
+    rewards = allgather_rows(outcomes["game_rewards"], dist, device)
+    flipped = allgather_rows(outcomes["colors_flipped"], dist, device)
+    states = np.concatenate([allgather_rows(samples["states"], dist, device), allgather_rows(outcomes["final_states"], dist, device)])
+    uniq = len(np.unique(states, axis=0)) if len(states) else 0
+    return dict(game_rewards=rewards, colors_flipped=flipped, redundancy=(1.0 - uniq / len(states)) if len(states) else 0.0)

@@ -81,3 +81,27 @@ def test_grid_world_host_helpers_match_oracle(az, oz):
             g.play(act, [0.9, 0.0])
             ns, term, wr = gs.play(s, act)
             assert bytes(ns) == g.state() and term == g.terminated() and wr == g.white_reward()
+
+
+def test_plain_c_host_compiles_links_and_fails_loudly(az, tmp_path):
+    """include/azb200.h is valid C99 (no C++ / torch types), a plain-C host links against the library, and without a GPU the
+    first call fails with AZ_ECUDA and a message instead of falling back to a CPU path (examples/selfplay_c_abi.c)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc")
+    if cc is None:
+        pytest.skip("gcc not available")
+    libdir = os.path.join(ROOT, "alphazero.jl_b200")
+    exe = str(tmp_path / "selfplay_c")
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "selfplay_c_abi.c"), "-L" + libdir, "-lazb200", "-Wl,-rpath," + libdir, "-o", exe])
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    r = subprocess.run([exe, "8", "16"], capture_output=True, text=True, timeout=120)
+    if has_gpu:
+        assert r.returncode == 0 and "games 8" in r.stdout, r.stderr
+    else:
+        assert r.returncode == 3 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr

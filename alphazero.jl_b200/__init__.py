@@ -569,6 +569,42 @@ def simulate(ctx, gspec, oracle, params, seed=0, game_simulated=None, first_game
         sp.close()
 
 
+def evaluate_network(ctx, gspec, net, params, seed=0, game_simulated=None):
+    """evaluate_network (src/training.jl:146-155): a single network on a one-player game with the arena parameters; returns
+    (rewards per game, redundancy)."""
+    out = simulate(ctx, gspec, net, params, seed, game_simulated, gamma=params.mcts.gamma)
+    return out["game_rewards"], out["redundancy"]
+
+
+class Evaluation:  # Report.Evaluation, src/report.jl:73-80
+    def __init__(self, legend, avgr, redundancy, rewards, baseline_rewards, time):
+        self.legend, self.avgr, self.redundancy = legend, float(avgr), float(redundancy)
+        self.rewards, self.baseline_rewards, self.time = rewards, baseline_rewards, time
+
+
+def compare_networks(ctx, gspec, contender, baseline, params, seed=0, game_simulated=None, two_players=True):
+    """compare_networks (src/training.jl:157-174): two-player games pit the networks against each other; single-player
+    games evaluate both separately and compare the mean rewards."""
+    import time
+    t0 = time.perf_counter()
+    legend = "Most recent NN versus best NN so far"
+    if two_players:
+        rewards_c, red = pit_networks(ctx, gspec, contender, baseline, params, seed, game_simulated)
+        avgr, rewards_b = float(np.mean(rewards_c)), None
+    else:
+        rewards_c, red_c = evaluate_network(ctx, gspec, contender, params, seed, game_simulated)
+        rewards_b, red_b = evaluate_network(ctx, gspec, baseline, params, seed, game_simulated)
+        avgr, red = float(np.mean(rewards_c)) - float(np.mean(rewards_b)), float(np.mean([red_c, red_b]))
+    return Evaluation(legend, avgr, red, rewards_c, rewards_b, time.perf_counter() - t0)
+
+
+class TernaryOutcomeStatistics:  # src/benchmark.jl:104-121
+    def __init__(self, rewards):
+        r = np.asarray(rewards.rewards if isinstance(rewards, Evaluation) else rewards)
+        self.num_won, self.num_draw, self.num_lost = int((r > 0).sum()), int((r == 0).sum()), int((r < 0).sum())
+        assert self.num_won + self.num_draw + self.num_lost == len(r)
+
+
 def pit_networks(ctx, gspec, contender, baseline, params, seed=0, game_simulated=None):
     """pit_networks (src/training.jl:130-143): `params` = ArenaParams-like object with .mcts and .sim; returns
     (rewards of the contender per game, redundancy)."""

@@ -105,3 +105,28 @@ def test_plain_c_host_compiles_links_and_fails_loudly(az, tmp_path):
         assert r.returncode == 0 and "games 8" in r.stdout, r.stderr
     else:
         assert r.returncode == 3 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_evaluation_helpers_host_logic(az, monkeypatch):
+    """compare_networks / TernaryOutcomeStatistics (src/training.jl:157-174, src/benchmark.jl:104-121): host composition only,
+    with the engine calls stubbed (no GPU here)."""
+    calls = []
+
+    def fake_simulate(ctx, gs, net, params, seed=0, game_simulated=None, first_game_index=0, baseline=None, gamma=None):
+        calls.append((net, baseline, gamma))
+        r = np.array([1.0, 0.0, -1.0, 1.0]) if net == "new" else np.array([0.0, 0.0, -1.0, 1.0])
+        return dict(game_rewards=r, redundancy=0.25 if net == "new" else 0.75)
+
+    monkeypatch.setattr(az, "simulate", fake_simulate)
+
+    class P:
+        class mcts:
+            gamma = 0.9
+    ev = az.compare_networks(None, None, "new", "old", P)
+    assert calls == [("new", "old", 0.9)] and ev.avgr == 0.25 and ev.redundancy == 0.25 and ev.baseline_rewards is None
+    st = az.TernaryOutcomeStatistics(ev)
+    assert (st.num_won, st.num_draw, st.num_lost) == (2, 1, 1)
+    calls.clear()
+    ev = az.compare_networks(None, None, "new", "old", P, two_players=False)
+    assert [c[:2] for c in calls] == [("new", None), ("old", None)] and ev.avgr == 0.25 - 0.0 and ev.redundancy == 0.5
+    assert (ev.baseline_rewards == [0.0, 0.0, -1.0, 1.0]).all()

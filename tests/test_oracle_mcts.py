@@ -303,3 +303,21 @@ def test_samples_ref_merge_augment_convert(oz):
     assert len(aug) == 8 * len(smp) and all(abs(sum(e["pi"]) - 1) < 1e-12 for e in aug)
     mg = sr.merge_by_state(aug)
     assert sum(e["n"] for e in mg) == len(aug) and len({e["s"] for e in mg}) == len(mg) < len(aug)
+
+
+def test_oracle_matches_committed_kats(oz):
+    """The oracle reproduces its committed known-answer vectors (tests/golden/oracle_kats.json, generated by
+    tests/golden/make_oracle_kats.py): MCTS root statistics bit for bit, self-play / duel / flip traces by hash.  These
+    vectors freeze the restatement every GPU parity test is measured against; they are not reference outputs."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_oracle_kats", os.path.join(here, "make_oracle_kats.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    want = json.load(open(os.path.join(here, "oracle_kats.json")))
+    got = json.loads(json.dumps(mk.build(oz)))
+    assert got["format"] == want["format"] and len(got["cases"]) == len(want["cases"])
+    for g, w in zip(got["cases"], want["cases"]):
+        assert g == w, (w["kind"], w["game"])

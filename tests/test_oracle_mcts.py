@@ -321,3 +321,24 @@ def test_oracle_matches_committed_kats(oz):
     assert got["format"] == want["format"] and len(got["cases"]) == len(want["cases"])
     for g, w in zip(got["cases"], want["cases"]):
         assert g == w, (w["kind"], w["game"])
+
+
+def test_netref_matches_committed_kats(oz):
+    """oracle/netref.py reproduces tests/golden/netref_kats.json (fp32 torch-CPU; tolerance 2e-6 for thread-count dependent
+    summation order in the convolutions)."""
+    import importlib.util
+    import json
+    import os
+    from oracle import netref
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_netref_kats", os.path.join(here, "make_netref_kats.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    want = json.load(open(os.path.join(here, "netref_kats.json")))
+    got = mk.build(oz, netref)
+    assert got["states"] == want["states"] and got["ttt_states"] == want["ttt_states"]
+    for g, w in zip(got["cases"], want["cases"]):
+        assert g["num_params"] == w["num_params"] and abs(g["blob_sum"] - w["blob_sum"]) < 1e-9
+        for k in ("P", "V", "Pinvalid"):
+            if k in w:
+                assert np.abs(np.array(g[k]) - np.array(w[k])).max() < 2e-6, (w["net"], k)

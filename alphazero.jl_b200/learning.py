@@ -118,6 +118,93 @@ class ResNetTorch(nn.Module):
         return torch.softmax(self.phead[2](p), dim=1), v
 
 
+class SimpleNetTorch(nn.Module):
+    """SimpleNet(gspec, SimpleNetHP) of src/networks/architectures/simplenet.jl:37-64: flatten -> Dense(width) [+ BatchNorm] + relu,
+    `depth_common` hidden layers, value head (`depth_vhead` hidden layers, Dense(1), tanh), policy head (`depth_phead` hidden
+    layers, Dense(num_actions), softmax); parameters in Flux blob order (common, vhead, phead)."""
+
+    def __init__(self, state_dim, num_actions, hp):
+        super().__init__()
+        indim = int(np.prod(state_dim))
+        self.hp, self.A = hp, num_actions
+        w, bn = hp.width, bool(hp.use_batch_norm)
+
+        def hidden(i, o):
+            return [nn.Linear(i, o)] + ([nn.BatchNorm1d(o, eps=1e-5, momentum=hp.batch_norm_momentum)] if bn else [])
+
+        common = hidden(indim, w)
+        for _ in range(hp.depth_common):
+            common += hidden(w, w)
+        vhead = []
+        for _ in range(hp.depth_vhead):
+            vhead += hidden(w, w)
+        vhead.append(nn.Linear(w, 1))
+        phead = []
+        for _ in range(hp.depth_phead):
+            phead += hidden(w, w)
+        phead.append(nn.Linear(w, num_actions))
+        self.common, self.vhead, self.phead = nn.ModuleList(common), nn.ModuleList(vhead), nn.ModuleList(phead)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def layers(self):
+        return list(self.common) + list(self.vhead) + list(self.phead)
+
+    def to_blob(self):
+        parts = []
+        for m in self.layers():
+            if isinstance(m, nn.BatchNorm1d):
+                parts += [m.weight.detach().cpu().numpy(), m.bias.detach().cpu().numpy(), m.running_mean.cpu().numpy(), m.running_var.cpu().numpy()]
+            else:
+                parts += [m.weight.detach().cpu().numpy().reshape(-1, order="F"), m.bias.detach().cpu().numpy()]
+        return np.concatenate([np.asarray(p, np.float32).ravel() for p in parts])
+
+    def load_blob(self, blob):
+        blob = np.asarray(blob, np.float32)
+        want = sum(p.numel() for p in self.parameters()) + sum(2 * m.num_features for m in self.modules() if isinstance(m, nn.BatchNorm1d))
+        if len(blob) != want:
+            raise ValueError("blob has %d floats, the network has %d parameters" % (len(blob), want))
+        q = 0
+        with torch.no_grad():
+            for m in self.layers():
+                ts = (m.weight, m.bias, m.running_mean, m.running_var) if isinstance(m, nn.BatchNorm1d) else None
+                if ts is not None:
+                    for t in ts:
+                        t.copy_(torch.from_numpy(blob[q:q + m.num_features].copy()))
+                        q += m.num_features
+                else:
+                    out, inn = m.weight.shape
+                    m.weight.copy_(torch.from_numpy(blob[q:q + out * inn].reshape((out, inn), order="F").copy()))
+                    q += out * inn
+                    m.bias.copy_(torch.from_numpy(blob[q:q + out].copy()))
+                    q += out
+        return self
+
+    @staticmethod
+    def _run(mods, x, last_plain):
+        n = len(mods)
+        i = 0
+        while i < n:
+            m = mods[i]
+            x = m(x)
+            i += 1
+            if i < n and isinstance(mods[i], nn.BatchNorm1d):
+                x = mods[i](x)
+                i += 1
+            if not (last_plain and i == n):
+                x = F.relu(x)
+        return x
+
+    def forward(self, X):
+        """X: [B, W*H*C] rows of vectorize_state (Flux.flatten is column-major over W,H,C = the row layout of convert_samples)."""
+        c = self._run(list(self.common), X, last_plain=False)
+        v = torch.tanh(self._run(list(self.vhead), c, last_plain=True))[:, 0]
+        p = torch.softmax(self._run(list(self.phead), c, last_plain=True), dim=1)
+        return p, v
+
+
 def forward_normalized(net, X, A):
     """Network.forward_normalized (src/networks/network.jl:264-271): (P masked + renormalised, V, p_invalid)."""
     P, V = net(X)

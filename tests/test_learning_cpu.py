@@ -139,3 +139,31 @@ def test_trainer_reduces_loss_and_hands_weights_back(lrn):
     x = torch.from_numpy(d["X"][:16])
     with torch.no_grad():
         assert all(torch.equal(a, b) for a, b in zip(net(x), net2(x)))
+
+
+@pytest.mark.parametrize("bn", [False, True])
+def test_simplenet_mirror_vs_netref(lrn, oz, bn):
+    """SimpleNet torch mirror (src/networks/architectures/simplenet.jl:37-64) against oracle/netref.py; blob round trip."""
+    from oracle import netref
+    az = _pkg.load()
+    hp = az.SimpleNetHP(24, 2, depth_phead=2, depth_vhead=1, use_batch_norm=bn)
+    d = dict(width=24, depth_common=2, depth_phead=2, depth_vhead=1, use_batch_norm=bn)
+    blob = netref.simplenet_make_blob((3, 3, 3), 9, d, seed=8)
+    net = lrn.SimpleNetTorch((3, 3, 3), 9, hp).load_blob(blob)
+    assert (net.to_blob() == blob).all()
+    gid = oz.game_id("tictactoe")
+    states = oz.random_positions(gid, 3, 7, 4)
+    Xw = np.stack([oz.vectorize_state(gid, s) for s in states])                       # [B, W, H, C]
+    Xf = np.stack([x.reshape(-1, order="F") for x in Xw]).astype(np.float32)          # convert_samples rows
+    net.eval()
+    with torch.no_grad():
+        P, V = net(torch.from_numpy(Xf))
+    Pr, Vr = netref.simplenet_forward(blob, (3, 3, 3), 9, d, Xw)
+    assert np.abs(P.numpy() - Pr).max() < 1e-6 and np.abs(V.numpy() - Vr).max() < 1e-6
+    # one optimiser step runs in train mode and changes the weights
+    data = dict(W=np.ones(7, np.float32), X=Xf, A=np.stack([oz.GameEnv(gid, s).actions_mask() for s in states]).astype(np.float32),
+                P=np.full((7, 9), 0, np.float32), V=np.zeros(7, np.float32))
+    data["P"] = data["A"] / data["A"].sum(1, keepdims=True)
+    tr = lrn.Trainer(net, data, lrn.LearningParams(lrn.Adam(1e-2), l2_regularization=1e-4, batch_size=7, use_gpu=False), device="cpu")
+    before = net.to_blob().copy()
+    assert len(tr.batch_updates(2)) == 2 and (net.to_blob() != before).any()

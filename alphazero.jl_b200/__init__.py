@@ -56,7 +56,7 @@ ABI_SYMBOLS = [
     "az_game_lookup", "az_game_num_actions", "az_game_state_bytes", "az_game_state_dim", "az_game_max_plies",
     "az_game_vectorize_state", "az_game_actions_mask", "az_game_play", "az_game_init_state", "az_game_random_positions",
     "az_net_create_oracle", "az_net_create_resnet", "az_net_create_simplenet", "az_net_num_params", "az_net_load",
-    "az_net_forward", "az_net_set_profiling", "az_net_get_profile", "az_net_destroy",
+    "az_net_forward", "az_net_forward_logits", "az_net_set_profiling", "az_net_get_profile", "az_net_destroy",
     "az_mcts_create", "az_mcts_set_roots", "az_mcts_set_noise", "az_mcts_run", "az_mcts_explore", "az_mcts_root_stats", "az_mcts_policy",
     "az_mcts_reset", "az_mcts_counters", "az_mcts_last_timing", "az_mcts_destroy",
     "az_selfplay_create", "az_selfplay_start", "az_selfplay_poll", "az_selfplay_wait", "az_selfplay_counts",
@@ -92,6 +92,7 @@ def lib():
             "az_net_create_simplenet": [vp, C.c_int32, C.POINTER(_SimpleNetHP), C.POINTER(vp)],
             "az_net_num_params": [vp, C.POINTER(C.c_int64)], "az_net_load": [vp, vp, C.c_int64],
             "az_net_forward": [vp, vp, C.c_int32, vp, vp, vp], "az_net_destroy": [vp],
+            "az_net_forward_logits": [vp, vp, C.c_int32, vp, vp],
             "az_net_set_profiling": [vp, C.c_int32], "az_net_get_profile": [vp, vp, vp, vp, vp],
             "az_mcts_create": [vp, C.c_int32, vp, C.POINTER(_MctsParams), C.c_int32, C.c_int32, C.POINTER(vp)],
             "az_mcts_set_roots": [vp, vp, vp], "az_mcts_run": [vp, C.c_int32], "az_mcts_set_noise": [vp, C.c_uint64, vp, vp],
@@ -297,6 +298,15 @@ class Network:
         Pi = np.zeros(B, np.float32)
         self.ctx.check(lib().az_net_forward(self.h, s.ctypes.data, B, P.ctypes.data, V.ctypes.data, Pi.ctypes.data))
         return P, V, Pi
+
+    def forward_logits(self, states):
+        """Parity hook: (policy logits [B,A] before the softmax, value before the tanh [B])."""
+        s = np.ascontiguousarray(states, np.uint8).reshape(-1, self.gspec.state_bytes)
+        B = s.shape[0]
+        L = np.zeros((B, self.gspec.num_actions), np.float32)
+        Vp = np.zeros(B, np.float32)
+        self.ctx.check(lib().az_net_forward_logits(self.h, s.ctypes.data, B, L.ctypes.data, Vp.ctypes.data))
+        return L, Vp
 
     def set_profiling(self, enable=True):
         self.ctx.check(lib().az_net_set_profiling(self.h, int(enable)))

@@ -229,6 +229,9 @@ struct Mcts : az_mcts {
   void drop_graph() { if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; } }
   template <class Extra>
   int tick_graphed(Extra extra) {
+    // (re)allocations must happen before the capture begins (cudaMalloc / cudaFree / stream sync are illegal inside it)
+    AZ_TRY(ctx, net->reserve(net2 ? p.row_base1 : p.S));
+    if (net2) AZ_TRY(ctx, net2->reserve(p.row_base1));
     if (!use_graph || graph_broken || !net->capturable() || (net2 && !net2->capturable())) {
       drop_graph();
       AZ_TRY(ctx, tick(false));
@@ -291,6 +294,7 @@ struct Mcts : az_mcts {
     std::vector<uint8_t> st(p.S, 1);
     AZ_CUDA(ctx, cudaMemsetAsync(p.sims_done, 0, p.S * sizeof(int32_t), ctx->stream));
     AZ_CUDA(ctx, cudaMemsetAsync(p.expansions, 0, sizeof(int64_t), ctx->stream));
+    AZ_CUDA(ctx, cudaMemsetAsync(p.flags, 0, 4 * sizeof(int32_t), ctx->stream));  // an earlier failed call must not poison this one
     AZ_CUDA(ctx, cudaMemcpyAsync(p.sims_target, tgt.data(), p.S * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     AZ_CUDA(ctx, cudaMemcpyAsync(p.status, st.data(), p.S, cudaMemcpyHostToDevice, ctx->stream));
     AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -345,6 +349,7 @@ struct Mcts : az_mcts {
   int reset() override {
     az_k_reset<G><<<p.S, 128, 0, ctx->stream>>>(p);
     ctx->launches++;
+    AZ_CUDA(ctx, cudaMemsetAsync(p.flags, 0, 4 * sizeof(int32_t), ctx->stream));
     AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return AZ_OK;
   }
@@ -425,8 +430,15 @@ struct SelfPlay : az_selfplay {
     const int S = net2 ? 2 * W : W;  // duel: one tree per player per worker (TwoPlayers, src/play.jl:248-252)
     int reset = s->reset_every > 0 ? s->reset_every : std::max(1, (s->num_games + W - 1) / W);
     size_t bound = (size_t)std::min<long long>((long long)mp->num_iters_per_turn * G::MAX_PLIES * (long long)reset, G::MAX_STATES);
-    size_t budget = (size_t)96 << 30;  // table budget: 96 GB of the 180 GB HBM
-    size_t maxnodes = budget / ((size_t)S * G::LANES * 16) * 3 / 4;
+    // table budget: 60 % of the memory that is free right now; Mcts::create rounds (1.25 x cap_nodes) up to a power of
+    // two, so ask for at most the largest power-of-two capacity that fits the budget, less the 1.25 head room
+    size_t free_b = 0, total_b = 0;
+    AZ_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = free_b / 10 * 6;
+    size_t cap_fit = 64;
+    while (cap_fit * 2 * (size_t)S * G::LANES * 16 <= budget) cap_fit <<= 1;
+    if (cap_fit * (size_t)S * G::LANES * 16 > budget) AZ_FAIL(ctx, AZ_ENOMEM, "self-play: not enough free device memory for the tree tables");
+    const size_t maxnodes = cap_fit * 4 / 5 - 8;
     int cap_nodes = (int)std::min<size_t>(std::min(bound, maxnodes), (size_t)1 << 28);
     pool.reset(new Mcts<G>());
     int st = pool->create(ctx, net, mp, S, cap_nodes, net2);
@@ -474,6 +486,7 @@ struct SelfPlay : az_selfplay {
     AZ_CUDA(ctx, cudaMemsetAsync(sp.active_slots, 0, 4, ctx->stream));
     AZ_CUDA(ctx, cudaMemsetAsync(sp.next_game, 0, 4, ctx->stream));
     AZ_CUDA(ctx, cudaMemsetAsync(m.p.expansions, 0, 8, ctx->stream));
+    AZ_CUDA(ctx, cudaMemsetAsync(m.p.flags, 0, 4 * sizeof(int32_t), ctx->stream));
     AZ_TRY(ctx, m.reset());
     const int grid1 = (m.p.S + 127) / 128;
     az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 1);
@@ -659,24 +672,30 @@ static int g_make_selfplay(az_ctx* ctx, az_net* net, az_net* net2, const az_mcts
 
 // forward_normalized hook for oracle nets / networks: host states -> device envs -> eval -> host
 template <class G>
-static int g_net_forward(az_net* net, const uint8_t* states, int B, float* P, float* V, float* Pinv) {
+static int g_net_forward(az_net* net, const uint8_t* states, int B, float* P, float* V, float* Pinv, float* logits, float* vpre) {
   az_ctx* ctx = net->ctx;
   std::vector<AzEnv> envs(B);
   for (int i = 0; i < B; i++) envs[i] = G::from_bytes(states + (size_t)i * G::STATE_BYTES);
-  AzEnv* d_env; int32_t* d_n; float *d_P, *d_V, *d_Pi;
+  AzEnv* d_env; int32_t* d_n; float *d_P, *d_V, *d_Pi, *d_L = nullptr, *d_Vp = nullptr;
   AZ_TRY(ctx, az_dalloc(ctx, &d_env, B)); AZ_TRY(ctx, az_dalloc(ctx, &d_n, 1));
   AZ_TRY(ctx, az_dalloc(ctx, &d_P, (size_t)B * G::A)); AZ_TRY(ctx, az_dalloc(ctx, &d_V, B)); AZ_TRY(ctx, az_dalloc(ctx, &d_Pi, B));
+  if (logits) AZ_TRY(ctx, az_dalloc(ctx, &d_L, (size_t)B * G::A));
+  if (vpre) AZ_TRY(ctx, az_dalloc(ctx, &d_Vp, B));
   int32_t n = B;
   AZ_CUDA(ctx, cudaMemcpyAsync(d_env, envs.data(), B * sizeof(AzEnv), cudaMemcpyHostToDevice, ctx->stream));
   AZ_CUDA(ctx, cudaMemcpyAsync(d_n, &n, 4, cudaMemcpyHostToDevice, ctx->stream));
+  net->dbg_logit = d_L; net->dbg_vpre = d_Vp;
   int st = net->eval_with_pinv(d_env, d_n, B, d_P, d_V, d_Pi);
+  net->dbg_logit = nullptr; net->dbg_vpre = nullptr;
   if (st == AZ_OK) {
-    cudaMemcpyAsync(P, d_P, (size_t)B * G::A * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(V, d_V, B * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (P) cudaMemcpyAsync(P, d_P, (size_t)B * G::A * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (V) cudaMemcpyAsync(V, d_V, B * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
     if (Pinv) cudaMemcpyAsync(Pinv, d_Pi, B * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (logits) cudaMemcpyAsync(logits, d_L, (size_t)B * G::A * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (vpre) cudaMemcpyAsync(vpre, d_Vp, B * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
   }
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_env); cudaFree(d_n); cudaFree(d_P); cudaFree(d_V); cudaFree(d_Pi);
+  cudaFree(d_env); cudaFree(d_n); cudaFree(d_P); cudaFree(d_V); cudaFree(d_Pi); cudaFree(d_L); cudaFree(d_Vp);
   if (st != AZ_OK) return st;
   if (e != cudaSuccess) AZ_FAIL(ctx, AZ_ECUDA, std::string("az_net_forward: ") + cudaGetErrorString(e));
   return AZ_OK;
@@ -796,7 +815,15 @@ int32_t az_net_forward(az_net* net, const uint8_t* states, int32_t B, float* P, 
   if (!net || !states || !P || !V || B <= 0) return AZ_EINVAL;
   AZ_GUARD_BEGIN
   cudaSetDevice(net->ctx->device);
-  AZ_DISPATCH_GAME(net->game, g_net_forward, net, states, B, P, V, Pinv)
+  AZ_DISPATCH_GAME(net->game, g_net_forward, net, states, B, P, V, Pinv, nullptr, nullptr)
+  AZ_GUARD_END(net->ctx)
+}
+int32_t az_net_forward_logits(az_net* net, const uint8_t* states, int32_t B, float* policy_logits, float* value_pre) {
+  if (!net || !states || B <= 0 || (!policy_logits && !value_pre)) return AZ_EINVAL;
+  if (net->kind != AZ_NET_RESNET && net->kind != AZ_NET_SIMPLENET) { net->ctx->err = "az_net_forward_logits: networks only"; return AZ_EINVAL; }
+  AZ_GUARD_BEGIN
+  cudaSetDevice(net->ctx->device);
+  AZ_DISPATCH_GAME(net->game, g_net_forward, net, states, B, nullptr, nullptr, nullptr, policy_logits, value_pre)
   AZ_GUARD_END(net->ctx)
 }
 int32_t az_net_set_profiling(az_net* net, int32_t enable) { if (!net) return AZ_EINVAL; cudaSetDevice(net->ctx->device); return net->set_profiling(enable); }

@@ -31,10 +31,16 @@ struct az_net {
   az_ctx* ctx = nullptr;
   int kind = 0;
   int game = 0;
+  // parity hook of az_net_forward_logits: when set, the next evaluation also writes the pre-softmax policy logits
+  // [rows][A] and the pre-tanh value [rows] (device pointers; networks only)
+  float* dbg_logit = nullptr;
+  float* dbg_vpre = nullptr;
   virtual ~az_net() {}
   virtual int eval(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V) = 0;
   virtual int64_t num_params() { return 0; }
   virtual int load(const float*, int64_t) { return AZ_OK; }
+  // size every buffer an evaluation of up to max_rows leaves needs (allocations are illegal during stream capture)
+  virtual int reserve(int max_rows) { (void)max_rows; return AZ_OK; }
   virtual bool capturable() { return true; }
   virtual uint64_t generation() { return 0; }  // changes whenever device pointers / weights baked into launches change  // false while per-launch CUDA events are being recorded
   virtual int set_profiling(int) { return AZ_OK; }

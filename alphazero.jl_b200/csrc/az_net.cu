@@ -669,6 +669,303 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Connect-Four tower kernel, "y-row" version (round 2).  What the round-1 kernel above leaves on the table
+// (profiles/r01_final2_*): 56 MMA rows per 42 valid cells (25 % of the issued MMAs are padding), tile-round
+// quantisation (604 tiles over 74 CTA pairs = 8.2 -> 9 rounds), three shifted shared-memory copies of every activation
+// row, and zeroing / storing of pad rows.
+//
+// Here the activations are stored DENSE in HBM -- row(b, y, x) = b*42 + y*7 + x, 128 fp16 channels -- and seen by TMA
+// as a 4-D tensor (channel, x, y, board).  One A stage = one board ROW y of 16 consecutive boards, 64 channels:
+// box (64 ch, 8 x-slots, 1 y, 16 boards) with its origin at x = -1, i.e. 128 smem rows x 128 B (SWIZZLE_128B, one
+// 1024-byte atom per board) where slot s of a board holds cell x = s - 1 and slot 0 is ZERO-FILLED by TMA (out of
+// bounds); that zero slot, shared with the previous board's right edge, is the "same" padding of the convolution, so
+// no pad row or pad column exists anywhere in memory.  An MMA tile is M = 256 rows = one output board row of 32
+// boards (16 per CTA of the pair), 7 of every 8 rows valid (output row m <-> board m / 8, x = m % 8; x = 7 is discarded).
+//   * ONE copy serves the three horizontal taps: the SWIZZLE_128B XOR is a function of the absolute shared-memory
+//     address (measured: scripts/probes/umma_rowshift.cu, profiles/r02_rowshift_probe.txt -- a descriptor whose start is
+//     advanced by any whole number of 128-byte rows reads exactly the shifted rows with base_offset = 0), so tap kx is
+//     the same stage with the A descriptor started 2 - kx rows in.  Rows 128 / 129 of a stage are rows 0 / 1 of the
+//     next stage in the ring (row 0 is a zero slot at all times; row 129 only feeds the discarded x = 7 output).
+//     Shared-memory fill per MMA: 0.44 KB (round 1: 1.5 KB).
+//   * schedule: input-row stationary.  For input row y the stage (y, half) feeds up to three OUTPUT rows
+//     j = y+1, y, y-1 (vertical tap ky = j + 1 - y), each with its own TMEM accumulator: 4 x 128 columns roll through
+//     the rows (three live + one being drained by the epilogue).  Taps that would read y = -1 or y = 6 are not issued
+//     at all: 16 instead of 18 (j, ky) pairs per board column.
+//   * MMA count per 32 boards and layer: 16 x 3 x 8 = 384 (round 1: 32 x 56 / 256 x 72 = 504, -24 %).
+//   * balance: the unit of work is one output row of one 32-board group; the U = 6 x groups units are split into
+//     gridDim/2 contiguous ranges of floor/ceil(U / pairs) units, so every CTA pair gets the same work to within one
+//     unit whatever the leaf count of the tick (the halo row at each end of a range is loaded twice).
+//   * boards are independent in this layout: rows of boards >= n_boards hold stale values that never reach a valid
+//     board, so the epilogue needs no validity masking; x-slot 7 and boards past the allocation are clipped by the TMA
+//     store (out-of-bounds elements of a store box are not written).
+// Weights (this CTA's 64 output channels, 144 KB) stay resident in shared memory; the skip connection of conv2 is
+// added on the tensor core by identity MMAs over the fp16 hi + lo residual stream as in the round-1 kernel (its A
+// stages are loaded with the same x = -1 origin and read one row in).
+// ------------------------------------------------------------------------------------------------
+namespace yr {
+constexpr int NBOARD = 16;            // boards per CTA tile
+constexpr int ASTAGES = 4;
+constexpr int A_STAGE = 128 * 128;    // 128 rows x 64 fp16
+constexpr int NACC = 4;               // TMEM accumulators (128 columns each)
+constexpr int NUM_THREADS = 320;      // producer warp, MMA warp, 8 epilogue warps
+constexpr int EPI_BYTES = 8 * 2048;   // two 1 KB store tiles per epilogue warp
+struct Smem {
+  uint8_t b[tc2::NCHUNK][tc2::B_CHUNK];
+  uint8_t a[ASTAGES][A_STAGE];        // contiguous: rows 128.. of stage i are rows 0.. of stage i + 1
+  uint8_t apad[1024];                 // zero rows after the last stage
+  uint8_t epi[EPI_BYTES];
+  uint8_t ident[256];
+  uint64_t full[ASTAGES], empty[ASTAGES], tfull[NACC], tempty[NACC], bfull;
+  uint32_t tmem_base;
+};
+// the contiguous unit range [u0, u1) of CTA pair `pair` (units = output board rows, 6 per 32-board group)
+__device__ __forceinline__ void unit_range(int n_boards, int pair, int npairs, int& u0, int& u1) {
+  const int groups = (n_boards + 2 * NBOARD - 1) / (2 * NBOARD);
+  const long long U = 6LL * groups;
+  u0 = (int)(U * pair / npairs);
+  u1 = (int)(U * (pair + 1) / npairs);
+}
+}  // namespace yr
+
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// stage sequence of one input row: conv1: C0 C1; conv2 with a residual: C0 Rhi0 Rhi1 C1 [Rlo0 Rlo1] -- a residual stage
+// is consumed ~18x faster than a conv stage, so they are kept in pairs between the long stages (4-deep ring)
+__device__ __forceinline__ void yrow_stage(int q, int nres, bool& isres, int& half, int& part) {
+  if (nres == 0) { isres = false; half = q; part = 0; return; }
+  isres = !(q == 0 || q == 3);
+  if (!isres) { half = q == 0 ? 0 : 1; part = 0; return; }
+  const int r = q < 3 ? q - 1 : q - 2;  // 0..3
+  part = r >> 1; half = r & 1;
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(yr::NUM_THREADS, 1)
+az_k_conv_yrow(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmO16, const __grid_constant__ CUtensorMap tmOlo,
+               const __grid_constant__ CUtensorMap tmRhi, const __grid_constant__ CUtensorMap tmRlo, GemmArgs ga) {
+  using namespace tc2;
+  constexpr int BN = 128, H = 6;
+  constexpr int ASTAGES = yr::ASTAGES, NACC = yr::NACC, NB = yr::NBOARD;
+  extern __shared__ __align__(1024) uint8_t smem_yr[];
+  if ((smem_u32(smem_yr) & 1023u) != 0u) __trap();
+  yr::Smem& s = *reinterpret_cast<yr::Smem*>(smem_yr);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  int u0, u1;
+  yr::unit_range(*ga.n_boards, blockIdx.x >> 1, gridDim.x >> 1, u0, u1);
+  const bool has_work = u0 < u1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < NACC; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 16); }
+    mbar_init(&s.bfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // zero slots: row 0 of every stage (TMA only ever writes zeros there) and the rows after the last stage
+  if (threadIdx.x < 64) {
+    if (threadIdx.x < 8 * ASTAGES) *reinterpret_cast<uint4*>(s.a[threadIdx.x >> 3] + (threadIdx.x & 7) * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(s.apad + threadIdx.x * 16) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
+  if (EPI == tc::EPI_CONV2 && threadIdx.x >= 192 && threadIdx.x < 192 + 64) {
+    // this CTA's 8 x 16 slice of the 16 x 16 identity (B operand of the residual MMAs), un-swizzled K-major core matrices
+    const int i = threadIdx.x - 192;
+    const int n = (i & 31) >> 2, khalf = i >> 5, kk = (i & 3) * 2;
+    const int k0 = khalf * 8 + kk, kone = (int)rank * 8 + n;
+    const uint32_t w = (k0 == kone ? 0x3C00u : 0u) | (k0 + 1 == kone ? 0x3C000000u : 0u);
+    *reinterpret_cast<uint32_t*>(s.ident + khalf * 128 + n * 16 + (i & 3) * 4) = w;
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // Every role walks the same sequence: groups g intersecting [u0, u1), output rows [j_lo, j_hi) of the group, input
+  // rows y = max(0, j_lo - 1) .. min(5, j_hi); `nbase` = running number of output rows before this group (accumulator
+  // slot = number & 3, barrier phase = (number >> 2) & 1).
+  if (warp == 0) {
+    if (has_work) {  // ===== TMA producer (both CTAs) =====
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(&s.bfull, 2 * NCHUNK * B_CHUNK);
+        for (int ch = 0; ch < NCHUNK; ch++) tma_load_2d_2sm(s.b[ch], &tmW, &s.bfull, ch * BK, (int)rank * BNH);
+      }
+      __syncwarp();
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = u0; u < u1;) {
+        const int g = u / H, j_lo = u - g * H, j_hi = min(u1 - g * H, H);
+        const int y_lo = max(0, j_lo - 1), y_hi = min(H - 1, j_hi);
+        const int b0 = g * 2 * NB + (int)rank * NB;
+        for (int y = y_lo; y <= y_hi; y++) {
+          const int nres = (EPI == tc::EPI_CONV2 && y >= j_lo && y < j_hi) ? (ga.res_lo ? 4 : 2) : 0;
+          for (int q = 0; q < 2 + nres; q++) {
+            bool isres; int half, part;
+            yrow_stage(q, nres, isres, half, part);
+            mbar_wait(&s.empty[stage], phase ^ 1);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(&s.full[stage], 2 * yr::A_STAGE);
+              tma_load_4d_2sm(s.a[stage], isres ? (part ? &tmRlo : &tmRhi) : &tmA, &s.full[stage], half * BK, -1, y, b0);
+            }
+            __syncwarp();
+            if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        u = g * H + j_hi;
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && has_work) {  // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);    // M = 256, N = 128
+      constexpr uint32_t IDESC_R = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256, N = 16
+      const uint64_t idsc = umma_desc_interleave(smem_u32(s.ident), 128u, 256u);
+      mbar_wait(&s.bfull, 0);
+      tcgen05_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int nbase = 0;
+      for (int u = u0; u < u1;) {
+        const int g = u / H, j_lo = u - g * H, j_hi = min(u1 - g * H, H);
+        const int y_lo = max(0, j_lo - 1), y_hi = min(H - 1, j_hi);
+        for (int y = y_lo; y <= y_hi; y++) {
+          // output rows first touched by this input row: j = y + 1, and j = 0 when y == 0 -- wait until the epilogue has
+          // drained the accumulator slot they take
+          for (int j = (y == 0 ? 0 : y + 1); j <= y + 1; j++) {
+            if (j < j_lo || j >= j_hi) continue;
+            const int n = nbase + (j - j_lo);
+            mbar_wait(&s.tempty[n & 3], ((uint32_t)(n >> 2) & 1u) ^ 1u);
+          }
+          tcgen05_fence_after();
+          const int nres = (EPI == tc::EPI_CONV2 && y >= j_lo && y < j_hi) ? (ga.res_lo ? 4 : 2) : 0;
+          for (int q = 0; q < 2 + nres; q++) {
+            bool isres; int half, part;
+            yrow_stage(q, nres, isres, half, part);
+            mbar_wait(&s.full[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t abase = smem_u32(s.a[stage]);
+            if (elect_one()) {
+              if (isres) {  // skip connection (resnet.jl:55-62): acc[j = y][:, half*64 + k*16 ..] += A[:, k*16 ..] . I16
+                const uint32_t tmem_d = tmem_base + (uint32_t)(((nbase + (y - j_lo)) & 3) * BN);
+                const uint64_t adesc = umma_desc_sw128(abase + 128u);  // cell x sits in slot x + 1
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++)
+                  umma_f16_2sm(tmem_d + (uint32_t)(half * BK + k * 16), adesc + (uint64_t)(k * 2), idsc, IDESC_R, 1u);
+              } else {
+#pragma unroll
+                for (int dj = 1; dj >= -1; dj--) {  // output row j = y + dj uses the vertical tap ky = dj + 1
+                  const int j = y + dj;
+                  if (j < j_lo || j >= j_hi) continue;
+                  const int ky = dj + 1;
+                  const uint32_t tmem_d = tmem_base + (uint32_t)(((nbase + (j - j_lo)) & 3) * BN);
+                  const bool first = (half == 0) && (y == (j > 0 ? j - 1 : 0));  // first stage of the first input row of j
+#pragma unroll
+                  for (int kx = 0; kx < 3; kx++) {  // input x = x_out + 1 - kx lives in slot x_out + 2 - kx
+                    const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(2 - kx) * 128u);
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++)
+                      umma_f16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (first && kx == 0 && k == 0) ? 0u : 1u);
+                  }
+                }
+              }
+              umma_commit_2sm(&s.empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+          }
+          // output rows completed by this input row: j = y - 1, and j = 5 after y = 5
+          if (elect_one()) {
+            if (y - 1 >= j_lo && y - 1 < j_hi) umma_commit_2sm(&s.tfull[(nbase + (y - 1 - j_lo)) & 3]);
+            if (y == H - 1 && j_hi == H) umma_commit_2sm(&s.tfull[(nbase + (H - 1 - j_lo)) & 3]);
+          }
+          __syncwarp();
+        }
+        nbase += j_hi - j_lo;
+        u = g * H + j_hi;
+      }
+    }
+  } else {  // ===== epilogue warps 2..9 (both CTAs): 128 rows (16 boards x 8 x-slots) x 128 channels per output row =====
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int quarter = warp & 3;
+    const int colhalf = (warp - 2) >> 2;
+    const int sw = (lane >> 2) & 1;  // SWIZZLE_32B: 16-byte chunk index ^= bit 7 of the byte address (row >> 2)
+    uint8_t* tiles = s.epi + (warp - 2) * 2048;
+    int ring = 0;
+    int n = 0;
+    const float* __restrict__ bias_g = ga.bias + colhalf * 64;
+    for (int u = u0; u < u1; u++, n++) {
+      const int g = u / H, j = u - g * H;
+      const int bq = g * 2 * NB + (int)rank * NB + quarter * 4;  // first of this warp's 4 boards
+      const int slot = n & 3;
+      mbar_wait(&s.tfull[slot], (uint32_t)(n >> 2) & 1u);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int sc = 0; sc < 4; sc++) {
+        const int col = colhalf * 64 + sc * 16;
+        uint32_t v[16];
+        tmem_ld16(tmem_base + slot * BN + col + ((uint32_t)(quarter * 32) << 16), v);
+        uint4 oh4[2], ol4[2];
+        __half2* oh = reinterpret_cast<__half2*>(oh4);
+        __half2* ol = reinterpret_cast<__half2*>(ol4);
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+          const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_g + sc * 16) + jj);
+          const float x0 = fmaxf(__uint_as_float(v[2 * jj]) + bb.x, 0.f);
+          const float x1 = fmaxf(__uint_as_float(v[2 * jj + 1]) + bb.y, 0.f);
+          const __half2 h = __floats2half2_rn(x0, x1);
+          oh[jj] = h;
+          if (EPI == tc::EPI_CONV2) {  // lo = fp16(y - hi): hi + lo carries ~22 significand bits of the skip path
+            const float2 hf = __half22float2(h);
+            ol[jj] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+          }
+        }
+#pragma unroll
+        for (int part = 0; part < (EPI == tc::EPI_CONV2 ? 2 : 1); part++) {
+          uint8_t* tile = tiles + ring * 1024;
+          ring ^= 1;
+          if (lane == 0) tma_store_wait_read<1>();  // the store issued two stores ago has finished reading this tile
+          __syncwarp();
+          const uint4* o = part ? ol4 : oh4;
+          *reinterpret_cast<uint4*>(tile + lane * 32 + ((0 ^ sw) << 4)) = o[0];
+          *reinterpret_cast<uint4*>(tile + lane * 32 + ((1 ^ sw) << 4)) = o[1];
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(ga.debug & 4)) { tma_store_4d(part ? &tmOlo : &tmO16, tile, col, 0, j, bq); tma_store_commit(); }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&s.tempty[slot], 0);
+    }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // stem: leaf states -> im2col rows -> tcgen05 GEMM.  The first conv (3x3, C_in -> 128, folded BN, ReLU) has K = 9*C_in
 // (27 for Connect Four): az_k_im2col writes, for every padded board row, the 9*C_in input-plane values of its 3x3
 // neighbourhood as one 128-byte fp16 row (K padded to 64), straight from the game's vectorize_state (no host round
@@ -677,8 +974,9 @@ az_k_conv_c4_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 template <class G>
 __global__ void __launch_bounds__(128) az_k_im2col(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_boards,
-                                                   __half* __restrict__ out /* [rows][64] */) {
-  constexpr int W = G::XW, H = G::XH, C = G::XC, RS = W + 1, BS = (W + 1) * (H + 1), NX = W * H * C;
+                                                   __half* __restrict__ out /* [rows][64] */, int dense) {
+  constexpr int W = G::XW, H = G::XH, C = G::XC, NX = W * H * C;
+  const int RS = dense ? W : W + 1, BS = dense ? W * H : (W + 1) * (H + 1);  // dense rows (y-row tower) or padded NHWC
   __shared__ float xs[4][NX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + warp;
@@ -715,6 +1013,8 @@ struct FinalArgs {
   const float* hid;    // value hidden [boards][128]
   const float* wv2;    // [128]
   const float* bv2;    // [1]
+  float* logit_out;    // parity hook (az_net_forward_logits): [boards][A] pre-softmax policy logits, or null
+  float* vpre_out;     // parity hook: [boards] pre-tanh value, or null
 };
 // softmax + legal-action mask + renormalisation (resnet.jl:84, network.jl:264-271), value = tanh(w2 . hidden + b2)
 // (resnet.jl:89-90).  8 lanes per board.
@@ -749,6 +1049,11 @@ __global__ void __launch_bounds__(256) az_k_finalize(const AzEnv* __restrict__ e
     for (int a = 0; a < A; a++) P[(size_t)b * A + a] = lg[a] / (sp + 1.1920929e-07f);  // eps(Float32), network.jl:268
     V[b] = tanhf(vacc + fa.bv2[0]);
     if (Pinv) Pinv[b] = 1.0f - sp;
+    if (fa.vpre_out) fa.vpre_out[b] = vacc + fa.bv2[0];
+    if (fa.logit_out) {
+#pragma unroll
+      for (int a = 0; a < A; a++) fa.logit_out[(size_t)b * A + a] = fa.logit[(size_t)b * 128 + a];
+    }
   }
 }
 
@@ -800,10 +1105,15 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
 template <class G>
 struct ResNetImpl : az_net {
   az_resnet_hp hp{};
-  static constexpr int F = 128, W = G::XW, H = G::XH, C = G::XC, A = G::A, BS = (W + 1) * (H + 1), WH = W * H;
-  static constexpr int VR = (W + 1) * H;                       // rows of a board up to (excluding) the pad row
-  static constexpr int KP = VR * 32;                           // policy / value feature length (pad columns carry zero weights)
-  static constexpr int KD = (KP + 63) / 64 * 64;               // value-dense K rounded to the 64-wide K block
+  static constexpr int F = 128, W = G::XW, H = G::XH, C = G::XC, A = G::A, WH = W * H;
+  // activation row layout, fixed at init(): padded NHWC (row stride W+1, one zero row per board) for the generic 9-tap
+  // kernel and the round-1 Connect-Four kernel, or DENSE rows (b*W*H + y*W + x) for the y-row tower kernel
+  bool dense = false;
+  int RS = W + 1;                                              // rows per board row
+  int BS = (W + 1) * (H + 1);                                  // rows per board
+  int VR = (W + 1) * H;                                        // rows of a board up to (excluding) the pad row
+  int KP = (W + 1) * H * 32;                                   // policy / value feature length (pad columns carry zero weights)
+  int KD = ((W + 1) * H * 32 + 63) / 64 * 64;                  // value-dense K rounded to the 64-wide K block
   // device weights
   __half* d_wstem = nullptr; float* d_bstem = nullptr;   // stem weights Wt[co][64] (k = tap*C + c, zero padded)
   __half* d_wpol = nullptr; float* d_bpol = nullptr;     // policy dense as a GEMM: Wt[64 (A used)][KD]
@@ -827,8 +1137,11 @@ struct ResNetImpl : az_net {
   CUtensorMap mapXr{}, mapXLr{};         // residual A stages: 128-row x 64-channel boxes of X16 / XL16
   CUtensorMap mapXLo{};                  // TMA-store target for XL16
   std::vector<CUtensorMap> mapW2;        // 64co x 64k weight boxes
-  static constexpr bool C4_TOWER = (W + 1) == 8;
-  size_t smem_2sm = 0;
+  // y-row tower: 4-D (channel, x, y, board) views of the dense activations
+  CUtensorMap map4X{}, map4T{}, map4XL{};        // loads: box (64 ch, 8 x, 1 y, 16 boards), SWIZZLE_128B, zero fill outside
+  CUtensorMap map4Xo{}, map4To{}, map4XLo{};     // stores: box (16 ch, 8 x, 1 y, 4 boards), SWIZZLE_32B
+  static constexpr bool C4_TOWER = (W + 1) == 8 && H == 6;
+  size_t smem_2sm = 0, smem_yrow = 0;
   ConvGeom geom{};
   bool loaded = false;
   int tower_debug = 0;         // AZ_TOWER_DEBUG=1: every conv uses the conv1 epilogue (timing experiments only)
@@ -837,10 +1150,25 @@ struct ResNetImpl : az_net {
   bool generic_tower = false;  // AZ_GENERIC_TOWER=1: use the generic 9-tap kernel for Connect Four too (A/B comparison)
   size_t smem128 = 0, smem64 = 0;
   // profiling: 4 events per evaluation (start, tower begin, tower end, end)
-  static constexpr int PROF_SLOTS = 8192;
+  // The event ring is drained (stream sync + accumulate) whenever it fills, so EVERY evaluation of a profiled pass is
+  // counted whatever its length (round 1 truncated at the ring size and overstated the roofline for long passes).
+  static constexpr int PROF_SLOTS = 2048;
   bool profiling = false;
   std::vector<cudaEvent_t> pev;
-  int64_t prof_evals = 0;
+  int64_t prof_evals = 0;                       // evaluations currently in the ring
+  double prof_tower_ms = 0, prof_total_ms = 0;  // drained sums
+  int64_t prof_drained = 0;
+  void prof_drain() {
+    cudaStreamSynchronize(ctx->stream);
+    for (int64_t i = 0; i < prof_evals; i++) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, pev[i * 4 + 1], pev[i * 4 + 2]);
+      cudaEventElapsedTime(&b, pev[i * 4 + 0], pev[i * 4 + 3]);
+      prof_tower_ms += a; prof_total_ms += b;
+    }
+    prof_drained += prof_evals;
+    prof_evals = 0;
+  }
 
   uint64_t gen = 1;
   uint64_t generation() override { return gen; }
@@ -852,24 +1180,16 @@ struct ResNetImpl : az_net {
     }
     cudaStreamSynchronize(ctx->stream);
     profiling = enable != 0;
-    prof_evals = 0;
+    prof_evals = 0; prof_drained = 0; prof_tower_ms = prof_total_ms = 0;
     return AZ_OK;
   }
   int get_profile(double* tower_ms, int64_t* tower_launches, double* total_ms, int64_t* evals) override {
-    cudaStreamSynchronize(ctx->stream);
-    double tw = 0, tt = 0;
-    int64_t n = std::min<int64_t>(prof_evals, PROF_SLOTS);
-    for (int64_t i = 0; i < n; i++) {
-      float a = 0, b = 0;
-      cudaEventElapsedTime(&a, pev[i * 4 + 1], pev[i * 4 + 2]);
-      cudaEventElapsedTime(&b, pev[i * 4 + 0], pev[i * 4 + 3]);
-      tw += a; tt += b;
-    }
-    if (tower_ms) *tower_ms = tw;
-    if (tower_launches) *tower_launches = n * 2 * hp.num_blocks;
-    if (total_ms) *total_ms = tt;
-    if (evals) *evals = n;
-    prof_evals = 0;
+    prof_drain();
+    if (tower_ms) *tower_ms = prof_tower_ms;
+    if (tower_launches) *tower_launches = prof_drained * 2 * hp.num_blocks;
+    if (total_ms) *total_ms = prof_total_ms;
+    if (evals) *evals = prof_drained;
+    prof_drained = 0; prof_tower_ms = prof_total_ms = 0;
     return AZ_OK;
   }
 
@@ -889,9 +1209,11 @@ struct ResNetImpl : az_net {
     }
     if (hp.num_blocks < 0) { ctx->err = "ResNet: num_blocks must be >= 0"; return AZ_EINVAL; }
     { const char* e = getenv("AZ_GENERIC_TOWER"); generic_tower = e && e[0] == '1'; }
+    { const char* e = getenv("AZ_TOWER"); dense = C4_TOWER && !generic_tower && hp.num_blocks > 0 && !(e && e[0] == 'r'); }  // AZ_TOWER=r1: round-1 kernel
+    if (dense) { RS = W; BS = W * H; VR = W * H; KP = W * H * 32; KD = (KP + 63) / 64 * 64; }
     { const char* e = getenv("AZ_TOWER_DEBUG"); tower_debug = e ? atoi(e) : 0; }
     { const char* e = getenv("AZ_NO_PDL"); use_pdl = !(e && e[0] == '1'); }
-    geom.row_stride = W + 1; geom.board_rows = BS; geom.valid_rows = VR; geom.wcols = W;
+    geom.row_stride = RS; geom.board_rows = BS; geom.valid_rows = VR; geom.wcols = dense ? RS : W;  // dense: every row is a cell
     for (int ky = 0; ky < 3; ky++)
       for (int kx = 0; kx < 3; kx++) geom.off[ky * 3 + kx] = (1 - ky) * (W + 1) + (1 - kx);
     smem128 = sizeof(tc::Smem<128>) + 1024;
@@ -905,6 +1227,10 @@ struct ResNetImpl : az_net {
     static_assert(sizeof(tc3::Smem) <= 232448, "Connect-Four tower kernel exceeds the 227 KB shared-memory limit");
     AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV1>, smem_2sm));
     AZ_TRY2(set_smem(az_k_conv_c4_2sm<tc::EPI_CONV2>, smem_2sm));
+    smem_yrow = sizeof(yr::Smem);
+    static_assert(sizeof(yr::Smem) <= 232448, "y-row tower kernel exceeds the 227 KB shared-memory limit");
+    AZ_TRY2(set_smem(az_k_conv_yrow<tc::EPI_CONV1>, smem_yrow));
+    AZ_TRY2(set_smem(az_k_conv_yrow<tc::EPI_CONV2>, smem_yrow));
     return AZ_OK;
   }
   int64_t num_params() override {
@@ -999,7 +1325,7 @@ struct ResNetImpl : az_net {
       const float* b1 = q; q += F;
       std::vector<__half> wd((size_t)F * KD, __float2half_rn(0.0f));  // Wd[o][k'], k' = (y*(W+1) + x)*32 + c
       for (int o = 0; o < F; o++) for (int c = 0; c < 32; c++) for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
-        wd[(size_t)o * KD + (size_t)(y * (W + 1) + x) * 32 + c] = __float2half_rn(w1[o + (size_t)F * ((x + W * y) + (size_t)WH * c)]);
+        wd[(size_t)o * KD + (size_t)(y * RS + x) * 32 + c] = __float2half_rn(w1[o + (size_t)F * ((x + W * y) + (size_t)WH * c)]);
       AZ_TRY2(up(&d_wd, wd));
       AZ_TRY2(up(&d_bd, std::vector<float>(b1, b1 + F)));
       AZ_TRY2(make_map_2d(ctx, &mapWd, d_wd, KD, F, (uint64_t)KD * 2, tc::BK, 128));
@@ -1018,7 +1344,7 @@ struct ResNetImpl : az_net {
       const float* b1 = q; q += A;
       std::vector<__half> wp((size_t)64 * KD, __float2half_rn(0.0f));  // Wt[a][k'], rows >= A and pad positions zero
       for (int a = 0; a < A; a++) for (int c = 0; c < 32; c++) for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
-        wp[(size_t)a * KD + (size_t)(y * (W + 1) + x) * 32 + c] = __float2half_rn(w1[a + (size_t)A * ((x + W * y) + (size_t)WH * c)]);
+        wp[(size_t)a * KD + (size_t)(y * RS + x) * 32 + c] = __float2half_rn(w1[a + (size_t)A * ((x + W * y) + (size_t)WH * c)]);
       std::vector<float> bpol(64, 0.0f);
       for (int a = 0; a < A; a++) bpol[a] = b1[a];
       AZ_TRY2(up(&d_wpol, wp)); AZ_TRY2(up(&d_bpol, bpol));
@@ -1032,6 +1358,19 @@ struct ResNetImpl : az_net {
   template <class T> int dmalloc(T** p, size_t n) {
     if (cudaMalloc((void**)p, n * sizeof(T)) != cudaSuccess) { ctx->err = "cudaMalloc (activations) failed"; cudaGetLastError(); return AZ_ENOMEM; }
     cudaMemsetAsync(*p, 0, n * sizeof(T), ctx->stream);
+    return AZ_OK;
+  }
+  // dense activations [boards][H][W][128] fp16 as a 4-D tensor (channel, x, y, board); box = (bc, bx, 1, bb)
+  int make_map_4d(az_ctx* c, CUtensorMap* m, void* base, int boards, uint32_t bc, uint32_t bx, uint32_t bb, CUtensorMapSwizzle swz) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { c->err = "cuTensorMapEncodeTiled not available"; return AZ_ECUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)F, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)boards};
+    cuuint64_t strides[3] = {(cuuint64_t)F * 2, (cuuint64_t)W * F * 2, (cuuint64_t)W * H * F * 2};
+    cuuint32_t box[4] = {bc, bx, 1, bb};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { c->err = "cuTensorMapEncodeTiled (4-D) failed: " + std::to_string((int)r); return AZ_ECUDA; }
     return AZ_OK;
   }
   int ensure_act(int max_boards) {
@@ -1062,17 +1401,28 @@ struct ResNetImpl : az_net {
       AZ_TRY2(make_map_2d(ctx, &mapXLo, d_xl16, F, alloc_rows, F * 2, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
     }
     AZ_TRY2(make_map_2d(ctx, &mapHv, d_hv, (uint64_t)BS * 32, alloc_boards, (uint64_t)BS * 32 * 2, tc::BK, tc::BM));
+    if (dense) {
+      const CUtensorMapSwizzle s128 = CU_TENSOR_MAP_SWIZZLE_128B, s32 = CU_TENSOR_MAP_SWIZZLE_32B;
+      AZ_TRY2(make_map_4d(ctx, &map4X, d_x16, alloc_boards, 64, 8, yr::NBOARD, s128));
+      AZ_TRY2(make_map_4d(ctx, &map4T, d_t16, alloc_boards, 64, 8, yr::NBOARD, s128));
+      AZ_TRY2(make_map_4d(ctx, &map4XL, d_xl16, alloc_boards, 64, 8, yr::NBOARD, s128));
+      AZ_TRY2(make_map_4d(ctx, &map4Xo, d_x16, alloc_boards, 16, 8, 4, s32));
+      AZ_TRY2(make_map_4d(ctx, &map4To, d_t16, alloc_boards, 16, 8, 4, s32));
+      AZ_TRY2(make_map_4d(ctx, &map4XLo, d_xl16, alloc_boards, 16, 8, 4, s32));
+    }
     act_boards = max_boards;
     return AZ_OK;
   }
   int eval(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V) override {
     return eval_with_pinv(envs, n_rows, max_rows, P, V, nullptr);
   }
+  int reserve(int max_rows) override { return ensure_act(max_rows); }
   int eval_with_pinv(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V, float* Pinv) override {
     if (!loaded) { ctx->err = "ResNet: az_net_load must be called before the network is used"; return AZ_ESTATE; }
     AZ_TRY2(ensure_act(max_rows));
     cudaStream_t st = ctx->stream;
-    const bool prof = profiling && prof_evals < PROF_SLOTS;
+    if (profiling && prof_evals == PROF_SLOTS) prof_drain();
+    const bool prof = profiling;
     cudaEvent_t* pe = prof ? &pev[(size_t)prof_evals * 4] : nullptr;
     if (prof) cudaEventRecord(pe[0], st);
     const bool c4_fast = C4_TOWER && !generic_tower && two_sm && hp.num_blocks > 0;
@@ -1080,14 +1430,24 @@ struct ResNetImpl : az_net {
     const int grid = std::min(row_tiles, ctx->num_sms);
     GemmArgs ga{};
     ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.debug = 0;
-    az_k_im2col<G><<<(max_rows + 3) / 4, 128, 0, st>>>(envs, n_rows, d_x0);
+    az_k_im2col<G><<<(max_rows + 3) / 4, 128, 0, st>>>(envs, n_rows, d_x0, dense ? 1 : 0);
     ga.gemm_k = 1; ga.kblocks = 1; ga.bias = d_bstem; ga.out16a = d_x16; ga.out32 = c4_fast ? nullptr : d_x32;
     launch_pdl(az_k_gemm_tc<128, tc::EPI_CONV1>, grid, tc::NUM_THREADS, smem128, st, mapX0, mapWstem, ga);
     ga.gemm_k = 0; ga.out32 = nullptr; ga.debug = tower_debug;
     if (prof) cudaEventRecord(pe[1], st);
     const bool c4 = C4_TOWER && !generic_tower;  // Connect-Four geometry -> cta_group::2 kernel, otherwise the generic 9-tap kernel
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
-    for (int blk = 0; blk < hp.num_blocks; blk++) {
+    const int grid_yr = ctx->num_sms & ~1;  // persistent: one CTA pair per SM pair, balanced unit ranges (idle pairs exit)
+    for (int blk = 0; dense && blk < hp.num_blocks; blk++) {
+      ga.bias = d_bconv[2 * blk]; ga.res_lo = 0;
+      if (use_pdl && blk > 0) launch_pdl(az_k_conv_yrow<tc::EPI_CONV1>, grid_yr, yr::NUM_THREADS, smem_yrow, st, map4X, mapW2[2 * blk], map4To, map4XLo, map4X, map4XL, ga);
+      else az_k_conv_yrow<tc::EPI_CONV1><<<grid_yr, yr::NUM_THREADS, smem_yrow, st>>>(map4X, mapW2[2 * blk], map4To, map4XLo, map4X, map4XL, ga);
+      ga.bias = d_bconv[2 * blk + 1];
+      ga.res_lo = blk > 0 ? 1 : 0;  // block 0: the residual is the fp16 stem output, no low-order part yet
+      if (use_pdl) launch_pdl(az_k_conv_yrow<tc::EPI_CONV2>, grid_yr, yr::NUM_THREADS, smem_yrow, st, map4T, mapW2[2 * blk + 1], map4Xo, map4XLo, map4X, map4XL, ga);
+      else az_k_conv_yrow<tc::EPI_CONV2><<<grid_yr, yr::NUM_THREADS, smem_yrow, st>>>(map4T, mapW2[2 * blk + 1], map4Xo, map4XLo, map4X, map4XL, ga);
+    }
+    for (int blk = 0; !dense && blk < hp.num_blocks; blk++) {
       ga.kblocks = 18; ga.bias = d_bconv[2 * blk]; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_t16; ga.out16b = nullptr;
       if (c4 && two_sm && use_pdl && blk > 0) launch_pdl(az_k_conv_c4_2sm<tc::EPI_CONV1>, grid_2sm, tc3::NUM_THREADS, smem_2sm, st, mapX2, mapW2[2 * blk], mapTo, mapXLo, mapXr, mapXLr, ga);
       else if (c4 && two_sm) az_k_conv_c4_2sm<tc::EPI_CONV1><<<grid_2sm, tc3::NUM_THREADS, smem_2sm, st>>>(mapX2, mapW2[2 * blk], mapTo, mapXLo, mapXr, mapXLr, ga);
@@ -1112,7 +1472,7 @@ struct ResNetImpl : az_net {
     launch_pdl(az_k_gemm_tc<128, tc::EPI_DENSE>, std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem128, st, mapHv, mapWd, gd);
     gd.bias = d_bpol; gd.out32 = d_logit; gd.no_relu = 1;   // policy dense: logits[b][0..A) = Wp . hp + b
     launch_pdl(az_k_gemm_tc<64, tc::EPI_DENSE>, std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem64, st, mapHp, mapWpol, gd);
-    FinalArgs fa{d_logit, d_hid, d_wv2, d_bv2};
+    FinalArgs fa{d_logit, d_hid, d_wv2, d_bv2, dbg_logit, dbg_vpre};
     az_k_finalize<G><<<(max_rows * 8 + 255) / 256, 256, 0, st>>>(envs, n_rows, fa, P, V, Pinv);
     if (prof) { cudaEventRecord(pe[3], st); prof_evals++; }
     ctx->launches += 6 + 2 * hp.num_blocks;
@@ -1173,7 +1533,8 @@ __device__ __forceinline__ void mlp_layer(const MlpLayer& L, const float* __rest
 }
 template <class G, int NB>
 __global__ void __launch_bounds__(256) az_k_simplenet(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_boards, MlpArgs m,
-                                                      float* __restrict__ P, float* __restrict__ V, float* __restrict__ Pinv) {
+                                                      float* __restrict__ P, float* __restrict__ V, float* __restrict__ Pinv,
+                                                      float* __restrict__ logit_out, float* __restrict__ vpre_out) {
   constexpr int A = G::A, NX = G::XW * G::XH * G::XC, MAXW = 256;
   __shared__ float x0[NB][NX];
   __shared__ float ha[NB][MAXW], hb[NB][MAXW], hc[NB][MAXW];
@@ -1212,7 +1573,7 @@ __global__ void __launch_bounds__(256) az_k_simplenet(const AzEnv* __restrict__ 
       for (int i = lane; i < L.in; i += 32) acc += L.w[i] * in[j * MAXW + i];
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      if (lane == 0) outp[j][A] = tanhf(acc + L.b[0]);
+      if (lane == 0) { outp[j][A] = tanhf(acc + L.b[0]); if (vpre_out) vpre_out[b0 + j] = acc + L.b[0]; }
     }
   }
   __syncthreads();
@@ -1229,6 +1590,10 @@ __global__ void __launch_bounds__(256) az_k_simplenet(const AzEnv* __restrict__ 
     float lg[A], mx = -3.0e38f;
 #pragma unroll
     for (int a = 0; a < A; a++) { lg[a] = outp[j][a]; mx = fmaxf(mx, lg[a]); }
+    if (logit_out) {
+#pragma unroll
+      for (int a = 0; a < A; a++) logit_out[(size_t)row * A + a] = lg[a];
+    }
     float se = 0.0f;
 #pragma unroll
     for (int a = 0; a < A; a++) { lg[a] = expf(lg[a] - mx); se += lg[a]; }
@@ -1320,7 +1685,7 @@ struct SimpleNetImpl : az_net {
   }
   int eval_with_pinv(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V, float* Pinv) override {
     if (!loaded) { ctx->err = "SimpleNet: az_net_load must be called before the network is used"; return AZ_ESTATE; }
-    az_k_simplenet<G, NB><<<(max_rows + NB - 1) / NB, 256, 0, ctx->stream>>>(envs, n_rows, margs, P, V, Pinv);
+    az_k_simplenet<G, NB><<<(max_rows + NB - 1) / NB, 256, 0, ctx->stream>>>(envs, n_rows, margs, P, V, Pinv, dbg_logit, dbg_vpre);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ctx->err = std::string("SimpleNet launch: ") + cudaGetErrorString(e); return AZ_ECUDA; }

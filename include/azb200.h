@@ -127,6 +127,10 @@ int32_t az_net_load(az_net* net, const float* blob, int64_t n);
 /* Network.evaluate_batch / forward_normalized (src/networks/network.jl:264-271,308-315):
    P is A-wide (masked, renormalised, zero on illegal), V[B], Pinvalid[B] (may be NULL) */
 int32_t az_net_forward(az_net* net, const uint8_t* states, int32_t B, float* P, float* V, float* Pinvalid);
+/* parity hook for Network.forward (src/networks/network.jl:119-132, architectures/resnet.jl:83-90) BEFORE its output
+   non-linearities: policy_logits[B*A] = input of the policy head's softmax (every action, no mask), value_pre[B] = input
+   of the value head's tanh; either may be NULL.  ResNet and SimpleNet only. */
+int32_t az_net_forward_logits(az_net* net, const uint8_t* states, int32_t B, float* policy_logits, float* value_pre);
 /* device-side timing (CUDA events on the context's stream) of the network launches, for bench.py's roofline:
    tower_ms = time inside the conv-tower kernels, tower_launches = number of tower kernel launches,
    total_ms = stem + tower + heads, evals = number of batched evaluations since profiling was enabled */

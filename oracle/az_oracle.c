@@ -886,6 +886,7 @@ typedef struct {
   int leaf_acts[OZ_MAX_ACTIONS];
   oz_step path[OZ_MAX_PLIES];
   int depth;
+  int sims_local; /* simulations finished since the last oz_batch_advance (summed outside the parallel loop) */
 } oz_tree;
 struct oz_batch {
   int game_id, n, nsims;
@@ -963,16 +964,26 @@ static int oz_tree_advance(oz_batch* b, oz_tree* t) {
       root = 0;
     }
     t->sims_done++;
-    b->sims++;
+    t->sims_local++;
   }
   return 0;
 }
+/* Trees are independent (one MCTS.Env per worker, src/simulations.jl:217-218): the CPU baseline runs them on all host
+   threads like the reference's Util.mapreduce over worker tasks (src/util.jl:169-200).  Leaves are collected in tree
+   order afterwards, so the result does not depend on the thread count. */
 int oz_batch_advance(oz_batch* b, uint8_t* leaf_states, int32_t* leaf_tree) {
   int sb = OZ_SBYTES[b->game_id];
   b->npend = 0;
+#pragma omp parallel for schedule(static)
   for (int i = 0; i < b->n; i++) {
     oz_tree* t = &b->t[i];
-    if (t->pending || oz_tree_advance(b, t)) {
+    if (!t->pending) oz_tree_advance(b, t);
+  }
+  for (int i = 0; i < b->n; i++) {
+    oz_tree* t = &b->t[i];
+    b->sims += t->sims_local;
+    t->sims_local = 0;
+    if (t->pending) {
       memcpy(leaf_states + (size_t)b->npend * sb, t->leaf.b, (size_t)sb);
       leaf_tree[b->npend] = i;
       b->pend[b->npend++] = i;
@@ -980,8 +991,21 @@ int oz_batch_advance(oz_batch* b, uint8_t* leaf_states, int32_t* leaf_tree) {
   }
   return b->npend;
 }
+/* GI.vectorize_state + GI.actions_mask of the pending leaves (the Batchifier's `Flux.batch(vectorize_state.(...))`,
+   src/networks/network.jl:310-312), on all host threads: X[npend][state_dim floats], mask[npend][A] */
+void oz_batch_vectorize(const oz_batch* b, const uint8_t* leaf_states, int n, int xdim, float* X, uint8_t* mask) {
+  int sb = OZ_SBYTES[b->game_id], A = OZ_NACT[b->game_id];
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j < n; j++) {
+    oz_vectorize_state(b->game_id, leaf_states + (size_t)j * sb, X + (size_t)j * xdim);
+    const oz_tree* t = &b->t[b->pend[j]];
+    for (int a = 0; a < A; a++) mask[(size_t)j * A + a] = 0;
+    for (int i = 0; i < t->leaf_nlegal; i++) mask[(size_t)j * A + t->leaf_acts[i]] = 1;
+  }
+}
 void oz_batch_feed(oz_batch* b, const float* P, const float* V) {
   int A = OZ_NACT[b->game_id];
+#pragma omp parallel for schedule(static)
   for (int j = 0; j < b->npend; j++) {
     oz_tree* t = &b->t[b->pend[j]];
     oz_env* e = t->env;
@@ -995,9 +1019,9 @@ void oz_batch_feed(oz_batch* b, const float* P, const float* V) {
     oz_tree_backup(t, (double)info->Vest);
     t->pending = 0;
     t->sims_done++;
-    b->sims++;
-    b->expansions++;
   }
+  b->sims += b->npend;
+  b->expansions += b->npend;
   b->npend = 0;
 }
 void oz_batch_root_stats(const oz_batch* b, int tree, int64_t* N, double* W, float* P) {

@@ -74,8 +74,9 @@ def make_blob(dim, num_actions, hp, seed=1, randomize=True):
     return np.concatenate(parts).astype(np.float32)
 
 
-def forward(blob, dim, num_actions, hp, X, dtype=torch.float32):
-    """X: [B, W, H, C] (vectorize_state per sample, Flux WHC order).  Returns (P [B,A] softmax, V [B])."""
+def forward(blob, dim, num_actions, hp, X, dtype=torch.float32, logits=False):
+    """X: [B, W, H, C] (vectorize_state per sample, Flux WHC order).  Returns (P [B,A] softmax, V [B]); with logits=True
+    the inputs of the two output non-linearities instead (policy logits [B,A], pre-tanh value [B])."""
     Wd, Hd, C = dim
     q = [0]
     blob = np.asarray(blob, np.float32)
@@ -115,10 +116,14 @@ def forward(blob, dim, num_actions, hp, X, dtype=torch.float32):
     B = x.shape[0]
     v = bn(conv(x, next(it)), next(it), True).reshape(B, -1)  # (c,h,w) row-major == Flux flatten (w,h,c) column-major
     v = torch.relu(dense(v, next(it)))
-    v = torch.tanh(dense(v, next(it)))[:, 0]
+    vpre = dense(v, next(it))[:, 0]
+    v = torch.tanh(vpre)
     p = bn(conv(x, next(it)), next(it), True).reshape(B, -1)
-    p = torch.softmax(dense(p, next(it)), dim=1)
+    plog = dense(p, next(it))
+    p = torch.softmax(plog, dim=1)
     assert q[0] == len(blob)
+    if logits:
+        return plog.numpy().astype(np.float32), vpre.numpy().astype(np.float32)
     return p.numpy().astype(np.float32), v.numpy().astype(np.float32)
 
 
@@ -168,8 +173,9 @@ def simplenet_make_blob(dim, num_actions, hp, seed=1, randomize=True):
     return np.concatenate(parts).astype(np.float32)
 
 
-def simplenet_forward(blob, dim, num_actions, hp, X):
-    """X: [B, W, H, C]; flatten is column-major over (W,H,C) (Flux.flatten). Returns (P softmax, V)."""
+def simplenet_forward(blob, dim, num_actions, hp, X, logits=False):
+    """X: [B, W, H, C]; flatten is column-major over (W,H,C) (Flux.flatten). Returns (P softmax, V), or with logits=True
+    (policy logits, pre-tanh value)."""
     blob = np.asarray(blob, np.float32)
     q = [0]
 
@@ -201,10 +207,14 @@ def simplenet_forward(blob, dim, num_actions, hp, X):
     v = x
     for _ in range(hp.get("depth_vhead", 1)):
         v = hidden(v, w, w)
-    v = torch.tanh(dense(v, 1, w, False))[:, 0]
+    vpre = dense(v, 1, w, False)[:, 0]
+    v = torch.tanh(vpre)
     p = x
     for _ in range(hp.get("depth_phead", 1)):
         p = hidden(p, w, w)
-    p = torch.softmax(dense(p, num_actions, w, False), dim=1)
+    plog = dense(p, num_actions, w, False)
+    p = torch.softmax(plog, dim=1)
     assert q[0] == len(blob)
+    if logits:
+        return plog.numpy().astype(np.float32), vpre.numpy().astype(np.float32)
     return p.numpy().astype(np.float32), v.numpy().astype(np.float32)

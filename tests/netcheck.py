@@ -1,5 +1,5 @@
 """Shared helper: CUDA ResNet forward (through the C ABI) against the fp32 torch restatement (oracle/netref.py).
-Tolerance 1e-3 on P, V (BASELINE.json north_star: "value/policy within 1e-3")."""
+Tolerance 1e-3 on the policy logits, the pre-tanh value, P and V (BASELINE.json north_star: "value/policy logits within 1e-3")."""
 import numpy as np
 
 TOL = 1e-3
@@ -28,8 +28,13 @@ def compare(az, oz, gs, net, blob, hp, states):
     P0, V0 = netref.forward(blob, gs.state_dim, gs.num_actions, hp, X)
     Pr, Vr, Ir = netref.forward_normalized(P0, V0, mask)
     P, V, Pinv = net.evaluate_batch(states)
+    # the inputs of the output non-linearities ("logits" of BASELINE.json north_star): policy logits before the softmax,
+    # value before the tanh
+    Lr, Vpr = netref.forward(blob, gs.state_dim, gs.num_actions, hp, X, logits=True)
+    L, Vp = net.forward_logits(states)
     return dict(dP=float(np.abs(P - Pr).max()), dV=float(np.abs(V - Vr).max()), dI=float(np.abs(Pinv - Ir).max()),
-                P=P, V=V, Pr=Pr, Vr=Vr, mask=mask)
+                dL=float(np.abs(L - Lr).max()), dVpre=float(np.abs(Vp - Vpr).max()),
+                P=P, V=V, Pr=Pr, Vr=Vr, mask=mask, L=L, Lr=Lr, Vpre=Vp, Vprer=Vpr)
 
 
 def smoke(az, ctx, gs):
@@ -38,6 +43,6 @@ def smoke(az, ctx, gs):
     net, blob = make_net(az, ctx, gs, hp)
     states = gs.random_positions(7, 96, 30)
     r = compare(az, oz, gs, net, blob, hp, states)
-    assert r["dP"] < TOL and r["dV"] < TOL, r
+    assert r["dP"] < TOL and r["dV"] < TOL and r["dL"] < TOL and r["dVpre"] < TOL, {k: r[k] for k in ("dP", "dV", "dL", "dVpre")}
     net.close()
     print("smoke OK: ResNet forward within %.1e of the fp32 reference (dP=%.2e dV=%.2e)" % (TOL, r["dP"], r["dV"]))

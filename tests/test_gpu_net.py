@@ -31,6 +31,8 @@ def test_resnet_forward_matches_fp32_reference(az, oz, ctx, blocks, batch, seed,
     states[0] = gs.init_state()
     r = netcheck.compare(az, oz, gs, net, blob, hp, states)
     assert r["dP"] < netcheck.TOL and r["dV"] < netcheck.TOL and r["dI"] < netcheck.TOL, (r["dP"], r["dV"], r["dI"])
+    # logits (inputs of softmax / tanh) within 1e-3 as well: the contract of BASELINE.json north_star
+    assert r["dL"] < netcheck.TOL and r["dVpre"] < netcheck.TOL, (r["dL"], r["dVpre"])
     assert (r["P"][~r["mask"]] == 0).all() and np.allclose(r["P"].sum(1), 1, atol=1e-5)
     # batch invariance: a state's output bits do not depend on its position in the batch
     P2, V2, _ = net.evaluate_batch(states[::-1].copy())
@@ -39,9 +41,12 @@ def test_resnet_forward_matches_fp32_reference(az, oz, ctx, blocks, batch, seed,
 
 
 def test_resnet_precision_stress(az, oz, ctx):
-    """fp16 tensor-core operands put a floor of ~2^-11 relative error per layer on the tower; with adversarially
-    randomised BatchNorm statistics the worst-case |dV| over 400 positions of a 7-block net can reach ~1e-3
-    (DESIGN.md "precision").  This test documents the distribution: RMS below 8e-4, max below 2.5e-3."""
+    """OUTSIDE the 1e-3 contract, and says so: fp16 tensor-core operands (11-bit significands; tf32 has the same 11)
+    put a floor of ~2^-12 relative rounding error per operand per layer on the tower.  Networks with Flux-initialised or
+    mildly perturbed BatchNorm statistics stay within 1e-3 (tests above); with ADVERSARIALLY randomised statistics
+    (gamma in [0.5, 1.5], sigma2 in [0.5, 1.5], large mu / beta: activations several times larger than a trained net's)
+    the worst case over 400 positions of a 7-block net exceeds it.  This test pins the measured distribution
+    (DESIGN.md "precision"): RMS error below 8e-4, worst case below 2.5e-3 on V, below 1e-3 on P."""
     gs = az.GameSpec("connect-four")
     hp = netcheck.c4_hp(7)
     states = gs.random_positions(11, 400, 38)
@@ -50,7 +55,7 @@ def test_resnet_precision_stress(az, oz, ctx):
         r = netcheck.compare(az, oz, gs, net, blob, hp, states)
         rms_v = float(np.sqrt(np.mean((r["V"] - r["Vr"]) ** 2)))
         rms_p = float(np.sqrt(np.mean((r["P"] - r["Pr"]) ** 2)))
-        print("seed %d: max dP %.2e dV %.2e  rms dP %.2e dV %.2e" % (seed, r["dP"], r["dV"], rms_p, rms_v))
+        print("seed %d: max dP %.2e dV %.2e dL %.2e dVpre %.2e  rms dP %.2e dV %.2e" % (seed, r["dP"], r["dV"], r["dL"], r["dVpre"], rms_p, rms_v))
         assert r["dP"] < 1e-3 and r["dV"] < 2.5e-3 and rms_v < 8e-4 and rms_p < 3e-4
         net.close()
 
@@ -216,6 +221,9 @@ def test_simplenet_forward_and_mcts(az, oz, ctx, game, hp):
     Pr, Vr, Ir = netref.forward_normalized(P0, V0, mask)
     P, V, Pinv = net.evaluate_batch(states)
     assert np.abs(P - Pr).max() < 1e-4 and np.abs(V - Vr).max() < 1e-4 and np.abs(Pinv - Ir).max() < 1e-4
+    Lr, Vpr = netref.simplenet_forward(blob, gs.state_dim, gs.num_actions, hp, X, logits=True)
+    L, Vp = net.forward_logits(states)
+    assert np.abs(L - Lr).max() < 1e-4 and np.abs(Vp - Vpr).max() < 1e-4
     # MCTS with the network as oracle, oracle replay with the network's own outputs: bit-exact
     nsims = 50
     mp = az.MctsParams(cpuct=1.0, num_iters_per_turn=nsims, dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0)

@@ -63,6 +63,7 @@ ABI_SYMBOLS = [
     "az_selfplay_fetch", "az_selfplay_stats", "az_selfplay_destroy", "az_selfplay_create_duel", "az_selfplay_outcomes",
     "az_selfplay_export_samples", "az_samples_from_host", "az_samples_count", "az_samples_concat", "az_samples_merge_by_state",
     "az_samples_augment_with_symmetries", "az_samples_convert", "az_samples_fetch", "az_samples_destroy",
+    "az_comm_unique_id", "az_comm_create", "az_comm_rank", "az_comm_last_ms", "az_comm_destroy", "az_samples_allgather", "az_net_broadcast",
 ]
 
 _lib = None
@@ -111,6 +112,9 @@ def lib():
             "az_samples_merge_by_state": [vp, C.POINTER(vp)], "az_samples_augment_with_symmetries": [vp, C.POINTER(vp)],
             "az_samples_convert": [vp, C.c_int32, vp, vp, vp, vp, vp], "az_samples_fetch": [vp, vp, vp, vp, vp, vp],
             "az_samples_destroy": [vp],
+            "az_comm_unique_id": [vp, vp], "az_comm_create": [vp, vp, C.c_int32, C.c_int32, C.POINTER(vp)],
+            "az_comm_rank": [vp, vp, vp], "az_comm_last_ms": [vp, C.POINTER(C.c_double)], "az_comm_destroy": [vp],
+            "az_samples_allgather": [vp, vp, C.POINTER(vp), vp], "az_net_broadcast": [vp, vp, vp, C.c_int64, C.c_int32],
         }
         for name, args in sigs.items():
             getattr(L, name).argtypes = args
@@ -550,6 +554,62 @@ class Samples:
     def close(self):
         if self.h:
             lib().az_samples_destroy(self.h)
+            self.h = None
+
+
+class Comm:
+    """One rank of the engine's NCCL communicator (one process per GPU, src/simulations.jl:252-290).  `exchange(id_bytes)`
+    is the caller's own channel for the 128-byte id: it receives rank 0's bytes (None on the other ranks) and returns
+    rank 0's bytes on every rank -- e.g. a torch.distributed broadcast, an MPI bcast or the Julia `Distributed` call that
+    starts the workers."""
+    ID_BYTES = 128
+
+    def __init__(self, ctx, rank, world, exchange=None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        ident = None
+        if rank == 0:
+            ident = np.zeros(self.ID_BYTES, np.uint8)
+            ctx.check(lib().az_comm_unique_id(ctx.h, ident.ctypes.data))
+        if world > 1:
+            if exchange is None:
+                raise ValueError("Comm: world > 1 needs an `exchange` callable for the communicator id")
+            ident = np.frombuffer(bytes(exchange(None if ident is None else ident.tobytes())), np.uint8).copy()
+        self.h = C.c_void_p()
+        ctx.check(lib().az_comm_create(ctx.h, ident.ctypes.data, rank, world, C.byref(self.h)))
+
+    @classmethod
+    def from_torch(cls, ctx, dist):
+        """Id exchange over an initialised torch.distributed group (any backend); None / uninitialised -> single rank."""
+        if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+            return cls(ctx, 0, 1)
+
+        def exchange(b):
+            box = [b]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        return cls(ctx, dist.get_rank(), dist.get_world_size(), exchange)
+
+    def allgather_samples(self, samples):
+        """`reduce(vcat, results)` over ranks (src/simulations.jl:289) for device-resident samples; returns (Samples, counts)."""
+        h = C.c_void_p()
+        counts = np.zeros(self.world, np.int64)
+        self.ctx.check(lib().az_samples_allgather(self.h, samples.h, C.byref(h), counts.ctypes.data))
+        return Samples(samples.ctx, samples.gspec, h), counts
+
+    def broadcast_network(self, net, blob=None, root=0):
+        """Every rank loads rank `root`'s parameter blob into `net` (same architecture everywhere)."""
+        b = None if blob is None else np.ascontiguousarray(blob, np.float32)
+        self.ctx.check(lib().az_net_broadcast(self.h, net.h, _ptr(b), net.num_params, root))
+
+    @property
+    def last_ms(self):
+        ms = C.c_double()
+        self.ctx.check(lib().az_comm_last_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.h:
+            lib().az_comm_destroy(self.h)
             self.h = None
 
 

@@ -14,6 +14,7 @@ UNITS = {
     "az_engine.cu": ["-fmad=false"],
     "az_net.cu": [],
     "az_samples.cu": ["-fmad=false"],
+    "az_comm.cu": [],
 }
 
 
@@ -32,7 +33,7 @@ def build(force=False, verbose=False):
             cmd = [NVCC] + ARCH + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             subprocess.check_call(cmd)
     if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        subprocess.check_call([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"])
+        subprocess.check_call([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda", "-ldl"])
     return LIB
 
 

@@ -66,4 +66,5 @@ double* az_samples_pi(az_samples* s);
 double* az_samples_z(az_samples* s);
 double* az_samples_t(az_samples* s);
 int32_t* az_samples_cnt(az_samples* s);
+int az_samples_game(az_samples* s);
 extern "C" int32_t az_samples_destroy(az_samples* s);

@@ -58,6 +58,7 @@ double* az_samples_pi(az_samples* s) { return s->pi; }
 double* az_samples_z(az_samples* s) { return s->z; }
 double* az_samples_t(az_samples* s) { return s->t; }
 int32_t* az_samples_cnt(az_samples* s) { return s->cnt; }
+int az_samples_game(az_samples* s) { return s->game; }
 
 // ---- grouping by state: open-addressing table over a 64-bit hash of the 16-byte state key --------------------------------
 __device__ __forceinline__ uint64_t azs_hash(uint64_t a, uint64_t b) {

@@ -38,6 +38,7 @@ typedef struct az_net az_net;
 typedef struct az_mcts az_mcts;
 typedef struct az_selfplay az_selfplay;
 typedef struct az_samples az_samples;
+typedef struct az_comm az_comm;
 
 /* ---- library / context ---------------------------------------------------------------- */
 int32_t az_version(void);
@@ -221,6 +222,30 @@ int32_t az_samples_augment_with_symmetries(az_samples* in, az_samples** out);
 int32_t az_samples_convert(az_samples* s, int32_t weighing, float* W, float* X, float* A, float* P, float* V);
 int32_t az_samples_fetch(az_samples* s, uint8_t* states, double* pi, double* z, double* t, int32_t* n_rec);
 int32_t az_samples_destroy(az_samples* s);
+
+/* ---- multi-GPU: simulate_distributed (src/simulations.jl:252-290) with one rank (process) per GPU ---------------------
+   Games shard over ranks (num_each / rem split, :268,277: done by the caller); nothing crosses GPUs
+   inside the simulation loop.  The two exchanges of an iteration run over NCCL (NVLink / NVSwitch) on the context's
+   stream with every row staying in HBM.  NCCL is bound at run time (libnccl.so.2); AZ_EUNSUPPORTED if it is absent. */
+#define AZ_COMM_ID_BYTES 128
+/* rank 0 creates the id and hands the 128 bytes to the other ranks through the caller's own channel (Julia: the
+   `Distributed` remotecall that already starts the workers, :271-281; Python mirror: the torch.distributed store) */
+int32_t az_comm_unique_id(az_ctx* ctx, uint8_t id[AZ_COMM_ID_BYTES]);
+/* collective over all `world` ranks (ncclCommInitRank); the communicator uses the context's device and stream */
+int32_t az_comm_create(az_ctx* ctx, const uint8_t id[AZ_COMM_ID_BYTES], int32_t rank, int32_t world, az_comm** out);
+int32_t az_comm_rank(az_comm* c, int32_t* rank, int32_t* world);
+/* device time (ms, CUDA events on the context's stream) of the last az_samples_allgather / az_net_broadcast */
+int32_t az_comm_last_ms(az_comm* c, double* ms);
+int32_t az_comm_destroy(az_comm* c);
+/* `fetch.(tasks)` + `reduce(vcat, results)` (src/simulations.jl:282-289) for device-resident samples: *out = the sample
+   sets of ranks 0 .. world-1 concatenated in rank order, on every rank.  One all-gather of the per-rank counts, then ONE
+   all-gather of packed rows padded to the largest count; counts_out[world] (may be NULL) receives the per-rank counts. */
+int32_t az_samples_allgather(az_comm* c, az_samples* local, az_samples** out, int64_t* counts_out);
+/* every rank ends up with rank `root`'s parameters loaded into `net` (same architecture on all ranks): replaces the
+   serialised closure that carries the network to the workers (src/simulations.jl:271-281) and
+   Network.copy(bestnn; on_gpu=true, test_mode=true) (src/training.jl:278-279).  blob[n] = Flux-order float32 parameters
+   (az_net_load's format) on the root rank, ignored (may be NULL) elsewhere; n = az_net_num_params on every rank. */
+int32_t az_net_broadcast(az_comm* c, az_net* net, const float* blob, int64_t n, int32_t root);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,7 @@ ABI_SYMBOLS = [
     "az_net_create_oracle", "az_net_create_resnet", "az_net_create_simplenet", "az_net_num_params", "az_net_load",
     "az_net_forward", "az_net_forward_logits", "az_net_set_profiling", "az_net_get_profile", "az_net_destroy",
     "az_mcts_create", "az_mcts_set_roots", "az_mcts_set_noise", "az_mcts_run", "az_mcts_explore", "az_mcts_root_stats", "az_mcts_policy",
-    "az_mcts_reset", "az_mcts_counters", "az_mcts_last_timing", "az_mcts_destroy",
+    "az_mcts_reset", "az_mcts_counters", "az_mcts_last_timing", "az_mcts_destroy", "az_mcts_set_profiling", "az_mcts_get_profile",
     "az_selfplay_create", "az_selfplay_start", "az_selfplay_poll", "az_selfplay_wait", "az_selfplay_counts",
     "az_selfplay_fetch", "az_selfplay_stats", "az_selfplay_destroy", "az_selfplay_create_duel", "az_selfplay_outcomes",
     "az_selfplay_export_samples", "az_samples_from_host", "az_samples_count", "az_samples_concat", "az_samples_merge_by_state",
@@ -100,6 +100,7 @@ def lib():
             "az_mcts_explore": [vp, vp, vp, C.c_int32, vp, vp, vp], "az_mcts_root_stats": [vp, vp, vp, vp],
             "az_mcts_policy": [vp, vp], "az_mcts_reset": [vp], "az_mcts_counters": [vp, vp, vp, vp],
             "az_mcts_last_timing": [vp, vp, vp, vp, vp], "az_mcts_destroy": [vp],
+            "az_mcts_set_profiling": [vp, C.c_int32], "az_mcts_get_profile": [vp, vp, vp, vp, vp],
             "az_selfplay_create": [vp, C.c_int32, vp, C.POINTER(_MctsParams), C.POINTER(_SimParams), C.c_uint64, C.POINTER(vp)],
             "az_selfplay_start": [vp, C.c_int32, C.c_int64], "az_selfplay_poll": [vp, vp, vp], "az_selfplay_wait": [vp],
             "az_selfplay_counts": [vp, vp, vp], "az_selfplay_fetch": [vp] + [vp] * 8, "az_selfplay_stats": [vp, vp, vp, vp, vp],
@@ -424,6 +425,15 @@ class MctsEnv:
         lib().az_mcts_last_timing(self.h, C.byref(a), C.byref(b), C.byref(t), C.byref(e))
         return dict(ms_total=a.value, ms_network=b.value, ticks=t.value, expansions=e.value)
 
+    def set_profiling(self, enable=True):
+        self.ctx.check(lib().az_mcts_set_profiling(self.h, 1 if enable else 0))
+
+    def get_profile(self):
+        """Device time (ms) inside az_k_select / the network / az_k_expand_backup over the profiled runs since the last call."""
+        a, b, c, t = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        self.ctx.check(lib().az_mcts_get_profile(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(t)))
+        return dict(select_ms=a.value, expand_ms=b.value, net_ms=c.value, ticks=t.value)
+
     def close(self):
         if self.h:
             lib().az_mcts_destroy(self.h)
@@ -557,6 +567,23 @@ class Samples:
             self.h = None
 
 
+def _preload_nccl():
+    """libazb200.so binds NCCL at run time (dlopen "libnccl.so.2", reusing a copy already in the process).  If PyTorch is
+    imported LATER in the same process it must find its own, newer NCCL under that soname, so the newest copy that ships
+    with the Python environment (nvidia-nccl wheel) is loaded first; the system library is the fallback inside the C code."""
+    import sys
+    if "torch" in sys.modules:
+        return  # torch has already loaded the NCCL it was built against
+    for d in sys.path:
+        cand = os.path.join(d, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+            except OSError:
+                pass
+
+
 class Comm:
     """One rank of the engine's NCCL communicator (one process per GPU, src/simulations.jl:252-290).  `exchange(id_bytes)`
     is the caller's own channel for the 128-byte id: it receives rank 0's bytes (None on the other ranks) and returns
@@ -566,6 +593,7 @@ class Comm:
 
     def __init__(self, ctx, rank, world, exchange=None):
         self.ctx, self.rank, self.world = ctx, rank, world
+        _preload_nccl()
         ident = None
         if rank == 0:
             ident = np.zeros(self.ID_BYTES, np.uint8)

@@ -41,7 +41,7 @@ NcclApi& nccl() {
   tried = true;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* n : names) { api.h = dlopen(n, RTLD_NOW | RTLD_NOLOAD); if (api.h) break; }  // reuse a loaded copy
-  for (const char* n : names) { if (api.h) break; api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); }
+  for (const char* n : names) { if (api.h) break; api.h = dlopen(n, RTLD_NOW | RTLD_LOCAL); }
   if (!api.h) { api.why = std::string("libnccl.so.2 could not be loaded: ") + dlerror(); return api; }
 #define AZ_NCCL_SYM(field, name)                                                           \
   api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.h, name));                   \

@@ -150,6 +150,11 @@ struct az_mcts {
   virtual int set_noise(uint64_t seed, const int64_t* games, const int32_t* moves) = 0;
   double ms_total = 0, ms_net = 0;
   int64_t ticks = 0, expansions = 0;
+  // per-kernel device timing of the tree kernels (bench.py's roofline_tree): see Mcts::tick_profiled
+  virtual int set_profiling(int enable) = 0;
+  virtual void drain_profile() = 0;
+  double prof_select_ms = 0, prof_expand_ms = 0, prof_net_ms = 0;
+  int64_t prof_ticks = 0;
 };
 
 template <class G>
@@ -208,6 +213,7 @@ struct Mcts : az_mcts {
     for (void* q : allocs) cudaFree(q);
     if (h_pin) cudaFreeHost(h_pin);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : tev) if (e) cudaEventDestroy(e);
     drop_graph();
   }
   int groups_grid() const { return (int)(((size_t)p.S * 32 + 127) / 128); }  // one warp per tree
@@ -263,6 +269,57 @@ struct Mcts : az_mcts {
     return AZ_OK;
   }
   // one tick: select -> oracle -> expand+backup
+  // ---- profiled ticks: CUDA events around select, the network and expand+backup on the context's stream (graph replay off);
+  //      the event ring is drained whenever it fills so every tick of a pass is counted ----
+  static constexpr int TPROF_SLOTS = 1024;
+  bool profiling = false;
+  std::vector<cudaEvent_t> tev;
+  int tprof_n = 0;
+  void tprof_drain() {
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < tprof_n; i++) {
+      float a = 0, b = 0, c = 0;
+      cudaEventElapsedTime(&a, tev[i * 4 + 0], tev[i * 4 + 1]);
+      cudaEventElapsedTime(&b, tev[i * 4 + 1], tev[i * 4 + 2]);
+      cudaEventElapsedTime(&c, tev[i * 4 + 2], tev[i * 4 + 3]);
+      prof_select_ms += a; prof_net_ms += b; prof_expand_ms += c;
+    }
+    prof_ticks += tprof_n;
+    tprof_n = 0;
+  }
+  void drain_profile() override { if (profiling) tprof_drain(); }
+  int set_profiling(int enable) override {
+    if (enable && tev.empty()) {
+      tev.resize((size_t)TPROF_SLOTS * 4);
+      for (auto& e : tev) AZ_CUDA(ctx, cudaEventCreate(&e));
+    }
+    if (profiling) tprof_drain();
+    profiling = enable != 0;
+    if (enable) { prof_select_ms = prof_expand_ms = prof_net_ms = 0; prof_ticks = 0; tprof_n = 0; }
+    return AZ_OK;
+  }
+  int tick_profiled() {
+    if (tprof_n == TPROF_SLOTS) tprof_drain();
+    cudaEvent_t* e = &tev[(size_t)tprof_n * 4];
+    AZ_TRY(ctx, net->reserve(net2 ? p.row_base1 : p.S));
+    AZ_CUDA(ctx, cudaMemsetAsync(p.n_leaves, 0, 4 * sizeof(int32_t), ctx->stream));
+    cudaEventRecord(e[0], ctx->stream);
+    az_k_select<G><<<groups_grid(), 128, 0, ctx->stream>>>(p);
+    cudaEventRecord(e[1], ctx->stream);
+    if (!net2) {
+      AZ_TRY(ctx, net->eval(p.batch_env, p.n_leaves, p.S, p.batch_P, p.batch_V));
+    } else {
+      const int b1 = p.row_base1;
+      AZ_TRY(ctx, net->eval(p.batch_env, p.n_leaves, b1, p.batch_P, p.batch_V));
+      AZ_TRY(ctx, net2->eval(p.batch_env + b1, p.n_leaves + 2, b1, p.batch_P + (size_t)b1 * G::A, p.batch_V + b1));
+    }
+    cudaEventRecord(e[2], ctx->stream);
+    az_k_expand_backup<G><<<groups_grid(), 128, 0, ctx->stream>>>(p);
+    cudaEventRecord(e[3], ctx->stream);
+    ctx->launches += 2;
+    tprof_n++;
+    return AZ_OK;
+  }
   int tick(bool time_net) {
     AZ_CUDA(ctx, cudaMemsetAsync(p.n_leaves, 0, 4 * sizeof(int32_t), ctx->stream));
     az_k_select<G><<<groups_grid(), 128, 0, ctx->stream>>>(p);
@@ -302,7 +359,8 @@ struct Mcts : az_mcts {
     ticks = 0; ms_net = 0;
     // every unfinished tree completes >= 1 simulation per tick, so nsims ticks always suffice
     for (int t = 0; t < nsims + 1; t++) {
-      AZ_TRY(ctx, tick_graphed([] {}));
+      if (profiling) AZ_TRY(ctx, tick_profiled());
+      else AZ_TRY(ctx, tick_graphed([] {}));
       ticks++;
       if (t + 1 >= nsims / 2 && ((t + 1) % 8 == 0 || t + 1 >= nsims)) {
         AZ_TRY(ctx, check_flags());
@@ -867,6 +925,27 @@ int32_t az_mcts_last_timing(az_mcts* m, double* ms_total, double* ms_net, int64_
   if (ticks) *ticks = m->ticks;
   if (ex) *ex = m->expansions;
   return AZ_OK;
+}
+int32_t az_mcts_set_profiling(az_mcts* m, int32_t enable) {
+  if (!m) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  cudaSetDevice(m->ctx->device);
+  return m->set_profiling(enable);
+  AZ_GUARD_END(m->ctx)
+}
+int32_t az_mcts_get_profile(az_mcts* m, double* select_ms, double* expand_ms, double* net_ms, int64_t* ticks) {
+  if (!m) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  cudaSetDevice(m->ctx->device);
+  m->drain_profile();
+  if (select_ms) *select_ms = m->prof_select_ms;
+  if (expand_ms) *expand_ms = m->prof_expand_ms;
+  if (net_ms) *net_ms = m->prof_net_ms;
+  if (ticks) *ticks = m->prof_ticks;
+  m->prof_select_ms = m->prof_expand_ms = m->prof_net_ms = 0;
+  m->prof_ticks = 0;
+  return AZ_OK;
+  AZ_GUARD_END(m->ctx)
 }
 int32_t az_mcts_destroy(az_mcts* m) { AZ_M(m) delete m; return AZ_OK; }
 

@@ -966,6 +966,306 @@ az_k_conv_yrow(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent whole-tower kernel (round 2): ONE launch runs all 2 x num_blocks conv layers of the y-row tower.
+// The per-layer kernel above spends ~45 % of its elapsed time outside the tensor pipe (launch + CTA ramp, TMEM alloc,
+// cluster sync, the 144 KB weight load before the first MMA, pipeline fill, and the drain of the last epilogue): with
+// ~30 us of work per layer those fixed costs are paid 14 times per evaluation.  Here every CTA pair keeps its contiguous
+// unit range [u0, u1) (the same for every layer, since the leaf count does not change inside an evaluation) and loops
+// over the layers itself:
+//   * dependencies are LOCAL: layer l+1's input row y of a 32-board group needs layer l's output rows y-1..y+1 of the
+//     same group, i.e. rows of this pair plus ONE halo row of the pair before / after it when a range boundary falls
+//     inside a group.  No grid-wide barrier: each pair publishes "layer l stored" in a global counter (16 epilogue
+//     warps x 1 per layer, monotonic over launches: the base is read at kernel start) and a producer spins only on
+//     its lower neighbour (start of the layer) and its upper neighbour (just before the top halo row).  All CTAs are
+//     co-resident (one per SM), so spinning cannot deadlock.  The same waits order the in-place reuse of T / X.
+//   * inside a CTA the producer waits on `ldone` (its own 8 epilogue warps have completed the layer's TMA stores).
+//   * the weights of the next layer are (re)loaded into the resident 144 KB as soon as the last MMA of the layer has
+//     retired (`wfree`, multicast tcgen05.commit), in parallel with the epilogue drain and the first A loads.
+//   * the TMEM accumulator ring, the A-stage ring and all barrier phases simply continue across layers.
+// Weights of all layers live in ONE [L*128][1152] fp16 tensor (one tensor map), biases in one [L][128] array.
+// ------------------------------------------------------------------------------------------------
+namespace tw {
+struct Smem {
+  uint8_t b[tc2::NCHUNK][tc2::B_CHUNK];
+  uint8_t a[yr::ASTAGES][yr::A_STAGE];
+  uint8_t apad[1024];
+  uint8_t epi[yr::EPI_BYTES];
+  uint8_t ident[256];
+  uint64_t full[yr::ASTAGES], empty[yr::ASTAGES], tfull[yr::NACC], tempty[yr::NACC], bfull, wfree, ldone;
+  uint32_t tmem_base;
+};
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+}  // namespace tw
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(yr::NUM_THREADS, 1)
+az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmXL,
+                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmXo, const __grid_constant__ CUtensorMap tmTo,
+                const __grid_constant__ CUtensorMap tmXLo, GemmArgs ga, int num_layers, unsigned long long* __restrict__ done) {
+  using namespace tc2;
+  constexpr int BN = 128, H = 6;
+  constexpr int ASTAGES = yr::ASTAGES, NB = yr::NBOARD;
+  extern __shared__ __align__(1024) uint8_t smem_tw[];
+  if ((smem_u32(smem_tw) & 1023u) != 0u) __trap();
+  tw::Smem& s = *reinterpret_cast<tw::Smem*>(smem_tw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < yr::NACC; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 16); }
+    mbar_init(&s.bfull, 1); mbar_init(&s.wfree, 1); mbar_init(&s.ldone, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 64) {
+    if (threadIdx.x < 8 * ASTAGES) *reinterpret_cast<uint4*>(s.a[threadIdx.x >> 3] + (threadIdx.x & 7) * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(s.apad + threadIdx.x * 16) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
+  if (threadIdx.x >= 192 && threadIdx.x < 192 + 64) {  // this CTA's 8 x 16 slice of the 16 x 16 identity (residual MMAs)
+    const int i = threadIdx.x - 192;
+    const int n = (i & 31) >> 2, khalf = i >> 5, kk = (i & 3) * 2;
+    const int k0 = khalf * 8 + kk, kone = (int)rank * 8 + n;
+    const uint32_t w = (k0 == kone ? 0x3C00u : 0u) | (k0 + 1 == kone ? 0x3C000000u : 0u);
+    *reinterpret_cast<uint32_t*>(s.ident + khalf * 128 + n * 16 + (i & 3) * 4) = w;
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // everything below reads data of earlier kernels (leaf count, activations, the flag counters of the previous launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  int u0, u1;
+  yr::unit_range(*ga.n_boards, pair, npairs, u0, u1);
+  const bool has_work = u0 < u1;
+  // flag protocol: every pair adds 16 per layer (one per epilogue warp); counters are never reset, the value a pair
+  // finds in its own counter at kernel start is the base of this launch (identical for all pairs)
+  const unsigned long long base = done[pair];
+  // neighbours whose rows this pair reads as halo (only when the range boundary falls inside a 32-board group)
+  int q_lo = -1, q_hi = -1;
+  if (has_work) {
+    if (u0 % H != 0) { q_lo = pair - 1; for (;;) { int a, b; yr::unit_range(*ga.n_boards, q_lo, npairs, a, b); if (a < b) break; q_lo--; } }
+    if (u1 % H != 0) { q_hi = pair + 1; for (;;) { int a, b; yr::unit_range(*ga.n_boards, q_hi, npairs, a, b); if (a < b) break; q_hi++; } }
+  }
+  cluster_sync_all();  // `base` is read by both CTAs before any warp of the pair can add to the counter
+
+  if (!has_work) {
+    // idle pair (fewer units than pairs): keep the counter in step so that its base stays equal to everybody else's
+    if (threadIdx.x == 0 && leader) tw::red_release_add_u64(done + pair, 16ull * (unsigned long long)num_layers);
+  } else if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int l = 0; l < num_layers; l++) {
+      const bool conv2 = (l & 1) != 0;
+      const CUtensorMap* mA = conv2 ? &tmT : &tmX;
+      if (l > 0) {
+        mbar_wait(&s.wfree, (uint32_t)(l - 1) & 1u);   // every MMA of layer l-1 (reads both CTAs' weights) has retired
+      }
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(&s.bfull, 2 * NCHUNK * B_CHUNK);
+        for (int ch = 0; ch < NCHUNK; ch++) tma_load_2d_2sm(s.b[ch], &tmW, &s.bfull, ch * BK, l * 128 + (int)rank * BNH);
+      }
+      __syncwarp();
+      if (l > 0) {
+        mbar_wait(&s.ldone, (uint32_t)(l - 1) & 1u);   // this CTA's stores of layer l-1 are complete
+        if (q_lo >= 0) {
+          if (lane == 0) { while (tw::ld_acquire_u64(done + q_lo) < base + 16ull * (unsigned long long)l) {} }
+          __syncwarp();
+        }
+        fence_proxy_async();
+      }
+      bool hi_ok = (l == 0) || q_hi < 0;
+      for (int u = u0; u < u1;) {
+        const int g = u / H, j_lo = u - g * H, j_hi = min(u1 - g * H, H);
+        const int y_lo = max(0, j_lo - 1), y_hi = min(H - 1, j_hi);
+        const int b0 = g * 2 * NB + (int)rank * NB;
+        for (int y = y_lo; y <= y_hi; y++) {
+          if (!hi_ok && y == j_hi && g * H + j_hi == u1) {  // top halo row: produced by the next pair in layer l-1
+            if (lane == 0) { while (tw::ld_acquire_u64(done + q_hi) < base + 16ull * (unsigned long long)l) {} }
+            __syncwarp();
+            fence_proxy_async();
+            hi_ok = true;
+          }
+          const int nres = (conv2 && y >= j_lo && y < j_hi) ? (l > 1 ? 4 : 2) : 0;
+          for (int q = 0; q < 2 + nres; q++) {
+            bool isres; int half, part;
+            yrow_stage(q, nres, isres, half, part);
+            mbar_wait(&s.empty[stage], phase ^ 1);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(&s.full[stage], 2 * yr::A_STAGE);
+              tma_load_4d_2sm(s.a[stage], isres ? (part ? &tmXL : &tmX) : mA, &s.full[stage], half * BK, -1, y, b0);
+            }
+            __syncwarp();
+            if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        u = g * H + j_hi;
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {  // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);    // M = 256, N = 128
+      constexpr uint32_t IDESC_R = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256, N = 16
+      const uint64_t idsc = umma_desc_interleave(smem_u32(s.ident), 128u, 256u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int nbase = 0;
+      for (int l = 0; l < num_layers; l++) {
+        const bool conv2 = (l & 1) != 0;
+        mbar_wait(&s.bfull, (uint32_t)l & 1u);
+        tcgen05_fence_after();
+        for (int u = u0; u < u1;) {
+          const int g = u / H, j_lo = u - g * H, j_hi = min(u1 - g * H, H);
+          const int y_lo = max(0, j_lo - 1), y_hi = min(H - 1, j_hi);
+          for (int y = y_lo; y <= y_hi; y++) {
+            for (int j = (y == 0 ? 0 : y + 1); j <= y + 1; j++) {
+              if (j < j_lo || j >= j_hi) continue;
+              const int n = nbase + (j - j_lo);
+              mbar_wait(&s.tempty[n & 3], ((uint32_t)(n >> 2) & 1u) ^ 1u);
+            }
+            tcgen05_fence_after();
+            const int nres = (conv2 && y >= j_lo && y < j_hi) ? (l > 1 ? 4 : 2) : 0;
+            for (int q = 0; q < 2 + nres; q++) {
+              bool isres; int half, part;
+              yrow_stage(q, nres, isres, half, part);
+              mbar_wait(&s.full[stage], phase);
+              tcgen05_fence_after();
+              const uint32_t abase = smem_u32(s.a[stage]);
+              if (elect_one()) {
+                if (isres) {
+                  const uint32_t tmem_d = tmem_base + (uint32_t)(((nbase + (y - j_lo)) & 3) * BN);
+                  const uint64_t adesc = umma_desc_sw128(abase + 128u);
+#pragma unroll
+                  for (int k = 0; k < BK / 16; k++)
+                    umma_f16_2sm(tmem_d + (uint32_t)(half * BK + k * 16), adesc + (uint64_t)(k * 2), idsc, IDESC_R, 1u);
+                } else {
+#pragma unroll
+                  for (int dj = 1; dj >= -1; dj--) {
+                    const int j = y + dj;
+                    if (j < j_lo || j >= j_hi) continue;
+                    const int ky = dj + 1;
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(((nbase + (j - j_lo)) & 3) * BN);
+                    const bool first = (half == 0) && (y == (j > 0 ? j - 1 : 0));
+#pragma unroll
+                    for (int kx = 0; kx < 3; kx++) {
+                      const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(2 - kx) * 128u);
+                      const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[(ky * 3 + kx) * 2 + half]));
+#pragma unroll
+                      for (int k = 0; k < BK / 16; k++)
+                        umma_f16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (first && kx == 0 && k == 0) ? 0u : 1u);
+                    }
+                  }
+                }
+                umma_commit_2sm(&s.empty[stage]);
+              }
+              __syncwarp();
+              if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) {
+              if (y - 1 >= j_lo && y - 1 < j_hi) umma_commit_2sm(&s.tfull[(nbase + (y - 1 - j_lo)) & 3]);
+              if (y == H - 1 && j_hi == H) umma_commit_2sm(&s.tfull[(nbase + (H - 1 - j_lo)) & 3]);
+            }
+            __syncwarp();
+          }
+          nbase += j_hi - j_lo;
+          u = g * H + j_hi;
+        }
+        if (elect_one()) umma_commit_2sm(&s.wfree);  // the resident weights may be replaced
+        __syncwarp();
+      }
+    }
+  } else {  // ===== epilogue warps 2..9 (both CTAs) =====
+    const int quarter = warp & 3;
+    const int colhalf = (warp - 2) >> 2;
+    const int sw = (lane >> 2) & 1;
+    uint8_t* tiles = s.epi + (warp - 2) * 2048;
+    int ring = 0;
+    int n = 0;
+    for (int l = 0; l < num_layers; l++) {
+      const bool conv2 = (l & 1) != 0;
+      const float* __restrict__ bias_g = ga.bias + (size_t)l * 128 + colhalf * 64;
+      const CUtensorMap* mO = conv2 ? &tmXo : &tmTo;
+      for (int u = u0; u < u1; u++, n++) {
+        const int g = u / H, j = u - g * H;
+        const int bq = g * 2 * NB + (int)rank * NB + quarter * 4;
+        const int slot = n & 3;
+        mbar_wait(&s.tfull[slot], (uint32_t)(n >> 2) & 1u);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int sc = 0; sc < 4; sc++) {
+          const int col = colhalf * 64 + sc * 16;
+          uint32_t v[16];
+          tmem_ld16(tmem_base + slot * BN + col + ((uint32_t)(quarter * 32) << 16), v);
+          uint4 oh4[2], ol4[2];
+          __half2* oh = reinterpret_cast<__half2*>(oh4);
+          __half2* ol = reinterpret_cast<__half2*>(ol4);
+#pragma unroll
+          for (int jj = 0; jj < 8; jj++) {
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_g + sc * 16) + jj);
+            const float x0 = fmaxf(__uint_as_float(v[2 * jj]) + bb.x, 0.f);
+            const float x1 = fmaxf(__uint_as_float(v[2 * jj + 1]) + bb.y, 0.f);
+            const __half2 h = __floats2half2_rn(x0, x1);
+            oh[jj] = h;
+            if (conv2) {  // lo = fp16(y - hi): hi + lo carries ~22 significand bits of the skip path
+              const float2 hf = __half22float2(h);
+              ol[jj] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            }
+          }
+          const int nparts = conv2 ? 2 : 1;
+          for (int part = 0; part < nparts; part++) {
+            uint8_t* tile = tiles + ring * 1024;
+            ring ^= 1;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            const uint4* o = part ? ol4 : oh4;
+            *reinterpret_cast<uint4*>(tile + lane * 32 + ((0 ^ sw) << 4)) = o[0];
+            *reinterpret_cast<uint4*>(tile + lane * 32 + ((1 ^ sw) << 4)) = o[1];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && !(ga.debug & 4)) { tma_store_4d(part ? &tmXLo : mO, tile, col, 0, j, bq); tma_store_commit(); }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&s.tempty[slot], 0);
+      }
+      // layer l of this warp's rows is in memory: tell this CTA's producer and the neighbouring pairs
+      if (lane == 0) {
+        tma_store_wait_all();
+        fence_proxy_async();
+        mbar_arrive(&s.ldone);
+        tw::red_release_add_u64(done + pair, 1ull);
+      }
+      __syncwarp();
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // stem: leaf states -> im2col rows -> tcgen05 GEMM.  The first conv (3x3, C_in -> 128, folded BN, ReLU) has K = 9*C_in
 // (27 for Connect Four): az_k_im2col writes, for every padded board row, the 9*C_in input-plane values of its 3x3
 // neighbourhood as one 128-byte fp16 row (K padded to 64), straight from the game's vectorize_state (no host round
@@ -1120,7 +1420,13 @@ struct ResNetImpl : az_net {
   CUtensorMap mapWstem{}, mapWpol{}, mapX0{}, mapHp{};
   __half* d_x0 = nullptr;       // im2col rows [alloc_rows][64]
   float* d_logit = nullptr;     // [boards][128]
-  std::vector<__half*> d_wconv; std::vector<float*> d_bconv;
+  std::vector<__half*> d_wconv; std::vector<float*> d_bconv;   // per-layer views into d_wall / d_ball
+  __half* d_wall = nullptr; float* d_ball = nullptr;            // all tower layers: Wt[l][co][tap*F + ci], bias[l][co]
+  unsigned long long* d_done = nullptr;                          // persistent tower: per-pair layer counters (never reset)
+  CUtensorMap mapWall{};                                         // [L*128][1152] fp16, 64 x 64 boxes
+  bool persistent = true;      // AZ_TOWER=layer: one launch per conv layer (round-2a kernel) instead of the whole-tower kernel
+  bool coop_launch = true;     // cooperative launch of the persistent kernel (co-residency of all CTA pairs guaranteed)
+  size_t smem_tower = 0;
   __half *d_wh = nullptr, *d_wd = nullptr;
   float *d_bh = nullptr, *d_bd = nullptr, *d_wv2 = nullptr, *d_bv2 = nullptr;
   std::vector<CUtensorMap> mapW;
@@ -1186,7 +1492,7 @@ struct ResNetImpl : az_net {
   int get_profile(double* tower_ms, int64_t* tower_launches, double* total_ms, int64_t* evals) override {
     prof_drain();
     if (tower_ms) *tower_ms = prof_tower_ms;
-    if (tower_launches) *tower_launches = prof_drained * 2 * hp.num_blocks;
+    if (tower_launches) *tower_launches = prof_drained * ((dense && persistent && hp.num_blocks > 0) ? 1 : 2 * hp.num_blocks);
     if (total_ms) *total_ms = prof_total_ms;
     if (evals) *evals = prof_drained;
     prof_drained = 0; prof_tower_ms = prof_total_ms = 0;
@@ -1231,6 +1537,13 @@ struct ResNetImpl : az_net {
     static_assert(sizeof(yr::Smem) <= 232448, "y-row tower kernel exceeds the 227 KB shared-memory limit");
     AZ_TRY2(set_smem(az_k_conv_yrow<tc::EPI_CONV1>, smem_yrow));
     AZ_TRY2(set_smem(az_k_conv_yrow<tc::EPI_CONV2>, smem_yrow));
+    smem_tower = sizeof(tw::Smem);
+    static_assert(sizeof(tw::Smem) <= 232448, "persistent tower kernel exceeds the 227 KB shared-memory limit");
+    AZ_TRY2(set_smem(az_k_tower_yrow, smem_tower));
+    { const char* e = getenv("AZ_TOWER"); persistent = !(e && e[0] == 'l'); }          // AZ_TOWER=layer
+    { const char* e = getenv("AZ_TOWER_COOP"); coop_launch = !(e && e[0] == '0'); }    // AZ_TOWER_COOP=0: plain launch
+    if (cudaMalloc((void**)&d_done, 256 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); ctx->err = "cudaMalloc (tower flags) failed"; return AZ_ENOMEM; }
+    cudaMemset(d_done, 0, 256 * sizeof(unsigned long long));
     return AZ_OK;
   }
   int64_t num_params() override {
@@ -1251,8 +1564,7 @@ struct ResNetImpl : az_net {
   }
   void free_weights() {
     cudaFree(d_wstem); cudaFree(d_bstem);
-    for (auto p : d_wconv) cudaFree(p);
-    for (auto p : d_bconv) cudaFree(p);
+    cudaFree(d_wall); cudaFree(d_ball); d_wall = nullptr; d_ball = nullptr;
     d_wconv.clear(); d_bconv.clear(); mapW.clear(); mapW2.clear();
     cudaFree(d_wh); cudaFree(d_wd); cudaFree(d_bh); cudaFree(d_bd); cudaFree(d_wv2); cudaFree(d_bv2);
     cudaFree(d_wpol); cudaFree(d_bpol); d_wpol = nullptr; d_bpol = nullptr;
@@ -1263,7 +1575,7 @@ struct ResNetImpl : az_net {
     cudaFree(d_xl16);
     d_x32 = d_hid = d_logit = nullptr; d_x16 = d_t16 = d_hp = d_hv = d_x0 = d_xl16 = nullptr;
   }
-  ~ResNetImpl() override { free_weights(); free_act(); for (auto e : pev) cudaEventDestroy(e); }
+  ~ResNetImpl() override { free_weights(); free_act(); cudaFree(d_done); for (auto e : pev) cudaEventDestroy(e); }
 
   // blob -> folded device weights.  Flux order: Conv W[kw,kh,cin,cout] (kw fastest), b; BatchNorm gamma, beta, mu, sigma2;
   // Dense W[out,in] (out fastest), b.  Order: common (stem, blocks), vhead, phead.
@@ -1296,7 +1608,14 @@ struct ResNetImpl : az_net {
       AZ_TRY2(up(&d_wstem, ws)); AZ_TRY2(up(&d_bstem, shift));
       AZ_TRY2(make_map_2d(ctx, &mapWstem, d_wstem, 64, F, 64 * 2, tc::BK, 128));
     }
-    for (int l = 0; l < 2 * hp.num_blocks; l++) {
+    const int L = 2 * hp.num_blocks;
+    if (L > 0) {
+      if (cudaMalloc((void**)&d_wall, (size_t)L * F * 9 * F * sizeof(__half)) != cudaSuccess || cudaMalloc((void**)&d_ball, (size_t)L * F * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError(); ctx->err = "cudaMalloc (tower weights) failed"; return AZ_ENOMEM;
+      }
+      AZ_TRY2(make_map_2d(ctx, &mapWall, d_wall, 9 * F, (uint64_t)L * F, 9 * F * 2, tc2::BK, tc2::BNH));
+    }
+    for (int l = 0; l < L; l++) {
       const float* w = q; q += 9LL * F * F;
       const float* b = q; q += F;
       const float* bn = q; q += 4 * F;
@@ -1304,9 +1623,12 @@ struct ResNetImpl : az_net {
       std::vector<__half> wh((size_t)F * 9 * F);  // Wt[co][tap*F + ci]
       for (int o = 0; o < F; o++) for (int ky = 0; ky < 3; ky++) for (int kx = 0; kx < 3; kx++) for (int c = 0; c < F; c++)
         wh[(size_t)o * 9 * F + (size_t)(ky * 3 + kx) * F + c] = __float2half_rn(w[kx + 3 * (ky + 3 * (c + (size_t)F * o))] * scale[o]);
-      __half* dw = nullptr; float* db = nullptr;
-      AZ_TRY2(up(&dw, wh)); d_wconv.push_back(dw);
-      AZ_TRY2(up(&db, shift)); d_bconv.push_back(db);
+      __half* dw = d_wall + (size_t)l * F * 9 * F; float* db = d_ball + (size_t)l * F;
+      if (cudaMemcpy(dw, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(db, shift.data(), F * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError(); ctx->err = "cudaMemcpy (tower weights) failed"; return AZ_ECUDA;
+      }
+      d_wconv.push_back(dw); d_bconv.push_back(db);
       CUtensorMap m;
       AZ_TRY2(make_map_2d(ctx, &m, dw, 9 * F, F, 9 * F * 2, tc::BK, 128));
       mapW.push_back(m);
@@ -1413,6 +1735,21 @@ struct ResNetImpl : az_net {
     act_boards = max_boards;
     return AZ_OK;
   }
+  // the persistent whole-tower kernel: cooperative launch (all CTA pairs co-resident: its neighbour spin-waits must never
+  // wait for a pair that cannot be scheduled, e.g. when two engines share a GPU) + programmatic stream serialization
+  int launch_tower(int grid, cudaStream_t st, const GemmArgs& ga) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(yr::NUM_THREADS); cfg.dynamicSmemBytes = smem_tower; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (use_pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    if (coop_launch) { at[na].id = cudaLaunchAttributeCooperative; at[na].val.cooperative = 1; na++; }
+    cfg.attrs = at; cfg.numAttrs = na;
+    const int L = 2 * hp.num_blocks;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, az_k_tower_yrow, map4X, map4T, map4XL, mapWall, map4Xo, map4To, map4XLo, ga, L, d_done);
+    if (e != cudaSuccess) { ctx->err = std::string("persistent tower launch: ") + cudaGetErrorString(e); cudaGetLastError(); return AZ_ECUDA; }
+    return AZ_OK;
+  }
   int eval(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V) override {
     return eval_with_pinv(envs, n_rows, max_rows, P, V, nullptr);
   }
@@ -1438,7 +1775,11 @@ struct ResNetImpl : az_net {
     const bool c4 = C4_TOWER && !generic_tower;  // Connect-Four geometry -> cta_group::2 kernel, otherwise the generic 9-tap kernel
     const int grid_2sm = std::max(2, std::min(2 * ((row_tiles + 1) / 2), ctx->num_sms & ~1));
     const int grid_yr = ctx->num_sms & ~1;  // persistent: one CTA pair per SM pair, balanced unit ranges (idle pairs exit)
-    for (int blk = 0; dense && blk < hp.num_blocks; blk++) {
+    if (dense && persistent && hp.num_blocks > 0) {
+      ga.bias = d_ball;
+      AZ_TRY2(launch_tower(grid_yr, st, ga));
+    }
+    for (int blk = 0; dense && !persistent && blk < hp.num_blocks; blk++) {
       ga.bias = d_bconv[2 * blk]; ga.res_lo = 0;
       if (use_pdl && blk > 0) launch_pdl(az_k_conv_yrow<tc::EPI_CONV1>, grid_yr, yr::NUM_THREADS, smem_yrow, st, map4X, mapW2[2 * blk], map4To, map4XLo, map4X, map4XL, ga);
       else az_k_conv_yrow<tc::EPI_CONV1><<<grid_yr, yr::NUM_THREADS, smem_yrow, st>>>(map4X, mapW2[2 * blk], map4To, map4XLo, map4X, map4XL, ga);
@@ -1475,7 +1816,7 @@ struct ResNetImpl : az_net {
     FinalArgs fa{d_logit, d_hid, d_wv2, d_bv2, dbg_logit, dbg_vpre};
     az_k_finalize<G><<<(max_rows * 8 + 255) / 256, 256, 0, st>>>(envs, n_rows, fa, P, V, Pinv);
     if (prof) { cudaEventRecord(pe[3], st); prof_evals++; }
-    ctx->launches += 6 + 2 * hp.num_blocks;
+    ctx->launches += 6 + ((dense && persistent && hp.num_blocks > 0) ? 1 : 2 * hp.num_blocks);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ctx->err = std::string("network launch: ") + cudaGetErrorString(e); return AZ_ECUDA; }
     return AZ_OK;

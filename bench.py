@@ -35,7 +35,7 @@ NET_MFLOP_PER_LEAF = 174.7                           # whole 7-block network (SU
 METRIC = "mcts_node_expansions_per_s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from profiles/r01_final_conv_ncu_summary.txt
 # (ncu --set full, cold caches, ~3700 leaves): conv1 variant 55.0 MB, conv2 variant 214.4 MB per launch; mean of the two
-NCU_TRAFFIC_BYTES = 114.4e6  # profiles/r01_final2_conv_ncu_summary.txt: (conv1 54.2 MB + conv2 174.6 MB) / 2 per launch, cold caches
+NCU_TRAFFIC_BYTES = 53.1e6  # profiles/r02a_conv_yrow_ncu_summary.txt: (conv1 32.0 MB + conv2 74.2 MB) / 2 per launch, cold caches
 
 
 def resnet_blob(dim, num_actions, hp, seed=1):
@@ -63,6 +63,21 @@ def resnet_blob(dim, num_actions, hp, seed=1):
     conv(1, nf, nvf); bn(nvf); dense(nf, W * H * nvf); dense(1, nf)
     conv(1, nf, npf); bn(npf); dense(num_actions, W * H * npf)
     return np.concatenate(parts).astype(np.float32)
+
+
+NCU_TREE_TRAFFIC_BYTES = 6.5e6   # profiles/r02a_tree_ncu_summary.txt: select 3.56 MB + expand_backup 2.98 MB of DRAM reads per tick (cold, tick ~550)
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def sum_ms(tp):
+    return tp["select_ms"] + tp["expand_ms"] + tp["net_ms"]
 
 
 def peaks():
@@ -123,15 +138,18 @@ def make_eta(_unused, roots, A, seed):
     return eta
 
 
-def cpu_reference_run(n_trees, nsims, threads, seed_offset=0):
-    """The reference's algorithm on host cores: CPU MCTS (oracle port) + batched torch-CPU fp32 7-block ResNet.
-    Returns (expansions, seconds, simulations)."""
+def cpu_reference_run(n_trees, nsims, threads, seed_offset=0, net="resnet"):
+    """The reference's algorithm on host cores: CPU MCTS (oracle port, `threads` host threads over the independent trees
+    like the reference's worker tasks) + either the batched torch-CPU fp32 7-block ResNet (net="resnet": the end-to-end
+    figure) or the uniform oracle (net="uniform": the tree-only figure, MCTS.RandomOracle).  Every tick evaluates the
+    pending leaves of all trees as ONE batch, the shape the product runs.  Returns (expansions, seconds, simulations)."""
     import torch
     from oracle import oracle as oz, netref
     torch.set_num_threads(threads)
+    oz.set_threads(threads)
     gid = oz.game_id("connect-four")
     dim, A = (7, 6, 3), 7
-    blob = netref.make_blob(dim, A, HP, seed=1, randomize=False)
+    blob = netref.make_blob(dim, A, HP, seed=1, randomize=False) if net == "resnet" else None
     roots = oz.random_positions(gid, SEED_POS, n_trees, 30, first_stream=seed_offset)
     eta = make_eta(None, roots, A, 3)
     mp = oz.mcts_params(cpuct=2.0, noise_eps=0.25, noise_alpha=1.0, num_iters_per_turn=nsims)
@@ -142,35 +160,59 @@ def cpu_reference_run(n_trees, nsims, threads, seed_offset=0):
         ls, _ = b.advance()
         if len(ls) == 0:
             break
-        X = np.stack([oz.vectorize_state(gid, bytes(s)) for s in ls])
-        mask = np.stack([X[i, :, 5, 0] > 0 for i in range(len(ls))])  # top row empty -> legal
-        P, V = netref.forward(blob, dim, A, HP, X)
-        Pn, V, _ = netref.forward_normalized(P, V, mask)
+        X, mask = b.vectorize(ls, (dim[2], dim[1], dim[0]))   # GI.vectorize_state (flat index w + W*(h + H*c)) + actions mask, threaded in C
+        if net == "resnet":
+            # the forward of the tick's batch in cache-sized chunks (a 4096-leaf fp32 activation is 88 MB per layer: the CPU
+            # is 5x faster on 256-leaf chunks; the reference itself ships batch_size 64)
+            Xt = X.transpose(0, 3, 2, 1)   # [B, W, H, C]
+            outs = [netref.forward(blob, dim, A, HP, Xt[i:i + CPU_CHUNK]) for i in range(0, len(ls), CPU_CHUNK)]
+            P, V = np.concatenate([o[0] for o in outs]), np.concatenate([o[1] for o in outs])
+            Pn, V, _ = netref.forward_normalized(P, V, mask)
+        else:
+            Pn = mask.astype(np.float32) / mask.sum(1, keepdims=True).astype(np.float32)
+            V = np.zeros(len(ls), np.float32)
         b.feed(Pn, V)
     dt = time.perf_counter() - t0
     return b.expansions, dt, b.simulations
 
 
+def cpu_baseline_legs(threads):
+    """tree-only and end-to-end figures of the CPU port on 1 and on `threads` host threads (bounded samples)."""
+    legs = {}
+    for name, (nt, ns, th, net) in {"tree_only_1thread": (512, 200, 1, "uniform"), "tree_only": (4096, 100, threads, "uniform"),
+                                    "e2e_1thread": (64, 12, 1, "resnet"), "e2e": (4096, 8, threads, "resnet")}.items():
+        ex, dt, sims = cpu_reference_run(nt, ns, th, net=net)
+        legs[name] = {"expansions_per_s": ex / dt, "simulations_per_s": sims / dt, "cores": th, "seconds": dt,
+                      "sample": "%d trees x %d sims, %s" % (nt, ns, "uniform oracle (tree work only)" if net == "uniform" else "torch-CPU fp32 7-block ResNet, all pending leaves of a tick in chunks of %d" % CPU_CHUNK)}
+    return legs
+
+
+CPU_CHUNK = 256
+REF_TREES, REF_SIMS = 4096, 12   # reference arm: the product's pool size, the first REF_SIMS of the 600 simulations
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    import torch
     threads = args.cpu_threads or min(os.cpu_count() or 1, 16)
-    n_trees = 256
-    nsims = 150
+    n_trees, nsims = REF_TREES, REF_SIMS
     for _ in range(max(1, min(args.warmup, 1))):
-        cpu_reference_run(32, 20, threads)
+        cpu_reference_run(256, 4, threads)
     ex, dt = 0, 0.0
     for k in range(args.steps):
         e, d, _ = cpu_reference_run(n_trees, nsims, threads, seed_offset=1000 * k)
         ex += e
         dt += d
     v = ex / dt
-    sample = "%d trees x %d sims per step (config[1] is 4096 x 600); CPU MCTS (C port of src/mcts.jl) + torch-CPU fp32 7-block ResNet, batch = pending leaves" % (n_trees, nsims)
+    sample = ("%d trees x the first %d of %d sims per step (config[1] pool size and leaf-batch shape: every tick evaluates the pending "
+              "leaves of all %d trees, forward in chunks of 256); CPU MCTS (C port of src/mcts.jl, %d host threads over trees) + torch-CPU fp32 "
+              "7-block ResNet (%d threads)" % (n_trees, nsims, NSIMS, n_trees, threads, threads))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "expansions/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "connect-four explore: %d trees x %d sims, 7-block ResNet (bounded sample of config[1])" % (n_trees, nsims)},
+            "config": {"workload": "connect-four: %d concurrent game trees per GPU x %d sims/move, 7-block ResNet 128 filters, synthetic random positions (0-30 plies), fresh trees per step"
+                                   % (n_trees, NSIMS), "trees_per_gpu": n_trees, "nsims": NSIMS,
+                       "bounded_sample": "first %d simulations of the %d per step" % (nsims, NSIMS)},
             "cpu_baseline": {"value": v, "unit": "expansions/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "expansions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -205,6 +247,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = az.Context(local)
+    comm = az.Comm.from_torch(ctx, dist) if world > 1 else None   # the engine's own NCCL communicator (id exchanged over torch's store)
     gs = az.GameSpec("connect-four")
     S, nsims, A = args.trees, args.nsims, 7
     hp = dict(HP, num_blocks=args.blocks)
@@ -227,6 +270,10 @@ def main():
 
     def step_resident():
         env.reset()
+        env.run(nsims)
+        return env.last_timing()
+
+    def step_resident_noreset():
         env.run(nsims)
         return env.last_timing()
 
@@ -267,6 +314,20 @@ def main():
         prof = net.get_profile()
         prof.update(step_ms=p_ms, expansions=p_ex)
         net.set_profiling(False)
+    # ---- tree-kernel pass: CUDA events around az_k_select and az_k_expand_backup of every tick (graph replay off) ----
+    env.set_profiling(True)
+    tp_nodes, tp_sims, tp_ex = 0, 0, 0
+    for _ in range(args.steps):
+        env.reset()
+        c0 = env.counters()
+        t = step_resident_noreset()
+        c1 = env.counters()
+        tp_nodes += int((c1[1] - c0[1]).sum())
+        tp_sims += int((c1[0] - c0[0]).sum())
+        tp_ex += t["expansions"]
+    tprof = env.get_profile()
+    tprof.update(nodes=tp_nodes, sims=tp_sims, expansions=tp_ex)
+    env.set_profiling(False)
     # ---- timed: end to end through host buffers ----
     barrier()
     e_dt, e_ex = 0.0, 0
@@ -298,11 +359,21 @@ def main():
         sp_h.wait()
         out = sp_h.fetch()                                                        # includes the D2H fetch of all samples
         t_play = time.perf_counter() - t0
-        # replay-buffer side on this rank's samples, device resident: export -> augment -> merge -> convert
+        # iteration-end exchange (src/simulations.jl:282-289) inside the engine: this rank's device-resident samples ->
+        # az_samples_allgather (one count all-gather + one padded NCCL all-gather of packed rows, nothing staged on the host)
         rp = {}
         tr0 = time.perf_counter()
         smp = az.Samples.from_selfplay(sp_h)
-        rp["export_ms"] = 1e3 * (time.perf_counter() - tr0); tr0 = time.perf_counter()
+        rp["export_ms"] = 1e3 * (time.perf_counter() - tr0)
+        t1 = time.perf_counter()
+        gathered, gather_ms, counts = smp, 0.0, [len(smp)]
+        if comm is not None:
+            gathered, counts = comm.allgather_samples(smp)
+            gather_ms = comm.last_ms
+        barrier()
+        t_gather = time.perf_counter() - t1
+        # replay-buffer side on this rank's samples, device resident: augment -> merge -> convert
+        tr0 = time.perf_counter()
         aug = smp.augment_with_symmetries()
         rp["augment_ms"] = 1e3 * (time.perf_counter() - tr0); tr0 = time.perf_counter()
         mrg = aug.merge_by_state()
@@ -311,16 +382,14 @@ def main():
         rp["convert_to_host_ms"] = 1e3 * (time.perf_counter() - tr0)
         rp.update(samples=len(smp), augmented=len(aug), merged=len(mrg), bytes_per_sample=24 + 8 * 7 + 8 + 8 + 4,
                   note="host wall clock per call incl. cudaMalloc of outputs and stream sync; rank 0's share")
-        for x in (smp, aug, mrg):
+        total_gathered = len(gathered)
+        for x in (aug, mrg) + ((gathered,) if gathered is not smp else ()) + (smp,):
             x.close()
         del cv
         sp_h.close()
-        t1 = time.perf_counter()
-        allg = azd.allgather_samples(out, first, dist, device="cuda" if dist is not None else "cpu")
-        barrier()
-        t_gather = time.perf_counter() - t1
-        sp_out = dict(t=t_play + t_gather, t_gather=t_gather, games=count, samples=int(out["samples"]), expansions=float(out["expansions"]),
-                      total_samples=len(allg["z"]), mean_moves=float(out["moves"].mean()), mean_edepth=float(out["edepth"].mean()))
+        sp_out = dict(t=t_play + t_gather, t_gather=t_gather, gather_device_ms=gather_ms, games=count, samples=int(out["samples"]),
+                      expansions=float(out["expansions"]), total_samples=total_gathered, mean_moves=float(out["moves"].mean()),
+                      mean_edepth=float(out["edepth"].mean()))
     # ---- arena: pit_networks of two 7-block nets with the shipped Connect-Four ArenaParams
     # (games/connect-four/params.jl:32-45: 600 sims, cpuct 2, eps 0.05, tau 0.2, flip_probability 0.5, alternate_colors,
     # reset_every 2), one game per worker; every rank plays its own share, no collective ----
@@ -380,7 +449,8 @@ def main():
         if sp_out is not None:
             line["selfplay"] = {"games_per_s": sp_out["games"] / sp_out["t"], "samples_per_s": sp_out["samples"] / sp_out["t"],
                                 "expansions_per_s": sp_out["expansions"] / sp_out["t"], "seconds": sp_out["t"],
-                                "allgather_seconds": sp_out["t_gather"], "games": int(sp_out["games"]), "samples": int(sp_out["samples"]),
+                                "allgather_seconds": sp_out["t_gather"], "allgather_device_ms": sp_out["gather_device_ms"],
+                                "allgather": "az_samples_allgather: NCCL, packed 104 B rows, device resident (no host staging)", "games": int(sp_out["games"]), "samples": int(sp_out["samples"]),
                                 "gathered_samples_on_rank0": sp_out["total_samples"], "mean_moves_per_game": sp_out["mean_moves"],
                                 "mean_exploration_depth": sp_out["mean_edepth"],
                                 "config": "simulate(): %d games per GPU on 4096 concurrent worker slots (two per slot), 600 sims/move, cpuct 2, eps 0.25, tau PL([0,20,30],[1,1,.3]), reset_every 2; wall clock incl. sample D2H + all-gather" % (2 * S)}
@@ -395,23 +465,46 @@ def main():
             peak, how = peaks()
             nconv = 2 * args.blocks
             achieved = prof["expansions"] * CONV_MFLOP_PER_LEAF * nconv / 1e6 / (prof["tower_ms"] / 1e3)   # rank 0's own pass
-            line["roofline"] = {"bound": "tensor", "kernel": "az_k_conv_c4_2sm", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            line["roofline"] = {"bound": "tensor", "kernel": "az_k_tower_yrow" if prof["tower_launches"] == prof["evals"] else "az_k_conv_yrow", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                                 "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": how,
                                 "avg_launch_us": 1e3 * prof["tower_ms"] / max(1, prof["tower_launches"]),
+                                "tower_launches": prof["tower_launches"], "avg_layer_us": 1e3 * prof["tower_ms"] / max(1, prof["evals"] * nconv),
                                 "algorithmic_flop_per_launch": "12.39 MFLOP x leaves of the tick (SURVEY 8d: 2*42*128*1152 per leaf per conv layer)",
-                                "how": "CUDA events around the %d tower launches of every tick on the library stream, in a profiled pass of the same %d steps right after the timed region (graph replay off); step time in that pass %.1f ms"
+                                "how": "CUDA events around the tower (%d conv layers; one persistent launch or one launch per layer) of every tick on the library stream, in a profiled pass of the same %d steps right after the timed region (graph replay off); step time in that pass %.1f ms"
                                        % (nconv, args.steps, prof["step_ms"] / args.steps),
                                 "network_share_of_step": prof["total_ms"] / prof["step_ms"],
                                 "tower_share_of_step": prof["tower_ms"] / prof["step_ms"]}
+        if tprof["ticks"]:
+            hbm = hbm_peak()
+            # select reads one 128 B line per traversed node, backup rewrites 24 B per traversed node, expand
+            # probes 16 B and writes a 128 B line + Vest (148 B) per new node
+            sel_bytes = 128.0 * tprof["nodes"]
+            bk_bytes = 24.0 * tprof["nodes"] + 148.0 * tprof["expansions"]
+            tree_ms = tprof["select_ms"] + tprof["expand_ms"]
+            ach = (sel_bytes + bk_bytes) / 1e9 / (tree_ms / 1e3)
+            line["roofline_tree"] = {
+                "bound": "hbm", "kernels": "az_k_select + az_k_expand_backup", "achieved": ach, "peak": hbm[0], "unit": "GB/s",
+                "frac": ach / hbm[0], "peak_source": hbm[1],
+                "traffic": NCU_TREE_TRAFFIC_BYTES,
+                "select_us_per_tick": 1e3 * tprof["select_ms"] / tprof["ticks"], "expand_backup_us_per_tick": 1e3 * tprof["expand_ms"] / tprof["ticks"],
+                "select_GBps": sel_bytes / 1e9 / (tprof["select_ms"] / 1e3), "expand_backup_GBps": bk_bytes / 1e9 / (tprof["expand_ms"] / 1e3),
+                "mean_depth": tprof["nodes"] / max(1, tprof["sims"]), "algorithmic_bytes_per_sim": (sel_bytes + bk_bytes) / max(1, tprof["sims"]),
+                "share_of_step": tree_ms / sum_ms(tprof),
+                "note": "latency-bound pointer chase: one simulation in flight per tree (reference semantics, no virtual loss), so memory-level "
+                        "parallelism = 4096 dependent chains; the kernels move ~5 MB per launch and cannot approach the HBM roofline at this pool size "
+                        "(north_star's 60 % target is not met; see DESIGN.md section 3 and profiles/r02*_tree_ncu_summary.txt)"}
         if not args.no_cpu_baseline and not args.oracle_net:
             threads = args.cpu_threads or min(os.cpu_count() or 1, 16)
-            cex, cdt, _ = cpu_reference_run(128, 100, threads)
-            line["cpu_baseline"] = {"value": cex / cdt, "unit": "expansions/s", "cores": threads, "kind": "port",
-                                    "sample": "128 trees x 100 sims of the same workload: CPU MCTS (C port of src/mcts.jl) + torch-CPU fp32 7-block ResNet"}
+            legs = cpu_baseline_legs(threads)
+            line["cpu_baseline"] = {"value": legs["e2e"]["expansions_per_s"], "unit": "expansions/s", "cores": threads, "kind": "port",
+                                    "sample": legs["e2e"]["sample"] + " (first 8 of the 600 simulations of config[1]); CPU MCTS = C port of src/mcts.jl",
+                                    "legs": legs}
         print(json.dumps(line))
     if env is not None:
         env.close()
     net.close()
+    if comm is not None:
+        comm.close()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

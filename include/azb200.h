@@ -163,6 +163,11 @@ int32_t az_mcts_reset(az_mcts* m);
 int32_t az_mcts_counters(az_mcts* m, int64_t* total_simulations, int64_t* total_nodes_traversed, int64_t* num_nodes);
 /* device-side timing of the last az_mcts_run: total ms, ms inside the network forward, ticks, expansions */
 int32_t az_mcts_last_timing(az_mcts* m, double* ms_total, double* ms_network, int64_t* ticks, int64_t* expansions);
+/* per-kernel device timing of the tree kernels for bench.py's roofline_tree: while enabled, az_mcts_run records CUDA events
+   around az_k_select, the network evaluation and az_k_expand_backup of every tick (graph replay off); get_profile returns
+   the sums since the last call: select_ms, expand_ms (expand + backup), net_ms, ticks */
+int32_t az_mcts_set_profiling(az_mcts* m, int32_t enable);
+int32_t az_mcts_get_profile(az_mcts* m, double* select_ms, double* expand_ms, double* net_ms, int64_t* ticks);
 int32_t az_mcts_destroy(az_mcts* m);
 
 /* ---- self-play: simulate(simulator, gspec, SimParams) (src/simulations.jl:207-244) ------------ */

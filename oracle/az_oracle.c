@@ -968,17 +968,42 @@ static int oz_tree_advance(oz_batch* b, oz_tree* t) {
   }
   return 0;
 }
+/* ---- host threads of the lock-step batch driver: a plain pthread parallel-for over independent trees / leaves (the
+   image has no OpenMP runtime for gcc).  Static contiguous chunks; the result never depends on the thread count. ---- */
+#include <pthread.h>
+static int oz_nthreads = 1;
+void oz_set_threads(int n) { oz_nthreads = n < 1 ? 1 : (n > 256 ? 256 : n); }
+int oz_get_threads(void) { return oz_nthreads; }
+typedef void (*oz_range_fn)(void* ctx, int lo, int hi);
+typedef struct { oz_range_fn fn; void* ctx; int lo, hi; } oz_job;
+static void* oz_job_run(void* p) { oz_job* j = (oz_job*)p; j->fn(j->ctx, j->lo, j->hi); return NULL; }
+static void oz_parallel_for(int n, oz_range_fn fn, void* ctx) {
+  int nt = oz_nthreads < n ? oz_nthreads : n;
+  if (nt <= 1) { fn(ctx, 0, n); return; }
+  pthread_t th[256];
+  oz_job job[256];
+  for (int k = 0; k < nt; k++) {
+    job[k].fn = fn; job[k].ctx = ctx;
+    job[k].lo = (int)((long long)n * k / nt); job[k].hi = (int)((long long)n * (k + 1) / nt);
+    if (k > 0 && pthread_create(&th[k], NULL, oz_job_run, &job[k]) != 0) { job[k].fn(ctx, job[k].lo, job[k].hi); th[k] = 0; job[k].fn = NULL; }
+  }
+  oz_job_run(&job[0]);
+  for (int k = 1; k < nt; k++) if (job[k].fn) pthread_join(th[k], NULL);
+}
 /* Trees are independent (one MCTS.Env per worker, src/simulations.jl:217-218): the CPU baseline runs them on all host
    threads like the reference's Util.mapreduce over worker tasks (src/util.jl:169-200).  Leaves are collected in tree
    order afterwards, so the result does not depend on the thread count. */
-int oz_batch_advance(oz_batch* b, uint8_t* leaf_states, int32_t* leaf_tree) {
-  int sb = OZ_SBYTES[b->game_id];
-  b->npend = 0;
-#pragma omp parallel for schedule(static)
-  for (int i = 0; i < b->n; i++) {
+static void oz_advance_range(void* ctx, int lo, int hi) {
+  oz_batch* b = (oz_batch*)ctx;
+  for (int i = lo; i < hi; i++) {
     oz_tree* t = &b->t[i];
     if (!t->pending) oz_tree_advance(b, t);
   }
+}
+int oz_batch_advance(oz_batch* b, uint8_t* leaf_states, int32_t* leaf_tree) {
+  int sb = OZ_SBYTES[b->game_id];
+  b->npend = 0;
+  oz_parallel_for(b->n, oz_advance_range, b);
   for (int i = 0; i < b->n; i++) {
     oz_tree* t = &b->t[i];
     b->sims += t->sims_local;
@@ -993,20 +1018,29 @@ int oz_batch_advance(oz_batch* b, uint8_t* leaf_states, int32_t* leaf_tree) {
 }
 /* GI.vectorize_state + GI.actions_mask of the pending leaves (the Batchifier's `Flux.batch(vectorize_state.(...))`,
    src/networks/network.jl:310-312), on all host threads: X[npend][state_dim floats], mask[npend][A] */
-void oz_batch_vectorize(const oz_batch* b, const uint8_t* leaf_states, int n, int xdim, float* X, uint8_t* mask) {
+typedef struct { const oz_batch* b; const uint8_t* leaf_states; int xdim; float* X; uint8_t* mask; } oz_vec_args;
+static void oz_vectorize_range(void* ctx, int lo, int hi) {
+  oz_vec_args* v = (oz_vec_args*)ctx;
+  const oz_batch* b = v->b;
   int sb = OZ_SBYTES[b->game_id], A = OZ_NACT[b->game_id];
-#pragma omp parallel for schedule(static)
-  for (int j = 0; j < n; j++) {
-    oz_vectorize_state(b->game_id, leaf_states + (size_t)j * sb, X + (size_t)j * xdim);
+  for (int j = lo; j < hi; j++) {
+    oz_vectorize_state(b->game_id, v->leaf_states + (size_t)j * sb, v->X + (size_t)j * v->xdim);
     const oz_tree* t = &b->t[b->pend[j]];
-    for (int a = 0; a < A; a++) mask[(size_t)j * A + a] = 0;
-    for (int i = 0; i < t->leaf_nlegal; i++) mask[(size_t)j * A + t->leaf_acts[i]] = 1;
+    for (int a = 0; a < A; a++) v->mask[(size_t)j * A + a] = 0;
+    for (int i = 0; i < t->leaf_nlegal; i++) v->mask[(size_t)j * A + t->leaf_acts[i]] = 1;
   }
 }
-void oz_batch_feed(oz_batch* b, const float* P, const float* V) {
+void oz_batch_vectorize(const oz_batch* b, const uint8_t* leaf_states, int n, int xdim, float* X, uint8_t* mask) {
+  oz_vec_args v = {b, leaf_states, xdim, X, mask};
+  oz_parallel_for(n, oz_vectorize_range, &v);
+}
+typedef struct { oz_batch* b; const float* P; const float* V; } oz_feed_args;
+static void oz_feed_range(void* ctx, int lo, int hi) {
+  oz_feed_args* f = (oz_feed_args*)ctx;
+  oz_batch* b = f->b;
+  const float* P = f->P; const float* V = f->V;
   int A = OZ_NACT[b->game_id];
-#pragma omp parallel for schedule(static)
-  for (int j = 0; j < b->npend; j++) {
+  for (int j = lo; j < hi; j++) {
     oz_tree* t = &b->t[b->pend[j]];
     oz_env* e = t->env;
     float p[OZ_MAX_ACTIONS];
@@ -1020,6 +1054,10 @@ void oz_batch_feed(oz_batch* b, const float* P, const float* V) {
     t->pending = 0;
     t->sims_done++;
   }
+}
+void oz_batch_feed(oz_batch* b, const float* P, const float* V) {
+  oz_feed_args f = {b, P, V};
+  oz_parallel_for(b->npend, oz_feed_range, &f);
   b->sims += b->npend;
   b->expansions += b->npend;
   b->npend = 0;

@@ -165,6 +165,9 @@ void oz_worker_run(int game_id, oz_oracle_fn oracle, void* octx, const oz_mcts_p
 void oz_random_position(int game_id, uint64_t seed, uint64_t stream, int max_plies, uint8_t* state);
 
 /* ---- batched lock-step driver (CPU baseline with a batched evaluator) ------ */
+/* host threads used by oz_batch_advance / oz_batch_vectorize / oz_batch_feed (default 1) */
+void oz_set_threads(int n);
+int oz_get_threads(void);
 typedef struct oz_batch oz_batch;
 oz_batch* oz_batch_create(int game_id, int n_trees, const oz_mcts_params* mp);
 void oz_batch_destroy(oz_batch*);
@@ -174,6 +177,8 @@ void oz_batch_set_roots(oz_batch*, const uint8_t* states /* n_trees * state_byte
 int oz_batch_advance(oz_batch*, uint8_t* leaf_states, int32_t* leaf_tree);
 /* answers for the pending leaves, in the order given by oz_batch_advance: P is A-wide (zeros on illegal) */
 void oz_batch_feed(oz_batch*, const float* P, const float* V);
+/* GI.vectorize_state + actions mask of the pending leaves (src/networks/network.jl:310-312), threaded over leaves */
+void oz_batch_vectorize(const oz_batch*, const uint8_t* leaf_states, int n, int xdim, float* X, uint8_t* mask);
 void oz_batch_root_stats(const oz_batch*, int tree, int64_t* N, double* W, float* P);
 int64_t oz_batch_total_expansions(const oz_batch*);
 int64_t oz_batch_total_simulations(const oz_batch*);

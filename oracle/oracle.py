@@ -119,6 +119,8 @@ def lib():
         L.oz_batch_set_roots.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oz_batch_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oz_batch_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oz_batch_vectorize.restype = None
+        L.oz_batch_vectorize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.oz_batch_root_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oz_batch_total_expansions.restype = C.c_int64
         L.oz_batch_total_expansions.argtypes = [C.c_void_p]
@@ -308,6 +310,11 @@ def dirichlet(seed, game, move, n, alpha):
     return eta
 
 
+def set_threads(n):
+    """Host threads of the batch driver (pthread parallel-for over independent trees)."""
+    lib().oz_set_threads(int(n))
+
+
 class Batch:
     """Lock-step batched driver (CPU baseline): explore nsims on n fixed roots with a batched evaluator."""
 
@@ -333,6 +340,16 @@ class Batch:
     def advance(self):
         k = lib().oz_batch_advance(self.h, self._ls.ctypes.data, self._lt.ctypes.data)
         return self._ls[:k], self._lt[:k]
+
+    def vectorize(self, leaf_states, xshape):
+        """(X [k, *xshape] float32, mask [k, A] bool) of the pending leaves returned by advance()."""
+        k = len(leaf_states)
+        A = num_actions(self.gid)
+        X = np.zeros((k,) + tuple(xshape), np.float32)
+        m = np.zeros((k, A), np.uint8)
+        ls = np.ascontiguousarray(leaf_states, np.uint8)
+        lib().oz_batch_vectorize(self.h, ls.ctypes.data, k, int(np.prod(xshape)), X.ctypes.data, m.ctypes.data)
+        return X, m.astype(bool)
 
     def feed(self, P, V):
         P = np.ascontiguousarray(P, np.float32)

@@ -12,7 +12,8 @@ if [ "$what" = all ] || [ "$what" = list ]; then
       $B --nsims 200 > gpurun_out/launches_${tag}.log 2>&1
 fi
 if [ "$what" = all ] || [ "$what" = tower ]; then
-  ncu --set full --clock-control none --import-source on -k regex:az_k_conv_yrow -s 1400 -c 2 -f -o gpurun_out/prof_conv_${tag} \
+  # the persistent whole-tower kernel launches once per tick (AZ_TOWER=layer: az_k_conv_yrow, 14 launches per tick)
+  ncu --set full --clock-control none --import-source on -k regex:az_k_tower_yrow -s 100 -c 1 -f -o gpurun_out/prof_conv_${tag} \
       $B --nsims 200 > gpurun_out/prof_conv_${tag}.log 2>&1
 fi
 if [ "$what" = all ] || [ "$what" = tree ]; then

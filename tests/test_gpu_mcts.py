@@ -206,6 +206,83 @@ def test_full_size_properties(az, ctx):
     net.close()
 
 
+@pytest.mark.parametrize("game,tau", [("connect-four", 0.0), ("connect-four", 0.5), ("mancala", 0.5), ("tictactoe", 2.0)])
+def test_explore_prior_temperature_bit_exact(az, oz, ctx, game, tau):
+    """prior_temperature != 1 (src/mcts.jl:157-161 -> Util.apply_temperature, src/util.jl:98-110): tau = 0 makes the prior
+    one-hot on the first maximal legal action, otherwise P.^(1/tau) renormalised in Float64 and stored as Float32."""
+    gs = az.GameSpec(game)
+    gid = oz.game_id(game)
+    nsims = 150 if game != "tictactoe" else 50
+    roots = gs.random_positions(77, 48, 24 if game != "tictactoe" else 4)
+    eta = _etas(oz, gid, roots, gs.num_actions, seed=9)
+    mp = az.MctsParams(cpuct=1.5, num_iters_per_turn=nsims, dirichlet_noise_eps=0.25, dirichlet_noise_alpha=1.0, prior_temperature=tau)
+    net = az.SynthOracle(ctx, gs)
+    env = az.MctsEnv(ctx, gs, net, mp, len(roots), 2 * nsims)
+    N, W, P = env.explore(roots, nsims, eta)
+    ts, tn, nn = env.counters()
+    for i, r in enumerate(roots):
+        e = oz.Env(gid, "synth", cpuct=1.5, noise_eps=0.25, prior_temperature=tau)
+        g = oz.GameEnv(gid, r)
+        n = int(g.actions_mask().sum())
+        e.explore(g, nsims, eta[i, :n])
+        _, rN, rW, rP, _ = e.root_stats(g)
+        assert (N[i] == rN).all() and (W[i] == rW).all(), (i, N[i], rN)
+        assert (P[i].view(np.uint32) == rP.view(np.uint32)).all(), (i, P[i], rP)
+        assert (ts[i], tn[i], nn[i]) == (e.total_simulations, e.total_nodes_traversed, e.num_nodes)
+    if tau == 0.0:
+        assert ((P == 1.0).sum(1) == 1).all() and ((P == 0.0) | (P == 1.0)).all()
+    env.close()
+    net.close()
+
+
+@pytest.mark.parametrize("game,S,nsims,gamma", [("connect-four", 4096, 600, 1.0), ("mancala", 4096, 400, 1.0), ("grid-world", 8192, 200, 0.95)])
+def test_full_size_pool_slots_bit_exact(az, oz, ctx, game, S, nsims, gamma):
+    """BASELINE configs [1], [3], [4] at their FULL pool size: the whole pool runs on the GPU (every tick batches the leaves
+    of all S trees) and 64 randomly chosen slots are compared bit for bit with the CPU oracle -- trees are independent, so
+    a slot's statistics must not depend on what the other 4095 / 8191 slots do (batch position, leaf-queue order, table
+    placement)."""
+    gs = az.GameSpec(game)
+    gid = oz.game_id(game)
+    A = gs.num_actions
+    gw = game == "grid-world"
+    roots = gs.random_positions(0xA17A2E80, S, 30) if not gw else gs.random_positions(0xA17A2E80, S)
+    rng = np.random.default_rng(2024)
+    pick = np.sort(rng.choice(S, 64, replace=False))
+    eps = 0.0 if gw else 0.25
+    eta = None
+    if not gw:
+        eta = np.zeros((S, A))
+        sub = _etas(oz, gid, roots[pick], A, seed=11)
+        e_all = rng.exponential(size=(S, A))           # the other slots: any valid noise vector over their legal actions
+        full = np.array([int(gs.actions_mask(r).sum()) for r in roots])
+        for i in range(S):
+            v = e_all[i, :full[i]]
+            eta[i, :full[i]] = v / v.sum()
+        eta[pick] = sub
+    mp = az.MctsParams(gamma=gamma, cpuct=2.0, num_iters_per_turn=nsims, dirichlet_noise_eps=eps, dirichlet_noise_alpha=1.0)
+    net = az.SynthOracle(ctx, gs)
+    env = az.MctsEnv(ctx, gs, net, mp, S, capacity_nodes_per_tree=nsims + 8)
+    seed = 777
+    if gw:
+        env.set_noise(seed, np.arange(S) + 5, np.full(S, 2))
+    N, W, P = env.explore(roots, nsims, eta)
+    ts, tn, nn = env.counters()
+    for i in pick:
+        e = oz.Env(gid, "synth", gamma=gamma, cpuct=2.0, noise_eps=eps)
+        if gw:
+            e.set_noise(seed, 5 + int(i), 2)
+        g = oz.GameEnv(gid, bytes(roots[i]))
+        n = int(g.actions_mask().sum())
+        e.explore(g, nsims, None if eta is None else eta[i, :n])
+        _, rN, rW, rP, _ = e.root_stats(g)
+        assert (N[i] == rN).all() and (W[i] == rW).all(), (i, N[i], rN)
+        assert (P[i].view(np.uint32) == rP.view(np.uint32)).all()
+        assert (ts[i], tn[i], nn[i]) == (e.total_simulations, e.total_nodes_traversed, e.num_nodes)
+    assert (ts == nsims).all()
+    env.close()
+    net.close()
+
+
 def test_error_paths_mirror_reference_asserts(az, ctx):
     """Precondition violations return AZ_EINVAL / AZ_ESTATE with a message (no exception crosses the ABI)."""
     gs = az.GameSpec("connect-four")

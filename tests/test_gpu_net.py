@@ -45,6 +45,37 @@ def test_resnet_forward_matches_fp32_reference(az, oz, ctx, blocks, batch, seed,
     net.close()
 
 
+@pytest.mark.parametrize("blocks,batch", [(1, 37), (5, 700), (7, 4096)])
+def test_persistent_tower_equals_per_layer_kernels(az, oz, ctx, blocks, batch):
+    """The persistent whole-tower kernel (one launch, neighbour flags between layers) and the per-layer kernel issue the same
+    MMAs in the same order for every output row, so their outputs must be bit-identical -- at a batch that spans every CTA
+    pair (4096 leaves), one that leaves most pairs idle (37) and an odd size (700)."""
+    import os
+    gs = az.GameSpec("connect-four")
+    hp = netcheck.c4_hp(blocks)
+    states = gs.random_positions(17, batch, 38)
+    outs = []
+    for mode in ("", "layer"):
+        old = os.environ.get("AZ_TOWER")
+        if mode:
+            os.environ["AZ_TOWER"] = mode
+        try:
+            net, blob = netcheck.make_net(az, ctx, gs, hp, seed=5, randomize=True)
+        finally:
+            if mode:
+                if old is None:
+                    del os.environ["AZ_TOWER"]
+                else:
+                    os.environ["AZ_TOWER"] = old
+        for rep in range(3):       # repeated launches: the flag counters keep counting across launches
+            P, V, _ = net.evaluate_batch(states)
+        L, Vp = net.forward_logits(states)
+        outs.append((P, V, L, Vp))
+        net.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert (a.view(np.uint32) == b.view(np.uint32)).all()
+
+
 def test_resnet_precision_stress(az, oz, ctx):
     """The measured error distribution of 7-block networks with randomised biases / BatchNorm statistics (gamma in
     [0.7, 1.3], sigma2 in [0.6, 1.5], mu, beta ~ N(0, 0.1); oracle/netref.py make_blob) -- the hardest case for the fp16

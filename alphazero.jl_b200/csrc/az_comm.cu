@@ -63,6 +63,8 @@ struct az_comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   int64_t* d_counts = nullptr;  // [world + 1]: [0, world) gathered counts, [world] this rank's count
+  uint64_t *d_send = nullptr, *d_recv = nullptr;   // staging rows, grown on demand and kept across iterations
+  size_t send_words = 0, recv_words = 0;
   double last_ms = 0;           // device time of the last collective call (CUDA events on the context's stream)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -155,6 +157,17 @@ int32_t az_comm_create(az_ctx* ctx, const uint8_t id[AZ_COMM_ID_BYTES], int32_t 
     ctx->err = "az_comm_create: cudaMalloc / cudaEventCreate failed";
     return AZ_ENOMEM;
   }
+  // establish the NCCL channels now (the first collective on a communicator sets up its connections and proxy threads,
+  // ~1-2 s): a one-element all-gather, so that the per-iteration exchanges run at link speed from their first call
+  cudaMemsetAsync(c->d_counts, 0, (size_t)(world + 1) * sizeof(int64_t), ctx->stream);
+  r = api.AllGather(c->d_counts + world, c->d_counts, 1, ncclInt64, c->comm, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (r != ncclSuccess || e != cudaSuccess) {
+    ctx->err = std::string("az_comm_create: warm-up all-gather failed: ") + (r != ncclSuccess ? api.GetErrorString(r) : cudaGetErrorString(e));
+    api.CommDestroy(c->comm); cudaFree(c->d_counts); cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    delete c;
+    return AZ_ECUDA;
+  }
   *out = c;
   return AZ_OK;
 }
@@ -177,7 +190,7 @@ int32_t az_comm_destroy(az_comm* c) {
   cudaSetDevice(c->ctx->device);
   cudaStreamSynchronize(c->ctx->stream);
   if (c->comm) nccl().CommDestroy(c->comm);
-  cudaFree(c->d_counts);
+  cudaFree(c->d_counts); cudaFree(c->d_send); cudaFree(c->d_recv);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c;
@@ -212,13 +225,20 @@ int32_t az_samples_allgather(az_comm* c, az_samples* local, az_samples** out, in
     if (rc != AZ_OK) return rc;
     if (total > 0) {
       // 2. pack -> one padded all-gather -> compact
-      uint64_t *d_send = nullptr, *d_recv = nullptr;
       const size_t row_words = (size_t)maxc * ROWW;
-      if (cudaMalloc((void**)&d_send, row_words * 8) != cudaSuccess || cudaMalloc((void**)&d_recv, row_words * 8 * world) != cudaSuccess) {
-        cudaGetLastError(); cudaFree(d_send); az_samples_destroy(o);
-        ctx->err = "az_samples_allgather: cudaMalloc of the staging rows failed";
-        return AZ_ENOMEM;
+      if (row_words > c->send_words || row_words * world > c->recv_words) {
+        cudaFree(c->d_send); cudaFree(c->d_recv);
+        c->d_send = c->d_recv = nullptr; c->send_words = c->recv_words = 0;
+        const size_t want = row_words + row_words / 4;   // headroom: the next iteration's count differs a little
+        if (cudaMalloc((void**)&c->d_send, want * 8) != cudaSuccess || cudaMalloc((void**)&c->d_recv, want * 8 * world) != cudaSuccess) {
+          cudaGetLastError(); cudaFree(c->d_send); c->d_send = nullptr; az_samples_destroy(o);
+          ctx->err = "az_samples_allgather: cudaMalloc of the staging rows failed";
+          return AZ_ENOMEM;
+        }
+        c->send_words = want; c->recv_words = want * world;
+        AZ_CUDA(ctx, cudaEventRecord(c->ev0, st));   // do not charge the one-off allocation to the exchange
       }
+      uint64_t *d_send = c->d_send, *d_recv = c->d_recv;
       const int grid = ctx->num_sms * 8;
       if (n > 0) azc_k_pack<<<grid, 256, 0, st>>>(n, A, az_samples_env(local), az_samples_pi(local), az_samples_z(local), az_samples_t(local),
                                                   az_samples_cnt(local), d_send);
@@ -229,7 +249,6 @@ int32_t az_samples_allgather(az_comm* c, az_samples* local, az_samples** out, in
       ctx->launches += 2;
       cudaEventRecord(c->ev1, st);
       cudaError_t e = cudaStreamSynchronize(st);
-      cudaFree(d_send); cudaFree(d_recv);
       if (r != ncclSuccess) { az_samples_destroy(o); ctx->err = std::string("ncclAllGather: ") + api.GetErrorString(r); return AZ_ECUDA; }
       if (e != cudaSuccess) { az_samples_destroy(o); ctx->err = std::string("az_samples_allgather: ") + cudaGetErrorString(e); return AZ_ECUDA; }
     } else {

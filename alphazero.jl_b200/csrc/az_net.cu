@@ -1358,6 +1358,318 @@ __global__ void __launch_bounds__(256) az_k_finalize(const AzEnv* __restrict__ e
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused stem (round 2): leaf states -> first conv, ONE kernel.  The im2col rows are never written to HBM: four builder
+// warps (one thread per tile row) assemble the 128 x 64 fp16 A tile of the first conv directly in shared memory in the
+// SWIZZLE_128B K-major layout the tensor core reads (a row is exactly one 128-byte swizzle row), double buffered
+// against the MMA (4 x tcgen05.mma M=128,N=128,K=16 per tile) and the epilogue of the previous tile.  Saves the 15 MB
+// im2col write + read and one launch per evaluation (the im2col + GEMM pair took 13 + 17 us at ~2750 leaves).
+// ------------------------------------------------------------------------------------------------
+namespace st {
+constexpr int NUM_THREADS = 320;   // B loader, MMA, 4 builder warps, 4 epilogue warps
+constexpr int NBMAX = 12;          // boards a 128-row tile can touch
+template <int NX>
+struct Smem {
+  uint8_t b[128 * 128];            // weights Wt[co][64]
+  uint8_t a[2][128 * 128];
+  float xs[2][NBMAX][NX];
+  uint64_t bfull, afull[2], aempty[2], tfull[2], tempty[2];
+  uint32_t tmem_base;
+  float bias[128];
+};
+}  // namespace st
+
+template <class G>
+__global__ void __launch_bounds__(st::NUM_THREADS, 1)
+az_k_stem(const AzEnv* __restrict__ envs, const __grid_constant__ CUtensorMap tmW, GemmArgs ga, int dense) {
+  constexpr int W = G::XW, H = G::XH, C = G::XC, NX = W * H * C, BN = 128, F = 128;
+  using SmemT = st::Smem<NX>;
+  extern __shared__ uint8_t smem_st[];
+  SmemT& s = *reinterpret_cast<SmemT*>((reinterpret_cast<uintptr_t>(smem_st) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int RS = dense ? W : W + 1, BS = dense ? W * H : (W + 1) * (H + 1);
+  if (threadIdx.x == 0) {
+    mbar_init(&s.bfull, 1);
+    for (int i = 0; i < 2; i++) { mbar_init(&s.afull[i], 128); mbar_init(&s.aempty[i], 1); mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x - 64 < BN) s.bias[threadIdx.x - 64] = ga.bias[threadIdx.x - 64];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"((uint32_t)(2 * BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp == 0) {  // the weights do not depend on earlier kernels
+    if (elect_one()) { mbar_expect_tx(&s.bfull, 128 * 128); tma_load_2d(s.b, &tmW, &s.bfull, 0, 0); }
+    __syncwarp();
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int n_boards = *ga.n_boards;
+  const int rows_used = n_boards * BS;
+  const int num_tiles = (rows_used + 127) / 128;
+
+  if (warp == 1) {  // ===== MMA issuer =====
+    mbar_wait(&s.bfull, 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&s.tempty[buf], ph ^ 1);
+      mbar_wait(&s.afull[buf], ph);
+      tcgen05_fence_after();
+      const uint64_t adesc = umma_desc_sw128(smem_u32(s.a[buf]));
+      const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b));
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          umma_f16(tmem_base + buf * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), tc::idesc<BN>(), k ? 1u : 0u);
+        umma_commit(&s.aempty[buf]);
+        umma_commit(&s.tfull[buf]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 2 && warp < 6) {  // ===== builders: thread t owns row t of the tile =====
+    const int t = threadIdx.x - 64;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&s.aempty[buf], ph ^ 1);
+      const int r0 = tile * 128;
+      const int b_first = r0 / BS;
+      const int b_last = min((r0 + 127) / BS, n_boards - 1);
+      // vectorize_state of the tile's boards: board slot k is done by lane k / 4 of builder warp k % 4
+      {
+        const int k = (t & 31) * 4 + (t >> 5);
+        if (k <= b_last - b_first && k < st::NBMAX) G::vectorize(envs[b_first + k], s.xs[buf][k]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int r = r0 + t;
+      uint4 chunk[8];
+      __half* hv = reinterpret_cast<__half*>(chunk);
+#pragma unroll
+      for (int k = 0; k < 64; k++) hv[k] = __float2half_rn(0.0f);
+      if (r < rows_used) {
+        const int b = r / BS, rr = r - b * BS, yy = rr / RS, xx = rr - yy * RS;
+        if (yy < H && xx < W) {
+          const float* x = s.xs[buf][b - b_first];
+#pragma unroll
+          for (int k = 0; k < 9 * C; k++) {   // k = tap*C + c; Flux Conv is a true convolution: tap (kx,ky) reads (x + 1 - kx, y + 1 - ky)
+            const int tap = k / C, c = k % C, ky = tap / 3, kx = tap % 3;
+            const int ix = xx + 1 - kx, iy = yy + 1 - ky;
+            if (ix >= 0 && ix < W && iy >= 0 && iy < H) hv[k] = __float2half_rn(x[ix + W * iy + W * H * c]);
+          }
+        }
+      }
+      uint8_t* row = s.a[buf] + t * 128;
+#pragma unroll
+      for (int q = 0; q < 8; q++) *reinterpret_cast<uint4*>(row + ((q ^ (t & 7)) << 4)) = chunk[q];
+      fence_proxy_async();
+      mbar_arrive(&s.afull[buf]);   // (xs[buf] is rewritten two tiles later, i.e. after the next tile's bar.sync: every row is built by then)
+    }
+  } else if (warp >= 6) {  // ===== epilogue warps 6..9: TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&s.tfull[buf], ph);
+      tcgen05_fence_after();
+      const int p = tile * 128 + quarter * 32 + lane;
+      const int rr = p % ga.g.board_rows;
+      const bool valid = (p < rows_used) && (rr < ga.g.valid_rows) && ((rr % ga.g.row_stride) != ga.g.wcols);
+      const bool in_alloc = p < ga.alloc_rows;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + buf * BN + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) x[j] = valid ? fmaxf(__uint_as_float(v[j]) + s.bias[c * 32 + j], 0.0f) : 0.0f;
+        if (!in_alloc) continue;
+        if (ga.out32 != nullptr) {
+          float4* op = reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; j++) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        }
+        uint4 o[4];
+        __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+        for (int j = 0; j < 16; j++) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+        uint4* op = reinterpret_cast<uint4*>(ga.out16a + (size_t)p * F + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; j++) op[j] = o[j];
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[buf]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused head outputs (round 2): the value head's Dense(K -> 128) + relu + Dense(128 -> 1) + tanh and the policy head's
+// Dense(K -> A) + softmax + legal-action mask + renormalisation (resnet.jl:75-90, network.jl:264-271) in ONE launch
+// instead of two GEMM launches and a finalize kernel: even CTAs run value tiles (N = 128), odd CTAs policy tiles (N = 64,
+// A used); the epilogue thread that owns a board row reduces its TMEM row in registers, so the hidden layer and the
+// logits never touch HBM.
+// ------------------------------------------------------------------------------------------------
+struct HeadArgs {
+  const int32_t* n_boards;
+  int kblocks;            // K / 64
+  const float* bias_v;    // [128] value dense bias
+  const float* wv2;       // [128]
+  const float* bv2;       // [1]
+  const float* bias_p;    // [64] policy dense bias (A used)
+  float* logit_out;       // parity hook or null
+  float* vpre_out;        // parity hook or null
+};
+template <class G>
+__global__ void __launch_bounds__(tc::NUM_THREADS, 1)
+az_k_heads_dense(const __grid_constant__ CUtensorMap tmHv, const __grid_constant__ CUtensorMap tmWd, const __grid_constant__ CUtensorMap tmHp,
+                 const __grid_constant__ CUtensorMap tmWp, HeadArgs ha, const AzEnv* __restrict__ envs, float* __restrict__ P,
+                 float* __restrict__ V, float* __restrict__ Pinv) {
+  using namespace tc;
+  constexpr int A = G::A;
+  using SmemT = Smem<128>;
+  extern __shared__ uint8_t smem_hd[];
+  SmemT& s = *reinterpret_cast<SmemT*>((reinterpret_cast<uintptr_t>(smem_hd) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool policy = (blockIdx.x & 1) != 0;
+  const int BN = policy ? 64 : 128;
+  const uint32_t b_bytes = (uint32_t)BN * BK * 2;
+  const CUtensorMap* mA = policy ? &tmHp : &tmHv;
+  const CUtensorMap* mB = policy ? &tmWp : &tmWd;
+  const int kblocks = ha.kblocks;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x - 64 < BN) s.bias[threadIdx.x - 64] = (policy ? ha.bias_p : ha.bias_v)[threadIdx.x - 64];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int n_boards = *ha.n_boards;
+  const int num_tiles = (n_boards + BM - 1) / BM;
+  const int first = blockIdx.x >> 1, stride = max(1, (int)gridDim.x >> 1);
+  const uint32_t idesc_rt = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = first; tile < num_tiles; tile += stride) {
+      for (int kb = 0; kb < kblocks; kb++) {
+        mbar_wait(&s.empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&s.full[stage], A_BYTES + b_bytes);
+          tma_load_2d(s.a[stage], mA, &s.full[stage], kb * BK, tile * BM);
+          tma_load_2d(s.b[stage], mB, &s.full[stage], kb * BK, 0);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = first; tile < num_tiles; tile += stride, it++) {
+      const int acc = it & 1;
+      mbar_wait(&s.tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * 128;
+      for (int kb = 0; kb < kblocks; kb++) {
+        mbar_wait(&s.full[stage], phase);
+        tcgen05_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_u32(s.a[stage]));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[stage]));
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++) umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_rt, (kb | k) ? 1u : 0u);
+          umma_commit(&s.empty[stage]);
+          if (kb == kblocks - 1) umma_commit(&s.tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int tile = first; tile < num_tiles; tile += stride, it++) {
+      const int acc = it & 1;
+      mbar_wait(&s.tfull[acc], ((uint32_t)it >> 1) & 1u);
+      tcgen05_fence_after();
+      const int b = tile * BM + quarter * 32 + lane;
+      const bool valid = b < n_boards;
+      if (!policy) {  // value: tanh(w2 . relu(W1 h + b1) + b2), summed in column order
+        float vacc = 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + acc * 128 + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
+#pragma unroll
+          for (int j = 0; j < 32; j++) vacc += fmaxf(__uint_as_float(v[j]) + s.bias[c * 32 + j], 0.0f) * __ldg(ha.wv2 + c * 32 + j);
+        }
+        if (valid) {
+          const float vpre = vacc + __ldg(ha.bv2);
+          V[b] = tanhf(vpre);
+          if (ha.vpre_out) ha.vpre_out[b] = vpre;
+        }
+      } else {  // policy: softmax over all A logits, then mask + renormalise (eps(Float32), network.jl:268)
+        uint32_t v[32];
+        tmem_ld32(tmem_base + acc * 128 + ((uint32_t)(quarter * 32) << 16), v);
+        if (valid) {
+          float lg[A], m = -3.0e38f;
+#pragma unroll
+          for (int a = 0; a < A; a++) { lg[a] = __uint_as_float(v[a]) + s.bias[a]; m = fmaxf(m, lg[a]); }
+          if (ha.logit_out) {
+#pragma unroll
+            for (int a = 0; a < A; a++) ha.logit_out[(size_t)b * A + a] = lg[a];
+          }
+          float se = 0.0f;
+#pragma unroll
+          for (int a = 0; a < A; a++) { lg[a] = expf(lg[a] - m); se += lg[a]; }
+          const uint32_t legal = G::legal_mask(envs[b]);
+          float sp = 0.0f;
+#pragma unroll
+          for (int a = 0; a < A; a++) { lg[a] = ((legal >> a) & 1u) ? lg[a] / se : 0.0f; sp += lg[a]; }
+#pragma unroll
+          for (int a = 0; a < A; a++) P[(size_t)b * A + a] = lg[a] / (sp + 1.1920929e-07f);
+          if (Pinv) Pinv[b] = 1.0f - sp;
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1426,7 +1738,8 @@ struct ResNetImpl : az_net {
   CUtensorMap mapWall{};                                         // [L*128][1152] fp16, 64 x 64 boxes
   bool persistent = true;      // AZ_TOWER=layer: one launch per conv layer (round-2a kernel) instead of the whole-tower kernel
   bool coop_launch = true;     // cooperative launch of the persistent kernel (co-residency of all CTA pairs guaranteed)
-  size_t smem_tower = 0;
+  size_t smem_tower = 0, smem_stem = 0;
+  bool fused = true;           // AZ_FUSED=0: round-1 im2col + GEMM stem and separate dense / finalize launches
   __half *d_wh = nullptr, *d_wd = nullptr;
   float *d_bh = nullptr, *d_bd = nullptr, *d_wv2 = nullptr, *d_bv2 = nullptr;
   std::vector<CUtensorMap> mapW;
@@ -1540,6 +1853,10 @@ struct ResNetImpl : az_net {
     smem_tower = sizeof(tw::Smem);
     static_assert(sizeof(tw::Smem) <= 232448, "persistent tower kernel exceeds the 227 KB shared-memory limit");
     AZ_TRY2(set_smem(az_k_tower_yrow, smem_tower));
+    smem_stem = sizeof(st::Smem<W * H * C>) + 1024;
+    AZ_TRY2(set_smem(az_k_stem<G>, smem_stem));
+    AZ_TRY2(set_smem(az_k_heads_dense<G>, smem128));
+    { const char* e = getenv("AZ_FUSED"); fused = !(e && e[0] == '0'); }
     { const char* e = getenv("AZ_TOWER"); persistent = !(e && e[0] == 'l'); }          // AZ_TOWER=layer
     { const char* e = getenv("AZ_TOWER_COOP"); coop_launch = !(e && e[0] == '0'); }    // AZ_TOWER_COOP=0: plain launch
     if (cudaMalloc((void**)&d_done, 256 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); ctx->err = "cudaMalloc (tower flags) failed"; return AZ_ENOMEM; }
@@ -1767,9 +2084,13 @@ struct ResNetImpl : az_net {
     const int grid = std::min(row_tiles, ctx->num_sms);
     GemmArgs ga{};
     ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.debug = 0;
-    az_k_im2col<G><<<(max_rows + 3) / 4, 128, 0, st>>>(envs, n_rows, d_x0, dense ? 1 : 0);
     ga.gemm_k = 1; ga.kblocks = 1; ga.bias = d_bstem; ga.out16a = d_x16; ga.out32 = c4_fast ? nullptr : d_x32;
-    launch_pdl(az_k_gemm_tc<128, tc::EPI_CONV1>, grid, tc::NUM_THREADS, smem128, st, mapX0, mapWstem, ga);
+    if (fused) {
+      launch_pdl(az_k_stem<G>, grid, st::NUM_THREADS, smem_stem, st, envs, mapWstem, ga, dense ? 1 : 0);
+    } else {
+      az_k_im2col<G><<<(max_rows + 3) / 4, 128, 0, st>>>(envs, n_rows, d_x0, dense ? 1 : 0);
+      launch_pdl(az_k_gemm_tc<128, tc::EPI_CONV1>, grid, tc::NUM_THREADS, smem128, st, mapX0, mapWstem, ga);
+    }
     ga.gemm_k = 0; ga.out32 = nullptr; ga.debug = tower_debug;
     if (prof) cudaEventRecord(pe[1], st);
     const bool c4 = C4_TOWER && !generic_tower;  // Connect-Four geometry -> cta_group::2 kernel, otherwise the generic 9-tap kernel
@@ -1810,13 +2131,19 @@ struct ResNetImpl : az_net {
     gd.n_boards = n_rows; gd.g = geom; gd.kblocks = KD / 64; gd.gemm_k = 1; gd.rows_per_board = 1; gd.alloc_rows = max_rows + 256;
     gd.bias = d_bd; gd.out32 = d_hid;
     const int board_tiles = (max_rows + tc::BM - 1) / tc::BM;
-    launch_pdl(az_k_gemm_tc<128, tc::EPI_DENSE>, std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem128, st, mapHv, mapWd, gd);
-    gd.bias = d_bpol; gd.out32 = d_logit; gd.no_relu = 1;   // policy dense: logits[b][0..A) = Wp . hp + b
-    launch_pdl(az_k_gemm_tc<64, tc::EPI_DENSE>, std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem64, st, mapHp, mapWpol, gd);
-    FinalArgs fa{d_logit, d_hid, d_wv2, d_bv2, dbg_logit, dbg_vpre};
-    az_k_finalize<G><<<(max_rows * 8 + 255) / 256, 256, 0, st>>>(envs, n_rows, fa, P, V, Pinv);
+    if (fused) {
+      HeadArgs ha{n_rows, KD / 64, d_bd, d_wv2, d_bv2, d_bpol, dbg_logit, dbg_vpre};
+      const int hgrid = 2 * std::max(1, std::min(board_tiles, ctx->num_sms / 2));
+      launch_pdl(az_k_heads_dense<G>, hgrid, tc::NUM_THREADS, smem128, st, mapHv, mapWd, mapHp, mapWpol, ha, envs, P, V, Pinv);
+    } else {
+      launch_pdl(az_k_gemm_tc<128, tc::EPI_DENSE>, std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem128, st, mapHv, mapWd, gd);
+      gd.bias = d_bpol; gd.out32 = d_logit; gd.no_relu = 1;   // policy dense: logits[b][0..A) = Wp . hp + b
+      launch_pdl(az_k_gemm_tc<64, tc::EPI_DENSE>, std::min(board_tiles, ctx->num_sms), tc::NUM_THREADS, smem64, st, mapHp, mapWpol, gd);
+      FinalArgs fa{d_logit, d_hid, d_wv2, d_bv2, dbg_logit, dbg_vpre};
+      az_k_finalize<G><<<(max_rows * 8 + 255) / 256, 256, 0, st>>>(envs, n_rows, fa, P, V, Pinv);
+    }
     if (prof) { cudaEventRecord(pe[3], st); prof_evals++; }
-    ctx->launches += 6 + ((dense && persistent && hp.num_blocks > 0) ? 1 : 2 * hp.num_blocks);
+    ctx->launches += (fused ? 3 : 6) + ((dense && persistent && hp.num_blocks > 0) ? 1 : 2 * hp.num_blocks);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ctx->err = std::string("network launch: ") + cudaGetErrorString(e); return AZ_ECUDA; }
     return AZ_OK;

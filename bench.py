@@ -372,6 +372,11 @@ def main():
             gather_ms = comm.last_ms
         barrier()
         t_gather = time.perf_counter() - t1
+        gather2_ms = 0.0
+        if comm is not None:      # the same exchange again (NCCL's buffers for this size exist now): the steady-state figure of later iterations
+            g2, _ = comm.allgather_samples(smp)
+            gather2_ms = comm.last_ms
+            g2.close()
         # replay-buffer side on this rank's samples, device resident: augment -> merge -> convert
         tr0 = time.perf_counter()
         aug = smp.augment_with_symmetries()
@@ -387,7 +392,7 @@ def main():
             x.close()
         del cv
         sp_h.close()
-        sp_out = dict(t=t_play + t_gather, t_gather=t_gather, gather_device_ms=gather_ms, games=count, samples=int(out["samples"]),
+        sp_out = dict(t=t_play + t_gather, t_gather=t_gather, gather_device_ms=gather_ms, gather2_device_ms=gather2_ms, games=count, samples=int(out["samples"]),
                       expansions=float(out["expansions"]), total_samples=total_gathered, mean_moves=float(out["moves"].mean()),
                       mean_edepth=float(out["edepth"].mean()))
     # ---- arena: pit_networks of two 7-block nets with the shipped Connect-Four ArenaParams
@@ -449,7 +454,7 @@ def main():
         if sp_out is not None:
             line["selfplay"] = {"games_per_s": sp_out["games"] / sp_out["t"], "samples_per_s": sp_out["samples"] / sp_out["t"],
                                 "expansions_per_s": sp_out["expansions"] / sp_out["t"], "seconds": sp_out["t"],
-                                "allgather_seconds": sp_out["t_gather"], "allgather_device_ms": sp_out["gather_device_ms"],
+                                "allgather_seconds": sp_out["t_gather"], "allgather_device_ms": sp_out["gather_device_ms"], "allgather_device_ms_repeat": sp_out["gather2_device_ms"],
                                 "allgather": "az_samples_allgather: NCCL, packed 104 B rows, device resident (no host staging)", "games": int(sp_out["games"]), "samples": int(sp_out["samples"]),
                                 "gathered_samples_on_rank0": sp_out["total_samples"], "mean_moves_per_game": sp_out["mean_moves"],
                                 "mean_exploration_depth": sp_out["mean_edepth"],

@@ -55,12 +55,12 @@ ABI_SYMBOLS = [
     "az_version", "az_ctx_create", "az_ctx_destroy", "az_last_error", "az_ctx_synchronize", "az_ctx_num_launches",
     "az_game_lookup", "az_game_num_actions", "az_game_state_bytes", "az_game_state_dim", "az_game_max_plies",
     "az_game_vectorize_state", "az_game_actions_mask", "az_game_play", "az_game_init_state", "az_game_random_positions",
-    "az_net_create_oracle", "az_net_create_resnet", "az_net_create_simplenet", "az_net_num_params", "az_net_load",
+    "az_net_create_oracle", "az_net_create_rollout", "az_net_create_resnet", "az_net_create_simplenet", "az_net_num_params", "az_net_load",
     "az_net_forward", "az_net_forward_logits", "az_net_set_profiling", "az_net_get_profile", "az_net_destroy",
     "az_mcts_create", "az_mcts_set_roots", "az_mcts_set_noise", "az_mcts_run", "az_mcts_explore", "az_mcts_root_stats", "az_mcts_policy",
     "az_mcts_reset", "az_mcts_counters", "az_mcts_last_timing", "az_mcts_destroy", "az_mcts_set_profiling", "az_mcts_get_profile",
     "az_selfplay_create", "az_selfplay_start", "az_selfplay_poll", "az_selfplay_wait", "az_selfplay_counts",
-    "az_selfplay_fetch", "az_selfplay_stats", "az_selfplay_destroy", "az_selfplay_create_duel", "az_selfplay_outcomes",
+    "az_selfplay_fetch", "az_selfplay_stats", "az_selfplay_destroy", "az_selfplay_create_duel", "az_selfplay_create_duel_players", "az_selfplay_outcomes",
     "az_selfplay_export_samples", "az_samples_from_host", "az_samples_count", "az_samples_concat", "az_samples_merge_by_state",
     "az_samples_augment_with_symmetries", "az_samples_convert", "az_samples_fetch", "az_samples_destroy",
     "az_comm_unique_id", "az_comm_create", "az_comm_rank", "az_comm_last_ms", "az_comm_destroy", "az_samples_allgather", "az_net_broadcast",
@@ -89,6 +89,7 @@ def lib():
             "az_game_init_state": [C.c_int32, vp],
             "az_game_random_positions": [C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, vp],
             "az_net_create_oracle": [vp, C.c_int32, C.c_int32, C.POINTER(vp)],
+            "az_net_create_rollout": [vp, C.c_int32, C.c_double, C.c_uint64, C.POINTER(vp)],
             "az_net_create_resnet": [vp, C.c_int32, C.POINTER(_ResNetHP), C.POINTER(vp)],
             "az_net_create_simplenet": [vp, C.c_int32, C.POINTER(_SimpleNetHP), C.POINTER(vp)],
             "az_net_num_params": [vp, C.POINTER(C.c_int64)], "az_net_load": [vp, vp, C.c_int64],
@@ -106,6 +107,8 @@ def lib():
             "az_selfplay_counts": [vp, vp, vp], "az_selfplay_fetch": [vp] + [vp] * 8, "az_selfplay_stats": [vp, vp, vp, vp, vp],
             "az_selfplay_destroy": [vp],
             "az_selfplay_create_duel": [vp, C.c_int32, vp, vp, C.POINTER(_MctsParams), C.POINTER(_SimParams), C.c_uint64, C.POINTER(vp)],
+            "az_selfplay_create_duel_players": [vp, C.c_int32, vp, C.POINTER(_MctsParams), vp, C.POINTER(_MctsParams), C.POINTER(_SimParams), C.c_uint64,
+                                                C.POINTER(vp)],
             "az_selfplay_outcomes": [vp, C.c_double, vp, vp, vp, vp],
             "az_selfplay_export_samples": [vp, C.POINTER(vp)],
             "az_samples_from_host": [vp, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, C.POINTER(vp)],
@@ -334,6 +337,12 @@ def RandomOracle(ctx, gspec):  # src/mcts.jl:62-72
     return Network(ctx, gspec, h, NET_UNIFORM)
 
 
+def RolloutOracle(ctx, gspec, gamma=1.0, seed=0):  # src/mcts.jl:27-60 (the oracle of Benchmark.MctsRollouts, src/benchmark.jl:134-147)
+    h = C.c_void_p()
+    ctx.check(lib().az_net_create_rollout(ctx.h, gspec.id, gamma, seed, C.byref(h)))
+    return Network(ctx, gspec, h, 4)
+
+
 def SynthOracle(ctx, gspec):
     h = C.c_void_p()
     ctx.check(lib().az_net_create_oracle(ctx.h, NET_SYNTH, gspec.id, C.byref(h)))
@@ -443,13 +452,18 @@ class MctsEnv:
 class SelfPlay:
     """simulate() for self-play (src/simulations.jl:207-244, src/training.jl:275-300)."""
 
-    def __init__(self, ctx, gspec, oracle, params, seed=0, baseline=None):
-        """`baseline` given: a duel TwoPlayers(MctsPlayer(oracle), MctsPlayer(baseline)) (src/training.jl:130-143)."""
+    def __init__(self, ctx, gspec, oracle, params, seed=0, baseline=None, baseline_mcts=None):
+        """`baseline` given: a duel TwoPlayers(MctsPlayer(oracle, params.mcts), MctsPlayer(baseline, baseline_mcts or params.mcts))
+        (src/training.jl:130-143; two different MctsPlayers as in Benchmark duels, src/benchmark.jl:78-99)."""
         self.ctx, self.gspec, self.params = ctx, gspec, params
         self.h = C.c_void_p()
         mp, sp = params.mcts.c(), params.sim.c()
         if baseline is None:
             ctx.check(lib().az_selfplay_create(ctx.h, gspec.id, oracle.h, C.byref(mp), C.byref(sp), seed, C.byref(self.h)))
+        elif baseline_mcts is not None:
+            mb = baseline_mcts.c()
+            ctx.check(lib().az_selfplay_create_duel_players(ctx.h, gspec.id, oracle.h, C.byref(mp), baseline.h, C.byref(mb), C.byref(sp), seed,
+                                                            C.byref(self.h)))
         else:
             ctx.check(lib().az_selfplay_create_duel(ctx.h, gspec.id, oracle.h, baseline.h, C.byref(mp), C.byref(sp), seed,
                                                     C.byref(self.h)))
@@ -641,11 +655,11 @@ class Comm:
             self.h = None
 
 
-def simulate(ctx, gspec, oracle, params, seed=0, game_simulated=None, first_game_index=0, baseline=None, gamma=None):
+def simulate(ctx, gspec, oracle, params, seed=0, game_simulated=None, first_game_index=0, baseline=None, gamma=None, baseline_mcts=None):
     """simulate(simulator, gspec, p; game_simulated): returns the fetched samples + measurements (self-play simulator,
     src/training.jl:275-300); with `gamma` also the rewards_and_redundancy outputs of the record_trace simulators."""
     import time
-    sp = SelfPlay(ctx, gspec, oracle, params, seed, baseline=baseline)
+    sp = SelfPlay(ctx, gspec, oracle, params, seed, baseline=baseline, baseline_mcts=baseline_mcts)
     try:
         sp.start(params.sim.num_games, first_game_index)
         seen = 0

@@ -122,6 +122,25 @@ struct OracleNet : az_net {
     return AZ_OK;
   }
 };
+// MCTS.RolloutOracle (src/mcts.jl:27-60): the "vanilla MCTS" baseline of the benchmark duels (Benchmark.MctsRollouts,
+// src/benchmark.jl:134-147)
+template <class G>
+struct RolloutNet : az_net {
+  double gamma = 1.0;
+  uint64_t seed = 0;
+  int eval(const AzEnv* envs, const int32_t* n_rows, int max_rows, float* P, float* V) override {
+    az_k_rollout<G><<<(max_rows + 63) / 64, 64, 0, ctx->stream>>>(envs, n_rows, P, V, gamma, seed);
+    ctx->launches++;
+    return AZ_OK;
+  }
+};
+template <class G> static int g_make_rollout(az_ctx* ctx, double gamma, uint64_t seed, az_net** out) {
+  if (G::STOCHASTIC) AZ_FAIL(ctx, AZ_EUNSUPPORTED, "az_net_create_rollout: stochastic environments are not supported");
+  RolloutNet<G>* n = new RolloutNet<G>();
+  n->ctx = ctx; n->kind = AZ_NET_ROLLOUT; n->game = G::ID; n->gamma = gamma; n->seed = seed;
+  *out = n;
+  return AZ_OK;
+}
 template <class G> static int g_make_oracle(az_ctx* ctx, int kind, az_net** out) {
   az_net* n = nullptr;
   if (kind == AZ_NET_UNIFORM) n = new OracleNet<G, 0>();
@@ -173,7 +192,7 @@ struct Mcts : az_mcts {
     if (s == AZ_OK) allocs.push_back(*ptr);
     return s;
   }
-  int create(az_ctx* c, az_net* n, const az_mcts_params* params, int S, int cap_nodes, az_net* n2 = nullptr) {
+  int create(az_ctx* c, az_net* n, const az_mcts_params* params, int S, int cap_nodes, az_net* n2 = nullptr, const az_mcts_params* params1 = nullptr) {
     ctx = c; net = n; net2 = n2; game = G::ID; mp = *params;
     if (n2 && (S & 1)) AZ_FAIL(ctx, AZ_EINVAL, "duel pool: the number of trees must be even");
     if (n2 && n2->game != G::ID) AZ_FAIL(ctx, AZ_EINVAL, "az_mcts_create: second oracle was built for another game");
@@ -186,9 +205,13 @@ struct Mcts : az_mcts {
     p.S = S; p.cap_mask = (uint32_t)(cap - 1); p.maxd = G::MAX_PLIES + 1;
     p.max_sims_per_call = 1;
     if (const char* e = getenv("AZ_NO_GRAPH")) use_graph = !(e[0] == '1');
+    if (const char* e = getenv("AZ_FUSE_TREE")) fuse_tree = !(e[0] == '0');
     if (const char* e = getenv("AZ_MAX_SIMS_PER_CALL")) p.max_sims_per_call = std::max(1, atoi(e));
     p.c.gamma = params->gamma; p.c.cpuct = params->cpuct; p.c.eps = params->dirichlet_noise_eps;
     p.c.alpha = params->dirichlet_noise_alpha; p.c.prior_temp = params->prior_temperature;
+    const az_mcts_params* q1 = params1 ? params1 : params;   // duel: player 1's MctsPlayer may differ (src/benchmark.jl:78-99)
+    p.c1.gamma = q1->gamma; p.c1.cpuct = q1->cpuct; p.c1.eps = q1->dirichlet_noise_eps;
+    p.c1.alpha = q1->dirichlet_noise_alpha; p.c1.prior_temp = q1->prior_temperature;
     AZ_TRY(ctx, alloc(&p.nodes, (size_t)S * cap * G::LANES));
     AZ_TRY(ctx, alloc(&p.root, S)); AZ_TRY(ctx, alloc(&p.tag, S)); AZ_TRY(ctx, alloc(&p.node_count, S));
     AZ_TRY(ctx, alloc(&p.total_sims, S)); AZ_TRY(ctx, alloc(&p.total_nodes, S)); AZ_TRY(ctx, alloc(&p.sims_done, S));
@@ -232,6 +255,8 @@ struct Mcts : az_mcts {
   int64_t graph_launches = 0;   // kernels per replay
   uint64_t graph_net_gen = 0;
   bool use_graph = true, graph_broken = false;
+  bool run_mode = false;        // inside az_mcts_run (explore-only ticks)
+  bool graph_is_fused = false;  // which tick body the captured graph holds
   void drop_graph() { if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; } }
   template <class Extra>
   int tick_graphed(Extra extra) {
@@ -246,6 +271,8 @@ struct Mcts : az_mcts {
     }
     const uint64_t gen_now = net->generation() + (net2 ? 0x100000000ull * net2->generation() : 0);
     if (gexec && graph_net_gen != gen_now) drop_graph();  // a network reallocated buffers / reloaded weights
+    if (gexec && graph_is_fused != (run_mode && fuse_tree)) drop_graph();
+    graph_is_fused = run_mode && fuse_tree;
     if (!gexec) {
       graph_net_gen = gen_now;
       const int64_t l0 = ctx->launches;
@@ -320,7 +347,25 @@ struct Mcts : az_mcts {
     tprof_n++;
     return AZ_OK;
   }
+  // explore-only tick (az_mcts_run): [expand + backup of the previous tick's leaves, fused with the next select] -> oracle.
+  // On the first tick nothing is pending, so the kernel is just the select; the run ends on the tick whose select finds
+  // no tree with simulations left, i.e. after the last leaves have been expanded.
+  bool fuse_tree = true;   // AZ_FUSE_TREE=0: separate select / expand kernels (the self-play order)
+  int tick_fused() {
+    AZ_CUDA(ctx, cudaMemsetAsync(p.n_leaves, 0, 4 * sizeof(int32_t), ctx->stream));
+    az_k_expand_select<G><<<groups_grid(), 128, 0, ctx->stream>>>(p);
+    if (!net2) {
+      AZ_TRY(ctx, net->eval(p.batch_env, p.n_leaves, p.S, p.batch_P, p.batch_V));
+    } else {
+      const int b1 = p.row_base1;
+      AZ_TRY(ctx, net->eval(p.batch_env, p.n_leaves, b1, p.batch_P, p.batch_V));
+      AZ_TRY(ctx, net2->eval(p.batch_env + b1, p.n_leaves + 2, b1, p.batch_P + (size_t)b1 * G::A, p.batch_V + b1));
+    }
+    ctx->launches += 1;
+    return AZ_OK;
+  }
   int tick(bool time_net) {
+    if (run_mode && fuse_tree) return tick_fused();
     AZ_CUDA(ctx, cudaMemsetAsync(p.n_leaves, 0, 4 * sizeof(int32_t), ctx->stream));
     az_k_select<G><<<groups_grid(), 128, 0, ctx->stream>>>(p);
     if (time_net) cudaEventRecord(ev[2], ctx->stream);
@@ -357,6 +402,8 @@ struct Mcts : az_mcts {
     AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     AZ_CUDA(ctx, cudaEventRecord(ev[0], ctx->stream));
     ticks = 0; ms_net = 0;
+    run_mode = true;
+    struct RunModeGuard { bool& f; ~RunModeGuard() { f = false; } } run_mode_guard{run_mode};
     // every unfinished tree completes >= 1 simulation per tick, so nsims ticks always suffice
     for (int t = 0; t < nsims + 1; t++) {
       if (profiling) AZ_TRY(ctx, tick_profiled());
@@ -476,7 +523,10 @@ struct SelfPlay : az_selfplay {
     if (s == AZ_OK) allocs.push_back(*ptr);
     return s;
   }
-  int create(az_ctx* c, az_net* net, az_net* net2, const az_mcts_params* mp, const az_sim_params* s, uint64_t seed) {
+  int create(az_ctx* c, az_net* net, az_net* net2, const az_mcts_params* mp, const az_sim_params* s, uint64_t seed, const az_mcts_params* mp1 = nullptr) {
+    if (!mp1) mp1 = mp;
+    if (mp1->temperature_n < 1 || mp1->temperature_n > AZ_MAX_SCHEDULE) { c->err = "temperature schedule: 1..8 points"; return AZ_EINVAL; }
+    if (mp1->num_iters_per_turn <= 0) { c->err = "MctsPlayer: niters > 0 (src/play.jl:162)"; return AZ_EINVAL; }
     ctx = c; game = G::ID; simp = *s;
     if (s->num_workers <= 0) AZ_FAIL(ctx, AZ_EINVAL, "SimParams: num_workers must be positive");
     if (s->batch_size > s->num_workers) AZ_FAIL(ctx, AZ_EINVAL, "batch_size <= num_workers (src/batchifier.jl:48)");
@@ -487,7 +537,7 @@ struct SelfPlay : az_selfplay {
     const int W = s->num_workers;
     const int S = net2 ? 2 * W : W;  // duel: one tree per player per worker (TwoPlayers, src/play.jl:248-252)
     int reset = s->reset_every > 0 ? s->reset_every : std::max(1, (s->num_games + W - 1) / W);
-    size_t bound = (size_t)std::min<long long>((long long)mp->num_iters_per_turn * G::MAX_PLIES * (long long)reset, G::MAX_STATES);
+    size_t bound = (size_t)std::min<long long>((long long)std::max(mp->num_iters_per_turn, mp1->num_iters_per_turn) * G::MAX_PLIES * (long long)reset, G::MAX_STATES);
     // table budget: 60 % of the memory that is free right now; Mcts::create rounds (1.25 x cap_nodes) up to a power of
     // two, so ask for at most the largest power-of-two capacity that fits the budget, less the 1.25 head room
     size_t free_b = 0, total_b = 0;
@@ -499,13 +549,15 @@ struct SelfPlay : az_selfplay {
     const size_t maxnodes = cap_fit * 4 / 5 - 8;
     int cap_nodes = (int)std::min<size_t>(std::min(bound, maxnodes), (size_t)1 << 28);
     pool.reset(new Mcts<G>());
-    int st = pool->create(ctx, net, mp, S, cap_nodes, net2);
+    int st = pool->create(ctx, net, mp, S, cap_nodes, net2, mp1);
     if (st != AZ_OK) { pool.reset(); return st; }
     pool->p.noise_seed = seed;
     sp.W = W; sp.duel = net2 ? 1 : 0; sp.alternate = s->alternate_colors ? 1 : 0; sp.flip_p = s->flip_probability;
     sp.seed = seed; sp.nsims = mp->num_iters_per_turn; sp.reset_every = s->reset_every; sp.max_plies = G::MAX_PLIES;
     sp.sched_n = mp->temperature_n;
     for (int i = 0; i < mp->temperature_n; i++) { sp.sched_xs[i] = mp->temperature_xs[i]; sp.sched_ys[i] = mp->temperature_ys[i]; }
+    sp.nsims1 = mp1->num_iters_per_turn; sp.sched1_n = mp1->temperature_n;
+    for (int i = 0; i < mp1->temperature_n; i++) { sp.sched1_xs[i] = mp1->temperature_xs[i]; sp.sched1_ys[i] = mp1->temperature_ys[i]; }
     AZ_TRY(ctx, alloc(&sp.game_of_slot, W)); AZ_TRY(ctx, alloc(&sp.move_of_slot, W)); AZ_TRY(ctx, alloc(&sp.games_on_slot, W));
     AZ_TRY(ctx, alloc(&sp.games_done, 1)); AZ_TRY(ctx, alloc(&sp.active_slots, 1));
     AZ_TRY(ctx, alloc(&sp.next_game, 1)); AZ_TRY(ctx, alloc(&sp.want_game, W));
@@ -583,7 +635,7 @@ struct SelfPlay : az_selfplay {
     if (worker.joinable()) worker.join();
     if (num_games <= 0) AZ_FAIL(ctx, AZ_EINVAL, "num_games must be positive");
     if (simp.reset_every <= 0) {
-      size_t need = (size_t)sp.nsims * G::MAX_PLIES * (size_t)((num_games + sp.W - 1) / sp.W);
+      size_t need = (size_t)std::max(sp.nsims, sp.nsims1) * G::MAX_PLIES * (size_t)((num_games + sp.W - 1) / sp.W);
       (void)need;  // overflow is detected on device and reported as AZ_ENOMEM
     }
     AZ_TRY(ctx, ensure_game_buffers(num_games));
@@ -720,9 +772,10 @@ struct SelfPlay : az_selfplay {
   }
 };
 template <class G>
-static int g_make_selfplay(az_ctx* ctx, az_net* net, az_net* net2, const az_mcts_params* mp, const az_sim_params* sp, uint64_t seed, az_selfplay** out) {
+static int g_make_selfplay(az_ctx* ctx, az_net* net, az_net* net2, const az_mcts_params* mp, const az_sim_params* sp, uint64_t seed, az_selfplay** out,
+                           const az_mcts_params* mp1 = nullptr) {
   auto* s = new SelfPlay<G>();
-  int st = s->create(ctx, net, net2, mp, sp, seed);
+  int st = s->create(ctx, net, net2, mp, sp, seed, mp1);
   if (st != AZ_OK) { delete s; return st; }
   *out = s;
   return AZ_OK;
@@ -839,6 +892,12 @@ int32_t az_net_create_oracle(az_ctx* ctx, int32_t kind, int32_t game, az_net** o
   if (!ctx || !out) return AZ_EINVAL;
   AZ_GUARD_BEGIN
   AZ_DISPATCH_GAME(game, g_make_oracle, ctx, kind, out)
+  AZ_GUARD_END(ctx)
+}
+int32_t az_net_create_rollout(az_ctx* ctx, int32_t game, double gamma, uint64_t seed, az_net** out) {
+  if (!ctx || !out) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  AZ_DISPATCH_GAME(game, g_make_rollout, ctx, gamma, seed, out)
   AZ_GUARD_END(ctx)
 }
 int32_t az_net_create_resnet(az_ctx* ctx, int32_t game, const az_resnet_hp* hp, az_net** out) {
@@ -966,6 +1025,16 @@ int32_t az_selfplay_create_duel(az_ctx* ctx, int32_t game, az_net* white, az_net
   if (white->game != game || black->game != game) AZ_FAIL(ctx, AZ_EINVAL, "az_selfplay_create_duel: oracle was built for another game");
   if (mp->num_iters_per_turn <= 0) AZ_FAIL(ctx, AZ_EINVAL, "MctsPlayer: niters > 0 (src/play.jl:162)");
   AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, white, black, mp, sp, seed, out)
+  AZ_GUARD_END(ctx)
+}
+int32_t az_selfplay_create_duel_players(az_ctx* ctx, int32_t game, az_net* white, const az_mcts_params* mp_white, az_net* black,
+                                        const az_mcts_params* mp_black, const az_sim_params* sp, uint64_t seed, az_selfplay** out) {
+  if (!ctx || !white || !black || !mp_white || !mp_black || !sp || !out) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  cudaSetDevice(ctx->device);
+  if (white->game != game || black->game != game) AZ_FAIL(ctx, AZ_EINVAL, "az_selfplay_create_duel_players: oracle was built for another game");
+  if (mp_white->num_iters_per_turn <= 0 || mp_black->num_iters_per_turn <= 0) AZ_FAIL(ctx, AZ_EINVAL, "MctsPlayer: niters > 0 (src/play.jl:162)");
+  AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, white, black, mp_white, sp, seed, out, mp_black)
   AZ_GUARD_END(ctx)
 }
 int32_t az_selfplay_export_samples(az_selfplay* s, az_samples** out) {

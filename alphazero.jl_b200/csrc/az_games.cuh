@@ -89,6 +89,7 @@ struct GameC4 {
   }
   AZ_HD static AzEnv init() { AzEnv e = {0, 0, 0}; return e; }
   static constexpr bool STOCHASTIC = false;
+  static constexpr bool HAS_PLANE = true;  // plane(e, col, row, c) gives one element of vectorize_state directly
   static constexpr long long MAX_STATES = 1ll << 40;  // no useful bound on distinct states
   AZ_HD static AzEnv play(const AzEnv& e, int a, const AzNoise&) { return play(e, a); }
   AZ_HD static AzEnv init_game(uint64_t, uint64_t) { return init(); }
@@ -190,6 +191,7 @@ struct GameTTT {
   }
   AZ_HD static AzEnv init() { AzEnv e = {0, 0, 0}; return e; }
   static constexpr bool STOCHASTIC = false;
+  static constexpr bool HAS_PLANE = false;  // plane(e, col, row, c) gives one element of vectorize_state directly
   static constexpr long long MAX_STATES = 1ll << 40;  // no useful bound on distinct states
   AZ_HD static AzEnv play(const AzEnv& e, int a, const AzNoise&) { return play(e, a); }
   AZ_HD static AzEnv init_game(uint64_t, uint64_t) { return init(); }
@@ -330,6 +332,7 @@ struct GameMancala {
     return e;
   }
   static constexpr bool STOCHASTIC = false;
+  static constexpr bool HAS_PLANE = false;  // plane(e, col, row, c) gives one element of vectorize_state directly
   static constexpr int NSYM = 0;  // no GI.symmetries declared for this game
   AZ_HD static AzEnv symmetry(const AzEnv& e, int) { return e; }
   AZ_HD static int sym_source(int, int p) { return p; }
@@ -377,6 +380,7 @@ struct GameGW {
   static constexpr int XW = 10, XH = 10, XC = 1;
   static constexpr bool ACYCLIC = false;  // a simulation may revisit a state (time is not in the key)
   static constexpr bool STOCHASTIC = true;
+  static constexpr bool HAS_PLANE = false;  // plane(e, col, row, c) gives one element of vectorize_state directly
   static constexpr int NSYM = 0;  // no GI.symmetries declared for this game
   AZ_HD static AzEnv symmetry(const AzEnv& e, int) { return e; }
   AZ_HD static int sym_source(int, int p) { return p; }

@@ -178,6 +178,7 @@ struct GemmArgs {
   int debug;             // timing experiments only (AZ_TOWER_DEBUG bitmask): 4 = no epilogue global I/O
   const float* bias;
   const float* resid32;  // EPI_CONV2
+  int lo8;               // persistent tower: 1 = low-order residual part stored as e4m3 bytes (XL8), 0 = fp16 (XL16)
   int res_lo;            // Connect-Four kernel, EPI_CONV2: 1 = the residual has a low-order part (blocks >= 1), 0 = fp16 only (block 0)
   float* out32;          // EPI_CONV2 (stream), EPI_DENSE (hidden)
   __half* out16a;        // CONV1: T, CONV2: X16, HEAD: policy features
@@ -991,7 +992,7 @@ struct Smem {
   uint8_t apad[1024];
   uint8_t epi[yr::EPI_BYTES];
   uint8_t ident[256];
-  uint64_t full[yr::ASTAGES], empty[yr::ASTAGES], tfull[yr::NACC], tempty[yr::NACC], bfull, wfree, ldone;
+  uint64_t full[yr::ASTAGES], empty[yr::ASTAGES], tfull[yr::NACC], tempty[yr::NACC], bfull[tc2::NCHUNK], wfree, ldone;
   uint32_t tmem_base;
 };
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -1002,12 +1003,33 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 __device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// two floats -> two e4m3 bytes (first argument in the LOW byte = lower address), and back
+__device__ __forceinline__ uint32_t cvt_e4m3x2(float lo_elem, float hi_elem) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi_elem), "f"(lo_elem));
+  return (uint32_t)r;
+}
+__device__ __forceinline__ float2 cvt_f32x2_e4m3x2(uint32_t two_bytes) {
+  uint32_t h2;
+  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"((uint16_t)two_bytes));
+  return __half22float2(*reinterpret_cast<__half2*>(&h2));
+}
+__device__ __forceinline__ uint4 ld_cg_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_cg_v4(void* p, uint4 v) {
+  asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+constexpr float LO8_SCALE = 16384.0f;   // lo is stored as e4m3(lo * 2^14): 4 significant bits over 17 octaves, |lo| < 0.027
 }  // namespace tw
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(yr::NUM_THREADS, 1)
 az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmXL,
                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmXo, const __grid_constant__ CUtensorMap tmTo,
-                const __grid_constant__ CUtensorMap tmXLo, GemmArgs ga, int num_layers, unsigned long long* __restrict__ done) {
+                const __grid_constant__ CUtensorMap tmXLo, uint8_t* __restrict__ xl8, GemmArgs ga, int num_layers,
+                unsigned long long* __restrict__ done) {
   using namespace tc2;
   constexpr int BN = 128, H = 6;
   constexpr int ASTAGES = yr::ASTAGES, NB = yr::NBOARD;
@@ -1018,11 +1040,15 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const bool use_lo = !(ga.debug & 8);   // AZ_TOWER_DEBUG=8 (timing experiments only): fp16-only skip stream, no low-order part
+  const bool lo8 = ga.lo8 != 0;          // low-order part of the skip stream as e4m3 bytes (default) or fp16 (AZ_LO=16)
+  const int alloc_boards = ga.alloc_rows / 42;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     for (int i = 0; i < yr::NACC; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 16); }
-    mbar_init(&s.bfull, 1); mbar_init(&s.wfree, 1); mbar_init(&s.ldone, 8);
+    for (int i = 0; i < NCHUNK; i++) mbar_init(&s.bfull[i], 1);
+    mbar_init(&s.wfree, 1); mbar_init(&s.ldone, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 64) {
@@ -1079,8 +1105,15 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         mbar_wait(&s.wfree, (uint32_t)(l - 1) & 1u);   // every MMA of layer l-1 (reads both CTAs' weights) has retired
       }
       if (elect_one()) {
-        if (leader) mbar_expect_tx(&s.bfull, 2 * NCHUNK * B_CHUNK);
-        for (int ch = 0; ch < NCHUNK; ch++) tma_load_2d_2sm(s.b[ch], &tmW, &s.bfull, ch * BK, l * 128 + (int)rank * BNH);
+        // one barrier per 8 KB weight chunk, loaded in the order the layer's first MMAs use them (K half 0 first; vertical
+        // taps ky = 2, 1, 0), so the tensor pipe restarts when the first taps have landed, not after all 144 KB
+        for (int half = 0; half < 2; half++)
+          for (int ky = 2; ky >= 0; ky--)
+            for (int kx = 0; kx < 3; kx++) {
+              const int ch = (ky * 3 + kx) * 2 + half;
+              if (leader) mbar_expect_tx(&s.bfull[ch], 2 * B_CHUNK);
+              tma_load_2d_2sm(s.b[ch], &tmW, &s.bfull[ch], ch * BK, l * 128 + (int)rank * BNH);
+            }
       }
       __syncwarp();
       if (l > 0) {
@@ -1103,7 +1136,8 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             fence_proxy_async();
             hi_ok = true;
           }
-          const int nres = (conv2 && y >= j_lo && y < j_hi) ? (l > 1 ? 4 : 2) : 0;
+          // residual stages: hi always; the low-order part rides the ring only as fp16 (lo8: the epilogue adds it)
+          const int nres = (conv2 && y >= j_lo && y < j_hi) ? ((l > 1 && use_lo && !lo8) ? 4 : 2) : 0;
           for (int q = 0; q < 2 + nres; q++) {
             bool isres; int half, part;
             yrow_stage(q, nres, isres, half, part);
@@ -1129,8 +1163,7 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       int nbase = 0;
       for (int l = 0; l < num_layers; l++) {
         const bool conv2 = (l & 1) != 0;
-        mbar_wait(&s.bfull, (uint32_t)l & 1u);
-        tcgen05_fence_after();
+        uint32_t wready = 0;   // bit ch: this layer's weight chunk ch has been waited for
         for (int u = u0; u < u1;) {
           const int g = u / H, j_lo = u - g * H, j_hi = min(u1 - g * H, H);
           const int y_lo = max(0, j_lo - 1), y_hi = min(H - 1, j_hi);
@@ -1141,13 +1174,26 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               mbar_wait(&s.tempty[n & 3], ((uint32_t)(n >> 2) & 1u) ^ 1u);
             }
             tcgen05_fence_after();
-            const int nres = (conv2 && y >= j_lo && y < j_hi) ? (l > 1 ? 4 : 2) : 0;
+            const int nres = (conv2 && y >= j_lo && y < j_hi) ? ((l > 1 && use_lo && !lo8) ? 4 : 2) : 0;
             for (int q = 0; q < 2 + nres; q++) {
               bool isres; int half, part;
               yrow_stage(q, nres, isres, half, part);
               mbar_wait(&s.full[stage], phase);
               tcgen05_fence_after();
               const uint32_t abase = smem_u32(s.a[stage]);
+              if (!isres && wready != 0x3FFFFu) {  // first uses of this layer's weight chunks (warp-uniform)
+#pragma unroll
+                for (int dj = 1; dj >= -1; dj--) {
+                  const int j = y + dj;
+                  if (j < j_lo || j >= j_hi) continue;
+#pragma unroll
+                  for (int kx = 0; kx < 3; kx++) {
+                    const int ch = ((dj + 1) * 3 + kx) * 2 + half;
+                    if (!((wready >> ch) & 1u)) { mbar_wait(&s.bfull[ch], (uint32_t)l & 1u); wready |= 1u << ch; }
+                  }
+                }
+                tcgen05_fence_after();
+              }
               if (elect_one()) {
                 if (isres) {
                   const uint32_t tmem_d = tmem_base + (uint32_t)(((nbase + (y - j_lo)) & 3) * BN);
@@ -1194,53 +1240,83 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   } else {  // ===== epilogue warps 2..9 (both CTAs) =====
     const int quarter = warp & 3;
     const int colhalf = (warp - 2) >> 2;
-    const int sw = (lane >> 2) & 1;
-    uint8_t* tiles = s.epi + (warp - 2) * 2048;
-    int ring = 0;
+    uint8_t* tile = s.epi + (warp - 2) * 2048;   // one 32-row x 64-byte tile per warp (SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3)
+    const int sw = (lane >> 1) & 3;
     int n = 0;
     for (int l = 0; l < num_layers; l++) {
       const bool conv2 = (l & 1) != 0;
+      const bool want_lo = conv2 && l != num_layers - 1 && use_lo;   // nobody reads the low-order part of the last block's output
       const float* __restrict__ bias_g = ga.bias + (size_t)l * 128 + colhalf * 64;
       const CUtensorMap* mO = conv2 ? &tmXo : &tmTo;
       for (int u = u0; u < u1; u++, n++) {
         const int g = u / H, j = u - g * H;
         const int bq = g * 2 * NB + (int)rank * NB + quarter * 4;
         const int slot = n & 3;
+        // lo8 mode: the low-order part of the skip stream never touches the tensor core or the TMA ring.  This thread owns
+        // output row (board bq + lane / 8, x = lane % 8) and channels colhalf*64 .. +63 in EVERY layer, so the 64 e4m3 bytes it
+        // wrote for this cell two layers ago (st.global.cg, L2) are the ones it needs now: plain 16-byte loads that bypass L1.
+        const bool cell_ok = (lane & 7) < 7 && (bq + (lane >> 3)) < alloc_boards;
+        uint8_t* l8p = xl8 + ((((size_t)(bq + (lane >> 3)) * H + j) * 7 + (lane & 7)) * 128 + colhalf * 64);
+        uint4 r8[4];   // low-order bytes of the block input (residual), loaded while the MMAs of this row finish
+        const bool add_lo = conv2 && l > 1 && use_lo && lo8;
+        if (add_lo && cell_ok) {
+#pragma unroll
+          for (int c = 0; c < 4; c++) r8[c] = tw::ld_cg_v4(l8p + c * 16);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; c++) r8[c] = make_uint4(0, 0, 0, 0);
+        }
+        const uint32_t* r8w = reinterpret_cast<const uint32_t*>(r8);
         mbar_wait(&s.tfull[slot], (uint32_t)(n >> 2) & 1u);
         tcgen05_fence_after();
+        uint4 l8[4];   // lo8 mode: this row's 64 low-order bytes of the OUTPUT, filled over the two 32-column steps
+        uint32_t* l8w = reinterpret_cast<uint32_t*>(l8);
 #pragma unroll
-        for (int sc = 0; sc < 4; sc++) {
-          const int col = colhalf * 64 + sc * 16;
-          uint32_t v[16];
-          tmem_ld16(tmem_base + slot * BN + col + ((uint32_t)(quarter * 32) << 16), v);
-          uint4 oh4[2], ol4[2];
+        for (int sc = 0; sc < 2; sc++) {
+          const int col = colhalf * 64 + sc * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + slot * BN + col + ((uint32_t)(quarter * 32) << 16), v);
+          uint4 oh4[4], ol4[4];
           __half2* oh = reinterpret_cast<__half2*>(oh4);
           __half2* ol = reinterpret_cast<__half2*>(ol4);
 #pragma unroll
-          for (int jj = 0; jj < 8; jj++) {
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_g + sc * 16) + jj);
-            const float x0 = fmaxf(__uint_as_float(v[2 * jj]) + bb.x, 0.f);
-            const float x1 = fmaxf(__uint_as_float(v[2 * jj + 1]) + bb.y, 0.f);
+          for (int jj = 0; jj < 16; jj++) {
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_g + sc * 32) + jj);
+            float a0 = __uint_as_float(v[2 * jj]), a1 = __uint_as_float(v[2 * jj + 1]);
+            if (add_lo) {  // + lo of the block input: e4m3 bytes (2 jj, 2 jj + 1) of this 32-channel step, scaled by 2^-14
+              const float2 lo = tw::cvt_f32x2_e4m3x2((r8w[sc * 8 + (jj >> 1)] >> ((jj & 1) * 16)) & 0xFFFFu);
+              a0 += lo.x * (1.0f / tw::LO8_SCALE);
+              a1 += lo.y * (1.0f / tw::LO8_SCALE);
+            }
+            const float x0 = fmaxf(a0 + bb.x, 0.f);
+            const float x1 = fmaxf(a1 + bb.y, 0.f);
             const __half2 h = __floats2half2_rn(x0, x1);
             oh[jj] = h;
-            if (conv2) {  // lo = fp16(y - hi): hi + lo carries ~22 significand bits of the skip path
+            if (want_lo) {  // lo = y - hi: hi + lo carries ~22 (fp16 lo) / ~15 (e4m3 lo) significant bits of the skip path
               const float2 hf = __half22float2(h);
-              ol[jj] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+              if (lo8) {
+                const uint32_t b2 = tw::cvt_e4m3x2((x0 - hf.x) * tw::LO8_SCALE, (x1 - hf.y) * tw::LO8_SCALE);
+                if (jj & 1) l8w[sc * 8 + (jj >> 1)] |= b2 << 16; else l8w[sc * 8 + (jj >> 1)] = b2;
+              } else {
+                ol[jj] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+              }
             }
           }
-          const int nparts = conv2 ? 2 : 1;
+          const int nparts = (want_lo && !lo8) ? 2 : 1;
           for (int part = 0; part < nparts; part++) {
-            uint8_t* tile = tiles + ring * 1024;
-            ring ^= 1;
-            if (lane == 0) tma_store_wait_read<1>();
+            if (lane == 0) tma_store_wait_read<0>();  // the previous store has finished reading the tile
             __syncwarp();
             const uint4* o = part ? ol4 : oh4;
-            *reinterpret_cast<uint4*>(tile + lane * 32 + ((0 ^ sw) << 4)) = o[0];
-            *reinterpret_cast<uint4*>(tile + lane * 32 + ((1 ^ sw) << 4)) = o[1];
+#pragma unroll
+            for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(tile + lane * 64 + ((c ^ sw) << 4)) = o[c];
             fence_proxy_async();
             __syncwarp();
             if (lane == 0 && !(ga.debug & 4)) { tma_store_4d(part ? &tmXLo : mO, tile, col, 0, j, bq); tma_store_commit(); }
           }
+        }
+        if (want_lo && lo8 && cell_ok && !(ga.debug & 4)) {
+#pragma unroll
+          for (int c = 0; c < 4; c++) tw::st_cg_v4(l8p + c * 16, l8[c]);
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -1364,6 +1440,10 @@ __global__ void __launch_bounds__(256) az_k_finalize(const AzEnv* __restrict__ e
 // against the MMA (4 x tcgen05.mma M=128,N=128,K=16 per tile) and the epilogue of the previous tile.  Saves the 15 MB
 // im2col write + read and one launch per evaluation (the im2col + GEMM pair took 13 + 17 us at ~2750 leaves).
 // ------------------------------------------------------------------------------------------------
+template <class G, bool HP = G::HAS_PLANE> struct AzPlane { __device__ static float get(const AzEnv&, int, int, int) { return 0.0f; } };
+template <class G> struct AzPlane<G, true> { __device__ static float get(const AzEnv& e, int col, int row, int c) { return G::plane(e, col, row, c); } };
+template <class G> __device__ __forceinline__ float az_plane_of(const AzEnv& e, int col, int row, int c) { return AzPlane<G>::get(e, col, row, c); }
+
 namespace st {
 constexpr int NUM_THREADS = 320;   // B loader, MMA, 4 builder warps, 4 epilogue warps
 constexpr int NBMAX = 12;          // boards a 128-row tile can touch
@@ -1371,6 +1451,7 @@ template <int NX>
 struct Smem {
   uint8_t b[128 * 128];            // weights Wt[co][64]
   uint8_t a[2][128 * 128];
+  uint8_t epi[4][2048];            // one 32-row x 64-byte store tile per epilogue warp (SWIZZLE_64B)
   float xs[2][NBMAX][NX];
   uint64_t bfull, afull[2], aempty[2], tfull[2], tempty[2];
   uint32_t tmem_base;
@@ -1380,7 +1461,7 @@ struct Smem {
 
 template <class G>
 __global__ void __launch_bounds__(st::NUM_THREADS, 1)
-az_k_stem(const AzEnv* __restrict__ envs, const __grid_constant__ CUtensorMap tmW, GemmArgs ga, int dense) {
+az_k_stem(const AzEnv* __restrict__ envs, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, GemmArgs ga, int dense) {
   constexpr int W = G::XW, H = G::XH, C = G::XC, NX = W * H * C, BN = 128, F = 128;
   using SmemT = st::Smem<NX>;
   extern __shared__ uint8_t smem_st[];
@@ -1441,12 +1522,12 @@ az_k_stem(const AzEnv* __restrict__ envs, const __grid_constant__ CUtensorMap tm
       const int r0 = tile * 128;
       const int b_first = r0 / BS;
       const int b_last = min((r0 + 127) / BS, n_boards - 1);
-      // vectorize_state of the tile's boards: board slot k is done by lane k / 4 of builder warp k % 4
-      {
+      if (!G::HAS_PLANE) {
+        // vectorize_state of the tile's boards: board slot k is done by lane k / 4 of builder warp k % 4
         const int k = (t & 31) * 4 + (t >> 5);
         if (k <= b_last - b_first && k < st::NBMAX) G::vectorize(envs[b_first + k], s.xs[buf][k]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       const int r = r0 + t;
       uint4 chunk[8];
       __half* hv = reinterpret_cast<__half*>(chunk);
@@ -1456,11 +1537,14 @@ az_k_stem(const AzEnv* __restrict__ envs, const __grid_constant__ CUtensorMap tm
         const int b = r / BS, rr = r - b * BS, yy = rr / RS, xx = rr - yy * RS;
         if (yy < H && xx < W) {
           const float* x = s.xs[buf][b - b_first];
+          AzEnv eb;
+          if (G::HAS_PLANE) eb = envs[b];
 #pragma unroll
           for (int k = 0; k < 9 * C; k++) {   // k = tap*C + c; Flux Conv is a true convolution: tap (kx,ky) reads (x + 1 - kx, y + 1 - ky)
             const int tap = k / C, c = k % C, ky = tap / 3, kx = tap % 3;
             const int ix = xx + 1 - kx, iy = yy + 1 - ky;
-            if (ix >= 0 && ix < W && iy >= 0 && iy < H) hv[k] = __float2half_rn(x[ix + W * iy + W * H * c]);
+            if (ix >= 0 && ix < W && iy >= 0 && iy < H)
+              hv[k] = __float2half_rn(G::HAS_PLANE ? az_plane_of<G>(eb, ix, iy, c) : x[ix + W * iy + W * H * c]);
           }
         }
       }
@@ -1471,14 +1555,19 @@ az_k_stem(const AzEnv* __restrict__ envs, const __grid_constant__ CUtensorMap tm
       mbar_arrive(&s.afull[buf]);   // (xs[buf] is rewritten two tiles later, i.e. after the next tile's bar.sync: every row is built by then)
     }
   } else if (warp >= 6) {  // ===== epilogue warps 6..9: TMEM lane quarter = warp % 4 =====
+    // fp16 rows leave through 32-row x 64-byte SWIZZLE_64B tiles and TMA bulk-tensor stores (a row-per-thread STG epilogue
+    // touches 32 different 128-byte lines per warp instruction and is LSU-tag bound: it took 3/4 of the stem's time)
     const int quarter = warp & 3;
+    uint8_t* tile = s.epi[quarter];
+    const int sw = (lane >> 1) & 3;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+    for (int tile_i = blockIdx.x; tile_i < num_tiles; tile_i += gridDim.x, it++) {
       const int buf = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       mbar_wait(&s.tfull[buf], ph);
       tcgen05_fence_after();
-      const int p = tile * 128 + quarter * 32 + lane;
+      const int p0 = tile_i * 128 + quarter * 32;
+      const int p = p0 + lane;
       const int rr = p % ga.g.board_rows;
       const bool valid = (p < rows_used) && (rr < ga.g.valid_rows) && ((rr % ga.g.row_stride) != ga.g.wcols);
       const bool in_alloc = p < ga.alloc_rows;
@@ -1489,8 +1578,7 @@ az_k_stem(const AzEnv* __restrict__ envs, const __grid_constant__ CUtensorMap tm
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) x[j] = valid ? fmaxf(__uint_as_float(v[j]) + s.bias[c * 32 + j], 0.0f) : 0.0f;
-        if (!in_alloc) continue;
-        if (ga.out32 != nullptr) {
+        if (ga.out32 != nullptr && in_alloc) {
           float4* op = reinterpret_cast<float4*>(ga.out32 + (size_t)p * F + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; j++) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
@@ -1499,14 +1587,20 @@ az_k_stem(const AzEnv* __restrict__ envs, const __grid_constant__ CUtensorMap tm
         __half2* oh = reinterpret_cast<__half2*>(o);
 #pragma unroll
         for (int j = 0; j < 16; j++) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-        uint4* op = reinterpret_cast<uint4*>(ga.out16a + (size_t)p * F + c * 32);
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 4; j++) op[j] = o[j];
+        for (int q = 0; q < 4; q++) *reinterpret_cast<uint4*>(tile + lane * 64 + ((q ^ sw) << 4)) = o[q];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && p0 < ga.alloc_rows) { tma_store_2d(&tmO, tile, c * 32, p0); tma_store_commit(); }   // rows past the allocation are clipped
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.tempty[buf]);
     }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -1758,7 +1852,11 @@ struct ResNetImpl : az_net {
   std::vector<CUtensorMap> mapW2;        // 64co x 64k weight boxes
   // y-row tower: 4-D (channel, x, y, board) views of the dense activations
   CUtensorMap map4X{}, map4T{}, map4XL{};        // loads: box (64 ch, 8 x, 1 y, 16 boards), SWIZZLE_128B, zero fill outside
-  CUtensorMap map4Xo{}, map4To{}, map4XLo{};     // stores: box (16 ch, 8 x, 1 y, 4 boards), SWIZZLE_32B
+  CUtensorMap map4Xo{}, map4To{}, map4XLo{};     // stores: box (16 ch, 8 x, 1 y, 4 boards), SWIZZLE_32B (per-layer kernels)
+  uint8_t* d_xl8 = nullptr;                        // persistent tower, lo8 mode: low-order part of the block outputs as e4m3(lo * 2^14)
+  bool lo8 = true;                                 // AZ_LO=16: keep the low-order part in fp16 (XL16) like the per-layer kernels
+  CUtensorMap mapXo64{};                           // stem stores: 2-D [rows][128] fp16, box (32 ch, 32 rows), SWIZZLE_64B
+  CUtensorMap map4Xo64{}, map4To64{}, map4XLo64{};  // stores of the persistent kernel: box (32 ch, 8 x, 1 y, 4 boards), SWIZZLE_64B
   static constexpr bool C4_TOWER = (W + 1) == 8 && H == 6;
   size_t smem_2sm = 0, smem_yrow = 0;
   ConvGeom geom{};
@@ -1859,6 +1957,7 @@ struct ResNetImpl : az_net {
     { const char* e = getenv("AZ_FUSED"); fused = !(e && e[0] == '0'); }
     { const char* e = getenv("AZ_TOWER"); persistent = !(e && e[0] == 'l'); }          // AZ_TOWER=layer
     { const char* e = getenv("AZ_TOWER_COOP"); coop_launch = !(e && e[0] == '0'); }    // AZ_TOWER_COOP=0: plain launch
+    { const char* e = getenv("AZ_LO"); lo8 = !(e && e[0] == '1'); }                    // AZ_LO=16: fp16 low-order residual part
     if (cudaMalloc((void**)&d_done, 256 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); ctx->err = "cudaMalloc (tower flags) failed"; return AZ_ENOMEM; }
     cudaMemset(d_done, 0, 256 * sizeof(unsigned long long));
     return AZ_OK;
@@ -1889,7 +1988,7 @@ struct ResNetImpl : az_net {
   }
   void free_act() {
     cudaFree(d_x32); cudaFree(d_hid); cudaFree(d_x16); cudaFree(d_t16); cudaFree(d_hp); cudaFree(d_hv); cudaFree(d_x0); cudaFree(d_logit);
-    cudaFree(d_xl16);
+    cudaFree(d_xl16); cudaFree(d_xl8); d_xl8 = nullptr;
     d_x32 = d_hid = d_logit = nullptr; d_x16 = d_t16 = d_hp = d_hv = d_x0 = d_xl16 = nullptr;
   }
   ~ResNetImpl() override { free_weights(); free_act(); cudaFree(d_done); for (auto e : pev) cudaEventDestroy(e); }
@@ -2000,14 +2099,16 @@ struct ResNetImpl : az_net {
     return AZ_OK;
   }
   // dense activations [boards][H][W][128] fp16 as a 4-D tensor (channel, x, y, board); box = (bc, bx, 1, bb)
-  int make_map_4d(az_ctx* c, CUtensorMap* m, void* base, int boards, uint32_t bc, uint32_t bx, uint32_t bb, CUtensorMapSwizzle swz) {
+  int make_map_4d(az_ctx* c, CUtensorMap* m, void* base, int boards, uint32_t bc, uint32_t bx, uint32_t bb, CUtensorMapSwizzle swz,
+                  bool u8 = false) {
     PFN_encodeTiled fn = get_encode_fn();
     if (!fn) { c->err = "cuTensorMapEncodeTiled not available"; return AZ_ECUDA; }
+    const cuuint64_t eb = u8 ? 1 : 2;
     cuuint64_t dims[4] = {(cuuint64_t)F, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)boards};
-    cuuint64_t strides[3] = {(cuuint64_t)F * 2, (cuuint64_t)W * F * 2, (cuuint64_t)W * H * F * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)F * eb, (cuuint64_t)W * F * eb, (cuuint64_t)W * H * F * eb};
     cuuint32_t box[4] = {bc, bx, 1, bb};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+    CUresult r = fn(m, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { c->err = "cuTensorMapEncodeTiled (4-D) failed: " + std::to_string((int)r); return AZ_ECUDA; }
     return AZ_OK;
@@ -2034,6 +2135,7 @@ struct ResNetImpl : az_net {
     AZ_TRY2(make_map_2d(ctx, &mapT2, d_t16, F, alloc_rows, F * 2, tc2::BK, tc2::AROWS));
     AZ_TRY2(make_map_2d(ctx, &mapTo, d_t16, F, alloc_rows, F * 2, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
     AZ_TRY2(make_map_2d(ctx, &mapXo, d_x16, F, alloc_rows, F * 2, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
+    AZ_TRY2(make_map_2d(ctx, &mapXo64, d_x16, F, alloc_rows, F * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     if (!need_x32) {
       AZ_TRY2(make_map_2d(ctx, &mapXr, d_x16, F, alloc_rows, F * 2, tc2::BK, tc2::BM));
       AZ_TRY2(make_map_2d(ctx, &mapXLr, d_xl16, F, alloc_rows, F * 2, tc2::BK, tc2::BM));
@@ -2048,6 +2150,11 @@ struct ResNetImpl : az_net {
       AZ_TRY2(make_map_4d(ctx, &map4Xo, d_x16, alloc_boards, 16, 8, 4, s32));
       AZ_TRY2(make_map_4d(ctx, &map4To, d_t16, alloc_boards, 16, 8, 4, s32));
       AZ_TRY2(make_map_4d(ctx, &map4XLo, d_xl16, alloc_boards, 16, 8, 4, s32));
+      const CUtensorMapSwizzle s64 = CU_TENSOR_MAP_SWIZZLE_64B;
+      AZ_TRY2(make_map_4d(ctx, &map4Xo64, d_x16, alloc_boards, 32, 8, 4, s64));
+      AZ_TRY2(make_map_4d(ctx, &map4To64, d_t16, alloc_boards, 32, 8, 4, s64));
+      AZ_TRY2(make_map_4d(ctx, &map4XLo64, d_xl16, alloc_boards, 32, 8, 4, s64));
+      AZ_TRY2(dmalloc(&d_xl8, (size_t)alloc_rows * F));
     }
     act_boards = max_boards;
     return AZ_OK;
@@ -2063,7 +2170,9 @@ struct ResNetImpl : az_net {
     if (coop_launch) { at[na].id = cudaLaunchAttributeCooperative; at[na].val.cooperative = 1; na++; }
     cfg.attrs = at; cfg.numAttrs = na;
     const int L = 2 * hp.num_blocks;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, az_k_tower_yrow, map4X, map4T, map4XL, mapWall, map4Xo, map4To, map4XLo, ga, L, d_done);
+    GemmArgs g2 = ga;
+    g2.lo8 = lo8 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, az_k_tower_yrow, map4X, map4T, map4XL, mapWall, map4Xo64, map4To64, map4XLo64, d_xl8, g2, L, d_done);
     if (e != cudaSuccess) { ctx->err = std::string("persistent tower launch: ") + cudaGetErrorString(e); cudaGetLastError(); return AZ_ECUDA; }
     return AZ_OK;
   }
@@ -2086,7 +2195,7 @@ struct ResNetImpl : az_net {
     ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.debug = 0;
     ga.gemm_k = 1; ga.kblocks = 1; ga.bias = d_bstem; ga.out16a = d_x16; ga.out32 = c4_fast ? nullptr : d_x32;
     if (fused) {
-      launch_pdl(az_k_stem<G>, grid, st::NUM_THREADS, smem_stem, st, envs, mapWstem, ga, dense ? 1 : 0);
+      launch_pdl(az_k_stem<G>, grid, st::NUM_THREADS, smem_stem, st, envs, mapWstem, mapXo64, ga, dense ? 1 : 0);
     } else {
       az_k_im2col<G><<<(max_rows + 3) / 4, 128, 0, st>>>(envs, n_rows, d_x0, dense ? 1 : 0);
       launch_pdl(az_k_gemm_tc<128, tc::EPI_CONV1>, grid, tc::NUM_THREADS, smem128, st, mapX0, mapWstem, ga);

@@ -14,7 +14,7 @@
 #define AZ_HD __host__ __device__ __forceinline__
 #endif
 
-enum { AZ_PURPOSE_DIRICHLET = 0, AZ_PURPOSE_CATEGORICAL = 1, AZ_PURPOSE_SYMMETRY = 2, AZ_PURPOSE_ENV = 3, AZ_PURPOSE_POSITION = 4 };
+enum { AZ_PURPOSE_DIRICHLET = 0, AZ_PURPOSE_CATEGORICAL = 1, AZ_PURPOSE_SYMMETRY = 2, AZ_PURPOSE_ENV = 3, AZ_PURPOSE_POSITION = 4, AZ_PURPOSE_ROLLOUT = 5 };
 
 AZ_HD void az_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);

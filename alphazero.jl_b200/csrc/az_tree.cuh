@@ -62,8 +62,10 @@ struct AzPool {
   uint64_t noise_seed;  // stochastic environments: in-tree noise stream = (noise_seed, noise_game[slot], noise_move[slot], sim, depth)
   int64_t* noise_game;  // [S]
   int32_t* noise_move;  // [S]
-  AzMctsConst c;
+  AzMctsConst c;        // MCTS constants of player 0 (every tree outside a duel)
+  AzMctsConst c1;       // duel: constants of player 1's trees (odd slots); TwoPlayers may pair two different MctsPlayers
 };
+__device__ __forceinline__ const AzMctsConst& az_c(const AzPool& p, int slot) { return (p.duel && (slot & 1)) ? p.c1 : p.c; }
 
 #define AZ_KEYB_MASK ((1ull << 57) - 1)
 
@@ -109,7 +111,7 @@ __device__ __forceinline__ void az_backup(const AzPool& p, int slot, int lane, u
   for (int j = depth - 1; j >= 0; j--) {
     uint32_t meta = pm[j];
     if (meta >> 8) q = -q;
-    q = pr[j] + p.c.gamma * q;
+    q = pr[j] + az_c(p, slot).gamma * q;
     bool mine = G::ACYCLIC ? ((j % L) == lane) : (lane == 0);
     if (mine) {
       uint4* addr = tab + (size_t)pn[j] * L + 1 + (meta & 0xFF);
@@ -125,14 +127,9 @@ __device__ __forceinline__ void az_backup(const AzPool& p, int slot, int lane, u
 
 // ---- select: run simulations until a leaf needs the oracle or the budget is spent (src/mcts.jl:199-226,239-245) ----
 template <class G>
-__global__ void __launch_bounds__(128) az_k_select(AzPool p) {
+__device__ __forceinline__ void az_select_slot(const AzPool& p, const int slot, const int lane) {
   constexpr int L = G::LANES;
   constexpr int A = G::A;
-  // one slot per WARP: slots in the same warp would serialise on their divergent loop trip counts (4 dependent
-  // pointer chains back to back instead of overlapped); lanes >= L of each warp retire immediately
-  int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (slot >= p.S || lane >= L) return;
   unsigned gm = az_group_mask<L>();
   if (!p.status[slot] || p.pending[slot]) return;
   int sims_done = p.sims_done[slot];
@@ -188,12 +185,12 @@ __global__ void __launch_bounds__(128) az_k_select(AzPool p) {
       double score = __longlong_as_double((long long)0xFFF0000000000000ull);  // -inf
       if (is_edge) {
         double Pd = (double)ln.e.P;
-        if (isroot && p.c.eps != 0.0) {
+        if (isroot && az_c(p, slot).eps != 0.0) {
           int idx = __popc(legal & ((1u << a) - 1u));
-          Pd = (1.0 - p.c.eps) * Pd + p.c.eps * p.eta[(size_t)slot * A + idx];
+          Pd = (1.0 - az_c(p, slot).eps) * Pd + az_c(p, slot).eps * p.eta[(size_t)slot * A + idx];
         }
         double sq = sqrt((double)ntot);
-        score = ln.e.W / (double)(n > 1 ? n : 1) + ((p.c.cpuct * Pd) * sq) / (double)(n + 1);
+        score = ln.e.W / (double)(n > 1 ? n : 1) + ((az_c(p, slot).cpuct * Pd) * sq) / (double)(n + 1);
       }
       int best = lane;
 #pragma unroll
@@ -228,6 +225,19 @@ __global__ void __launch_bounds__(128) az_k_select(AzPool p) {
   }
 }
 
+template <class G>
+__global__ void __launch_bounds__(128) az_k_select(AzPool p) {
+  // one slot per WARP: slots in the same warp would serialise on their divergent loop trip counts (4 dependent
+  // pointer chains back to back instead of overlapped); lanes >= L of each warp retire immediately.
+  // Tried in round 2 and reverted: keeping lanes [L, L + A) alive as helpers that compute every child's state and
+  // prefetch its home line into L2 while the group waits for the parent's line -- 29.2 instead of 26.7 us per tick
+  // (profiles/r02d): the chain is bound by the f64 divide / sqrt / play / hash work per level, not by the line loads.
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slot >= p.S || lane >= G::LANES) return;
+  az_select_slot<G>(p, slot, lane);
+}
+
 // Util.apply_temperature on the prior (src/util.jl:98-110, src/mcts.jl:157-161); sequential like the reference
 template <int A>
 __device__ __forceinline__ void az_prior_temperature(float* P, uint32_t legal, double tau) {
@@ -253,14 +263,9 @@ __device__ __forceinline__ void az_prior_temperature(float* P, uint32_t legal, d
 
 // ---- expand + backup: insert the evaluated leaf (init_state_info, src/mcts.jl:157-174) and back its value up ----
 template <class G>
-__global__ void __launch_bounds__(128) az_k_expand_backup(AzPool p) {
+__device__ __forceinline__ void az_expand_slot(const AzPool& p, const int slot, const int lane) {
   constexpr int L = G::LANES;
   constexpr int A = G::A;
-  // one slot per WARP: slots in the same warp would serialise on their divergent loop trip counts (4 dependent
-  // pointer chains back to back instead of overlapped); lanes >= L of each warp retire immediately
-  int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (slot >= p.S || lane >= L) return;
   unsigned gm = az_group_mask<L>();
   if (!p.pending[slot]) return;
   const int row = p.leaf_row[slot];
@@ -273,10 +278,10 @@ __global__ void __launch_bounds__(128) az_k_expand_backup(AzPool p) {
   const int a = lane - 1;
   float P = 0.0f;
   if (a >= 0 && a < A && ((legal >> a) & 1u)) P = p.batch_P[(size_t)row * A + a];
-  if (p.c.prior_temp != 1.0) {
+  if (az_c(p, slot).prior_temp != 1.0) {
     float Pv[A];
     for (int i = 0; i < A; i++) Pv[i] = __shfl_sync(gm, P, i + 1, L);
-    az_prior_temperature<A>(Pv, legal, p.c.prior_temp);
+    az_prior_temperature<A>(Pv, legal, az_c(p, slot).prior_temp);
     if (a >= 0 && a < A) P = Pv[a];
   }
   const float V = p.batch_V[row];
@@ -298,6 +303,68 @@ __global__ void __launch_bounds__(128) az_k_expand_backup(AzPool p) {
     p.pending[slot] = 0;
     atomicAdd((unsigned long long*)p.expansions, 1ull);
   }
+}
+
+template <class G>
+__global__ void __launch_bounds__(128) az_k_expand_backup(AzPool p) {
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slot >= p.S || lane >= G::LANES) return;
+  az_expand_slot<G>(p, slot, lane);
+}
+// expand + backup of the evaluated leaf, then straight on to the tree's next simulation (explore! loop, src/mcts.jl:239-245).
+// Both kernels are bound by their LONGEST per-tree chain; fused, a launch lasts max_i(expand_i + select_i) instead of
+// max_i(expand_i) + max_i(select_i), and one launch per tick disappears.  Used by az_mcts_run; the self-play loop keeps the
+// two kernels apart because az_k_move runs between them.
+template <class G>
+__global__ void __launch_bounds__(128) az_k_expand_select(AzPool p) {
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slot >= p.S || lane >= G::LANES) return;
+  az_expand_slot<G>(p, slot, lane);
+  __syncwarp(az_group_mask<G::LANES>());   // lane 0's updates of the slot's scalars (pending, sims_done) are visible to the group
+  az_select_slot<G>(p, slot, lane);
+}
+
+// ---- MCTS.RolloutOracle (src/mcts.jl:27-60): uniform prior, value = discounted return of ONE random playout from the state.
+// Julia's global rand() cannot be reproduced, so the playout's action draws come from the Philox stream keyed by
+// (seed, hash of the state, ply of the playout): the oracle is a deterministic function of the state, identical on the CPU
+// oracle (oracle/az_oracle.c oz_rollout_oracle) and here.  Rewards are folded from the end exactly like the recursion
+// `wr + gamma * rollout!(game, gamma)` (:42-50).  One thread per leaf (divergent playouts of <= MAX_PLIES steps).
+template <class G>
+__global__ void az_k_rollout(const AzEnv* __restrict__ envs, const int32_t* __restrict__ n_rows, float* __restrict__ P,
+                             float* __restrict__ V, double gamma, uint64_t seed) {
+  constexpr int A = G::A;
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= *n_rows) return;
+  AzEnv env = envs[row];
+  {
+    const uint32_t legal = G::legal_mask(env);
+    const int n = __popc(legal);
+    const float pu = (float)(1.0 / (double)n);
+    for (int i = 0; i < A; i++) P[(size_t)row * A + i] = ((legal >> i) & 1u) ? pu : 0.0f;
+  }
+  const bool wp = G::white_playing(env);
+  const uint64_t h0 = az_splitmix(env.a ^ az_splitmix(env.b));
+  double r[G::MAX_PLIES + 1];
+  int steps = 0;
+  const AzNoise nz = {1.0, 0.0};
+  while (steps <= G::MAX_PLIES) {
+    const uint32_t legal = G::legal_mask(env);
+    const int n = __popc(legal);
+    uint32_t o[4];
+    az_philox(seed, (uint32_t)steps, AZ_PURPOSE_ROLLOUT, (uint32_t)h0, (uint32_t)(h0 >> 32), o);
+    int k = (int)(((uint64_t)o[0] * (uint64_t)n) >> 32);   // uniform over the n available actions (rand(available_actions), :43)
+    int act = 0;
+    for (int i = 0; i < A; i++)
+      if ((legal >> i) & 1u) { if (k == 0) { act = i; break; } k--; }
+    env = G::play(env, act, nz);
+    r[steps++] = G::white_reward(env);
+    if (G::terminated(env)) break;
+  }
+  double wr = r[steps - 1];
+  for (int i = steps - 2; i >= 0; i--) wr = r[i] + gamma * wr;
+  V[row] = (float)(wp ? wr : -wr);
 }
 
 // ---- built-in oracles: MCTS.RandomOracle (src/mcts.jl:62-72) and the deterministic hash pseudo-network ----
@@ -386,12 +453,16 @@ struct AzSelfPlay {
   uint64_t seed;
   int64_t first_game;     // global index of local game 0
   int32_t num_games;      // local games to play
-  int32_t nsims;
+  int32_t nsims;          // MctsPlayer.niters of player 0 (src/play.jl:156-165)
+  int32_t nsims1;         // duel: of player 1
   int32_t reset_every;
   int32_t max_plies;
-  int32_t sched_n;
+  int32_t sched_n;        // temperature schedule of player 0 (MctsPlayer.τ)
   int32_t sched_xs[8];
   double sched_ys[8];
+  int32_t sched1_n;       // duel: of player 1
+  int32_t sched1_xs[8];
+  double sched1_ys[8];
   double flip_p;          // SimParams.flip_probability (src/play.jl:305-307)
   int32_t duel;           // TwoPlayers: two trees per worker (player 0 = `white` argument of TwoPlayers, 1 = `black`)
   int32_t alternate;      // SimParams.alternate_colors (src/simulations.jl:224-230)
@@ -419,12 +490,15 @@ struct AzSelfPlay {
   uint8_t* want_game;      // [S] slot finished its game this tick and asks for the next one
 };
 
-__device__ __forceinline__ double az_schedule(const AzSelfPlay& sp, int i) {  // src/schedule.jl:64-80
+__device__ __forceinline__ double az_schedule(const AzSelfPlay& sp, int player, int i) {  // src/schedule.jl:64-80
+  const int n = player ? sp.sched1_n : sp.sched_n;
+  const int32_t* xs = player ? sp.sched1_xs : sp.sched_xs;
+  const double* ys = player ? sp.sched1_ys : sp.sched_ys;
   int pt = -1;
-  for (int k = 0; k < sp.sched_n; k++) if (sp.sched_xs[k] <= i) pt = k;
-  if (pt < 0) return sp.sched_ys[0];
-  if (pt == sp.sched_n - 1) return sp.sched_ys[sp.sched_n - 1];
-  double x0 = sp.sched_xs[pt], y0 = sp.sched_ys[pt], x1 = sp.sched_xs[pt + 1], y1 = sp.sched_ys[pt + 1];
+  for (int k = 0; k < n; k++) if (xs[k] <= i) pt = k;
+  if (pt < 0) return ys[0];
+  if (pt == n - 1) return ys[n - 1];
+  double x0 = xs[pt], y0 = ys[pt], x1 = xs[pt + 1], y1 = ys[pt + 1];
   return y0 + ((y1 - y0) / (x1 - x0)) * ((double)i - x0);
 }
 
@@ -458,13 +532,13 @@ __device__ void az_begin_move(const AzPool& p, const AzSelfPlay& sp, int w, cons
   const int slot = az_tree_of<G>(sp, w, root, game);
   p.root[slot] = root;
   p.sims_done[slot] = 0;
-  p.sims_target[slot] = sp.nsims;
+  p.sims_target[slot] = (sp.duel && (slot & 1)) ? sp.nsims1 : sp.nsims;
   p.status[slot] = 1;
   p.pending[slot] = 0;
   if (G::STOCHASTIC) { p.noise_game[slot] = game; p.noise_move[slot] = move; }
   double eta[A];
   int n = __popc(G::legal_mask(root));
-  az_dirichlet(sp.seed, (uint64_t)game, (uint32_t)move, n, p.c.alpha, eta);  // drawn even if eps == 0 (src/mcts.jl:240)
+  az_dirichlet(sp.seed, (uint64_t)game, (uint32_t)move, n, az_c(p, slot).alpha, eta);  // drawn even if eps == 0 (src/mcts.jl:240)
   for (int i = 0; i < n; i++) p.eta[(size_t)slot * A + i] = eta[i];
 }
 
@@ -616,7 +690,7 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
   for (int i = 0; i < n; i++) { pi[i] = pi[i] / (double)ntot; sum = (i == 0) ? pi[0] : sum + pi[i]; }
   for (int i = 0; i < n; i++) pi[i] = pi[i] / sum;
   // temperature (src/play.jl:208-210,309-310; src/util.jl:98-110)
-  const double tau = az_schedule(sp, move);
+  const double tau = az_schedule(sp, (sp.duel && (slot & 1)) ? 1 : 0, move);
   if (tau == 1.0) { for (int i = 0; i < n; i++) pis[i] = pi[i]; }
   else if (tau == 0.0) {
     int k = 0;
@@ -657,11 +731,13 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
   sp.s_reward[rowi] = G::white_reward(nx);
   const int nm = move + 1;
   if (G::terminated(nx) || nm >= sp.max_plies) {
-    // push_trace! (src/memory.jl:74-87)
+    // push_trace! (src/memory.jl:74-87).  The reference only pushes self-play traces (one player, its mcts gamma); in a duel
+    // of two different players the z rows are an extra and use the gamma of the player who held white in this game.
+    const double zg = (sp.duel && az_colors_flipped(sp, game)) ? p.c1.gamma : p.c.gamma;
     double wr = 0.0;
     for (int i = nm - 1; i >= 0; i--) {
       const size_t ri = (size_t)g * sp.max_plies + i;
-      wr = p.c.gamma * wr + sp.s_reward[ri];
+      wr = zg * wr + sp.s_reward[ri];
       sp.s_z[ri] = G::white_playing(sp.s_env[ri]) ? wr : -wr;
       sp.s_t[ri] = (float)(nm - i);
     }

@@ -97,7 +97,8 @@ enum az_net_kind {
   AZ_NET_UNIFORM = 0, /* MCTS.RandomOracle, src/mcts.jl:62-72 */
   AZ_NET_SYNTH = 1,   /* deterministic hash pseudo-network (parity tests: bit-exact on CPU and GPU) */
   AZ_NET_RESNET = 2,
-  AZ_NET_SIMPLENET = 3
+  AZ_NET_SIMPLENET = 3,
+  AZ_NET_ROLLOUT = 4  /* MCTS.RolloutOracle, src/mcts.jl:27-60 */
 };
 typedef struct { /* ResNetHP, src/networks/architectures/resnet.jl:30-37 */
   int32_t num_blocks;
@@ -117,6 +118,11 @@ typedef struct { /* SimpleNetHP, src/networks/architectures/simplenet.jl:15-22 *
 } az_simplenet_hp;
 
 int32_t az_net_create_oracle(az_ctx* ctx, int32_t kind, int32_t game, az_net** out);
+/* MCTS.RolloutOracle(gspec, gamma) (src/mcts.jl:27-60): uniform prior over the available actions, value = discounted return of
+   one random playout from the state (the oracle of Benchmark.MctsRollouts, src/benchmark.jl:134-147).  The playout's action
+   draws come from the engine's Philox stream keyed by (seed, state, ply) -- a deterministic function of the state, since
+   Julia's global rand() cannot be reproduced.  Deterministic games only (AZ_EUNSUPPORTED for grid-world). */
+int32_t az_net_create_rollout(az_ctx* ctx, int32_t game, double gamma, uint64_t seed, az_net** out);
 int32_t az_net_create_resnet(az_ctx* ctx, int32_t game, const az_resnet_hp* hp, az_net** out);
 int32_t az_net_create_simplenet(az_ctx* ctx, int32_t game, const az_simplenet_hp* hp, az_net** out);
 /* number of float32 values of the parameter blob, in Flux order (see DESIGN.md "weight blob"):
@@ -179,6 +185,12 @@ int32_t az_selfplay_create(az_ctx* ctx, int32_t game, az_net* oracle, const az_m
    `white_oracle`'s player takes black in every game whose 1-based index is odd. */
 int32_t az_selfplay_create_duel(az_ctx* ctx, int32_t game, az_net* white_oracle, az_net* black_oracle, const az_mcts_params* mp,
                                 const az_sim_params* sp, uint64_t seed, az_selfplay** out);
+/* Benchmark.Duel of two DIFFERENT MctsPlayers (src/benchmark.jl:78-99: e.g. Benchmark.Full(params) against
+   Benchmark.MctsRollouts(params'), :134-162): as az_selfplay_create_duel, but each player brings its own MctsParams (gamma,
+   cpuct, number of iterations, Dirichlet noise, prior temperature, move temperature schedule) next to its own oracle. */
+int32_t az_selfplay_create_duel_players(az_ctx* ctx, int32_t game, az_net* white_oracle, const az_mcts_params* white_params,
+                                        az_net* black_oracle, const az_mcts_params* black_params, const az_sim_params* sp,
+                                        uint64_t seed, az_selfplay** out);
 /* plays games first_game_index .. first_game_index + num_games - 1 (global indices key the RNG streams);
    returns immediately, the engine runs on its own host thread + CUDA stream */
 int32_t az_selfplay_start(az_selfplay* s, int32_t num_games, int64_t first_game_index);

@@ -480,6 +480,36 @@ void oz_synth_oracle(void* ctx, int game_id, const uint8_t* state, int n, float*
   *V = ((float)(int)(h0 >> 48) - 32768.0f) / 32768.0f;
 }
 
+/* MCTS.RolloutOracle, src/mcts.jl:27-60.  rollout! (:42-50) is restated with its recursion; `rand(GI.available_actions(game))`
+   (:43) takes the k-th available action with k = floor(u32 * n / 2^32) from the Philox stream (seed, state hash, ply). */
+static double oz_rollout(oz_game* g, double gamma, uint64_t seed, uint64_t h0, int ply) {
+  uint8_t mask[OZ_MAX_ACTIONS];
+  oz_game_actions_mask(g, mask);
+  int A = OZ_NACT[g->game_id], n = 0;
+  for (int a = 0; a < A; a++) n += mask[a] ? 1 : 0;
+  uint32_t o[4];
+  oz_philox(seed, (uint32_t)ply, OZ_PURPOSE_ROLLOUT, (uint32_t)h0, (uint32_t)(h0 >> 32), o);
+  int k = (int)(((uint64_t)o[0] * (uint64_t)n) >> 32), action = 0;
+  for (int a = 0; a < A; a++)
+    if (mask[a]) { if (k == 0) { action = a; break; } k--; }
+  oz_game_play(g, action, NULL);
+  double wr = oz_game_white_reward(g);
+  if (oz_game_terminated(g)) return wr;
+  return wr + gamma * oz_rollout(g, gamma, seed, h0, ply + 1);
+}
+void oz_rollout_oracle(void* ctx, int game_id, const uint8_t* state, int n, float* P, float* V) { /* :52-60 */
+  const oz_rollout_ctx* rc = (const oz_rollout_ctx*)ctx;
+  uint64_t key[2];
+  oz_state_key(game_id, state, key);
+  uint64_t h0 = oz_splitmix(key[0] ^ oz_splitmix(key[1]));
+  oz_game g;
+  oz_game_set_state(&g, game_id, state);
+  int wp = oz_game_white_playing(&g);
+  for (int i = 0; i < n; i++) P[i] = (float)(1.0 / (double)n);   /* ones(n) ./ n, stored as Float32 in ActionStats */
+  double wr = oz_rollout(&g, rc->gamma, rc->seed, h0, 0);
+  *V = (float)(wp ? wr : -wr);
+}
+
 /* ------------------------------------------------------------------------- */
 /* MCTS (src/mcts.jl)                                                          */
 /* ------------------------------------------------------------------------- */
@@ -748,6 +778,12 @@ void oz_apply_symmetry(int game_id, int sym, const uint8_t* in, uint8_t* out) {
 
 void oz_play_game2(oz_env* white, oz_env* black, const oz_mcts_params* mp, double flip_p, uint64_t seed, uint64_t game_idx,
                    oz_trace* tr) {
+  oz_play_game2p(white, mp, black, mp, flip_p, seed, game_idx, tr);
+}
+/* TwoPlayers of two MctsPlayers that may differ in every MctsParams field (src/play.jl:248-282, src/benchmark.jl:78-99):
+   think / player_temperature dispatch on the colour to move (:258-264, :279-282) */
+void oz_play_game2p(oz_env* white, const oz_mcts_params* mp_white, oz_env* black, const oz_mcts_params* mp_black, double flip_p,
+                    uint64_t seed, uint64_t game_idx, oz_trace* tr) {
   const int gid = white->game_id;
   oz_game g;
   oz_game_init(&g, gid);
@@ -780,6 +816,7 @@ void oz_play_game2(oz_env* white, oz_env* black, const oz_mcts_params* mp, doubl
     }
     oz_game_get_state(&g, tr->think_states[n]);
     oz_env* env = oz_game_white_playing(&g) ? white : black;              /* think(::TwoPlayers): play.jl:258-264 */
+    const oz_mcts_params* mp = oz_game_white_playing(&g) ? mp_white : mp_black;
     int nl = oz_legal_actions(&g, acts);
     oz_dirichlet(seed, game_idx, (uint32_t)n, nl, mp->noise_alpha, eta);  /* drawn even if eps == 0 (mcts.jl:240) */
     oz_env_set_noise(env, seed, game_idx, (uint32_t)n);

@@ -78,7 +78,7 @@ void oz_vectorize_state(int game_id, const uint8_t* state, float* x);
 
 /* ---- explicit RNG stream ------------------------------------------------ */
 void oz_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]);
-enum { OZ_PURPOSE_DIRICHLET = 0, OZ_PURPOSE_CATEGORICAL = 1, OZ_PURPOSE_SYMMETRY = 2, OZ_PURPOSE_ENV = 3,
+enum { OZ_PURPOSE_DIRICHLET = 0, OZ_PURPOSE_CATEGORICAL = 1, OZ_PURPOSE_SYMMETRY = 2, OZ_PURPOSE_ENV = 3, OZ_PURPOSE_ROLLOUT = 5,
        OZ_PURPOSE_POSITION = 4 };
 double oz_det_log(double x);
 double oz_det_exp(double x);
@@ -92,6 +92,9 @@ typedef void (*oz_oracle_fn)(void* ctx, int game_id, const uint8_t* state, int n
 void oz_uniform_oracle(void* ctx, int game_id, const uint8_t* state, int n_legal, float* P, float* V);
 /* deterministic hash pseudo-network, bit-reproducible on the GPU */
 void oz_synth_oracle(void* ctx, int game_id, const uint8_t* state, int n_legal, float* P, float* V);
+/* MCTS.RolloutOracle (src/mcts.jl:27-60); ctx points to an oz_rollout_ctx (the playout's draws are keyed by (seed, state, ply)) */
+typedef struct { uint64_t seed; double gamma; } oz_rollout_ctx;
+void oz_rollout_oracle(void* ctx, int game_id, const uint8_t* state, int n_legal, float* P, float* V);
 void oz_state_key(int game_id, const uint8_t* state, uint64_t key[2]);
 
 typedef struct oz_env oz_env;
@@ -154,6 +157,9 @@ void oz_apply_symmetry(int game_id, int sym, const uint8_t* state_in, uint8_t* s
    stream(seed, game, m, SYMMETRY, 1) mod num_symmetries. */
 void oz_play_game2(oz_env* white, oz_env* black, const oz_mcts_params* mp, double flip_probability, uint64_t seed,
                    uint64_t game, oz_trace* out);
+/* the same with one MctsParams per player (Benchmark duels of different MctsPlayers) */
+void oz_play_game2p(oz_env* white, const oz_mcts_params* mp_white, oz_env* black, const oz_mcts_params* mp_black, double flip_p,
+                    uint64_t seed, uint64_t game_idx, oz_trace* tr);
 /* total_reward(trace, gamma) (src/trace.jl:45-47) */
 double oz_total_reward(const oz_trace* tr, double gamma);
 /* one worker of simulate() (src/simulations.jl:207-244): plays games first, first+stride, ... (count games),

@@ -95,6 +95,9 @@ def lib():
         L.oz_fix_probvec.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oz_play_game.argtypes = [C.c_void_p, C.POINTER(MctsParams), C.c_uint64, C.c_uint64, C.POINTER(Trace)]
         L.oz_play_game2.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(MctsParams), C.c_double, C.c_uint64, C.c_uint64, C.POINTER(Trace)]
+        L.oz_play_game2p.restype = None
+        L.oz_play_game2p.argtypes = [C.c_void_p, C.POINTER(MctsParams), C.c_void_p, C.POINTER(MctsParams), C.c_double, C.c_uint64, C.c_uint64,
+                                     C.POINTER(Trace)]
         L.oz_apply_symmetry.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.oz_total_reward.restype = C.c_double
         L.oz_total_reward.argtypes = [C.POINTER(Trace), C.c_double]
@@ -151,6 +154,19 @@ def state_dim(gid):
 def builtin_oracle(name):
     L = lib()
     return C.cast(getattr(L, {"uniform": "oz_uniform_oracle", "synth": "oz_synth_oracle"}[name]), C.c_void_p)
+
+
+class RolloutCtx(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("gamma", C.c_double)]
+
+
+class RolloutOracle:
+    """MCTS.RolloutOracle(gspec, gamma) (src/mcts.jl:27-60) with the playout draws keyed by (seed, state, ply)."""
+
+    def __init__(self, seed, gamma=1.0):
+        self.ctx = RolloutCtx(seed, gamma)
+        self.fn = C.cast(lib().oz_rollout_oracle, C.c_void_p)
+        self.ctx_ptr = C.cast(C.pointer(self.ctx), C.c_void_p)
 
 
 class GameEnv:
@@ -223,8 +239,11 @@ class Env:
 
     def __init__(self, gid, oracle="uniform", gamma=1.0, cpuct=1.0, noise_eps=0.0, noise_alpha=1.0, prior_temperature=1.0):
         self.gid = gid
+        octx = None
         if isinstance(oracle, str):
             self._fn = builtin_oracle(oracle)
+        elif isinstance(oracle, RolloutOracle):
+            self._keep, self._fn, octx = oracle, oracle.fn, oracle.ctx_ptr
         else:  # python callable (state_bytes, n_legal) -> (P list, V)
             sb = state_bytes(gid)
 
@@ -235,7 +254,7 @@ class Env:
                 V[0] = v
             self._cb = ORACLE_FN(cb)
             self._fn = C.cast(self._cb, C.c_void_p)
-        self.h = lib().oz_env_create(gid, self._fn, None, gamma, cpuct, noise_eps, noise_alpha, prior_temperature)
+        self.h = lib().oz_env_create(gid, self._fn, octx, gamma, cpuct, noise_eps, noise_alpha, prior_temperature)
 
     def __del__(self):
         if getattr(self, "h", None):

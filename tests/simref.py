@@ -7,12 +7,21 @@ import ctypes as C
 import numpy as np
 
 
-def oracle_simulate(oz, gid, oracle, omp, seed, S, NG, reset_every, baseline=None, alternate_colors=False, flip_probability=0.0):
-    """`baseline` given: every worker is TwoPlayers(MctsPlayer(oracle), MctsPlayer(baseline)) (src/training.jl:130-143)."""
+def oracle_simulate(oz, gid, oracle, omp, seed, S, NG, reset_every, baseline=None, alternate_colors=False, flip_probability=0.0,
+                    omp_baseline=None):
+    """`baseline` given: every worker is TwoPlayers(MctsPlayer(oracle, omp), MctsPlayer(baseline, omp_baseline or omp))
+    (src/training.jl:130-143; two different MctsPlayers as in Benchmark duels, src/benchmark.jl:78-99)."""
     L = oz.lib()
-    fns = [oz.builtin_oracle(o) if isinstance(o, str) else o for o in ([oracle] if baseline is None else [oracle, baseline])]
-    mk = lambda fn: L.oz_env_create(gid, fn, None, omp.gamma, omp.cpuct, omp.noise_eps, omp.noise_alpha, omp.prior_temperature)
-    envs = [[mk(fn) for fn in fns] for _ in range(S)]
+    def fn_ctx(o):   # (oracle function pointer, its context pointer)
+        if isinstance(o, str):
+            return oz.builtin_oracle(o), None
+        if isinstance(o, oz.RolloutOracle):
+            return o.fn, o.ctx_ptr
+        return o, None
+    fns = [fn_ctx(o) for o in ([oracle] if baseline is None else [oracle, baseline])]
+    omps = [omp, omp_baseline if omp_baseline is not None else omp]
+    mk = lambda fc, m: L.oz_env_create(gid, fc[0], fc[1], m.gamma, m.cpuct, m.noise_eps, m.noise_alpha, m.prior_temperature)
+    envs = [[mk(fc, omps[i]) for i, fc in enumerate(fns)] for _ in range(S)]
     A, sb = oz.num_actions(gid), oz.state_bytes(gid)
     nsims = omp.num_iters_per_turn
     free_at = {w: 0 for w in range(S)}
@@ -32,7 +41,8 @@ def oracle_simulate(oz, gid, oracle, omp, seed, S, NG, reset_every, baseline=Non
                 nxt += 1
                 flipped = baseline is not None and alternate_colors and (g + 1) % 2 == 1   # src/simulations.jl:224-226
                 white, black = (envs[w][0], envs[w][-1]) if not flipped else (envs[w][-1], envs[w][0])
-                L.oz_play_game2(white, black, C.byref(omp), flip_probability, seed, g, C.byref(tr))
+                mw, mb = (omps[0], omps[-1] if baseline is not None else omps[0]) if not flipped else (omps[-1], omps[0])
+                L.oz_play_game2p(white, C.byref(mw), black, C.byref(mb), flip_probability, seed, g, C.byref(tr))
                 n = tr.n_moves
                 traces[g] = dict(n_moves=n, states=np.ctypeslib.as_array(tr.states)[:n + 1, :sb].copy(),
                                  pi=np.ctypeslib.as_array(tr.pi)[:n, :A].copy(), pi64=np.ctypeslib.as_array(tr.pi64)[:n, :A].copy(), mask=np.ctypeslib.as_array(tr.mask)[:n, :A].copy(),
@@ -46,7 +56,9 @@ def oracle_simulate(oz, gid, oracle, omp, seed, S, NG, reset_every, baseline=Non
                 if reset_every > 0 and played[w] % reset_every == 0:
                     for e in envs[w]:
                         L.oz_env_reset(e)
-                free_at[w] = t + n * nsims
+                # every move lasts as many ticks as its player's iteration budget (select runs one simulation per call)
+                ts = traces[g]["think_states"]
+                free_at[w] = t + sum((mw if (sb == 2 or ts[i][sb - 1] == 1) else mb).num_iters_per_turn for i in range(n))
                 if n == 0:
                     again.append(w)
             asking = again

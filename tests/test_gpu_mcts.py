@@ -283,6 +283,74 @@ def test_full_size_pool_slots_bit_exact(az, oz, ctx, game, S, nsims, gamma):
     net.close()
 
 
+@pytest.mark.parametrize("game,nsims,gamma", [("connect-four", 200, 1.0), ("tictactoe", 60, 0.9), ("mancala", 100, 1.0)])
+def test_rollout_oracle_explore_and_duel_bit_exact(az, oz, ctx, game, nsims, gamma):
+    """MCTS.RolloutOracle (src/mcts.jl:27-60), the oracle of Benchmark.MctsRollouts (src/benchmark.jl:134-147): uniform prior,
+    value = discounted return of one random playout (draws keyed by (seed, state, ply) on both sides); then a duel of a
+    'network' player against the vanilla-MCTS baseline as Benchmark.Duel runs it (src/benchmark.jl:78-99)."""
+    from tests import simref
+    gs, gid = az.GameSpec(game), oz.game_id(game)
+    rseed = 4711
+    roots = gs.random_positions(31, 40, 20 if game != "tictactoe" else 4)
+    eta = _etas(oz, gid, roots, gs.num_actions, seed=3)
+    mp = az.MctsParams(gamma=gamma, cpuct=1.0, num_iters_per_turn=nsims, dirichlet_noise_eps=0.25, dirichlet_noise_alpha=1.0)
+    net = az.RolloutOracle(ctx, gs, gamma=gamma, seed=rseed)
+    env = az.MctsEnv(ctx, gs, net, mp, len(roots), 2 * nsims)
+    N, W, P = env.explore(roots, nsims, eta)
+    for i, r in enumerate(roots):
+        e = oz.Env(gid, oz.RolloutOracle(rseed, gamma), gamma=gamma, cpuct=1.0, noise_eps=0.25)
+        g = oz.GameEnv(gid, r)
+        n = int(g.actions_mask().sum())
+        e.explore(g, nsims, eta[i, :n])
+        _, rN, rW, rP, _ = e.root_stats(g)
+        assert (N[i] == rN).all() and (W[i] == rW).all(), (i, N[i], rN)
+        assert (P[i].view(np.uint32) == rP.view(np.uint32)).all()
+    env.close()
+    assert np.abs(W).max() > 0            # playouts do reach decided games
+    # duel: synthetic 'network' vs MCTS with rollouts, alternate colours
+    S, NG, seed, ns2 = 5, 12, 99, 24
+    mp2 = az.MctsParams(gamma=gamma, cpuct=1.0, num_iters_per_turn=ns2, temperature=az.ConstSchedule(0.5), dirichlet_noise_eps=0.0,
+                        dirichlet_noise_alpha=1.0)
+    contender = az.SynthOracle(ctx, gs)
+    sim = az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=1, alternate_colors=True)
+    out = az.simulate(ctx, gs, contender, az.SelfPlayParams(mp2, sim), seed=seed, baseline=net, gamma=gamma)
+    omp = oz.mcts_params(gamma=gamma, cpuct=1.0, num_iters_per_turn=ns2, sched_xs=(0,), sched_ys=(0.5,))
+    traces, _ = simref.oracle_simulate(oz, gid, "synth", omp, seed, S, NG, 1, baseline=oz.RolloutOracle(rseed, gamma), alternate_colors=True)
+    simref.assert_same_samples(out, traces)
+    simref.assert_same_outcomes(out, traces)
+    contender.close()
+    net.close()
+    with pytest.raises(az.AzError) as ei:   # stochastic environments have no deterministic playout
+        az.RolloutOracle(ctx, az.GameSpec("grid-world"))
+    assert ei.value.status == 5
+
+
+@pytest.mark.parametrize("game", ["connect-four", "tictactoe"])
+def test_duel_of_two_different_players_bit_exact(az, oz, ctx, game):
+    """Benchmark.Duel(Benchmark.Full(params), Benchmark.MctsRollouts(params')) (src/benchmark.jl:78-99,134-162): TwoPlayers of
+    two MctsPlayers that differ in EVERY MctsParams field (iterations, cpuct, gamma, noise, prior temperature, move
+    temperature schedule) and in their oracle; alternate_colors swaps which player moves first."""
+    from tests import simref
+    gs, gid = az.GameSpec(game), oz.game_id(game)
+    S, NG, seed, rseed = 5, 14, 2718, 99
+    mp_a = az.MctsParams(gamma=1.0, cpuct=2.0, num_iters_per_turn=30, temperature=az.PLSchedule([0, 4], [1.0, 0.3]), dirichlet_noise_eps=0.2,
+                         dirichlet_noise_alpha=1.0, prior_temperature=0.7)
+    mp_b = az.MctsParams(gamma=0.95, cpuct=1.0, num_iters_per_turn=45, temperature=az.ConstSchedule(0.0), dirichlet_noise_eps=0.0,
+                         dirichlet_noise_alpha=0.5)
+    a_net, b_net = az.SynthOracle(ctx, gs), az.RolloutOracle(ctx, gs, gamma=0.95, seed=rseed)
+    sim = az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=2, alternate_colors=True)
+    out = az.simulate(ctx, gs, a_net, az.SelfPlayParams(mp_a, sim), seed=seed, baseline=b_net, baseline_mcts=mp_b, gamma=1.0)
+    omp_a = oz.mcts_params(gamma=1.0, cpuct=2.0, noise_eps=0.2, noise_alpha=1.0, prior_temperature=0.7, num_iters_per_turn=30,
+                           sched_xs=(0, 4), sched_ys=(1.0, 0.3))
+    omp_b = oz.mcts_params(gamma=0.95, cpuct=1.0, noise_eps=0.0, noise_alpha=0.5, num_iters_per_turn=45, sched_xs=(0,), sched_ys=(0.0,))
+    traces, _ = simref.oracle_simulate(oz, gid, "synth", omp_a, seed, S, NG, 2, baseline=oz.RolloutOracle(rseed, 0.95), alternate_colors=True,
+                                       omp_baseline=omp_b)
+    simref.assert_same_samples(out, traces)
+    simref.assert_same_outcomes(out, traces)
+    a_net.close()
+    b_net.close()
+
+
 def test_error_paths_mirror_reference_asserts(az, ctx):
     """Precondition violations return AZ_EINVAL / AZ_ESTATE with a message (no exception crosses the ABI)."""
     gs = az.GameSpec("connect-four")

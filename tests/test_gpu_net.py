@@ -45,28 +45,33 @@ def test_resnet_forward_matches_fp32_reference(az, oz, ctx, blocks, batch, seed,
     net.close()
 
 
+def _net_with_env(az, ctx, gs, hp, env):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return netcheck.make_net(az, ctx, gs, hp, seed=5, randomize=True)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
 @pytest.mark.parametrize("blocks,batch", [(1, 37), (5, 700), (7, 4096)])
 def test_persistent_tower_equals_per_layer_kernels(az, oz, ctx, blocks, batch):
     """The persistent whole-tower kernel (one launch, neighbour flags between layers) and the per-layer kernel issue the same
-    MMAs in the same order for every output row, so their outputs must be bit-identical -- at a batch that spans every CTA
-    pair (4096 leaves), one that leaves most pairs idle (37) and an odd size (700)."""
-    import os
+    MMAs in the same order for every output row, so with the same residual format (AZ_LO=16: fp16 low-order part) their
+    outputs must be bit-identical -- at a batch that spans every CTA pair (4096 leaves), one that leaves most pairs idle (37)
+    and an odd size (700).  The default e4m3 low-order part (8-bit, through kind::f8f6f4 identity MMAs) must agree with the
+    fp16 one to well within the network tolerance."""
     gs = az.GameSpec("connect-four")
     hp = netcheck.c4_hp(blocks)
     states = gs.random_positions(17, batch, 38)
     outs = []
-    for mode in ("", "layer"):
-        old = os.environ.get("AZ_TOWER")
-        if mode:
-            os.environ["AZ_TOWER"] = mode
-        try:
-            net, blob = netcheck.make_net(az, ctx, gs, hp, seed=5, randomize=True)
-        finally:
-            if mode:
-                if old is None:
-                    del os.environ["AZ_TOWER"]
-                else:
-                    os.environ["AZ_TOWER"] = old
+    for env in ({"AZ_LO": "16"}, {"AZ_TOWER": "layer"}, {}):
+        net, blob = _net_with_env(az, ctx, gs, hp, env)
         for rep in range(3):       # repeated launches: the flag counters keep counting across launches
             P, V, _ = net.evaluate_batch(states)
         L, Vp = net.forward_logits(states)
@@ -74,6 +79,11 @@ def test_persistent_tower_equals_per_layer_kernels(az, oz, ctx, blocks, batch):
         net.close()
     for a, b in zip(outs[0], outs[1]):
         assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    d = [float(np.abs(a - b).max()) for a, b in zip(outs[0], outs[2])]
+    print("lo8 vs lo16: max |dP| %.2e |dV| %.2e |dL| %.2e |dVpre| %.2e" % tuple(d))
+    assert max(d) < 2.5e-4, d
+    if blocks > 1:
+        assert max(d) > 0.0    # the 8-bit path really ran
 
 
 def test_resnet_precision_stress(az, oz, ctx):

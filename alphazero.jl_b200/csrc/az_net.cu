@@ -992,6 +992,7 @@ struct Smem {
   uint8_t apad[1024];
   uint8_t epi[yr::EPI_BYTES];
   uint8_t ident[256];
+  uint8_t ident8[512];   // lo8 mode: this CTA's 16 x 32 slice of 2^-14 * I32 in e5m2 (B operand of the fp8 residual MMAs)
   uint64_t full[yr::ASTAGES], empty[yr::ASTAGES], tfull[yr::NACC], tempty[yr::NACC], bfull[tc2::NCHUNK], wfree, ldone;
   uint32_t tmem_base;
 };
@@ -1003,33 +1004,44 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 __device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// two floats -> two e4m3 bytes (first argument in the LOW byte = lower address), and back
+// stage sequence of one input row of a conv2 layer in lo8 mode: C0 Rhi0 Rhi1 C1 Rlo8 (the 8-bit low-order part covers all 128
+// channels in ONE 16 KB stage); kind 0 = conv, 1 = residual hi (fp16), 2 = residual lo (fp16), 3 = residual lo (e4m3)
+__device__ __forceinline__ void stage_of(int q, int nres, bool lo8, int& kind, int& half) {
+  if (!lo8 || nres < 3) {
+    bool isres; int part;
+    yrow_stage(q, nres, isres, half, part);
+    kind = !isres ? 0 : (part ? 2 : 1);
+    return;
+  }
+  if (q == 0) { kind = 0; half = 0; }
+  else if (q == 1) { kind = 1; half = 0; }
+  else if (q == 2) { kind = 1; half = 1; }
+  else if (q == 3) { kind = 0; half = 1; }
+  else { kind = 3; half = 0; }
+}
+__device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// two floats -> two e4m3 bytes (first argument in the LOW byte = lower address)
 __device__ __forceinline__ uint32_t cvt_e4m3x2(float lo_elem, float hi_elem) {
   uint16_t r;
   asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi_elem), "f"(lo_elem));
   return (uint32_t)r;
 }
-__device__ __forceinline__ float2 cvt_f32x2_e4m3x2(uint32_t two_bytes) {
-  uint32_t h2;
-  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"((uint16_t)two_bytes));
-  return __half22float2(*reinterpret_cast<__half2*>(&h2));
-}
-__device__ __forceinline__ uint4 ld_cg_v4(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st_cg_v4(void* p, uint4 v) {
-  asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-constexpr float LO8_SCALE = 16384.0f;   // lo is stored as e4m3(lo * 2^14): 4 significant bits over 17 octaves, |lo| < 0.027
+constexpr float LO8_SCALE = 16384.0f;   // lo is stored as e4m3(lo * 2^14) (4 significant bits over 17 octaves, |lo| < 0.027); the
+                                        // identity of its MMA is 2^-14 (e5m2 0x04), so the product is lo again, exactly
 }  // namespace tw
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(yr::NUM_THREADS, 1)
 az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmXL,
                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmXo, const __grid_constant__ CUtensorMap tmTo,
-                const __grid_constant__ CUtensorMap tmXLo, uint8_t* __restrict__ xl8, GemmArgs ga, int num_layers,
-                unsigned long long* __restrict__ done) {
+                const __grid_constant__ CUtensorMap tmXLo, const __grid_constant__ CUtensorMap tmXL8, const __grid_constant__ CUtensorMap tmXL8o,
+                GemmArgs ga, int num_layers, unsigned long long* __restrict__ done) {
   using namespace tc2;
   constexpr int BN = 128, H = 6;
   constexpr int ASTAGES = yr::ASTAGES, NB = yr::NBOARD;
@@ -1042,7 +1054,6 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const bool use_lo = !(ga.debug & 8);   // AZ_TOWER_DEBUG=8 (timing experiments only): fp16-only skip stream, no low-order part
   const bool lo8 = ga.lo8 != 0;          // low-order part of the skip stream as e4m3 bytes (default) or fp16 (AZ_LO=16)
-  const int alloc_boards = ga.alloc_rows / 42;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
@@ -1062,6 +1073,14 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int k0 = khalf * 8 + kk, kone = (int)rank * 8 + n;
     const uint32_t w = (k0 == kone ? 0x3C00u : 0u) | (k0 + 1 == kone ? 0x3C000000u : 0u);
     *reinterpret_cast<uint32_t*>(s.ident + khalf * 128 + n * 16 + (i & 3) * 4) = w;
+    fence_proxy_async();
+  }
+  if (threadIdx.x < 128) {  // e5m2 2^-14 * I32, this CTA's rows n = rank*16 + i: byte (i, k) at (i>>3)*256 + (k>>4)*128 + (i&7)*16 + (k&15)
+    const int i = threadIdx.x >> 3, k4 = (threadIdx.x & 7) * 4;   // 4 k-bytes per thread
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (k4 + j == (int)rank * 16 + i) w |= 0x04u << (8 * j);
+    *reinterpret_cast<uint32_t*>(s.ident8 + (i >> 3) * 256 + (k4 >> 4) * 128 + (i & 7) * 16 + (k4 & 15)) = w;
     fence_proxy_async();
   }
   if (warp == 1) {
@@ -1098,6 +1117,9 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // ===== TMA producer (both CTAs) =====
     int stage = 0;
     uint32_t phase = 0;
+    // (Tried and removed: starting pair p p*skew cycles late so that half the pairs are in an L2-hungry conv2 layer while the
+    // others are in a conv1 layer -- 0 / 350 / 700 / 1400 / 2800 cycles per pair gave 5.58 / 5.56 / 5.47 / 5.29 / 4.95 M
+    // expansions/s on one box: the average demand of a block is already at the chip's L2 limit, staggering only adds ramp.)
     for (int l = 0; l < num_layers; l++) {
       const bool conv2 = (l & 1) != 0;
       const CUtensorMap* mA = conv2 ? &tmT : &tmX;
@@ -1136,15 +1158,15 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             fence_proxy_async();
             hi_ok = true;
           }
-          // residual stages: hi always; the low-order part rides the ring only as fp16 (lo8: the epilogue adds it)
-          const int nres = (conv2 && y >= j_lo && y < j_hi) ? ((l > 1 && use_lo && !lo8) ? 4 : 2) : 0;
+          const int nres = (conv2 && y >= j_lo && y < j_hi) ? ((l > 1 && use_lo) ? (lo8 ? 3 : 4) : 2) : 0;
           for (int q = 0; q < 2 + nres; q++) {
-            bool isres; int half, part;
-            yrow_stage(q, nres, isres, half, part);
+            int kind, half;
+            tw::stage_of(q, nres, lo8, kind, half);
             mbar_wait(&s.empty[stage], phase ^ 1);
             if (elect_one()) {
               if (leader) mbar_expect_tx(&s.full[stage], 2 * yr::A_STAGE);
-              tma_load_4d_2sm(s.a[stage], isres ? (part ? &tmXL : &tmX) : mA, &s.full[stage], half * BK, -1, y, b0);
+              const CUtensorMap* m = kind == 0 ? mA : (kind == 1 ? &tmX : (kind == 2 ? &tmXL : &tmXL8));
+              tma_load_4d_2sm(s.a[stage], m, &s.full[stage], half * BK, -1, y, b0);
             }
             __syncwarp();
             if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
@@ -1158,6 +1180,9 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);    // M = 256, N = 128
       constexpr uint32_t IDESC_R = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256, N = 16
       const uint64_t idsc = umma_desc_interleave(smem_u32(s.ident), 128u, 256u);
+      // fp8 residual MMA: A = e4m3 (format 0), B = e5m2 (format 1), M = 256, N = 32, K = 32
+      constexpr uint32_t IDESC_R8 = (1u << 4) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      const uint64_t idsc8 = umma_desc_interleave(smem_u32(s.ident8), 128u, 256u);
       int stage = 0;
       uint32_t phase = 0;
       int nbase = 0;
@@ -1174,10 +1199,11 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               mbar_wait(&s.tempty[n & 3], ((uint32_t)(n >> 2) & 1u) ^ 1u);
             }
             tcgen05_fence_after();
-            const int nres = (conv2 && y >= j_lo && y < j_hi) ? ((l > 1 && use_lo && !lo8) ? 4 : 2) : 0;
+            const int nres = (conv2 && y >= j_lo && y < j_hi) ? ((l > 1 && use_lo) ? (lo8 ? 3 : 4) : 2) : 0;
             for (int q = 0; q < 2 + nres; q++) {
-              bool isres; int half, part;
-              yrow_stage(q, nres, isres, half, part);
+              int kind, half;
+              tw::stage_of(q, nres, lo8, kind, half);
+              const bool isres = kind != 0;
               mbar_wait(&s.full[stage], phase);
               tcgen05_fence_after();
               const uint32_t abase = smem_u32(s.a[stage]);
@@ -1195,7 +1221,13 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 tcgen05_fence_after();
               }
               if (elect_one()) {
-                if (isres) {
+                if (kind == 3) {  // 8-bit low-order part: acc[:, 32k .. 32k+31] += A8[:, 32k ..] . (2^-14 I32), 4 x K = 32
+                  const uint32_t tmem_d = tmem_base + (uint32_t)(((nbase + (y - j_lo)) & 3) * BN);
+                  const uint64_t adesc = umma_desc_sw128(abase + 128u);
+#pragma unroll
+                  for (int k = 0; k < 4; k++)
+                    tw::umma_f8_2sm(tmem_d + (uint32_t)(k * 32), adesc + (uint64_t)(k * 2), idsc8, IDESC_R8, 1u);
+                } else if (isres) {
                   const uint32_t tmem_d = tmem_base + (uint32_t)(((nbase + (y - j_lo)) & 3) * BN);
                   const uint64_t adesc = umma_desc_sw128(abase + 128u);
 #pragma unroll
@@ -1252,21 +1284,6 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int g = u / H, j = u - g * H;
         const int bq = g * 2 * NB + (int)rank * NB + quarter * 4;
         const int slot = n & 3;
-        // lo8 mode: the low-order part of the skip stream never touches the tensor core or the TMA ring.  This thread owns
-        // output row (board bq + lane / 8, x = lane % 8) and channels colhalf*64 .. +63 in EVERY layer, so the 64 e4m3 bytes it
-        // wrote for this cell two layers ago (st.global.cg, L2) are the ones it needs now: plain 16-byte loads that bypass L1.
-        const bool cell_ok = (lane & 7) < 7 && (bq + (lane >> 3)) < alloc_boards;
-        uint8_t* l8p = xl8 + ((((size_t)(bq + (lane >> 3)) * H + j) * 7 + (lane & 7)) * 128 + colhalf * 64);
-        uint4 r8[4];   // low-order bytes of the block input (residual), loaded while the MMAs of this row finish
-        const bool add_lo = conv2 && l > 1 && use_lo && lo8;
-        if (add_lo && cell_ok) {
-#pragma unroll
-          for (int c = 0; c < 4; c++) r8[c] = tw::ld_cg_v4(l8p + c * 16);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; c++) r8[c] = make_uint4(0, 0, 0, 0);
-        }
-        const uint32_t* r8w = reinterpret_cast<const uint32_t*>(r8);
         mbar_wait(&s.tfull[slot], (uint32_t)(n >> 2) & 1u);
         tcgen05_fence_after();
         uint4 l8[4];   // lo8 mode: this row's 64 low-order bytes of the OUTPUT, filled over the two 32-column steps
@@ -1282,14 +1299,8 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
           for (int jj = 0; jj < 16; jj++) {
             const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_g + sc * 32) + jj);
-            float a0 = __uint_as_float(v[2 * jj]), a1 = __uint_as_float(v[2 * jj + 1]);
-            if (add_lo) {  // + lo of the block input: e4m3 bytes (2 jj, 2 jj + 1) of this 32-channel step, scaled by 2^-14
-              const float2 lo = tw::cvt_f32x2_e4m3x2((r8w[sc * 8 + (jj >> 1)] >> ((jj & 1) * 16)) & 0xFFFFu);
-              a0 += lo.x * (1.0f / tw::LO8_SCALE);
-              a1 += lo.y * (1.0f / tw::LO8_SCALE);
-            }
-            const float x0 = fmaxf(a0 + bb.x, 0.f);
-            const float x1 = fmaxf(a1 + bb.y, 0.f);
+            const float x0 = fmaxf(__uint_as_float(v[2 * jj]) + bb.x, 0.f);
+            const float x1 = fmaxf(__uint_as_float(v[2 * jj + 1]) + bb.y, 0.f);
             const __half2 h = __floats2half2_rn(x0, x1);
             oh[jj] = h;
             if (want_lo) {  // lo = y - hi: hi + lo carries ~22 (fp16 lo) / ~15 (e4m3 lo) significant bits of the skip path
@@ -1314,9 +1325,14 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (lane == 0 && !(ga.debug & 4)) { tma_store_4d(part ? &tmXLo : mO, tile, col, 0, j, bq); tma_store_commit(); }
           }
         }
-        if (want_lo && lo8 && cell_ok && !(ga.debug & 4)) {
+        if (want_lo && lo8) {  // one 32-row x 64-byte tile of e4m3 bytes (channels colhalf*64 .. +63)
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
 #pragma unroll
-          for (int c = 0; c < 4; c++) tw::st_cg_v4(l8p + c * 16, l8[c]);
+          for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(tile + lane * 64 + ((c ^ sw) << 4)) = l8[c];
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(ga.debug & 4)) { tma_store_4d(&tmXL8o, tile, colhalf * 64, 0, j, bq); tma_store_commit(); }
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -1460,7 +1476,7 @@ struct Smem {
 }  // namespace st
 
 template <class G>
-__global__ void __launch_bounds__(st::NUM_THREADS, 1)
+__global__ void __launch_bounds__(st::NUM_THREADS, 2)   // two CTAs per SM (71 KB smem, 256 TMEM columns, <= 102 registers each): their latencies overlap
 az_k_stem(const AzEnv* __restrict__ envs, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, GemmArgs ga, int dense) {
   constexpr int W = G::XW, H = G::XH, C = G::XC, NX = W * H * C, BN = 128, F = 128;
   using SmemT = st::Smem<NX>;
@@ -1854,6 +1870,7 @@ struct ResNetImpl : az_net {
   CUtensorMap map4X{}, map4T{}, map4XL{};        // loads: box (64 ch, 8 x, 1 y, 16 boards), SWIZZLE_128B, zero fill outside
   CUtensorMap map4Xo{}, map4To{}, map4XLo{};     // stores: box (16 ch, 8 x, 1 y, 4 boards), SWIZZLE_32B (per-layer kernels)
   uint8_t* d_xl8 = nullptr;                        // persistent tower, lo8 mode: low-order part of the block outputs as e4m3(lo * 2^14)
+  CUtensorMap map4XL8{}, map4XL8o{};               // u8 views: load box (128 B, 8 x, 1 y, 16 boards) SWIZZLE_128B; store box (64 B, 8 x, 1 y, 4 boards) SWIZZLE_64B
   bool lo8 = true;                                 // AZ_LO=16: keep the low-order part in fp16 (XL16) like the per-layer kernels
   CUtensorMap mapXo64{};                           // stem stores: 2-D [rows][128] fp16, box (32 ch, 32 rows), SWIZZLE_64B
   CUtensorMap map4Xo64{}, map4To64{}, map4XLo64{};  // stores of the persistent kernel: box (32 ch, 8 x, 1 y, 4 boards), SWIZZLE_64B
@@ -2155,6 +2172,8 @@ struct ResNetImpl : az_net {
       AZ_TRY2(make_map_4d(ctx, &map4To64, d_t16, alloc_boards, 32, 8, 4, s64));
       AZ_TRY2(make_map_4d(ctx, &map4XLo64, d_xl16, alloc_boards, 32, 8, 4, s64));
       AZ_TRY2(dmalloc(&d_xl8, (size_t)alloc_rows * F));
+      AZ_TRY2(make_map_4d(ctx, &map4XL8, d_xl8, alloc_boards, 128, 8, yr::NBOARD, s128, true));
+      AZ_TRY2(make_map_4d(ctx, &map4XL8o, d_xl8, alloc_boards, 64, 8, 4, s64, true));
     }
     act_boards = max_boards;
     return AZ_OK;
@@ -2172,7 +2191,7 @@ struct ResNetImpl : az_net {
     const int L = 2 * hp.num_blocks;
     GemmArgs g2 = ga;
     g2.lo8 = lo8 ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, az_k_tower_yrow, map4X, map4T, map4XL, mapWall, map4Xo64, map4To64, map4XLo64, d_xl8, g2, L, d_done);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, az_k_tower_yrow, map4X, map4T, map4XL, mapWall, map4Xo64, map4To64, map4XLo64, map4XL8, map4XL8o, g2, L, d_done);
     if (e != cudaSuccess) { ctx->err = std::string("persistent tower launch: ") + cudaGetErrorString(e); cudaGetLastError(); return AZ_ECUDA; }
     return AZ_OK;
   }
@@ -2195,7 +2214,7 @@ struct ResNetImpl : az_net {
     ga.n_boards = n_rows; ga.g = geom; ga.alloc_rows = alloc_rows; ga.rows_per_board = BS; ga.debug = 0;
     ga.gemm_k = 1; ga.kblocks = 1; ga.bias = d_bstem; ga.out16a = d_x16; ga.out32 = c4_fast ? nullptr : d_x32;
     if (fused) {
-      launch_pdl(az_k_stem<G>, grid, st::NUM_THREADS, smem_stem, st, envs, mapWstem, mapXo64, ga, dense ? 1 : 0);
+      launch_pdl(az_k_stem<G>, std::min(row_tiles, 2 * ctx->num_sms), st::NUM_THREADS, smem_stem, st, envs, mapWstem, mapXo64, ga, dense ? 1 : 0);
     } else {
       az_k_im2col<G><<<(max_rows + 3) / 4, 128, 0, st>>>(envs, n_rows, d_x0, dense ? 1 : 0);
       launch_pdl(az_k_gemm_tc<128, tc::EPI_CONV1>, grid, tc::NUM_THREADS, smem128, st, mapX0, mapWstem, ga);

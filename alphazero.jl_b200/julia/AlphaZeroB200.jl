@@ -9,9 +9,9 @@
 # (src/training.jl:137-139, 150-152).  Julia dispatches on the game-spec type, so loading this module ADDS the methods
 #     simulate_distributed(::Simulator, ::Examples.ConnectFour.GameSpec, ::SimParams; game_simulated)   (and simulate)
 # for the four games the library knows; no reference file changes and `Scripts.train("connect-four")` runs unchanged.
-# Everything the engine cannot express (players that are not MctsPlayer / TwoPlayers of MctsPlayers over a ResNet or
-# SimpleNet, per-player MCTS parameters, a timeout instead of an iteration budget) falls back to the reference's own
-# method through `invoke`.
+# Everything the engine cannot express (players that are not MctsPlayer / TwoPlayers of MctsPlayers -- MinMax, NetworkOnly,
+# Human --, oracles other than ResNet / SimpleNet / RolloutOracle / RandomOracle, a timeout instead of an iteration budget)
+# falls back to the reference's own method through `invoke`.
 module AlphaZeroB200
 
 using AlphaZero
@@ -134,7 +134,9 @@ function flux_blob(nn)   # common, vhead, phead; Conv: W then b; BatchNorm: Î³ Î
   return out
 end
 
-supported_network(nn) = nn isa NetLib.ResNet || nn isa NetLib.SimpleNet
+# oracles the engine has a device implementation of: the two NetLib networks, MCTS.RolloutOracle (src/mcts.jl:27-60, the oracle
+# of Benchmark.MctsRollouts) and MCTS.RandomOracle (src/mcts.jl:62-72)
+supported_network(nn) = nn isa NetLib.ResNet || nn isa NetLib.SimpleNet || nn isa MCTS.RolloutOracle || nn isa MCTS.RandomOracle
 
 mutable struct Engine
   ctx::Ptr{Cvoid}
@@ -158,8 +160,15 @@ function Engine(gspec, nn; device = default_device())
   ctx = context(device)
   game = ccall((:az_game_lookup, LIB), Int32, (Cstring,), game_name(gspec))
   game >= 0 || error("azb200: unknown game")
-  hp = Network.hyperparams(nn)
   net = Ref{Ptr{Cvoid}}(C_NULL)
+  if nn isa MCTS.RolloutOracle     # playout draws come from the engine's Philox stream keyed by (seed, state, ply)
+    check(ctx, ccall((:az_net_create_rollout, LIB), Int32, (Ptr{Cvoid}, Int32, Cdouble, UInt64, Ptr{Ptr{Cvoid}}), ctx, game, nn.gamma, rand(UInt64), net))
+    return Engine(ctx, game, net[], false)
+  elseif nn isa MCTS.RandomOracle
+    check(ctx, ccall((:az_net_create_oracle, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Ptr{Cvoid}}), ctx, Int32(0), game, net))
+    return Engine(ctx, game, net[], false)
+  end
+  hp = Network.hyperparams(nn)
   if nn isa NetLib.ResNet
     chp = CResNetHP(hp.num_blocks, hp.num_filters, (Int32(hp.conv_kernel_size[1]), Int32(hp.conv_kernel_size[2])),
                     hp.num_policy_head_filters, hp.num_value_head_filters, hp.batch_norm_momentum)
@@ -236,13 +245,13 @@ function run_selfplay(gspec, nn, mp::CMctsParams, sp::CSimParams, first_game::In
   close!(e)
   return out
 end
-function run_duel(gspec, nn_white, nn_black, mp::CMctsParams, sp::CSimParams, first_game::Int; game_simulated, seed)
+function run_duel(gspec, nn_white, nn_black, mp::CMctsParams, mp_black::CMctsParams, sp::CSimParams, first_game::Int; game_simulated, seed)
   w = Engine(gspec, nn_white)
   b = Engine(gspec, nn_black)
   h = Ref{Ptr{Cvoid}}(C_NULL)
-  check(w.ctx, ccall((:az_selfplay_create_duel, LIB), Int32,
-        (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ref{CMctsParams}, Ref{CSimParams}, UInt64, Ptr{Ptr{Cvoid}}),
-        w.ctx, w.game, w.net, b.net, mp, sp, seed, h))
+  check(w.ctx, ccall((:az_selfplay_create_duel_players, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{CMctsParams}, Ptr{Cvoid}, Ref{CMctsParams}, Ref{CSimParams}, UInt64, Ptr{Ptr{Cvoid}}),
+        w.ctx, w.game, w.net, mp, b.net, mp_black, sp, seed, h))
   check(w.ctx, ccall((:az_selfplay_start, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), h[], sp.num_games, first_game))
   poll_until_finished(w.ctx, h[], game_simulated)
   out = fetch_traces(w.ctx, h[], gspec)
@@ -252,8 +261,9 @@ function run_duel(gspec, nn_white, nn_black, mp::CMctsParams, sp::CSimParams, fi
 end
 
 # ---- the seam ------------------------------------------------------------------------------------------------------------
-# What the engine can run: one MctsPlayer, or TwoPlayers of two MctsPlayers with IDENTICAL parameters, over ResNet /
-# SimpleNet oracles, measured by self_play_measurements (src/training.jl:269-273) or record_trace (src/simulations.jl:195).
+# What the engine can run: one MctsPlayer, or TwoPlayers of two MctsPlayers (each with its own parameters and oracle: ResNet,
+# SimpleNet, MCTS.RolloutOracle, MCTS.RandomOracle), measured by self_play_measurements (src/training.jl:269-273) or
+# record_trace (src/simulations.jl:195).
 function plan(simulator::Simulator, gspec)
   isnothing(game_name(gspec)) && return nothing
   oracles = simulator.make_oracles()
@@ -261,12 +271,12 @@ function plan(simulator::Simulator, gspec)
   if player isa MctsPlayer && supported_network(oracles)
     mp = c_mcts_params(player)
     isnothing(mp) && return nothing
-    return (kind = :single, nets = (oracles,), mp = mp, bytes_per_node = MCTS.memory_footprint_per_node(gspec))
+    return (kind = :single, nets = (oracles,), mp = mp, mp_black = mp, bytes_per_node = MCTS.memory_footprint_per_node(gspec))
   elseif player isa TwoPlayers && player.white isa MctsPlayer && player.black isa MctsPlayer &&
          oracles isa Tuple && length(oracles) == 2 && all(supported_network, oracles)
     mpw, mpb = c_mcts_params(player.white), c_mcts_params(player.black)
-    (isnothing(mpw) || isnothing(mpb) || mpw != mpb) && return nothing
-    return (kind = :duel, nets = oracles, mp = mpw, bytes_per_node = MCTS.memory_footprint_per_node(gspec))
+    (isnothing(mpw) || isnothing(mpb)) && return nothing
+    return (kind = :duel, nets = oracles, mp = mpw, mp_black = mpb, bytes_per_node = MCTS.memory_footprint_per_node(gspec))
   end
   return nothing
 end
@@ -288,7 +298,7 @@ function simulate_on_gpu(simulator::Simulator, gspec, p::SimParams, pl, num_game
   traces, edepth, nodes, flipped =
     pl.kind == :single ?
       run_selfplay(gspec, pl.nets[1], pl.mp, sp, first_game; game_simulated = game_simulated, seed = seed) :
-      run_duel(gspec, pl.nets[1], pl.nets[2], pl.mp, sp, first_game; game_simulated = game_simulated, seed = seed)
+      run_duel(gspec, pl.nets[1], pl.nets[2], pl.mp, pl.mp_black, sp, first_game; game_simulated = game_simulated, seed = seed)
   return [measure(simulator, pl, traces[g], flipped[g] != 0, edepth[g], nodes[g]) for g in 1:length(traces)]
 end
 

@@ -69,21 +69,29 @@ def test_persistent_tower_equals_per_layer_kernels(az, oz, ctx, blocks, batch):
     gs = az.GameSpec("connect-four")
     hp = netcheck.c4_hp(blocks)
     states = gs.random_positions(17, batch, 38)
-    outs = []
+    outs, errs = [], []
     for env in ({"AZ_LO": "16"}, {"AZ_TOWER": "layer"}, {}):
         net, blob = _net_with_env(az, ctx, gs, hp, env)
         for rep in range(3):       # repeated launches: the flag counters keep counting across launches
             P, V, _ = net.evaluate_batch(states)
         L, Vp = net.forward_logits(states)
         outs.append((P, V, L, Vp))
+        if batch <= 700:
+            r = netcheck.compare(az, oz, gs, net, blob, hp, states)
+            errs.append((r["rmsL"], r["rmsVpre"], r["dL"], r["dVpre"]))
         net.close()
     for a, b in zip(outs[0], outs[1]):
         assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    # e4m3 low-order part: a different (equally valid) rounding of the skip stream, so single outputs move by about the
+    # network's own fp16 noise; what must hold is that its error against the fp32 reference is no larger than the fp16 one's
     d = [float(np.abs(a - b).max()) for a, b in zip(outs[0], outs[2])]
     print("lo8 vs lo16: max |dP| %.2e |dV| %.2e |dL| %.2e |dVpre| %.2e" % tuple(d))
-    assert max(d) < 2.5e-4, d
+    assert max(d) < 2.5e-3, d
     if blocks > 1:
         assert max(d) > 0.0    # the 8-bit path really ran
+    if errs:
+        print("vs fp32 reference (rmsL, rmsVpre, maxL, maxVpre): lo16 %s  lo8 %s" % (errs[0], errs[2]))
+        assert errs[2][0] <= 1.2 * errs[0][0] + 2e-5 and errs[2][1] <= 1.2 * errs[0][1] + 2e-5, (errs[0], errs[2])
 
 
 def test_resnet_precision_stress(az, oz, ctx):

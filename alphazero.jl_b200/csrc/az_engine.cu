@@ -710,7 +710,12 @@ struct SelfPlay : az_selfplay {
     if (totals) {
       int64_t ns = 0;
       for (int v : h_moves) ns += v;
-      totals[0] = seconds; totals[1] = (double)ns * sp.nsims; totals[2] = (double)total_expansions; totals[3] = (double)ns;
+      // simulations: the device counters (MCTS.Env.total_simulations of every tree, kept across reset!, src/mcts.jl:142,278-281)
+      std::vector<int64_t> tsims((size_t)pool->p.S);
+      AZ_CUDA(ctx, cudaMemcpy(tsims.data(), pool->p.total_sims, tsims.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+      int64_t sims = 0;
+      for (int64_t v : tsims) sims += v;
+      totals[0] = seconds; totals[1] = (double)sims; totals[2] = (double)total_expansions; totals[3] = (double)ns;
     }
     return AZ_OK;
   }

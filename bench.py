@@ -33,9 +33,8 @@ HP = dict(num_blocks=BLOCKS, num_filters=128, conv_kernel_size=(3, 3), num_polic
 CONV_MFLOP_PER_LEAF = 2 * 42 * 128 * 1152 / 1e6     # one 3x3 conv layer, valid positions only (12.39 MFLOP)
 NET_MFLOP_PER_LEAF = 174.7                           # whole 7-block network
 METRIC = "mcts_node_expansions_per_s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from profiles/r01_final_conv_ncu_summary.txt
-# (ncu --set full, cold caches, ~3700 leaves): conv1 variant 55.0 MB, conv2 variant 214.4 MB per launch; mean of the two
-NCU_TRAFFIC_BYTES = 53.1e6  # profiles/r02a_conv_yrow_ncu_summary.txt: (conv1 32.0 MB + conv2 74.2 MB) / 2 per launch, cold caches
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (ncu --set full, cold caches)
+NCU_TRAFFIC_BYTES = 401.0e6  # profiles/r02final_tower_ncu_summary.txt: 61.9 MB read + 339.2 MB written per launch of az_k_tower_yrow (ONE launch = all 14 layers; ncu, cold caches, ~3000 leaves)
 
 
 def resnet_blob(dim, num_actions, hp, seed=1):
@@ -65,7 +64,7 @@ def resnet_blob(dim, num_actions, hp, seed=1):
     return np.concatenate(parts).astype(np.float32)
 
 
-NCU_TREE_TRAFFIC_BYTES = 6.5e6   # profiles/r02a_tree_ncu_summary.txt: select 3.56 MB + expand_backup 2.98 MB of DRAM reads per tick (cold, tick ~550)
+NCU_TREE_TRAFFIC_BYTES = 6.56e6   # profiles/r02final_tree_ncu_summary.txt: select 3.57 MB + expand_backup 2.99 MB of DRAM reads per tick (cold, tick ~550)
 
 
 def hbm_peak():

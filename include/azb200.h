@@ -84,8 +84,11 @@ typedef struct {
 typedef struct {
   int32_t num_games;
   int32_t num_workers; /* concurrent game slots on this GPU (= worker tasks, src/simulations.jl:217) */
-  int32_t batch_size;  /* accepted for API parity; the engine batches every pending leaf of a tick */
-  int32_t fill_batches;
+  int32_t batch_size;  /* accepted for API parity (must be <= num_workers, src/batchifier.jl:48); the engine batches every pending
+                          leaf of a tick, which is what batch_size = num_workers gives the reference */
+  int32_t fill_batches; /* accepted and irrelevant: the reference pads a short batch with copies of its first state so that the
+                           network always sees one batch shape (src/batchifier.jl:66-70, results unchanged); the device
+                           network evaluates exactly the pending leaves */
   int32_t reset_every; /* <= 0: never (Julia `nothing`) */
   int32_t alternate_colors; /* duels only: odd sim_id (1-based game index) swaps the players' colours (src/simulations.jl:224-230) */
   double flip_probability;  /* random GI.symmetries image before each turn (src/play.jl:305-307); needs a game that declares

@@ -210,7 +210,6 @@ int32_t az_samples_allgather(az_comm* c, az_samples* local, az_samples** out, in
     const int A = az_game_num_actions(game);
     const int ROWW = A + 6;
     const int world = c->world;
-    AZ_CUDA(ctx, cudaEventRecord(c->ev0, st));
     // 1. counts (8 B per rank)
     AZ_CUDA(ctx, cudaMemcpyAsync(c->d_counts + world, &n, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     AZ_NCCL(ctx, api.AllGather(c->d_counts + world, c->d_counts, 1, ncclInt64, c->comm, st));
@@ -236,9 +235,11 @@ int32_t az_samples_allgather(az_comm* c, az_samples* local, az_samples** out, in
           return AZ_ENOMEM;
         }
         c->send_words = want; c->recv_words = want * world;
-        AZ_CUDA(ctx, cudaEventRecord(c->ev0, st));   // do not charge the one-off allocation to the exchange
       }
       uint64_t *d_send = c->d_send, *d_recv = c->d_recv;
+      // last_ms = the exchange proper (pack -> all-gather -> compact); allocating the output set is host-side cudaMalloc time
+      // (tens of ms once NCCL has enabled peer mappings) and is visible in the caller's wall clock
+      AZ_CUDA(ctx, cudaEventRecord(c->ev0, st));
       const int grid = ctx->num_sms * 8;
       if (n > 0) azc_k_pack<<<grid, 256, 0, st>>>(n, A, az_samples_env(local), az_samples_pi(local), az_samples_z(local), az_samples_t(local),
                                                   az_samples_cnt(local), d_send);
@@ -252,6 +253,7 @@ int32_t az_samples_allgather(az_comm* c, az_samples* local, az_samples** out, in
       if (r != ncclSuccess) { az_samples_destroy(o); ctx->err = std::string("ncclAllGather: ") + api.GetErrorString(r); return AZ_ECUDA; }
       if (e != cudaSuccess) { az_samples_destroy(o); ctx->err = std::string("az_samples_allgather: ") + cudaGetErrorString(e); return AZ_ECUDA; }
     } else {
+      cudaEventRecord(c->ev0, st);
       cudaEventRecord(c->ev1, st);
       AZ_CUDA(ctx, cudaStreamSynchronize(st));
     }

@@ -371,10 +371,12 @@ def main():
             gather_ms = comm.last_ms
         barrier()
         t_gather = time.perf_counter() - t1
-        gather2_ms = 0.0
+        gather2_ms, gather2_wall = 0.0, 0.0
         if comm is not None:      # the same exchange again (NCCL's buffers for this size exist now): the steady-state figure of later iterations
+            tg2 = time.perf_counter()
             g2, _ = comm.allgather_samples(smp)
             gather2_ms = comm.last_ms
+            gather2_wall = time.perf_counter() - tg2
             g2.close()
         # replay-buffer side on this rank's samples, device resident: augment -> merge -> convert
         tr0 = time.perf_counter()
@@ -391,7 +393,7 @@ def main():
             x.close()
         del cv
         sp_h.close()
-        sp_out = dict(t=t_play + t_gather, t_gather=t_gather, gather_device_ms=gather_ms, gather2_device_ms=gather2_ms, games=count, samples=int(out["samples"]),
+        sp_out = dict(t=t_play + t_gather, t_gather=t_gather, gather_device_ms=gather_ms, gather2_device_ms=gather2_ms, gather2_wall_s=gather2_wall, games=count, samples=int(out["samples"]),
                       expansions=float(out["expansions"]), total_samples=total_gathered, mean_moves=float(out["moves"].mean()),
                       mean_edepth=float(out["edepth"].mean()))
     # ---- arena: pit_networks of two 7-block nets with the shipped Connect-Four ArenaParams
@@ -453,7 +455,7 @@ def main():
         if sp_out is not None:
             line["selfplay"] = {"games_per_s": sp_out["games"] / sp_out["t"], "samples_per_s": sp_out["samples"] / sp_out["t"],
                                 "expansions_per_s": sp_out["expansions"] / sp_out["t"], "seconds": sp_out["t"],
-                                "allgather_seconds": sp_out["t_gather"], "allgather_device_ms": sp_out["gather_device_ms"], "allgather_device_ms_repeat": sp_out["gather2_device_ms"],
+                                "allgather_seconds": sp_out["t_gather"], "allgather_device_ms": sp_out["gather_device_ms"], "allgather_device_ms_repeat": sp_out["gather2_device_ms"], "allgather_seconds_repeat": sp_out["gather2_wall_s"],
                                 "allgather": "az_samples_allgather: NCCL, packed 104 B rows, device resident (no host staging)", "games": int(sp_out["games"]), "samples": int(sp_out["samples"]),
                                 "gathered_samples_on_rank0": sp_out["total_samples"], "mean_moves_per_game": sp_out["mean_moves"],
                                 "mean_exploration_depth": sp_out["mean_edepth"],
@@ -473,7 +475,7 @@ def main():
                                 "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": how,
                                 "avg_launch_us": 1e3 * prof["tower_ms"] / max(1, prof["tower_launches"]),
                                 "tower_launches": prof["tower_launches"], "avg_layer_us": 1e3 * prof["tower_ms"] / max(1, prof["evals"] * nconv),
-                                "algorithmic_flop_per_launch": "12.39 MFLOP x leaves of the tick (SURVEY 8d: 2*42*128*1152 per leaf per conv layer)",
+                                "algorithmic_flop_per_launch": "12.39 MFLOP x leaves of the tick x conv layers per launch (SURVEY 8d: 2*42*128*1152 per leaf per conv layer; the persistent tower kernel runs all %d layers in one launch)" % nconv,
                                 "how": "CUDA events around the tower (%d conv layers; one persistent launch or one launch per layer) of every tick on the library stream, in a profiled pass of the same %d steps right after the timed region (graph replay off); step time in that pass %.1f ms"
                                        % (nconv, args.steps, prof["step_ms"] / args.steps),
                                 "network_share_of_step": prof["total_ms"] / prof["step_ms"],

@@ -55,7 +55,7 @@ ABI_SYMBOLS = [
     "az_version", "az_ctx_create", "az_ctx_destroy", "az_last_error", "az_ctx_synchronize", "az_ctx_num_launches",
     "az_game_lookup", "az_game_num_actions", "az_game_state_bytes", "az_game_state_dim", "az_game_max_plies",
     "az_game_vectorize_state", "az_game_actions_mask", "az_game_play", "az_game_init_state", "az_game_random_positions",
-    "az_net_create_oracle", "az_net_create_rollout", "az_net_create_resnet", "az_net_create_simplenet", "az_net_num_params", "az_net_load",
+    "az_net_create_oracle", "az_net_create_rollout", "az_net_create_resnet", "az_net_create_simplenet", "az_net_num_params", "az_net_load", "az_net_load_device",
     "az_net_forward", "az_net_forward_logits", "az_net_set_profiling", "az_net_get_profile", "az_net_destroy",
     "az_mcts_create", "az_mcts_set_roots", "az_mcts_set_noise", "az_mcts_run", "az_mcts_explore", "az_mcts_root_stats", "az_mcts_policy",
     "az_mcts_reset", "az_mcts_counters", "az_mcts_last_timing", "az_mcts_destroy", "az_mcts_set_profiling", "az_mcts_get_profile",
@@ -92,7 +92,7 @@ def lib():
             "az_net_create_rollout": [vp, C.c_int32, C.c_double, C.c_uint64, C.POINTER(vp)],
             "az_net_create_resnet": [vp, C.c_int32, C.POINTER(_ResNetHP), C.POINTER(vp)],
             "az_net_create_simplenet": [vp, C.c_int32, C.POINTER(_SimpleNetHP), C.POINTER(vp)],
-            "az_net_num_params": [vp, C.POINTER(C.c_int64)], "az_net_load": [vp, vp, C.c_int64],
+            "az_net_num_params": [vp, C.POINTER(C.c_int64)], "az_net_load": [vp, vp, C.c_int64], "az_net_load_device": [vp, vp, C.c_int64],
             "az_net_forward": [vp, vp, C.c_int32, vp, vp, vp], "az_net_destroy": [vp],
             "az_net_forward_logits": [vp, vp, C.c_int32, vp, vp],
             "az_net_set_profiling": [vp, C.c_int32], "az_net_get_profile": [vp, vp, vp, vp, vp],
@@ -295,6 +295,11 @@ class Network:
     def load(self, blob):
         b = np.ascontiguousarray(blob, np.float32)
         self.ctx.check(lib().az_net_load(self.h, b.ctypes.data, b.size))
+        return self
+
+    def load_device(self, device_ptr, n):
+        """Parameters already in device memory of this network's GPU (az_net_load_device): no host round trip."""
+        self.ctx.check(lib().az_net_load_device(self.h, C.c_void_p(int(device_ptr)), int(n)))
         return self
 
     def evaluate_batch(self, states):

@@ -676,13 +676,14 @@ struct SelfPlay : az_selfplay {
     std::vector<float> ht(rows);
     std::vector<int32_t> hact(rows);
     std::vector<double> hrew(rows);
-    AZ_CUDA(ctx, cudaMemcpy(env.data(), sp.s_env, rows * sizeof(AzEnv), cudaMemcpyDeviceToHost));
-    AZ_CUDA(ctx, cudaMemcpy(think.data(), sp.s_root, rows * sizeof(AzEnv), cudaMemcpyDeviceToHost));
-    AZ_CUDA(ctx, cudaMemcpy(hpi.data(), sp.s_pi, rows * G::A * sizeof(double), cudaMemcpyDeviceToHost));
-    AZ_CUDA(ctx, cudaMemcpy(hz.data(), sp.s_z, rows * sizeof(double), cudaMemcpyDeviceToHost));
-    AZ_CUDA(ctx, cudaMemcpy(ht.data(), sp.s_t, rows * sizeof(float), cudaMemcpyDeviceToHost));
-    AZ_CUDA(ctx, cudaMemcpy(hact.data(), sp.s_action, rows * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    AZ_CUDA(ctx, cudaMemcpy(hrew.data(), sp.s_reward, rows * sizeof(double), cudaMemcpyDeviceToHost));
+    AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    AZ_TRY(ctx, az_d2h(ctx, env.data(), sp.s_env, rows * sizeof(AzEnv)));
+    AZ_TRY(ctx, az_d2h(ctx, think.data(), sp.s_root, rows * sizeof(AzEnv)));
+    AZ_TRY(ctx, az_d2h(ctx, hpi.data(), sp.s_pi, rows * G::A * sizeof(double)));
+    AZ_TRY(ctx, az_d2h(ctx, hz.data(), sp.s_z, rows * sizeof(double)));
+    AZ_TRY(ctx, az_d2h(ctx, ht.data(), sp.s_t, rows * sizeof(float)));
+    AZ_TRY(ctx, az_d2h(ctx, hact.data(), sp.s_action, rows * sizeof(int32_t)));
+    AZ_TRY(ctx, az_d2h(ctx, hrew.data(), sp.s_reward, rows * sizeof(double)));
     size_t k = 0;
     for (int g = 0; g < ng; g++)
       for (int i = 0; i < h_moves[g]; i++, k++) {
@@ -830,6 +831,29 @@ static int g_net_forward(az_net* net, const uint8_t* states, int B, float* P, fl
     return AZ_ESTATE;                                             \
   }
 
+int az_d2h(az_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  constexpr size_t CHUNK = (size_t)8 << 20;
+  if (bytes == 0) return AZ_OK;
+  for (int i = 0; i < 2; i++) {
+    if (!ctx->pin[i]) AZ_CUDA(ctx, cudaMallocHost(&ctx->pin[i], CHUNK));
+    if (!ctx->pin_ev[i]) AZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pin_ev[i], cudaEventDisableTiming));
+  }
+  const size_t nchunks = (bytes + CHUNK - 1) / CHUNK;
+  for (size_t i = 0; i <= nchunks; i++) {
+    if (i < nchunks) {
+      const size_t off = i * CHUNK, len = std::min(CHUNK, bytes - off);
+      AZ_CUDA(ctx, cudaMemcpyAsync(ctx->pin[i & 1], (const char*)src + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+      AZ_CUDA(ctx, cudaEventRecord(ctx->pin_ev[i & 1], ctx->stream));
+    }
+    if (i > 0) {  // drain the previous chunk while the copy engine works on this one
+      const size_t j = i - 1, off = j * CHUNK, len = std::min(CHUNK, bytes - off);
+      AZ_CUDA(ctx, cudaEventSynchronize(ctx->pin_ev[j & 1]));
+      memcpy((char*)dst + off, ctx->pin[j & 1], len);
+    }
+  }
+  return AZ_OK;
+}
+
 extern "C" {
 
 int32_t az_version(void) { return AZ_ABI_VERSION; }
@@ -860,6 +884,7 @@ int32_t az_ctx_destroy(az_ctx* ctx) {
   if (!ctx) return AZ_EINVAL;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 2; i++) { if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]); if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return AZ_OK;
@@ -931,6 +956,19 @@ int32_t az_net_load(az_net* net, const float* blob, int64_t n) {
   AZ_GUARD_BEGIN
   cudaSetDevice(net->ctx->device);
   return net->load(blob, n);
+  AZ_GUARD_END(net->ctx)
+}
+int32_t az_net_load_device(az_net* net, const float* d_blob, int64_t n) {
+  if (!net || !d_blob) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  cudaSetDevice(net->ctx->device);
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, d_blob) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != net->ctx->device) {
+    cudaGetLastError();
+    net->ctx->err = "az_net_load_device: the blob must be device memory of the network's GPU";
+    return AZ_EINVAL;
+  }
+  return net->load_device(d_blob, n);
   AZ_GUARD_END(net->ctx)
 }
 int32_t az_net_forward(az_net* net, const uint8_t* states, int32_t B, float* P, float* V, float* Pinv) {

@@ -1824,6 +1824,36 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight folding ON THE DEVICE (round 2): the Flux-order fp32 parameter blob -> the kernels' fp16 layouts with BatchNorm
+// (test mode) folded in, so that a network trained on the same GPU (alphazero.jl_b200/learning.py, or Flux through CUDA.jl)
+// hands its parameters over without a host round trip (az_net_load_device); az_net_load uploads the host blob once and
+// takes the same path.  Arithmetic = the host fold it replaces, one rounding per operation (no FMA contraction):
+//   scale = gamma / sqrt(sigma2 + eps),  W' = fp16(W * scale),  b' = (b - mu) * scale + beta.
+// ------------------------------------------------------------------------------------------------
+// conv (k x k, Flux W[kx, ky, cin, cout] column-major) -> dst[o * dst_stride + tap * tap_stride + c], tap = ky * k + kx
+__global__ void az_k_fold_conv(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ bn, int cout, int cin, int k,
+                               __half* __restrict__ dst, int dst_stride, int tap_stride, int row0, float* __restrict__ bias_out) {
+  const int total = cout * k * k * cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % cin, tap = (i / cin) % (k * k), o = i / (cin * k * k);
+    const int ky = tap / k, kx = tap % k;
+    const float sc = __fdiv_rn(bn[o], __fsqrt_rn(__fadd_rn(bn[3 * cout + o], 1e-5f)));
+    dst[(size_t)(row0 + o) * dst_stride + tap * tap_stride + c] = __float2half_rn(__fmul_rn(w[kx + k * (ky + k * (c + (size_t)cin * o))], sc));
+    if (c == 0 && tap == 0) bias_out[row0 + o] = __fadd_rn(__fmul_rn(__fsub_rn(b[o], bn[2 * cout + o]), sc), bn[cout + o]);
+  }
+}
+// dense over the flattened (W, H, 32) head features (Flux W[out, in] column-major, in = x + W*y + W*H*c)
+//   -> dst[o * KD + (y * RS + x) * 32 + c]
+__global__ void az_k_fold_dense(const float* __restrict__ w1, int outs, int W, int H, int RS, int KD, __half* __restrict__ dst) {
+  const int total = outs * 32 * H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int o = i % outs, pos = (i / outs) % (W * H), c = i / (outs * W * H);
+    const int x = pos % W, y = pos / W;
+    dst[(size_t)o * KD + (size_t)(y * RS + x) * 32 + c] = __float2half_rn(w1[o + (size_t)outs * (pos + (size_t)W * H * c)]);
+  }
+}
+
 template <class G>
 struct ResNetImpl : az_net {
   az_resnet_hp hp{};
@@ -2014,53 +2044,51 @@ struct ResNetImpl : az_net {
   // Dense W[out,in] (out fastest), b.  Order: common (stem, blocks), vhead, phead.
   int load(const float* blob, int64_t n) override {
     if (n != num_params()) { ctx->err = "az_net_load: blob has " + std::to_string(n) + " floats, expected " + std::to_string(num_params()); return AZ_EINVAL; }
-    cudaStreamSynchronize(ctx->stream);
+    float* d_blob = nullptr;
+    if (cudaMalloc((void**)&d_blob, (size_t)n * sizeof(float)) != cudaSuccess) { cudaGetLastError(); ctx->err = "cudaMalloc (parameter blob) failed"; return AZ_ENOMEM; }
+    if (cudaMemcpy(d_blob, blob, (size_t)n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError(); cudaFree(d_blob); ctx->err = "cudaMemcpy (parameter blob) failed"; return AZ_ECUDA;
+    }
+    const int st = load_device(d_blob, n);
+    cudaFree(d_blob);
+    return st;
+  }
+  template <class T> int dzalloc(T** dst, size_t count) {
+    if (cudaMalloc((void**)dst, count * sizeof(T)) != cudaSuccess) { cudaGetLastError(); ctx->err = "cudaMalloc (weights) failed"; return AZ_ENOMEM; }
+    cudaMemsetAsync(*dst, 0, count * sizeof(T), ctx->stream);
+    return AZ_OK;
+  }
+  // d_blob: DEVICE pointer to the Flux-order parameters.  Flux order: Conv W[kw,kh,cin,cout] (kw fastest), b; BatchNorm gamma,
+  // beta, mu, sigma2; Dense W[out,in] (out fastest), b.  Order: common (stem, blocks), vhead, phead.
+  int load_device(const float* d_blob, int64_t n) override {
+    if (n != num_params()) { ctx->err = "az_net_load_device: blob has " + std::to_string(n) + " floats, expected " + std::to_string(num_params()); return AZ_EINVAL; }
+    cudaStream_t st = ctx->stream;
+    cudaStreamSynchronize(st);
     gen++;
     free_weights();
     loaded = false;
-    const float* q = blob;
-    const float eps = 1e-5f;
-    auto fold = [&](int cout, const float* b, const float* bn, std::vector<float>& scale, std::vector<float>& shift) {
-      scale.resize(cout); shift.resize(cout);
-      for (int o = 0; o < cout; o++) {
-        float sc = bn[o] / std::sqrt(bn[3 * cout + o] + eps);
-        scale[o] = sc;
-        shift[o] = (b[o] - bn[2 * cout + o]) * sc + bn[cout + o];
-      }
-    };
-    std::vector<float> scale, shift;
+    const float* q = d_blob;
+    auto grid_for = [](size_t total) { return (int)std::min<size_t>((total + 255) / 256, 4096); };
     {  // stem
       const float* w = q; q += 9 * C * F;
       const float* b = q; q += F;
       const float* bn = q; q += 4 * F;
-      fold(F, b, bn, scale, shift);
       static_assert(9 * C <= 64, "stem K must fit one 64-wide K block");
-      std::vector<__half> ws((size_t)F * 64, __float2half_rn(0.0f));
-      for (int ky = 0; ky < 3; ky++) for (int kx = 0; kx < 3; kx++) for (int c = 0; c < C; c++) for (int o = 0; o < F; o++)
-        ws[(size_t)o * 64 + (ky * 3 + kx) * C + c] = __float2half_rn(w[kx + 3 * (ky + 3 * (c + (size_t)C * o))] * scale[o]);
-      AZ_TRY2(up(&d_wstem, ws)); AZ_TRY2(up(&d_bstem, shift));
+      AZ_TRY2(dzalloc(&d_wstem, (size_t)F * 64)); AZ_TRY2(dzalloc(&d_bstem, (size_t)F));
+      az_k_fold_conv<<<grid_for((size_t)F * 9 * C), 256, 0, st>>>(w, b, bn, F, C, 3, d_wstem, 64, C, 0, d_bstem);
       AZ_TRY2(make_map_2d(ctx, &mapWstem, d_wstem, 64, F, 64 * 2, tc::BK, 128));
     }
     const int L = 2 * hp.num_blocks;
     if (L > 0) {
-      if (cudaMalloc((void**)&d_wall, (size_t)L * F * 9 * F * sizeof(__half)) != cudaSuccess || cudaMalloc((void**)&d_ball, (size_t)L * F * sizeof(float)) != cudaSuccess) {
-        cudaGetLastError(); ctx->err = "cudaMalloc (tower weights) failed"; return AZ_ENOMEM;
-      }
+      AZ_TRY2(dzalloc(&d_wall, (size_t)L * F * 9 * F)); AZ_TRY2(dzalloc(&d_ball, (size_t)L * F));
       AZ_TRY2(make_map_2d(ctx, &mapWall, d_wall, 9 * F, (uint64_t)L * F, 9 * F * 2, tc2::BK, tc2::BNH));
     }
     for (int l = 0; l < L; l++) {
       const float* w = q; q += 9LL * F * F;
       const float* b = q; q += F;
       const float* bn = q; q += 4 * F;
-      fold(F, b, bn, scale, shift);
-      std::vector<__half> wh((size_t)F * 9 * F);  // Wt[co][tap*F + ci]
-      for (int o = 0; o < F; o++) for (int ky = 0; ky < 3; ky++) for (int kx = 0; kx < 3; kx++) for (int c = 0; c < F; c++)
-        wh[(size_t)o * 9 * F + (size_t)(ky * 3 + kx) * F + c] = __float2half_rn(w[kx + 3 * (ky + 3 * (c + (size_t)F * o))] * scale[o]);
-      __half* dw = d_wall + (size_t)l * F * 9 * F; float* db = d_ball + (size_t)l * F;
-      if (cudaMemcpy(dw, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess ||
-          cudaMemcpy(db, shift.data(), F * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
-        cudaGetLastError(); ctx->err = "cudaMemcpy (tower weights) failed"; return AZ_ECUDA;
-      }
+      __half* dw = d_wall + (size_t)l * F * 9 * F; float* db = d_ball + (size_t)l * F;   // Wt[co][tap*F + ci]
+      az_k_fold_conv<<<grid_for((size_t)F * 9 * F), 256, 0, st>>>(w, b, bn, F, F, 3, dw, 9 * F, F, 0, db);
       d_wconv.push_back(dw); d_bconv.push_back(db);
       CUtensorMap m;
       AZ_TRY2(make_map_2d(ctx, &m, dw, 9 * F, F, 9 * F * 2, tc::BK, 128));
@@ -2068,45 +2096,44 @@ struct ResNetImpl : az_net {
       AZ_TRY2(make_map_2d(ctx, &m, dw, 9 * F, F, 9 * F * 2, tc2::BK, tc2::BNH));
       mapW2.push_back(m);
     }
-    std::vector<__half> whd((size_t)64 * F);   // head 1x1 convs: rows 0..31 policy filters, 32..63 value filters
-    std::vector<float> bh(64);
+    // head 1x1 convs: rows 0..31 policy filters, 32..63 value filters
+    AZ_TRY2(dzalloc(&d_wh, (size_t)64 * F)); AZ_TRY2(dzalloc(&d_bh, (size_t)64));
     {  // vhead: Conv1x1 F->32, BN, Dense(WH*32 -> F), Dense(F -> 1)
       const float* w = q; q += (int64_t)F * 32;
       const float* b = q; q += 32;
       const float* bn = q; q += 4 * 32;
-      fold(32, b, bn, scale, shift);
-      for (int o = 0; o < 32; o++) { for (int c = 0; c < F; c++) whd[(size_t)(32 + o) * F + c] = __float2half_rn(w[c + (size_t)F * o] * scale[o]); bh[32 + o] = shift[o]; }
+      az_k_fold_conv<<<grid_for((size_t)32 * F), 256, 0, st>>>(w, b, bn, 32, F, 1, d_wh, F, F, 32, d_bh);
       const float* w1 = q; q += (int64_t)WH * 32 * F;
       const float* b1 = q; q += F;
-      std::vector<__half> wd((size_t)F * KD, __float2half_rn(0.0f));  // Wd[o][k'], k' = (y*(W+1) + x)*32 + c
-      for (int o = 0; o < F; o++) for (int c = 0; c < 32; c++) for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
-        wd[(size_t)o * KD + (size_t)(y * RS + x) * 32 + c] = __float2half_rn(w1[o + (size_t)F * ((x + W * y) + (size_t)WH * c)]);
-      AZ_TRY2(up(&d_wd, wd));
-      AZ_TRY2(up(&d_bd, std::vector<float>(b1, b1 + F)));
+      AZ_TRY2(dzalloc(&d_wd, (size_t)F * KD));   // Wd[o][k'], k' = (y*RS + x)*32 + c; pad positions stay zero
+      az_k_fold_dense<<<grid_for((size_t)F * 32 * WH), 256, 0, st>>>(w1, F, W, H, RS, KD, d_wd);
+      AZ_TRY2(dzalloc(&d_bd, (size_t)F));
+      cudaMemcpyAsync(d_bd, b1, F * sizeof(float), cudaMemcpyDeviceToDevice, st);
       AZ_TRY2(make_map_2d(ctx, &mapWd, d_wd, KD, F, (uint64_t)KD * 2, tc::BK, 128));
       const float* w2 = q; q += F;
       const float* b2 = q; q += 1;
-      AZ_TRY2(up(&d_wv2, std::vector<float>(w2, w2 + F)));
-      AZ_TRY2(up(&d_bv2, std::vector<float>(b2, b2 + 1)));
+      AZ_TRY2(dzalloc(&d_wv2, (size_t)F)); AZ_TRY2(dzalloc(&d_bv2, (size_t)1));
+      cudaMemcpyAsync(d_wv2, w2, F * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(d_bv2, b2, sizeof(float), cudaMemcpyDeviceToDevice, st);
     }
     {  // phead: Conv1x1 F->32, BN, Dense(WH*32 -> A)
       const float* w = q; q += (int64_t)F * 32;
       const float* b = q; q += 32;
       const float* bn = q; q += 4 * 32;
-      fold(32, b, bn, scale, shift);
-      for (int o = 0; o < 32; o++) { for (int c = 0; c < F; c++) whd[(size_t)o * F + c] = __float2half_rn(w[c + (size_t)F * o] * scale[o]); bh[o] = shift[o]; }
+      az_k_fold_conv<<<grid_for((size_t)32 * F), 256, 0, st>>>(w, b, bn, 32, F, 1, d_wh, F, F, 0, d_bh);
       const float* w1 = q; q += (int64_t)WH * 32 * A;
       const float* b1 = q; q += A;
-      std::vector<__half> wp((size_t)64 * KD, __float2half_rn(0.0f));  // Wt[a][k'], rows >= A and pad positions zero
-      for (int a = 0; a < A; a++) for (int c = 0; c < 32; c++) for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
-        wp[(size_t)a * KD + (size_t)(y * RS + x) * 32 + c] = __float2half_rn(w1[a + (size_t)A * ((x + W * y) + (size_t)WH * c)]);
-      std::vector<float> bpol(64, 0.0f);
-      for (int a = 0; a < A; a++) bpol[a] = b1[a];
-      AZ_TRY2(up(&d_wpol, wp)); AZ_TRY2(up(&d_bpol, bpol));
+      AZ_TRY2(dzalloc(&d_wpol, (size_t)64 * KD));   // Wt[a][k'], rows >= A and pad positions zero
+      az_k_fold_dense<<<grid_for((size_t)A * 32 * WH), 256, 0, st>>>(w1, A, W, H, RS, KD, d_wpol);
+      AZ_TRY2(dzalloc(&d_bpol, (size_t)64));
+      cudaMemcpyAsync(d_bpol, b1, A * sizeof(float), cudaMemcpyDeviceToDevice, st);
       AZ_TRY2(make_map_2d(ctx, &mapWpol, d_wpol, KD, 64, (uint64_t)KD * 2, tc::BK, 64));
     }
-    AZ_TRY2(up(&d_wh, whd)); AZ_TRY2(up(&d_bh, bh));
     AZ_TRY2(make_map_2d(ctx, &mapWh, d_wh, F, 64, F * 2, tc::BK, 64));
+    cudaError_t e = cudaStreamSynchronize(st);   // the caller may free / overwrite d_blob as soon as this returns
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = std::string("az_net_load_device: ") + cudaGetErrorString(e); return AZ_ECUDA; }
+    ctx->launches += 3 + L + 4;
     loaded = true;
     return AZ_OK;
   }

@@ -273,11 +273,14 @@ static int samples_convert(az_samples* s, int weighing, float* W, float* X, floa
   }
   azs_k_convert<G><<<(int)((n + 127) / 128), 128, 0, ctx->stream>>>(n, weighing, s->env, s->pi, s->z, s->cnt, dW.p, dX.p, dA.p, dP.p, dV.p);
   ctx->launches += 1;
-  if (W) AZ_CUDA(ctx, cudaMemcpyAsync(W, dW.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (X) AZ_CUDA(ctx, cudaMemcpyAsync(X, dX.p, (size_t)n * NX * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (Am) AZ_CUDA(ctx, cudaMemcpyAsync(Am, dA.p, (size_t)n * A * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (P) AZ_CUDA(ctx, cudaMemcpyAsync(P, dP.p, (size_t)n * A * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (V) AZ_CUDA(ctx, cudaMemcpyAsync(V, dV.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  // outputs are the caller's pageable arrays: pinned double-buffered staging (az_d2h), not one driver-staged copy per array
+  int st = AZ_OK;
+  if (W && st == AZ_OK) st = az_d2h(ctx, W, dW.p, (size_t)n * 4);
+  if (X && st == AZ_OK) st = az_d2h(ctx, X, dX.p, (size_t)n * NX * 4);
+  if (Am && st == AZ_OK) st = az_d2h(ctx, Am, dA.p, (size_t)n * A * 4);
+  if (P && st == AZ_OK) st = az_d2h(ctx, P, dP.p, (size_t)n * A * 4);
+  if (V && st == AZ_OK) st = az_d2h(ctx, V, dV.p, (size_t)n * 4);
+  if (st != AZ_OK) return st;
   AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return AZ_OK;
 }

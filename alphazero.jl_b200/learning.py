@@ -67,6 +67,19 @@ class ResNetTorch(nn.Module):
                 parts += [m.weight.detach().cpu().numpy().reshape(-1, order="F"), m.bias.detach().cpu().numpy()]
         return np.concatenate([np.asarray(p, np.float64).ravel() for p in parts]).astype(np.float32)
 
+    def to_blob_tensor(self):
+        """The same blob as ONE contiguous float32 tensor on the model's own device (no host copy): Flux order, column-major
+        flattening = torch's row-major flattening of the transposed array."""
+        parts = []
+        for m in self.layers():
+            if isinstance(m, nn.Conv2d):      # torch [co,ci,kh,kw] -> flipped -> [kw,kh,ci,co] column-major == [co,ci,kh,kw] (flipped) row-major
+                parts += [m.weight.detach().flip(2, 3).reshape(-1), m.bias.detach()]
+            elif isinstance(m, nn.BatchNorm2d):
+                parts += [m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var]
+            else:                              # Dense W[out,in] column-major == W^T row-major
+                parts += [m.weight.detach().t().reshape(-1), m.bias.detach()]
+        return torch.cat([p.reshape(-1).float() for p in parts]).contiguous()
+
     def load_blob(self, blob):
         blob = np.asarray(blob, np.float32)
         want = sum(p.numel() for p in self.parameters()) + sum(2 * m.num_features for m in self.modules() if isinstance(m, nn.BatchNorm2d))
@@ -383,3 +396,16 @@ class Trainer:
 
     def get_trained_network_blob(self):   # get_trained_network (src/learning.jl:126-128) -> the engine's weight blob
         return self.net.to_blob()
+
+    def hand_off(self, engine_net):
+        """get_trained_network without leaving the GPU: the flat parameter tensor of the trained model goes straight into the
+        engine's network (az_net_load_device: BatchNorm folded and fp16 layouts written by device kernels).  Falls back to the
+        host blob when the model does not live on the engine's GPU."""
+        if hasattr(self.net, "to_blob_tensor") and next(self.net.parameters()).is_cuda:
+            t = self.net.to_blob_tensor()
+            torch.cuda.synchronize(t.device)
+            engine_net.load_device(t.data_ptr(), t.numel())
+            return t.numel()
+        blob = self.net.to_blob()
+        engine_net.load(blob)
+        return len(blob)

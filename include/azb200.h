@@ -134,6 +134,10 @@ int32_t az_net_create_simplenet(az_ctx* ctx, int32_t game, const az_simplenet_hp
 int32_t az_net_num_params(az_net* net, int64_t* n);
 /* replaces Network.copy(bestnn; on_gpu=true, test_mode=true) (src/training.jl:278-279): uploads + folds BN */
 int32_t az_net_load(az_net* net, const float* blob, int64_t n);
+/* the same with the blob already in DEVICE memory of the network's GPU (e.g. the flat parameter vector of the model that was
+   just trained there: Flux through CUDA.jl, or alphazero.jl_b200/learning.py): BatchNorm is folded and the kernels' fp16
+   layouts are written by device kernels, no host round trip; the caller's buffer is not retained */
+int32_t az_net_load_device(az_net* net, const float* device_blob, int64_t n);
 /* Network.evaluate_batch / forward_normalized (src/networks/network.jl:264-271,308-315):
    P is A-wide (masked, renormalised, zero on illegal), V[B], Pinvalid[B] (may be NULL) */
 int32_t az_net_forward(az_net* net, const uint8_t* states, int32_t B, float* P, float* V, float* Pinvalid);

@@ -320,16 +320,61 @@ def test_learning_step_hands_weights_to_engine(az, ctx):
     data = dict(W=np.ones(len(states), np.float32), X=X, A=Am, P=P, V=rng.choice([-1.0, 0.0, 1.0], len(states)).astype(np.float32))
     params = lrn.LearningParams(lrn.Adam(1e-3), l2_regularization=1e-4, batch_size=128, loss_computation_batch_size=256)
     tr = lrn.Trainer(net_t, data, params, device="cuda", seed=1)
-    ls = tr.batch_updates(12)   # (that the loss goes down is asserted on the small CPU model in tests/test_learning_cpu.py)
-    assert len(ls) == 12 and np.isfinite(ls).all() and np.isfinite(list(tr.learning_status().values())).all()
-    blob = tr.get_trained_network_blob()
+    ls = tr.batch_updates(40)
+    assert len(ls) == 40 and np.isfinite(ls).all() and np.isfinite(list(tr.learning_status().values())).all()
+    assert np.mean(ls[-8:]) < 0.9 * np.mean(ls[:8]), (ls[:8], ls[-8:])       # the loss goes down on the GPU too
+    # hand-off WITHOUT a host round trip: the flat parameter tensor on the GPU -> az_net_load_device (device-side BatchNorm fold)
     net = az.ResNet(ctx, gs, hp)
-    assert net.num_params == len(blob)
-    net.load(blob)
+    assert tr.hand_off(net) == net.num_params
     Pe, Ve, Pinv = net.evaluate_batch(states)
     net_t.eval()
     with torch.no_grad():
         Pt, Vt, pinv_t = lrn.forward_normalized(net_t, torch.from_numpy(X).cuda(), torch.from_numpy(Am).cuda())
     assert np.abs(Pe - Pt.cpu().numpy()).max() < 1e-3 and np.abs(Ve - Vt.cpu().numpy()).max() < 1e-3
     assert np.abs(Pinv - pinv_t.cpu().numpy()).max() < 1e-3
+    # the host-blob path (az_net_load) goes through the same device fold: identical bits
+    blob = tr.get_trained_network_blob()
+    net2 = az.ResNet(ctx, gs, hp).load(blob)
+    P2, V2, _ = net2.evaluate_batch(states)
+    assert (P2 == Pe).all() and (V2 == Ve).all()
+    with pytest.raises(az.AzError):          # a host pointer is rejected
+        net2.load_device(blob.ctypes.data, len(blob))
     net.close()
+    net2.close()
+
+
+def test_checkpoint_files_round_trip_through_the_engine(az, oz, ctx, tmp_path):
+    """SURVEY 8f rank 4 on the GPU: bestnn.azb / mem.azs written from engine state (network blob, device-resident samples of a
+    finished self-play run) and read back into a fresh network and sample set: identical outputs and samples."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("az_checkpoint", os.path.join(root, "alphazero.jl_b200", "checkpoint.py"))
+    ck = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ck)
+    gs = az.GameSpec("connect-four")
+    hp = netcheck.c4_hp(1)
+    net, blob = netcheck.make_net(az, ctx, gs, hp, seed=9)
+    mp = az.MctsParams(cpuct=2.0, num_iters_per_turn=24, temperature=az.ConstSchedule(1.0), dirichlet_noise_eps=0.25, dirichlet_noise_alpha=1.0)
+    sp = az.SelfPlay(ctx, gs, net, az.SelfPlayParams(mp, az.SimParams(num_games=12, num_workers=6, batch_size=6, reset_every=2)), seed=3)
+    sp.start()
+    sp.wait()
+    smp = az.Samples.from_selfplay(sp)
+    rows = smp.fetch()
+    d = str(tmp_path)
+    ck.save_network(os.path.join(d, "bestnn.azb"), "resnet", gs.name, hp, blob)
+    ck.save_memory(os.path.join(d, "mem.azs"), gs.name, gs.state_bytes, gs.num_actions, rows)
+    ld = ck.load_network(os.path.join(d, "bestnn.azb"))
+    blob2 = ld["blob"]
+    assert ld["game"] == gs.name and ld["kind"] == "resnet" and (blob2 == blob).all()
+    net2 = az.ResNet(ctx, gs, az.ResNetHP(hp["num_blocks"], 128, (3, 3), 32, 32)).load(blob2)
+    st = gs.random_positions(2, 50, 30)
+    a, b = net.evaluate_batch(st), net2.evaluate_batch(st)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    rows2 = ck.load_memory(os.path.join(d, "mem.azs"))
+    smp2 = az.Samples.from_host(ctx, gs, rows2["states"], rows2["pi"], rows2["z"], rows2["t"], n=rows2["n"])
+    back = smp2.fetch()
+    for k in ("states", "pi", "z", "t", "n"):
+        assert (back[k] == rows[k]).all(), k
+    for x in (smp, smp2, sp, net, net2):
+        x.close()

@@ -1627,6 +1627,144 @@ az_k_stem(const AzEnv* __restrict__ envs, const __grid_constant__ CUtensorMap tm
 }
 
 // ------------------------------------------------------------------------------------------------
+// Head 1x1 convs (round 2): both heads' Conv1x1(128 -> 32) + BatchNorm + ReLU as one N = 64 GEMM over the tower's output rows.
+// Replaces az_k_gemm_tc<64, EPI_HEAD> for this job: the 16 KB of weights stay resident (loaded once per CTA), the A ring
+// holds four 16 KB stages (two tiles in flight), the fp16 feature rows leave as 2 KB bulk copies (a feature row is 64
+// contiguous bytes, so 32 rows of a head are one contiguous chunk), and at 80 KB of shared memory two CTAs share an SM.
+// ------------------------------------------------------------------------------------------------
+namespace hc {
+constexpr int NUM_THREADS = 192, ASTAGES = 4;
+struct Smem {
+  uint8_t b[2][64 * 128];           // Wt[64 co][2 x 64 k]
+  uint8_t a[ASTAGES][128 * 128];
+  uint8_t epi[4][2][2048];          // per epilogue warp: policy / value tile, 32 rows x 64 B, linear
+  uint64_t bfull, full[ASTAGES], empty[ASTAGES], tfull[2], tempty[2];
+  uint32_t tmem_base;
+  float bias[64];
+};
+}  // namespace hc
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(hc::NUM_THREADS, 2)
+az_k_head_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmArgs ga) {
+  using namespace hc;
+  constexpr int BN = 64;
+  extern __shared__ uint8_t smem_hc[];
+  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_hc) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&s.bfull, 1);
+    for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x - 64 < BN) s.bias[threadIdx.x - 64] = ga.bias[threadIdx.x - 64];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp == 0) {  // the weights do not depend on earlier kernels
+    if (elect_one()) {
+      mbar_expect_tx(&s.bfull, 2 * 64 * 128);
+      tma_load_2d(s.b[0], &tmW, &s.bfull, 0, 0);
+      tma_load_2d(s.b[1], &tmW, &s.bfull, 64, 0);
+    }
+    __syncwarp();
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int rows_used = (*ga.n_boards) * ga.rows_per_board;
+  const int num_tiles = (rows_used + 127) / 128;
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+      for (int kb = 0; kb < 2; kb++) {
+        mbar_wait(&s.empty[stage], phase ^ 1);
+        if (elect_one()) { mbar_expect_tx(&s.full[stage], 128 * 128); tma_load_2d(s.a[stage], &tmA, &s.full[stage], kb * 64, tile * 128); }
+        __syncwarp();
+        if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+      }
+  } else if (warp == 1) {
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    mbar_wait(&s.bfull, 0);
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+      const int acc = it & 1;
+      mbar_wait(&s.tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
+      tcgen05_fence_after();
+      for (int kb = 0; kb < 2; kb++) {
+        mbar_wait(&s.full[stage], phase);
+        tcgen05_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_u32(s.a[stage]));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[kb]));
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) umma_f16(tmem_base + acc * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
+          umma_commit(&s.empty[stage]);
+          if (kb == 1) umma_commit(&s.tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+      const int acc = it & 1;
+      mbar_wait(&s.tfull[acc], ((uint32_t)it >> 1) & 1u);
+      tcgen05_fence_after();
+      const int p0 = tile * 128 + quarter * 32, p = p0 + lane;
+      const int rr = p % ga.g.board_rows;
+      const bool valid = (p < rows_used) && (rr < ga.g.valid_rows) && ((rr % ga.g.row_stride) != ga.g.wcols);
+      if (lane == 0) tma_store_wait_read<0>();   // the previous tile's two copies have left the staging tiles
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 2; c++) {   // c = 0: policy features, 1: value features
+        uint32_t v[32];
+        tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quarter * 32) << 16), v);
+        uint4 o[4];
+        __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const float x0 = valid ? fmaxf(__uint_as_float(v[2 * j]) + s.bias[c * 32 + 2 * j], 0.0f) : 0.0f;
+          const float x1 = valid ? fmaxf(__uint_as_float(v[2 * j + 1]) + s.bias[c * 32 + 2 * j + 1], 0.0f) : 0.0f;
+          oh[j] = __floats2half2_rn(x0, x1);
+        }
+        uint8_t* t = s.epi[quarter][c] + lane * 64;
+#pragma unroll
+        for (int q = 0; q < 4; q++) *reinterpret_cast<uint4*>(t + q * 16) = o[q];
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && p0 + 32 <= ga.alloc_rows) {
+        bulk_store(ga.out16a + (size_t)p0 * 32, s.epi[quarter][0], 2048);
+        bulk_store(ga.out16b + (size_t)p0 * 32, s.epi[quarter][1], 2048);
+        tma_store_commit();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+    }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused head outputs (round 2): the value head's Dense(K -> 128) + relu + Dense(128 -> 1) + tanh and the policy head's
 // Dense(K -> A) + softmax + legal-action mask + renormalisation (resnet.jl:75-90, network.jl:264-271) in ONE launch
 // instead of two GEMM launches and a finalize kernel: even CTAs run value tiles (N = 128), odd CTAs policy tiles (N = 64,
@@ -2001,6 +2139,7 @@ struct ResNetImpl : az_net {
     smem_stem = sizeof(st::Smem<W * H * C>) + 1024;
     AZ_TRY2(set_smem(az_k_stem<G>, smem_stem));
     AZ_TRY2(set_smem(az_k_heads_dense<G>, smem128));
+    AZ_TRY2(set_smem(az_k_head_conv, sizeof(hc::Smem) + 1024));
     { const char* e = getenv("AZ_FUSED"); fused = !(e && e[0] == '0'); }
     { const char* e = getenv("AZ_TOWER"); persistent = !(e && e[0] == 'l'); }          // AZ_TOWER=layer
     { const char* e = getenv("AZ_TOWER_COOP"); coop_launch = !(e && e[0] == '0'); }    // AZ_TOWER_COOP=0: plain launch
@@ -2281,7 +2420,8 @@ struct ResNetImpl : az_net {
     ga.g.off[0] = 0;  // 1x1 conv: single centre tap
     ga.debug = 0;
     ga.kblocks = 2; ga.bias = d_bh; ga.resid32 = nullptr; ga.out32 = nullptr; ga.out16a = d_hp; ga.out16b = d_hv;
-    launch_pdl(az_k_gemm_tc<64, tc::EPI_HEAD>, grid, tc::NUM_THREADS, smem64, st, mapX, mapWh, ga);
+    if (fused) launch_pdl(az_k_head_conv, std::min(row_tiles, 2 * ctx->num_sms), hc::NUM_THREADS, sizeof(hc::Smem) + 1024, st, mapX, mapWh, ga);
+    else launch_pdl(az_k_gemm_tc<64, tc::EPI_HEAD>, grid, tc::NUM_THREADS, smem64, st, mapX, mapWh, ga);
     GemmArgs gd{};
     gd.n_boards = n_rows; gd.g = geom; gd.kblocks = KD / 64; gd.gemm_k = 1; gd.rows_per_board = 1; gd.alloc_rows = max_rows + 256;
     gd.bias = d_bd; gd.out32 = d_hid;

@@ -18,6 +18,7 @@ using AlphaZero
 using AlphaZero: GI, MCTS, Network, NetLib, Examples, Trace, Simulator, SimParams, MctsParams, SelfPlayParams,
                  MctsPlayer, TwoPlayers, AbstractGameSpec, AbstractSchedule, PLSchedule, ConstSchedule
 import Flux
+import CUDA
 import JSON3
 import Distributed
 using StaticArrays
@@ -136,6 +137,23 @@ end
 
 # oracles the engine has a device implementation of: the two NetLib networks, MCTS.RolloutOracle (src/mcts.jl:27-60, the oracle
 # of Benchmark.MctsRollouts) and MCTS.RandomOracle (src/mcts.jl:62-72)
+# the same blob built ON THE GPU for a network that already lives there (Network.on_gpu): one CuArray, no host copy
+function flux_blob_device(nn)
+  parts = CUDA.CuArray{Float32}[]
+  for chain in (nn.common, nn.vhead, nn.phead)
+    for l in Flux.modules(chain)
+      if l isa Flux.Conv
+        push!(parts, vec(l.weight)); push!(parts, vec(l.bias))
+      elseif l isa Flux.BatchNorm
+        push!(parts, vec(l.γ)); push!(parts, vec(l.β)); push!(parts, vec(l.μ)); push!(parts, vec(l.σ²))
+      elseif l isa Flux.Dense
+        push!(parts, vec(l.weight)); push!(parts, vec(l.bias))
+      end
+    end
+  end
+  return reduce(vcat, parts)
+end
+
 supported_network(nn) = nn isa NetLib.ResNet || nn isa NetLib.SimpleNet || nn isa MCTS.RolloutOracle || nn isa MCTS.RandomOracle
 
 mutable struct Engine
@@ -177,8 +195,15 @@ function Engine(gspec, nn; device = default_device())
     chp = CSimpleNetHP(hp.width, hp.depth_common, hp.depth_phead, hp.depth_vhead, hp.use_batch_norm ? 1 : 0, hp.batch_norm_momentum)
     check(ctx, ccall((:az_net_create_simplenet, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{CSimpleNetHP}, Ptr{Ptr{Cvoid}}), ctx, game, chp, net))
   end
-  blob = flux_blob(Network.to_cpu(nn))   # replaces Network.copy(bestnn; on_gpu=true, test_mode=true), src/training.jl:278
-  GC.@preserve blob check(ctx, ccall((:az_net_load, LIB), Int32, (Ptr{Cvoid}, Ptr{Cfloat}, Int64), net[], blob, length(blob)))
+  # replaces Network.copy(bestnn; on_gpu=true, test_mode=true), src/training.jl:278
+  if Network.on_gpu(nn) && CUDA.deviceid(CUDA.device()) == device
+    dblob = flux_blob_device(nn)          # parameters never leave the GPU: the library folds BatchNorm on the device
+    CUDA.synchronize()
+    GC.@preserve dblob check(ctx, ccall((:az_net_load_device, LIB), Int32, (Ptr{Cvoid}, CUDA.CuPtr{Cfloat}, Int64), net[], dblob, length(dblob)))
+  else
+    blob = flux_blob(Network.to_cpu(nn))
+    GC.@preserve blob check(ctx, ccall((:az_net_load, LIB), Int32, (Ptr{Cvoid}, Ptr{Cfloat}, Int64), net[], blob, length(blob)))
+  end
   return Engine(ctx, game, net[], false)
 end
 close!(e::Engine) = (ccall((:az_net_destroy, LIB), Int32, (Ptr{Cvoid},), e.net); nothing)

@@ -328,9 +328,16 @@ def test_learning_step_hands_weights_to_engine(az, ctx):
     assert tr.hand_off(net) == net.num_params
     Pe, Ve, Pinv = net.evaluate_batch(states)
     net_t.eval()
-    with torch.no_grad():
-        Pt, Vt, pinv_t = lrn.forward_normalized(net_t, torch.from_numpy(X).cuda(), torch.from_numpy(Am).cuda())
-    assert np.abs(Pe - Pt.cpu().numpy()).max() < 1e-3 and np.abs(Ve - Vt.cpu().numpy()).max() < 1e-3
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False   # the comparison target is true fp32
+    try:
+        with torch.no_grad():
+            Pt, Vt, pinv_t = lrn.forward_normalized(net_t, torch.from_numpy(X).cuda(), torch.from_numpy(Am).cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    # a TRAINED network (BatchNorm statistics have moved): P within 1e-3, V within the measured fp16 bound of tests/netcheck.py
+    dP, dV = np.abs(Pe - Pt.cpu().numpy()).max(), np.abs(Ve - Vt.cpu().numpy()).max()
+    assert dP < 1e-3 and dV < netcheck.LOGIT_TOL_PERTURBED, (dP, dV)
     assert np.abs(Pinv - pinv_t.cpu().numpy()).max() < 1e-3
     # the host-blob path (az_net_load) goes through the same device fold: identical bits
     blob = tr.get_trained_network_blob()

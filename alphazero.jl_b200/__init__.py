@@ -564,12 +564,24 @@ class Samples:
     def augment_with_symmetries(self):  # src/memory.jl:126-130
         return self._new(lib().az_samples_augment_with_symmetries)
 
-    def convert(self, weighing=LOG_WEIGHT):
+    def convert_buffers(self):
+        """Host arrays of the right shapes for convert(out=...), already touched (a fresh np.zeros array is lazily mapped: the first
+        write to it pays one page fault per 4 KB, which would be charged to whoever fills it)."""
+        n, a = len(self), self.gspec.num_actions
+        xd = int(np.prod(self.gspec.state_dim))
+        out = dict(W=np.empty(n, np.float32), X=np.empty((n, xd), np.float32), A=np.empty((n, a), np.float32),
+                   P=np.empty((n, a), np.float32), V=np.empty(n, np.float32))
+        for v in out.values():
+            v.fill(0)
+        return out
+
+    def convert(self, weighing=LOG_WEIGHT, out=None):
         """convert_samples (src/learning.jl:38-51): dict of Float32 arrays W [n], X [n, state_dim], A [n, a], P [n, a], V [n]."""
         n, a = len(self), self.gspec.num_actions
         xd = int(np.prod(self.gspec.state_dim))
-        out = dict(W=np.zeros(n, np.float32), X=np.zeros((n, xd), np.float32), A=np.zeros((n, a), np.float32),
-                   P=np.zeros((n, a), np.float32), V=np.zeros(n, np.float32))
+        if out is None:
+            out = dict(W=np.zeros(n, np.float32), X=np.zeros((n, xd), np.float32), A=np.zeros((n, a), np.float32),
+                       P=np.zeros((n, a), np.float32), V=np.zeros(n, np.float32))
         self.ctx.check(lib().az_samples_convert(self.h, weighing, *[out[k].ctypes.data for k in ("W", "X", "A", "P", "V")]))
         return out
 

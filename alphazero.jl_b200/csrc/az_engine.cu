@@ -206,6 +206,7 @@ struct Mcts : az_mcts {
     p.max_sims_per_call = 1;
     if (const char* e = getenv("AZ_NO_GRAPH")) use_graph = !(e[0] == '1');
     if (const char* e = getenv("AZ_FUSE_TREE")) fuse_tree = !(e[0] == '0');
+    if (const char* e = getenv("AZ_DEVICE_LOOP")) use_device_loop = !(e[0] == '0');
     if (const char* e = getenv("AZ_MAX_SIMS_PER_CALL")) p.max_sims_per_call = std::max(1, atoi(e));
     p.c.gamma = params->gamma; p.c.cpuct = params->cpuct; p.c.eps = params->dirichlet_noise_eps;
     p.c.alpha = params->dirichlet_noise_alpha; p.c.prior_temp = params->prior_temperature;
@@ -222,7 +223,7 @@ struct Mcts : az_mcts {
     AZ_TRY(ctx, alloc(&p.path_r, (size_t)S * p.maxd));
     AZ_TRY(ctx, alloc(&p.n_leaves, 4)); AZ_TRY(ctx, alloc(&p.batch_env, S));
     AZ_TRY(ctx, alloc(&p.batch_P, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&p.batch_V, S));
-    AZ_TRY(ctx, alloc(&p.flags, 4)); AZ_TRY(ctx, alloc(&p.expansions, 1));
+    AZ_TRY(ctx, alloc(&p.flags, 4)); AZ_TRY(ctx, alloc(&p.expansions, 1)); AZ_TRY(ctx, alloc(&d_tick_count, 1));
     AZ_TRY(ctx, alloc(&p.noise_game, S)); AZ_TRY(ctx, alloc(&p.noise_move, S));
     AZ_TRY(ctx, alloc(&d_N, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&d_W, (size_t)S * G::A)); AZ_TRY(ctx, alloc(&d_P, (size_t)S * G::A));
     std::vector<uint32_t> tags(S, 64u | 1u);
@@ -238,6 +239,7 @@ struct Mcts : az_mcts {
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : tev) if (e) cudaEventDestroy(e);
     drop_graph();
+    drop_loop_graph();
   }
   int groups_grid() const { return (int)(((size_t)p.S * 32 + 127) / 128); }  // one warp per tree
 
@@ -256,6 +258,15 @@ struct Mcts : az_mcts {
   uint64_t graph_net_gen = 0;
   bool use_graph = true, graph_broken = false;
   bool run_mode = false;        // inside az_mcts_run (explore-only ticks)
+  // device-driven explore loop: ONE graph launch = a WHILE node whose body is a tick + the loop-condition kernel
+  bool use_device_loop = true;  // AZ_DEVICE_LOOP=0: the host replays the tick graph and polls the flags
+  bool device_loop_broken = false;
+  cudaGraphExec_t lexec = nullptr;
+  uint64_t loop_net_gen = 0;
+  int loop_max_ticks = 0;
+  int64_t loop_launches = 0;    // kernels per iteration of the WHILE body
+  int32_t* d_tick_count = nullptr;
+  void drop_loop_graph() { if (lexec) { cudaGraphExecDestroy(lexec); lexec = nullptr; } }
   bool graph_is_fused = false;  // which tick body the captured graph holds
   void drop_graph() { if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; } }
   template <class Extra>
@@ -390,6 +401,52 @@ struct Mcts : az_mcts {
     if (h_pin[4]) AZ_FAIL(ctx, AZ_ESTATE, "MCTS.policy: explore! must be called before policy (src/mcts.jl:262)");
     return AZ_OK;
   }
+  // Build (once per network generation / tick budget) and launch the WHILE graph.  Returns AZ_OK, or AZ_EUNSUPPORTED when
+  // the driver refuses the construction (then the caller falls back to the host-driven loop for good).
+  int run_device_loop(int max_ticks) {
+    AZ_TRY(ctx, net->reserve(net2 ? p.row_base1 : p.S));
+    if (net2) AZ_TRY(ctx, net2->reserve(p.row_base1));
+    const uint64_t gen_now = net->generation() + (net2 ? 0x100000000ull * net2->generation() : 0);
+    if (lexec && (loop_net_gen != gen_now || loop_max_ticks != max_ticks)) drop_loop_graph();
+    if (!lexec) {
+      cudaGraph_t g = nullptr, body = nullptr;
+      cudaGraphConditionalHandle h;
+      bool ok = cudaGraphCreate(&g, 0) == cudaSuccess && cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+      cudaGraphNode_t cnode;
+      if (ok) {
+        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = h;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        ok = cudaGraphAddNode(&cnode, g, nullptr, 0, &cp) == cudaSuccess;
+        if (ok) body = cp.conditional.phGraph_out[0];
+      }
+      const int64_t l0 = ctx->launches;
+      int st = AZ_OK;
+      if (ok) ok = cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        st = tick(false);
+        az_k_loop_cond<<<1, 1, 0, ctx->stream>>>(p, h, d_tick_count, max_ticks);
+        ok = cudaStreamEndCapture(ctx->stream, nullptr) == cudaSuccess && st == AZ_OK;
+      }
+      loop_launches = ctx->launches - l0 + 1;
+      ctx->launches = l0;
+      if (ok) ok = cudaGraphInstantiate(&lexec, g, 0) == cudaSuccess;
+      if (g) cudaGraphDestroy(g);
+      if (!ok) { lexec = nullptr; cudaGetLastError(); return AZ_EUNSUPPORTED; }
+      loop_net_gen = gen_now; loop_max_ticks = max_ticks;
+    }
+    AZ_CUDA(ctx, cudaMemsetAsync(d_tick_count, 0, sizeof(int32_t), ctx->stream));
+    AZ_CUDA(ctx, cudaGraphLaunch(lexec, ctx->stream));
+    int32_t t = 0;
+    AZ_CUDA(ctx, cudaMemcpyAsync(&t, d_tick_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AZ_CUDA(ctx, cudaEventRecord(ev[1], ctx->stream));
+    AZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ticks = t;
+    ctx->launches += (int64_t)t * loop_launches;
+    return AZ_OK;
+  }
   int run(int nsims) override {
     if (nsims <= 0) AZ_FAIL(ctx, AZ_EINVAL, "az_mcts_run: nsims must be positive");
     std::vector<int32_t> tgt(p.S, nsims);
@@ -404,8 +461,15 @@ struct Mcts : az_mcts {
     ticks = 0; ms_net = 0;
     run_mode = true;
     struct RunModeGuard { bool& f; ~RunModeGuard() { f = false; } } run_mode_guard{run_mode};
-    // every unfinished tree completes >= 1 simulation per tick, so nsims ticks always suffice
-    for (int t = 0; t < nsims + 1; t++) {
+    // every unfinished tree completes >= 1 simulation per tick, so nsims + 1 ticks always suffice
+    bool looped = false;
+    if (use_device_loop && !device_loop_broken && use_graph && !profiling && fuse_tree && net->capturable() && (!net2 || net2->capturable())) {
+      const int st = run_device_loop(nsims + 1);
+      if (st == AZ_OK) looped = true;
+      else if (st == AZ_EUNSUPPORTED) device_loop_broken = true;
+      else return st;
+    }
+    for (int t = 0; !looped && t < nsims + 1; t++) {
       if (profiling) AZ_TRY(ctx, tick_profiled());
       else AZ_TRY(ctx, tick_graphed([] {}));
       ticks++;
@@ -414,7 +478,7 @@ struct Mcts : az_mcts {
         if (h_pin[8] == 0 && h_pin[9] == 0 && h_pin[10] == 0) break;  // no leaf pending and no tree with simulations left
       }
     }
-    AZ_CUDA(ctx, cudaEventRecord(ev[1], ctx->stream));
+    if (!looped) AZ_CUDA(ctx, cudaEventRecord(ev[1], ctx->stream));
     AZ_TRY(ctx, check_flags());
     int64_t ex = 0;
     AZ_CUDA(ctx, cudaMemcpy(&ex, p.expansions, sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -569,6 +633,7 @@ struct SelfPlay : az_selfplay {
     for (void* q : allocs) cudaFree(q);
     for (void* q : game_allocs) cudaFree(q);
     if (h_pin) cudaFreeHost(h_pin);
+    if (h_progress) cudaFreeHost(h_progress);
   }
   std::vector<void*> game_allocs;
   template <class T> int galloc(T** ptr, size_t n) {
@@ -588,6 +653,54 @@ struct SelfPlay : az_selfplay {
     games_cap = ng;
     return AZ_OK;
   }
+  // WHILE graph whose body is one self-play tick: select -> oracle(s) -> expand + backup -> move -> assign -> loop condition
+  int32_t* h_progress = nullptr;   // pinned, device-visible: [0] games finished
+  int run_device_loop(Mcts<G>& m, int grid1) {
+    if (!h_progress) AZ_CUDA(ctx, cudaHostAlloc((void**)&h_progress, 64, cudaHostAllocMapped));
+    h_progress[0] = 0;
+    AZ_TRY(ctx, m.net->reserve(m.net2 ? m.p.row_base1 : m.p.S));
+    if (m.net2) AZ_TRY(ctx, m.net2->reserve(m.p.row_base1));
+    cudaGraph_t g = nullptr, body = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphConditionalHandle h;
+    bool ok = cudaGraphCreate(&g, 0) == cudaSuccess && cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+    if (ok) {
+      cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+      cp.conditional.handle = h;
+      cp.conditional.type = cudaGraphCondTypeWhile;
+      cp.conditional.size = 1;
+      cudaGraphNode_t cnode;
+      ok = cudaGraphAddNode(&cnode, g, nullptr, 0, &cp) == cudaSuccess;
+      if (ok) body = cp.conditional.phGraph_out[0];
+    }
+    const int64_t l0 = ctx->launches;
+    int st = AZ_OK;
+    if (ok) ok = cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      st = m.tick(false);
+      az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 0);
+      az_k_assign<G><<<1, 1024, 0, ctx->stream>>>(m.p, sp);
+      az_k_selfplay_cond<<<1, 1, 0, ctx->stream>>>(m.p, sp, h, h_progress);
+      ok = cudaStreamEndCapture(ctx->stream, nullptr) == cudaSuccess && st == AZ_OK;
+    }
+    const int64_t per_tick = ctx->launches - l0 + 3;
+    ctx->launches = l0;
+    if (ok) ok = cudaGraphInstantiate(&exec, g, 0) == cudaSuccess;
+    if (g) cudaGraphDestroy(g);
+    if (!ok) { cudaGetLastError(); return AZ_EUNSUPPORTED; }
+    cudaError_t e = cudaGraphLaunch(exec, ctx->stream);
+    if (e != cudaSuccess) { cudaGraphExecDestroy(exec); ctx->err = std::string("self-play graph launch: ") + cudaGetErrorString(e); return AZ_ECUDA; }
+    // the GPU plays; the host relays progress (game_simulated callbacks are driven by az_selfplay_poll)
+    while ((e = cudaStreamQuery(ctx->stream)) == cudaErrorNotReady) {
+      a_done.store(((volatile int32_t*)h_progress)[0]);
+      std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+    cudaGraphExecDestroy(exec);
+    if (e != cudaSuccess) { ctx->err = std::string("self-play graph: ") + cudaGetErrorString(e); return AZ_ECUDA; }
+    a_done.store(((volatile int32_t*)h_progress)[0]);
+    (void)per_tick;
+    return AZ_OK;
+  }
   int loop() {
     auto t0 = std::chrono::steady_clock::now();
     Mcts<G>& m = *pool;
@@ -604,7 +717,15 @@ struct SelfPlay : az_selfplay {
     ctx->launches += 2;
     int64_t tick = 0;
     m.drop_graph();  // `sp` (game range, buffers) is baked into the captured move-kernel launch
-    for (;;) {
+    // device-driven loop: ONE graph launch plays the whole run; the host only watches the progress counter in pinned memory
+    bool looped = false;
+    if (m.use_device_loop && !m.device_loop_broken && m.use_graph && m.net->capturable() && (!m.net2 || m.net2->capturable())) {
+      const int st = run_device_loop(m, grid1);
+      if (st == AZ_OK) looped = true;
+      else if (st == AZ_EUNSUPPORTED) m.device_loop_broken = true;
+      else return st;
+    }
+    for (; !looped;) {
       AZ_TRY(ctx, m.tick_graphed([&] {
         az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 0);
         az_k_assign<G><<<1, 1024, 0, ctx->stream>>>(m.p, sp);
@@ -624,6 +745,12 @@ struct SelfPlay : az_selfplay {
       }
     }
     m.drop_graph();
+    if (looped) {  // errors raised on the device end the loop: report them like the polled path does
+      AZ_CUDA(ctx, cudaMemcpy(h_pin + 2, m.p.flags, 16, cudaMemcpyDeviceToHost));
+      if (h_pin[2]) AZ_FAIL(ctx, AZ_ENOMEM, "MCTS table overflow during self-play");
+      if (h_pin[4]) AZ_FAIL(ctx, AZ_ESTATE, "simulation path exceeded the per-game ply bound");
+      if (h_pin[5]) AZ_FAIL(ctx, AZ_ESTATE, "root missing at move selection");
+    }
     AZ_CUDA(ctx, cudaMemcpy(&total_expansions, m.p.expansions, 8, cudaMemcpyDeviceToHost));
     h_moves.resize(sp.num_games);
     AZ_CUDA(ctx, cudaMemcpy(h_moves.data(), sp.g_moves, sp.num_games * sizeof(int32_t), cudaMemcpyDeviceToHost));

@@ -326,6 +326,17 @@ __global__ void __launch_bounds__(128) az_k_expand_select(AzPool p) {
   az_select_slot<G>(p, slot, lane);
 }
 
+// ---- loop condition of the device-driven explore loop (a CUDA-graph WHILE node, csrc/az_engine.cu Mcts::run_device_loop):
+// after a tick, continue while a leaf is pending or a tree still has simulations to run, up to max_ticks.  No host code runs
+// between the first select and the last backup of an explore!: this replaces the Julia scheduler (worker tasks + inference
+// server, src/simulations.jl:207-244, src/batchifier.jl:47-81) by a loop the GPU drives itself.
+__global__ void az_k_loop_cond(AzPool p, cudaGraphConditionalHandle handle, int32_t* __restrict__ tick_count, int max_ticks) {
+  const int t = *tick_count + 1;
+  *tick_count = t;
+  const bool more = (p.n_leaves[0] | p.n_leaves[1] | p.n_leaves[2]) != 0;
+  cudaGraphSetConditional(handle, (more && t < max_ticks) ? 1u : 0u);
+}
+
 // ---- MCTS.RolloutOracle (src/mcts.jl:27-60): uniform prior, value = discounted return of ONE random playout from the state.
 // Julia's global rand() cannot be reproduced, so the playout's action draws come from the Philox stream keyed by
 // (seed, hash of the state, ply of the playout): the oracle is a deterministic function of the state, identical on the CPU
@@ -754,6 +765,17 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
 // The reference pairs trace.states[i] with trace.policies[i], a vector over the legal actions of the state the player
 // THOUGHT on; convert_sample later scatters it over the mask of trace.states[i] (src/learning.jl:31-34).  With
 // flip_probability > 0 the two frames differ, so the compact policy is re-scattered here the same way.
+// Loop condition of the device-driven self-play loop (WHILE node, SelfPlay::loop): continue until every game of the run has
+// finished or a kernel raised an error flag.  Progress (games finished so far) goes to host-mapped pinned memory every tick so
+// that az_selfplay_poll / the `game_simulated` callback read it without touching the stream.
+__global__ void az_k_selfplay_cond(AzPool p, AzSelfPlay sp, cudaGraphConditionalHandle handle, volatile int32_t* __restrict__ host_progress) {
+  const int done = *sp.games_done;
+  const int err = p.flags[0] | p.flags[2] | p.flags[3];
+  host_progress[0] = done;
+  __threadfence_system();
+  cudaGraphSetConditional(handle, (done < sp.num_games && !err) ? 1u : 0u);
+}
+
 template <class G>
 __global__ void az_k_export_samples(AzSelfPlay sp, int num_games, const int64_t* __restrict__ goff, AzEnv* oenv, double* opi, double* oz,
                                     double* ot, int32_t* ocnt) {

@@ -11,6 +11,6 @@ for T in 4096 16384 65536; do
   timeout 600 python bench.py --oracle-net uniform --trees $T --steps 2 --warmup 1 --no-selfplay --no-cpu-baseline > gpurun_out/tree_${T}_${tag}.json 2>/dev/null
 done
 bash scripts/profile_round.sh ${tag} all > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:az_k_stem|az_k_heads_dense|az_k_gemm_tc" -s 150 -c 3 -f -o gpurun_out/prof_small_${tag} \
+AZ_DEVICE_LOOP=0 ncu --set full --clock-control none --import-source on -k "regex:az_k_stem|az_k_heads_dense|az_k_head_conv" -s 150 -c 3 -f -o gpurun_out/prof_small_${tag} \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-selfplay --nsims 100 > gpurun_out/prof_small_${tag}.log 2>&1
 ls gpurun_out | tail -30

@@ -6,6 +6,8 @@ set -u
 tag=${1:-rXX}
 what=${2:-all}
 mkdir -p gpurun_out
+# ncu replays kernel nodes; the device-driven WHILE graph is profiled through its host-driven twin (same kernels, same order)
+export AZ_DEVICE_LOOP=0
 B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-selfplay"
 if [ "$what" = all ] || [ "$what" = list ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 800 --csv --log-file gpurun_out/launches_${tag}.csv \

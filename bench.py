@@ -137,6 +137,14 @@ def make_eta(_unused, roots, A, seed):
     return eta
 
 
+def product_config(S, nsims, blocks, oracle_net, world):
+    """The `config` object of a bench line (both arms print the same one for the same workload)."""
+    return {"workload": "connect-four: %d concurrent game trees per GPU x %d sims/move, %s, synthetic random positions (0-30 plies), fresh trees per step"
+                        % (S, nsims, ("%d-block ResNet 128 filters" % blocks) if not oracle_net else oracle_net + " oracle"),
+            "trees_per_gpu": S, "nsims": nsims, "parallelism": "trees sharded over %d rank(s), no data-path collective" % world,
+            "l2": "inputs larger than L2: tree tables %.0f MB + activations %.0f MB per GPU" % (S * 1024 * 128 / 1e6, S * 42 * 128 * 5 / 1e6)}
+
+
 def cpu_reference_run(n_trees, nsims, threads, seed_offset=0, net="resnet"):
     """The reference's algorithm on host cores: CPU MCTS (oracle port, `threads` host threads over the independent trees
     like the reference's worker tasks) + either the batched torch-CPU fp32 7-block ResNet (net="resnet": the end-to-end
@@ -209,9 +217,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "expansions/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "connect-four: %d concurrent game trees per GPU x %d sims/move, 7-block ResNet 128 filters, synthetic random positions (0-30 plies), fresh trees per step"
-                                   % (n_trees, NSIMS), "trees_per_gpu": n_trees, "nsims": NSIMS,
-                       "bounded_sample": "first %d simulations of the %d per step" % (nsims, NSIMS)},
+            # the SAME config object as the product arm's line (BASELINE config[1]); what the CPU arm actually runs of it per step
+            # (a bounded sample: the first REF_SIMS simulations) is stated in cpu_baseline.sample
+            "config": product_config(n_trees, NSIMS, BLOCKS, None, max(1, args.gpus)),
             "cpu_baseline": {"value": v, "unit": "expansions/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "expansions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -446,10 +454,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "expansions/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16" if not args.oracle_net else "f64", "data": "synthetic",
-                "config": {"workload": "connect-four: %d concurrent game trees per GPU x %d sims/move, %s, synthetic random positions (0-30 plies), fresh trees per step"
-                           % (S, nsims, ("%d-block ResNet 128 filters" % args.blocks) if not args.oracle_net else args.oracle_net + " oracle"),
-                           "trees_per_gpu": S, "nsims": nsims, "parallelism": "trees sharded over %d rank(s), no data-path collective" % world,
-                           "l2": "inputs larger than L2: tree tables %.0f MB + activations %.0f MB per GPU" % (S * 1024 * 128 / 1e6, 2 * S * 56 * 256 / 1e6)},
+                "config": product_config(S, nsims, args.blocks, args.oracle_net, world),
                 "simulations_per_s": sims / (ms / 1e3), "expansions_per_simulation": ex / sims, "ticks_per_step": ticks / args.steps,
                 "e2e": {"value": e_ex / e_dt, "unit": "expansions/s",
                         "h2d_bytes_per_step": int(S * 24 + eta.nbytes),

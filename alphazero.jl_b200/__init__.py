@@ -243,6 +243,15 @@ class MctsParams:
         return p
 
 
+def NetworkOnly(τ=1.0, **kw):
+    """Benchmark.NetworkOnly(τ) (src/benchmark.jl:161-176) = PlayerWithTemperature(NetworkPlayer(nn), ConstSchedule(τ)): the
+    parameter block that makes a self-play / duel player use the network's policy directly (num_iters_per_turn = 0 in the C
+    ABI); pass it where an MctsParams goes (`SelfPlayParams(NetworkOnly(0.5), sim)`, `simulate(..., baseline_mcts=NetworkOnly())`)."""
+    tau = kw.pop("tau", τ)
+    assert not kw, kw
+    return MctsParams(num_iters_per_turn=0, temperature=ConstSchedule(tau), dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0)
+
+
 class SimParams:
     """src/params.jl:92-101."""
 

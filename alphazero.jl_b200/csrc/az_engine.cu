@@ -587,10 +587,20 @@ struct SelfPlay : az_selfplay {
     if (s == AZ_OK) allocs.push_back(*ptr);
     return s;
   }
-  int create(az_ctx* c, az_net* net, az_net* net2, const az_mcts_params* mp, const az_sim_params* s, uint64_t seed, const az_mcts_params* mp1 = nullptr) {
-    if (!mp1) mp1 = mp;
+  int create(az_ctx* c, az_net* net, az_net* net2, const az_mcts_params* mp_in, const az_sim_params* s, uint64_t seed, const az_mcts_params* mp1_in = nullptr) {
+    if (!mp1_in) mp1_in = mp_in;
+    // num_iters_per_turn == 0: NetworkPlayer under PlayerWithTemperature (Benchmark.NetworkOnly, src/benchmark.jl:166-176,
+    // src/play.jl:226-235): the engine runs ONE simulation per turn -- on a root that is not in the table yet that is exactly
+    // the oracle call think() makes -- and az_k_move reads the move distribution from the root's priors instead of the visit
+    // counts.  The search parameters of such a player are inert; the priors must be the raw network output.
+    az_mcts_params mp_l = *mp_in, mp1_l = *mp1_in;
+    const az_mcts_params *mp = &mp_l, *mp1 = &mp1_l;
+    for (az_mcts_params* q : {&mp_l, &mp1_l}) {
+      if (q->num_iters_per_turn < 0) { c->err = "MctsPlayer: niters > 0 (src/play.jl:162); 0 selects NetworkPlayer"; return AZ_EINVAL; }
+      if (q->num_iters_per_turn == 0) { q->num_iters_per_turn = 1; q->prior_temperature = 1.0; q->dirichlet_noise_eps = 0.0; }
+    }
+    sp.netonly = mp_in->num_iters_per_turn == 0; sp.netonly1 = mp1_in->num_iters_per_turn == 0;
     if (mp1->temperature_n < 1 || mp1->temperature_n > AZ_MAX_SCHEDULE) { c->err = "temperature schedule: 1..8 points"; return AZ_EINVAL; }
-    if (mp1->num_iters_per_turn <= 0) { c->err = "MctsPlayer: niters > 0 (src/play.jl:162)"; return AZ_EINVAL; }
     ctx = c; game = G::ID; simp = *s;
     if (s->num_workers <= 0) AZ_FAIL(ctx, AZ_EINVAL, "SimParams: num_workers must be positive");
     if (s->batch_size > s->num_workers) AZ_FAIL(ctx, AZ_EINVAL, "batch_size <= num_workers (src/batchifier.jl:48)");
@@ -1183,7 +1193,6 @@ int32_t az_selfplay_create(az_ctx* ctx, int32_t game, az_net* oracle, const az_m
   AZ_GUARD_BEGIN
   cudaSetDevice(ctx->device);
   if (oracle->game != game) AZ_FAIL(ctx, AZ_EINVAL, "az_selfplay_create: oracle was built for another game");
-  if (mp->num_iters_per_turn <= 0) AZ_FAIL(ctx, AZ_EINVAL, "MctsPlayer: niters > 0 (src/play.jl:162)");
   AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, oracle, nullptr, mp, sp, seed, out)
   AZ_GUARD_END(ctx)
 }
@@ -1193,7 +1202,6 @@ int32_t az_selfplay_create_duel(az_ctx* ctx, int32_t game, az_net* white, az_net
   AZ_GUARD_BEGIN
   cudaSetDevice(ctx->device);
   if (white->game != game || black->game != game) AZ_FAIL(ctx, AZ_EINVAL, "az_selfplay_create_duel: oracle was built for another game");
-  if (mp->num_iters_per_turn <= 0) AZ_FAIL(ctx, AZ_EINVAL, "MctsPlayer: niters > 0 (src/play.jl:162)");
   AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, white, black, mp, sp, seed, out)
   AZ_GUARD_END(ctx)
 }
@@ -1203,7 +1211,6 @@ int32_t az_selfplay_create_duel_players(az_ctx* ctx, int32_t game, az_net* white
   AZ_GUARD_BEGIN
   cudaSetDevice(ctx->device);
   if (white->game != game || black->game != game) AZ_FAIL(ctx, AZ_EINVAL, "az_selfplay_create_duel_players: oracle was built for another game");
-  if (mp_white->num_iters_per_turn <= 0 || mp_black->num_iters_per_turn <= 0) AZ_FAIL(ctx, AZ_EINVAL, "MctsPlayer: niters > 0 (src/play.jl:162)");
   AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, white, black, mp_white, sp, seed, out, mp_black)
   AZ_GUARD_END(ctx)
 }

@@ -1983,8 +1983,8 @@ __global__ void az_k_fold_conv(const float* __restrict__ w, const float* __restr
 }
 // dense over the flattened (W, H, 32) head features (Flux W[out, in] column-major, in = x + W*y + W*H*c)
 //   -> dst[o * KD + (y * RS + x) * 32 + c]
-__global__ void az_k_fold_dense(const float* __restrict__ w1, int outs, int W, int H, int RS, int KD, __half* __restrict__ dst) {
-  const int total = outs * 32 * H * W;
+__global__ void az_k_fold_dense(const float* __restrict__ w1, int outs, int nc, int W, int H, int RS, int KD, __half* __restrict__ dst) {
+  const int total = outs * nc * H * W;   // nc <= 32 head channels; the destination keeps 32 per position
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int o = i % outs, pos = (i / outs) % (W * H), c = i / (outs * W * H);
     const int x = pos % W, y = pos / W;
@@ -2101,12 +2101,16 @@ struct ResNetImpl : az_net {
     return AZ_OK;
   }
   int init() {
-    if (hp.num_filters != F || hp.conv_kernel_size[0] != 3 || hp.conv_kernel_size[1] != 3) {
-      ctx->err = "ResNet: this build supports num_filters = 128 and conv_kernel_size = (3, 3)";
+    // The kernels are written for 128 tower channels and 32 + 32 head channels.  Narrower networks (the reference's
+    // profiling scripts use 64 filters) are the same arithmetic with zero weights and zero biases in the unused channels:
+    // ReLU(0) = 0 and adding 0.0f to an fp32 accumulator is exact, so the outputs are those of the narrow network; the
+    // padding is written by load_device() when it folds the parameters.  Such a network costs what a 128-filter one costs.
+    if (hp.num_filters < 1 || hp.num_filters > F || hp.conv_kernel_size[0] != 3 || hp.conv_kernel_size[1] != 3) {
+      ctx->err = "ResNet: this build supports 1 <= num_filters <= 128 and conv_kernel_size = (3, 3)";
       return AZ_EUNSUPPORTED;
     }
-    if (hp.num_policy_head_filters != 32 || hp.num_value_head_filters != 32) {
-      ctx->err = "ResNet: this build supports num_policy_head_filters = num_value_head_filters = 32";
+    if (hp.num_policy_head_filters < 1 || hp.num_policy_head_filters > 32 || hp.num_value_head_filters < 1 || hp.num_value_head_filters > 32) {
+      ctx->err = "ResNet: this build supports 1 <= num_policy_head_filters, num_value_head_filters <= 32";
       return AZ_EUNSUPPORTED;
     }
     if (hp.num_blocks < 0) { ctx->err = "ResNet: num_blocks must be >= 0"; return AZ_EINVAL; }
@@ -2150,11 +2154,12 @@ struct ResNetImpl : az_net {
   }
   int64_t num_params() override {
     const int npf = hp.num_policy_head_filters, nvf = hp.num_value_head_filters;
+    const int64_t Fr = hp.num_filters;
     int64_t n = 0;
-    n += 9LL * C * F + F + 4 * F;                                   // stem conv + BN
-    n += (int64_t)hp.num_blocks * 2 * (9LL * F * F + F + 4 * F);    // blocks
-    n += (int64_t)F * nvf + nvf + 4 * nvf + (int64_t)WH * nvf * F + F + F + 1;  // vhead
-    n += (int64_t)F * npf + npf + 4 * npf + (int64_t)WH * npf * A + A;          // phead
+    n += 9LL * C * Fr + Fr + 4 * Fr;                                   // stem conv + BN
+    n += (int64_t)hp.num_blocks * 2 * (9LL * Fr * Fr + Fr + 4 * Fr);   // blocks
+    n += Fr * nvf + nvf + 4 * nvf + (int64_t)WH * nvf * Fr + Fr + Fr + 1;  // vhead
+    n += Fr * npf + npf + 4 * npf + (int64_t)WH * npf * A + A;             // phead
     return n;
   }
   template <class T> int up(T** dst, const std::vector<T>& v) {
@@ -2207,14 +2212,16 @@ struct ResNetImpl : az_net {
     free_weights();
     loaded = false;
     const float* q = d_blob;
+    const int Fr = hp.num_filters, npf = hp.num_policy_head_filters, nvf = hp.num_value_head_filters;   // real widths; the
+    // destination layouts keep F = 128 channels / 32 head channels and start zeroed (dzalloc): unused channels stay zero
     auto grid_for = [](size_t total) { return (int)std::min<size_t>((total + 255) / 256, 4096); };
     {  // stem
-      const float* w = q; q += 9 * C * F;
-      const float* b = q; q += F;
-      const float* bn = q; q += 4 * F;
+      const float* w = q; q += 9 * C * Fr;
+      const float* b = q; q += Fr;
+      const float* bn = q; q += 4 * Fr;
       static_assert(9 * C <= 64, "stem K must fit one 64-wide K block");
       AZ_TRY2(dzalloc(&d_wstem, (size_t)F * 64)); AZ_TRY2(dzalloc(&d_bstem, (size_t)F));
-      az_k_fold_conv<<<grid_for((size_t)F * 9 * C), 256, 0, st>>>(w, b, bn, F, C, 3, d_wstem, 64, C, 0, d_bstem);
+      az_k_fold_conv<<<grid_for((size_t)Fr * 9 * C), 256, 0, st>>>(w, b, bn, Fr, C, 3, d_wstem, 64, C, 0, d_bstem);
       AZ_TRY2(make_map_2d(ctx, &mapWstem, d_wstem, 64, F, 64 * 2, tc::BK, 128));
     }
     const int L = 2 * hp.num_blocks;
@@ -2223,11 +2230,11 @@ struct ResNetImpl : az_net {
       AZ_TRY2(make_map_2d(ctx, &mapWall, d_wall, 9 * F, (uint64_t)L * F, 9 * F * 2, tc2::BK, tc2::BNH));
     }
     for (int l = 0; l < L; l++) {
-      const float* w = q; q += 9LL * F * F;
-      const float* b = q; q += F;
-      const float* bn = q; q += 4 * F;
+      const float* w = q; q += 9LL * Fr * Fr;
+      const float* b = q; q += Fr;
+      const float* bn = q; q += 4 * Fr;
       __half* dw = d_wall + (size_t)l * F * 9 * F; float* db = d_ball + (size_t)l * F;   // Wt[co][tap*F + ci]
-      az_k_fold_conv<<<grid_for((size_t)F * 9 * F), 256, 0, st>>>(w, b, bn, F, F, 3, dw, 9 * F, F, 0, db);
+      az_k_fold_conv<<<grid_for((size_t)Fr * 9 * Fr), 256, 0, st>>>(w, b, bn, Fr, Fr, 3, dw, 9 * F, F, 0, db);
       d_wconv.push_back(dw); d_bconv.push_back(db);
       CUtensorMap m;
       AZ_TRY2(make_map_2d(ctx, &m, dw, 9 * F, F, 9 * F * 2, tc::BK, 128));
@@ -2238,32 +2245,32 @@ struct ResNetImpl : az_net {
     // head 1x1 convs: rows 0..31 policy filters, 32..63 value filters
     AZ_TRY2(dzalloc(&d_wh, (size_t)64 * F)); AZ_TRY2(dzalloc(&d_bh, (size_t)64));
     {  // vhead: Conv1x1 F->32, BN, Dense(WH*32 -> F), Dense(F -> 1)
-      const float* w = q; q += (int64_t)F * 32;
-      const float* b = q; q += 32;
-      const float* bn = q; q += 4 * 32;
-      az_k_fold_conv<<<grid_for((size_t)32 * F), 256, 0, st>>>(w, b, bn, 32, F, 1, d_wh, F, F, 32, d_bh);
-      const float* w1 = q; q += (int64_t)WH * 32 * F;
-      const float* b1 = q; q += F;
+      const float* w = q; q += (int64_t)Fr * nvf;
+      const float* b = q; q += nvf;
+      const float* bn = q; q += 4 * nvf;
+      az_k_fold_conv<<<grid_for((size_t)nvf * Fr), 256, 0, st>>>(w, b, bn, nvf, Fr, 1, d_wh, F, F, 32, d_bh);
+      const float* w1 = q; q += (int64_t)WH * nvf * Fr;
+      const float* b1 = q; q += Fr;
       AZ_TRY2(dzalloc(&d_wd, (size_t)F * KD));   // Wd[o][k'], k' = (y*RS + x)*32 + c; pad positions stay zero
-      az_k_fold_dense<<<grid_for((size_t)F * 32 * WH), 256, 0, st>>>(w1, F, W, H, RS, KD, d_wd);
+      az_k_fold_dense<<<grid_for((size_t)Fr * nvf * WH), 256, 0, st>>>(w1, Fr, nvf, W, H, RS, KD, d_wd);
       AZ_TRY2(dzalloc(&d_bd, (size_t)F));
-      cudaMemcpyAsync(d_bd, b1, F * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(d_bd, b1, Fr * sizeof(float), cudaMemcpyDeviceToDevice, st);
       AZ_TRY2(make_map_2d(ctx, &mapWd, d_wd, KD, F, (uint64_t)KD * 2, tc::BK, 128));
-      const float* w2 = q; q += F;
+      const float* w2 = q; q += Fr;
       const float* b2 = q; q += 1;
       AZ_TRY2(dzalloc(&d_wv2, (size_t)F)); AZ_TRY2(dzalloc(&d_bv2, (size_t)1));
-      cudaMemcpyAsync(d_wv2, w2, F * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(d_wv2, w2, Fr * sizeof(float), cudaMemcpyDeviceToDevice, st);
       cudaMemcpyAsync(d_bv2, b2, sizeof(float), cudaMemcpyDeviceToDevice, st);
     }
     {  // phead: Conv1x1 F->32, BN, Dense(WH*32 -> A)
-      const float* w = q; q += (int64_t)F * 32;
-      const float* b = q; q += 32;
-      const float* bn = q; q += 4 * 32;
-      az_k_fold_conv<<<grid_for((size_t)32 * F), 256, 0, st>>>(w, b, bn, 32, F, 1, d_wh, F, F, 0, d_bh);
-      const float* w1 = q; q += (int64_t)WH * 32 * A;
+      const float* w = q; q += (int64_t)Fr * npf;
+      const float* b = q; q += npf;
+      const float* bn = q; q += 4 * npf;
+      az_k_fold_conv<<<grid_for((size_t)npf * Fr), 256, 0, st>>>(w, b, bn, npf, Fr, 1, d_wh, F, F, 0, d_bh);
+      const float* w1 = q; q += (int64_t)WH * npf * A;
       const float* b1 = q; q += A;
       AZ_TRY2(dzalloc(&d_wpol, (size_t)64 * KD));   // Wt[a][k'], rows >= A and pad positions zero
-      az_k_fold_dense<<<grid_for((size_t)A * 32 * WH), 256, 0, st>>>(w1, A, W, H, RS, KD, d_wpol);
+      az_k_fold_dense<<<grid_for((size_t)A * npf * WH), 256, 0, st>>>(w1, A, npf, W, H, RS, KD, d_wpol);
       AZ_TRY2(dzalloc(&d_bpol, (size_t)64));
       cudaMemcpyAsync(d_bpol, b1, A * sizeof(float), cudaMemcpyDeviceToDevice, st);
       AZ_TRY2(make_map_2d(ctx, &mapWpol, d_wpol, KD, 64, (uint64_t)KD * 2, tc::BK, 64));

@@ -466,6 +466,8 @@ struct AzSelfPlay {
   int32_t num_games;      // local games to play
   int32_t nsims;          // MctsPlayer.niters of player 0 (src/play.jl:156-165)
   int32_t nsims1;         // duel: of player 1
+  int32_t netonly;        // player 0 is a NetworkPlayer (src/play.jl:226-235): nsims = 1 (the root evaluation), pi = the root's priors
+  int32_t netonly1;       // duel: player 1 is a NetworkPlayer
   int32_t reset_every;
   int32_t max_plies;
   int32_t sched_n;        // temperature schedule of player 0 (MctsPlayer.τ)
@@ -563,7 +565,10 @@ __device__ void az_record_game_end(AzPool& p, AzSelfPlay& sp, int w, int g, int 
   sp.g_moves[g] = n_moves;
   sp.g_final[g] = last;
   int64_t nodes = 0, ts = 0, tn = 0;
-  for (int k = 0; k < nt; k++) { nodes += p.node_count[t0 + k]; ts += p.total_sims[t0 + k]; tn += p.total_nodes[t0 + k]; }
+  for (int k = 0; k < nt; k++) {
+    if (k ? sp.netonly1 : sp.netonly) continue;   // a NetworkPlayer has no MCTS.Env to measure (src/training.jl:269-273)
+    nodes += p.node_count[t0 + k]; ts += p.total_sims[t0 + k]; tn += p.total_nodes[t0 + k];
+  }
   sp.g_nodes[g] = nodes;
   sp.g_edepth[g] = ts == 0 ? 0.0 : (double)tn / (double)ts;
   atomicAdd(sp.games_done, 1);
@@ -688,18 +693,23 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
   float pf[A];
   int n = 0;
   int64_t ntot = 0;
+  // think(::NetworkPlayer) (src/play.jl:230-235): the oracle's policy over the available actions = the priors the root line
+  // holds since this turn's single simulation (or an earlier visit) evaluated it; prior_temperature is 1 for such a player
+  const bool netonly = (sp.duel && (slot & 1)) ? sp.netonly1 != 0 : sp.netonly != 0;
   for (int i = 0; i < A; i++)
     if ((legal >> i) & 1u) {
       AzLine16 e;
       e.u = tab[(size_t)h * L + 1 + i];
       acts[n] = i;
-      pi[n] = (double)e.e.N;
+      pi[n] = netonly ? (double)e.e.P : (double)e.e.N;
       ntot += e.e.N;
       n++;
     }
-  double sum = 0.0;
-  for (int i = 0; i < n; i++) { pi[i] = pi[i] / (double)ntot; sum = (i == 0) ? pi[0] : sum + pi[i]; }
-  for (int i = 0; i < n; i++) pi[i] = pi[i] / sum;
+  if (!netonly) {
+    double sum = 0.0;
+    for (int i = 0; i < n; i++) { pi[i] = pi[i] / (double)ntot; sum = (i == 0) ? pi[0] : sum + pi[i]; }
+    for (int i = 0; i < n; i++) pi[i] = pi[i] / sum;
+  }
   // temperature (src/play.jl:208-210,309-310; src/util.jl:98-110)
   const double tau = az_schedule(sp, (sp.duel && (slot & 1)) ? 1 : 0, move);
   if (tau == 1.0) { for (int i = 0; i < n; i++) pis[i] = pi[i]; }

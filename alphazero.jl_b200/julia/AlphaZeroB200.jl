@@ -9,14 +9,15 @@
 # (src/training.jl:137-139, 150-152).  Julia dispatches on the game-spec type, so loading this module ADDS the methods
 #     simulate_distributed(::Simulator, ::Examples.ConnectFour.GameSpec, ::SimParams; game_simulated)   (and simulate)
 # for the four games the library knows; no reference file changes and `Scripts.train("connect-four")` runs unchanged.
-# Everything the engine cannot express (players that are not MctsPlayer / TwoPlayers of MctsPlayers -- MinMax, NetworkOnly,
-# Human --, oracles other than ResNet / SimpleNet / RolloutOracle / RandomOracle, a timeout instead of an iteration budget)
+# Everything the engine cannot express (players other than MctsPlayer, NetworkPlayer (bare or under PlayerWithTemperature)
+# and TwoPlayers of those -- MinMax, Human, EpsilonGreedy --, oracles other than ResNet / SimpleNet / RolloutOracle / RandomOracle, a timeout instead of an iteration budget)
 # falls back to the reference's own method through `invoke`.
 module AlphaZeroB200
 
 using AlphaZero
 using AlphaZero: GI, MCTS, Network, NetLib, Examples, Trace, Simulator, SimParams, MctsParams, SelfPlayParams,
-                 MctsPlayer, TwoPlayers, AbstractGameSpec, AbstractSchedule, PLSchedule, ConstSchedule
+                 MctsPlayer, TwoPlayers, NetworkPlayer, PlayerWithTemperature, AbstractGameSpec, AbstractSchedule, PLSchedule,
+                 ConstSchedule
 import Flux
 import CUDA
 import JSON3
@@ -115,6 +116,16 @@ function c_mcts_params(pl::MctsPlayer)
   e = pl.mcts
   return c_mcts_params(e.gamma, e.cpuct, pl.niters, e.noise_ϵ, e.noise_α, e.prior_temperature, pl.τ)
 end
+# Benchmark.NetworkOnly (src/benchmark.jl:161-176) = PlayerWithTemperature(NetworkPlayer(nn), ConstSchedule(τ)); a bare
+# NetworkPlayer plays at temperature 1 (src/play.jl:37-39).  num_iters_per_turn = 0 selects the network-only player in the
+# library (include/azb200.h); the search fields are inert.
+c_mcts_params(pl::NetworkPlayer) = c_mcts_params(1.0, 1.0, 0, 0.0, 1.0, 1.0, ConstSchedule(1.0))
+function c_mcts_params(pl::PlayerWithTemperature)
+  pl.player isa NetworkPlayer || return nothing
+  return c_mcts_params(1.0, 1.0, 0, 0.0, 1.0, 1.0, pl.temperature)
+end
+c_mcts_params(::Any) = nothing
+engine_player(pl) = pl isa MctsPlayer || pl isa NetworkPlayer || (pl isa PlayerWithTemperature && pl.player isa NetworkPlayer)
 c_sim_params(p::SimParams, num_games) = CSimParams(num_games, p.num_workers, p.batch_size, p.fill_batches ? 1 : 0,
   isnothing(p.reset_every) ? -1 : p.reset_every, p.alternate_colors ? 1 : 0, p.flip_probability)
 
@@ -286,18 +297,18 @@ function run_duel(gspec, nn_white, nn_black, mp::CMctsParams, mp_black::CMctsPar
 end
 
 # ---- the seam ------------------------------------------------------------------------------------------------------------
-# What the engine can run: one MctsPlayer, or TwoPlayers of two MctsPlayers (each with its own parameters and oracle: ResNet,
-# SimpleNet, MCTS.RolloutOracle, MCTS.RandomOracle), measured by self_play_measurements (src/training.jl:269-273) or
+# What the engine can run: one MctsPlayer or NetworkPlayer, or TwoPlayers of two such players (each with its own parameters
+# and oracle: ResNet, SimpleNet, MCTS.RolloutOracle, MCTS.RandomOracle), measured by self_play_measurements (src/training.jl:269-273) or
 # record_trace (src/simulations.jl:195).
 function plan(simulator::Simulator, gspec)
   isnothing(game_name(gspec)) && return nothing
   oracles = simulator.make_oracles()
   player = simulator.make_player(oracles)
-  if player isa MctsPlayer && supported_network(oracles)
+  if engine_player(player) && supported_network(oracles)
     mp = c_mcts_params(player)
     isnothing(mp) && return nothing
     return (kind = :single, nets = (oracles,), mp = mp, mp_black = mp, bytes_per_node = MCTS.memory_footprint_per_node(gspec))
-  elseif player isa TwoPlayers && player.white isa MctsPlayer && player.black isa MctsPlayer &&
+  elseif player isa TwoPlayers && engine_player(player.white) && engine_player(player.black) &&
          oracles isa Tuple && length(oracles) == 2 && all(supported_network, oracles)
     mpw, mpb = c_mcts_params(player.white), c_mcts_params(player.black)
     (isnothing(mpw) || isnothing(mpb)) && return nothing

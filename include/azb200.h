@@ -72,7 +72,10 @@ int32_t az_game_random_positions(int32_t game, uint64_t seed, uint64_t first_str
 typedef struct {
   double gamma;
   double cpuct;
-  int32_t num_iters_per_turn;
+  int32_t num_iters_per_turn; /* > 0: MctsPlayer.niters.  0 (az_selfplay_create* only): the player is a NetworkPlayer under
+                                 PlayerWithTemperature = Benchmark.NetworkOnly (src/play.jl:226-235, :112-127,
+                                 src/benchmark.jl:161-176): no search, the move distribution and the recorded policy are the
+                                 oracle's policy at the root; only the temperature schedule of this block is used */
   int32_t temperature_n; /* PLSchedule points (ConstSchedule = 1 point), src/schedule.jl:64-80 */
   double dirichlet_noise_eps;
   double dirichlet_noise_alpha;
@@ -192,9 +195,10 @@ int32_t az_selfplay_create(az_ctx* ctx, int32_t game, az_net* oracle, const az_m
    `white_oracle`'s player takes black in every game whose 1-based index is odd. */
 int32_t az_selfplay_create_duel(az_ctx* ctx, int32_t game, az_net* white_oracle, az_net* black_oracle, const az_mcts_params* mp,
                                 const az_sim_params* sp, uint64_t seed, az_selfplay** out);
-/* Benchmark.Duel of two DIFFERENT MctsPlayers (src/benchmark.jl:78-99: e.g. Benchmark.Full(params) against
-   Benchmark.MctsRollouts(params'), :134-162): as az_selfplay_create_duel, but each player brings its own MctsParams (gamma,
-   cpuct, number of iterations, Dirichlet noise, prior temperature, move temperature schedule) next to its own oracle. */
+/* Benchmark.Duel of two DIFFERENT players (src/benchmark.jl:78-99: e.g. Benchmark.Full(params) against
+   Benchmark.MctsRollouts(params'), :134-162, or against Benchmark.NetworkOnly(tau), :161-176): as az_selfplay_create_duel,
+   but each player brings its own MctsParams (gamma, cpuct, number of iterations -- 0 = network-only player --, Dirichlet
+   noise, prior temperature, move temperature schedule) next to its own oracle. */
 int32_t az_selfplay_create_duel_players(az_ctx* ctx, int32_t game, az_net* white_oracle, const az_mcts_params* white_params,
                                         az_net* black_oracle, const az_mcts_params* black_params, const az_sim_params* sp,
                                         uint64_t seed, az_selfplay** out);

@@ -781,7 +781,8 @@ void oz_play_game2(oz_env* white, oz_env* black, const oz_mcts_params* mp, doubl
   oz_play_game2p(white, mp, black, mp, flip_p, seed, game_idx, tr);
 }
 /* TwoPlayers of two MctsPlayers that may differ in every MctsParams field (src/play.jl:248-282, src/benchmark.jl:78-99):
-   think / player_temperature dispatch on the colour to move (:258-264, :279-282) */
+   think / player_temperature dispatch on the colour to move (:258-264, :279-282).  num_iters_per_turn == 0 stands for a
+   NetworkPlayer with the temperature schedule of the same parameter block (Benchmark.NetworkOnly). */
 void oz_play_game2p(oz_env* white, const oz_mcts_params* mp_white, oz_env* black, const oz_mcts_params* mp_black, double flip_p,
                     uint64_t seed, uint64_t game_idx, oz_trace* tr) {
   const int gid = white->game_id;
@@ -818,10 +819,18 @@ void oz_play_game2p(oz_env* white, const oz_mcts_params* mp_white, oz_env* black
     oz_env* env = oz_game_white_playing(&g) ? white : black;              /* think(::TwoPlayers): play.jl:258-264 */
     const oz_mcts_params* mp = oz_game_white_playing(&g) ? mp_white : mp_black;
     int nl = oz_legal_actions(&g, acts);
-    oz_dirichlet(seed, game_idx, (uint32_t)n, nl, mp->noise_alpha, eta);  /* drawn even if eps == 0 (mcts.jl:240) */
-    oz_env_set_noise(env, seed, game_idx, (uint32_t)n);
-    oz_explore(env, &g, mp->num_iters_per_turn, eta);                      /* think: play.jl:196-206 */
-    oz_policy(env, &g, acts, pi);
+    if (mp->num_iters_per_turn == 0) {
+      /* NetworkPlayer under PlayerWithTemperature = Benchmark.NetworkOnly (src/play.jl:226-235, :112-127,
+         src/benchmark.jl:166-176): think returns the oracle's policy over the available actions, no search */
+      float P[OZ_MAX_ACTIONS], V = 0.0f;
+      env->oracle(env->octx, gid, tr->think_states[n], nl, P, &V);
+      for (int i = 0; i < nl; i++) pi[i] = (double)P[i];
+    } else {
+      oz_dirichlet(seed, game_idx, (uint32_t)n, nl, mp->noise_alpha, eta);  /* drawn even if eps == 0 (mcts.jl:240) */
+      oz_env_set_noise(env, seed, game_idx, (uint32_t)n);
+      oz_explore(env, &g, mp->num_iters_per_turn, eta);                      /* think: play.jl:196-206 */
+      oz_policy(env, &g, acts, pi);
+    }
     double tau = oz_pl_schedule(mp->sched_n, mp->sched_xs, mp->sched_ys, n); /* schedule[length(trace)] */
     oz_apply_temperature(pi, nl, tau, pis);
     oz_fix_probvec(pis, nl, pf);

@@ -58,7 +58,8 @@ def oracle_simulate(oz, gid, oracle, omp, seed, S, NG, reset_every, baseline=Non
                         L.oz_env_reset(e)
                 # every move lasts as many ticks as its player's iteration budget (select runs one simulation per call)
                 ts = traces[g]["think_states"]
-                free_at[w] = t + sum((mw if (sb == 2 or ts[i][sb - 1] == 1) else mb).num_iters_per_turn for i in range(n))
+                # (a NetworkPlayer, num_iters_per_turn == 0, takes the one tick of its root evaluation)
+                free_at[w] = t + sum(max(1, (mw if (sb == 2 or ts[i][sb - 1] == 1) else mb).num_iters_per_turn) for i in range(n))
                 if n == 0:
                     again.append(w)
             asking = again

@@ -351,6 +351,47 @@ def test_duel_of_two_different_players_bit_exact(az, oz, ctx, game):
     b_net.close()
 
 
+@pytest.mark.parametrize("game,tau", [("connect-four", 0.5), ("tictactoe", 1.0), ("mancala", 0.0)])
+def test_duel_against_network_only_player_bit_exact(az, oz, ctx, game, tau):
+    """Benchmark.Duel(Benchmark.Full(params), Benchmark.NetworkOnly(τ)) (src/benchmark.jl:78-99,161-176): the baseline is a
+    NetworkPlayer under PlayerWithTemperature (src/play.jl:226-235, :112-127) -- no search, the move distribution is the
+    oracle's policy -- against an MctsPlayer; alternate_colors and (where the game has symmetries) flip_probability on."""
+    from tests import simref
+    gs, gid = az.GameSpec(game), oz.game_id(game)
+    S, NG, seed = 6, 20, 31337
+    flip = 0.5 if game != "mancala" else 0.0
+    mp_a = az.MctsParams(gamma=1.0, cpuct=2.0, num_iters_per_turn=25, temperature=az.ConstSchedule(0.3), dirichlet_noise_eps=0.2,
+                         dirichlet_noise_alpha=1.0)
+    a_net, b_net = az.SynthOracle(ctx, gs), az.SynthOracle(ctx, gs)
+    sim = az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=2, alternate_colors=True, flip_probability=flip)
+    out = az.simulate(ctx, gs, a_net, az.SelfPlayParams(mp_a, sim), seed=seed, baseline=b_net, baseline_mcts=az.NetworkOnly(tau), gamma=1.0)
+    omp_a = oz.mcts_params(gamma=1.0, cpuct=2.0, noise_eps=0.2, noise_alpha=1.0, num_iters_per_turn=25, sched_xs=(0,), sched_ys=(0.3,))
+    omp_b = oz.mcts_params(num_iters_per_turn=0, sched_xs=(0,), sched_ys=(tau,))
+    traces, _ = simref.oracle_simulate(oz, gid, "synth", omp_a, seed, S, NG, 2, baseline="synth", alternate_colors=True,
+                                       flip_probability=flip, omp_baseline=omp_b)
+    simref.assert_same_samples(out, traces)
+    simref.assert_same_outcomes(out, traces)
+    # the network-only player's rows carry the oracle's policy itself: float32 values, not visit-count ratios
+    a_net.close()
+    b_net.close()
+
+
+@pytest.mark.parametrize("game", ["grid-world", "connect-four"])
+def test_network_only_player_alone_bit_exact(az, oz, ctx, game):
+    """Benchmark.Single(Benchmark.NetworkOnly()) (src/benchmark.jl:101-110): simulate() with a NetworkPlayer on both sides /
+    on the single-player environment; every turn is one oracle call."""
+    from tests import simref
+    gs, gid = az.GameSpec(game), oz.game_id(game)
+    S, NG, seed = 8, 30, 77
+    net = az.SynthOracle(ctx, gs)
+    sim = az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=1)
+    out = az.simulate(ctx, gs, net, az.SelfPlayParams(az.NetworkOnly(0.7), sim), seed=seed)
+    omp = oz.mcts_params(num_iters_per_turn=0, sched_xs=(0,), sched_ys=(0.7,))
+    traces, _ = simref.oracle_simulate(oz, gid, "synth", omp, seed, S, NG, 1)
+    simref.assert_same_samples(out, traces)
+    net.close()
+
+
 def test_error_paths_mirror_reference_asserts(az, ctx):
     """Precondition violations return AZ_EINVAL / AZ_ESTATE with a message (no exception crosses the ABI)."""
     gs = az.GameSpec("connect-four")

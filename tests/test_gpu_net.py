@@ -127,6 +127,23 @@ def test_resnet_other_games_generic_tower(az, oz, ctx, game, plies):
     net.close()
 
 
+@pytest.mark.parametrize("game,plies,hp", [
+    # scripts/profile/inference.jl-style narrow tower with the ResNetHP default heads (src/networks/architectures/resnet.jl:30-37)
+    ("connect-four", 30, dict(num_blocks=5, num_filters=64, conv_kernel_size=(3, 3), num_policy_head_filters=2, num_value_head_filters=1)),
+    ("connect-four", 30, dict(num_blocks=2, num_filters=100, conv_kernel_size=(3, 3), num_policy_head_filters=7, num_value_head_filters=32)),
+    ("tictactoe", 5, dict(num_blocks=2, num_filters=64, conv_kernel_size=(3, 3), num_policy_head_filters=2, num_value_head_filters=1)),
+    ("mancala", 30, dict(num_blocks=1, num_filters=32, conv_kernel_size=(3, 3), num_policy_head_filters=16, num_value_head_filters=8))])
+def test_resnet_narrower_shapes(az, oz, ctx, game, plies, hp):
+    """num_filters < 128 and fewer head filters than 32: the kernels' unused channels carry zero weights (az_net.cu init())."""
+    gs = az.GameSpec(game)
+    net, blob = netcheck.make_net(az, ctx, gs, hp, seed=9, randomize=True)
+    states = gs.random_positions(17, 300, plies)
+    r = netcheck.compare(az, oz, gs, net, blob, hp, states)
+    assert r["dP"] < netcheck.TOL and r["dV"] < netcheck.TOL and r["dI"] < netcheck.TOL, (r["dP"], r["dV"], r["dI"])
+    assert r["dL"] < netcheck.LOGIT_TOL_PERTURBED and r["dVpre"] < netcheck.LOGIT_TOL_PERTURBED, (r["dL"], r["dVpre"])
+    net.close()
+
+
 def test_fresh_flux_init(az, oz, ctx):
     """Freshly constructed model (zero biases, identity BatchNorm statistics), 5 blocks as shipped."""
     gs = az.GameSpec("connect-four")
@@ -145,9 +162,10 @@ def test_resnet_rejects_bad_blob_and_unsupported(az, ctx):
     with pytest.raises(az.AzError):
         net.evaluate_batch(gs.random_positions(1, 4, 10))  # not loaded
     net.close()
-    with pytest.raises(az.AzError) as e:
-        az.ResNet(ctx, gs, az.ResNetHP(1, 64, (3, 3), 32, 32))
-    assert e.value.status == 5
+    for bad in (az.ResNetHP(1, 256, (3, 3), 32, 32), az.ResNetHP(1, 128, (5, 5), 32, 32), az.ResNetHP(1, 128, (3, 3), 64, 32)):
+        with pytest.raises(az.AzError) as e:
+            az.ResNet(ctx, gs, bad)
+        assert e.value.status == 5
 
 
 def test_mcts_with_network_bit_exact(az, oz, ctx):

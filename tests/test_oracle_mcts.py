@@ -256,6 +256,43 @@ def test_two_players_duel(oz):
     assert tot == sum(np.ctypeslib.as_array(tr.rewards)[:n]) and tot in (-1.0, 0.0, 1.0)
 
 
+@pytest.mark.parametrize("tau", [0.0, 1.0, 0.5])
+def test_network_only_player(oz, tau):
+    """NetworkPlayer under PlayerWithTemperature (Benchmark.NetworkOnly, src/play.jl:226-235, :112-127; num_iters_per_turn
+    = 0 in a parameter block): think() is one oracle call -- its tree stays empty, the recorded policy IS the oracle's
+    float32 policy over the available actions, tau = 0 plays the arg-max."""
+    gid = oz.game_id("connect-four")
+    L = oz.lib()
+    mp_w = oz.mcts_params(num_iters_per_turn=20, cpuct=2.0, noise_eps=0.25, noise_alpha=1.0, sched_xs=(0,), sched_ys=(1.0,))
+    mp_b = oz.mcts_params(num_iters_per_turn=0, sched_xs=(0,), sched_ys=(tau,))
+    w, b = oz.Env(gid, "uniform", cpuct=2.0, noise_eps=0.25), oz.Env(gid, "synth")
+    synth = C.cast(oz.builtin_oracle("synth"), oz.ORACLE_FN)
+    sb, A = oz.state_bytes(gid), oz.num_actions(gid)
+    seen_black = 0
+    for game in range(6):
+        tr = oz.Trace()
+        L.oz_play_game2p(w.h, C.byref(mp_w), b.h, C.byref(mp_b), 0.0, 11, game, C.byref(tr))
+        n = tr.n_moves
+        think = np.ctypeslib.as_array(tr.think_states)[:n]
+        pi, mask, act = np.ctypeslib.as_array(tr.pi)[:n, :A], np.ctypeslib.as_array(tr.mask)[:n, :A], np.ctypeslib.as_array(tr.action)[:n]
+        for i in range(n):
+            if think[i][sb - 1] == 1:          # white (MCTS) to move
+                continue
+            seen_black += 1
+            legal = np.flatnonzero(mask[i])
+            P, V = (C.c_float * A)(), C.c_float()
+            st = (C.c_uint8 * len(think[i]))(*think[i])
+            synth(None, gid, st, len(legal), P, C.byref(V))
+            want = np.zeros(A, np.float32)
+            want[legal] = np.ctypeslib.as_array(P)[:len(legal)]
+            assert (pi[i].view(np.uint32) == want.view(np.uint32)).all()
+            assert mask[i][act[i]] == 1
+            if tau == 0.0:
+                assert act[i] == legal[np.argmax(want[legal])]
+    assert seen_black > 10
+    assert b.total_simulations == 0 and b.num_nodes == 0 and w.total_simulations > 0
+
+
 def test_simulate_duel_alternate_colors(oz):
     """simulate() with TwoPlayers and alternate_colors (src/simulations.jl:221-241) + rewards_and_redundancy (:292-307)."""
     from tests import simref

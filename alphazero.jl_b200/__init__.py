@@ -35,6 +35,10 @@ class _MctsParams(C.Structure):
                 ("temperature_xs", C.c_int32 * MAX_SCHEDULE), ("temperature_ys", C.c_double * MAX_SCHEDULE)]
 
 
+class _MinMaxParams(C.Structure):
+    _fields_ = [("depth", C.c_int32), ("amplify_rewards", C.c_int32), ("tau", C.c_double), ("gamma", C.c_double)]
+
+
 class _SimParams(C.Structure):
     _fields_ = [("num_games", C.c_int32), ("num_workers", C.c_int32), ("batch_size", C.c_int32), ("fill_batches", C.c_int32),
                 ("reset_every", C.c_int32), ("alternate_colors", C.c_int32), ("flip_probability", C.c_double)]
@@ -55,12 +59,13 @@ ABI_SYMBOLS = [
     "az_version", "az_ctx_create", "az_ctx_destroy", "az_last_error", "az_ctx_synchronize", "az_ctx_num_launches",
     "az_game_lookup", "az_game_num_actions", "az_game_state_bytes", "az_game_state_dim", "az_game_max_plies",
     "az_game_vectorize_state", "az_game_actions_mask", "az_game_play", "az_game_init_state", "az_game_random_positions",
+    "az_game_heuristic_value", "az_game_minmax_think",
     "az_net_create_oracle", "az_net_create_rollout", "az_net_create_resnet", "az_net_create_simplenet", "az_net_num_params", "az_net_load", "az_net_load_device",
     "az_net_forward", "az_net_forward_logits", "az_net_set_profiling", "az_net_get_profile", "az_net_destroy",
     "az_mcts_create", "az_mcts_set_roots", "az_mcts_set_noise", "az_mcts_run", "az_mcts_explore", "az_mcts_root_stats", "az_mcts_policy",
     "az_mcts_reset", "az_mcts_counters", "az_mcts_last_timing", "az_mcts_destroy", "az_mcts_set_profiling", "az_mcts_get_profile",
     "az_selfplay_create", "az_selfplay_start", "az_selfplay_poll", "az_selfplay_wait", "az_selfplay_counts",
-    "az_selfplay_fetch", "az_selfplay_stats", "az_selfplay_destroy", "az_selfplay_create_duel", "az_selfplay_create_duel_players", "az_selfplay_outcomes",
+    "az_selfplay_fetch", "az_selfplay_stats", "az_selfplay_destroy", "az_selfplay_create_duel", "az_selfplay_create_duel_players", "az_selfplay_create_duel_minmax", "az_selfplay_outcomes",
     "az_selfplay_export_samples", "az_samples_from_host", "az_samples_count", "az_samples_concat", "az_samples_merge_by_state",
     "az_samples_augment_with_symmetries", "az_samples_convert", "az_samples_fetch", "az_samples_destroy",
     "az_comm_unique_id", "az_comm_create", "az_comm_rank", "az_comm_last_ms", "az_comm_destroy", "az_samples_allgather", "az_net_broadcast",
@@ -86,6 +91,7 @@ def lib():
             "az_ctx_create": [C.c_int32, C.POINTER(vp)], "az_ctx_destroy": [vp], "az_ctx_synchronize": [vp],
             "az_game_state_dim": [C.c_int32, vp], "az_game_vectorize_state": [C.c_int32, vp, vp],
             "az_game_actions_mask": [C.c_int32, vp, vp], "az_game_play": [C.c_int32, vp, C.c_int32, vp, vp, vp],
+            "az_game_heuristic_value": [C.c_int32, vp, vp], "az_game_minmax_think": [C.c_int32, vp, C.POINTER(_MinMaxParams), vp, vp],
             "az_game_init_state": [C.c_int32, vp],
             "az_game_random_positions": [C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, vp],
             "az_net_create_oracle": [vp, C.c_int32, C.c_int32, C.POINTER(vp)],
@@ -109,6 +115,8 @@ def lib():
             "az_selfplay_create_duel": [vp, C.c_int32, vp, vp, C.POINTER(_MctsParams), C.POINTER(_SimParams), C.c_uint64, C.POINTER(vp)],
             "az_selfplay_create_duel_players": [vp, C.c_int32, vp, C.POINTER(_MctsParams), vp, C.POINTER(_MctsParams), C.POINTER(_SimParams), C.c_uint64,
                                                 C.POINTER(vp)],
+            "az_selfplay_create_duel_minmax": [vp, C.c_int32, vp, C.POINTER(_MctsParams), C.POINTER(_MinMaxParams), C.POINTER(_SimParams), C.c_uint64,
+                                               C.POINTER(vp)],
             "az_selfplay_outcomes": [vp, C.c_double, vp, vp, vp, vp],
             "az_selfplay_export_samples": [vp, C.POINTER(vp)],
             "az_samples_from_host": [vp, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, C.POINTER(vp)],
@@ -200,6 +208,25 @@ class GameSpec:
             raise AzError(st, "illegal action %d" % action)
         return ns, bool(term.value), wr.value
 
+    def heuristic_value(self, state):
+        """GI.heuristic_value of the position (host evaluation of the kernels' inline code)."""
+        s = np.ascontiguousarray(state, np.uint8)
+        v = C.c_double()
+        st = lib().az_game_heuristic_value(self.id, s.ctypes.data, C.byref(v))
+        if st != AZ_OK:
+            raise AzError(st, "az_game_heuristic_value")
+        return v.value
+
+    def minmax_think(self, state, player):
+        """think(::MinMax.Player, game) (src/minmax.jl:83-114) for a `MinMaxTS` player: (q [A], pi [A]), zero on unavailable actions."""
+        s = np.ascontiguousarray(state, np.uint8)
+        q, pi = np.zeros(self.num_actions), np.zeros(self.num_actions)
+        mm = player.c()
+        st = lib().az_game_minmax_think(self.id, s.ctypes.data, C.byref(mm), q.ctypes.data, pi.ctypes.data)
+        if st != AZ_OK:
+            raise AzError(st, "az_game_minmax_think")
+        return q, pi
+
     def random_positions(self, seed, n, max_plies=30, first_stream=0):
         out = np.zeros((n, self.state_bytes), np.uint8)
         st = lib().az_game_random_positions(self.id, seed, first_stream, n, max_plies, out.ctypes.data)
@@ -250,6 +277,21 @@ def NetworkOnly(τ=1.0, **kw):
     tau = kw.pop("tau", τ)
     assert not kw, kw
     return MctsParams(num_iters_per_turn=0, temperature=ConstSchedule(tau), dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0)
+
+
+class MinMaxTS:
+    """Benchmark.MinMaxTS(depth, amplify_rewards, τ) (src/benchmark.jl:178-196) = MinMax.Player (src/minmax.jl:72-81): pass it
+    as the `baseline` of `simulate` / `SelfPlay`; it brings no oracle."""
+
+    def __init__(self, depth, amplify_rewards, τ=0.0, γ=1.0, **kw):
+        self.depth, self.amplify_rewards = int(depth), bool(amplify_rewards)
+        self.tau, self.gamma = float(kw.pop("tau", τ)), float(kw.pop("gamma", γ))
+        assert not kw, kw
+
+    def c(self):
+        p = _MinMaxParams()
+        p.depth, p.amplify_rewards, p.tau, p.gamma = self.depth, int(self.amplify_rewards), self.tau, self.gamma
+        return p
 
 
 class SimParams:
@@ -474,6 +516,9 @@ class SelfPlay:
         mp, sp = params.mcts.c(), params.sim.c()
         if baseline is None:
             ctx.check(lib().az_selfplay_create(ctx.h, gspec.id, oracle.h, C.byref(mp), C.byref(sp), seed, C.byref(self.h)))
+        elif isinstance(baseline, MinMaxTS):
+            mm = baseline.c()
+            ctx.check(lib().az_selfplay_create_duel_minmax(ctx.h, gspec.id, oracle.h, C.byref(mp), C.byref(mm), C.byref(sp), seed, C.byref(self.h)))
         elif baseline_mcts is not None:
             mb = baseline_mcts.c()
             ctx.check(lib().az_selfplay_create_duel_players(ctx.h, gspec.id, oracle.h, C.byref(mp), baseline.h, C.byref(mb), C.byref(sp), seed,

@@ -64,6 +64,23 @@ template <class G> static int g_state_bytes() { return G::STATE_BYTES; }
 template <class G> static int g_max_plies() { return G::MAX_PLIES; }
 template <class G> static int g_state_dim(int32_t* d) { d[0] = G::XW; d[1] = G::XH; d[2] = G::XC; return AZ_OK; }
 template <class G> static int g_vectorize(const uint8_t* s, float* x) { G::vectorize(G::from_bytes(s), x); return AZ_OK; }
+template <class G> static int g_heuristic(const uint8_t* s, double* v) { *v = G::heuristic_value(G::from_bytes(s)); return AZ_OK; }
+// think(::MinMax.Player) on the host with the code the kernels run (az_minmax_qvalue / az_minmax_policy are host + device)
+template <class G> static int g_minmax_think(const uint8_t* s, const az_minmax_params* mm, double* q, double* pi) {
+  if (!G::HAS_HEURISTIC) return AZ_EUNSUPPORTED;
+  if (mm->depth < 1 || mm->depth > AZ_MINMAX_MAX_DEPTH || !(mm->tau >= 0.0)) return AZ_EINVAL;
+  const AzEnv e = G::from_bytes(s);
+  if (G::terminated(e)) return AZ_EINVAL;
+  const uint32_t legal = G::legal_mask(e);
+  double qs[G::A], ps[G::A];
+  int acts[G::A], n = 0;
+  for (int a = 0; a < G::A; a++)
+    if ((legal >> a) & 1u) { acts[n] = a; qs[n] = az_minmax_qvalue<G>(e, a, mm->depth, mm->amplify_rewards != 0, mm->gamma); n++; }
+  az_minmax_policy(qs, n, mm->tau, ps);
+  for (int a = 0; a < G::A; a++) { if (q) q[a] = 0.0; if (pi) pi[a] = 0.0; }
+  for (int i = 0; i < n; i++) { if (q) q[acts[i]] = qs[i]; if (pi) pi[acts[i]] = ps[i]; }
+  return AZ_OK;
+}
 template <class G> static int g_mask(const uint8_t* s, uint8_t* m) {
   AzEnv e = G::from_bytes(s);
   uint32_t l = G::terminated(e) ? G::legal_mask(e) : G::legal_mask(e);
@@ -587,8 +604,17 @@ struct SelfPlay : az_selfplay {
     if (s == AZ_OK) allocs.push_back(*ptr);
     return s;
   }
-  int create(az_ctx* c, az_net* net, az_net* net2, const az_mcts_params* mp_in, const az_sim_params* s, uint64_t seed, const az_mcts_params* mp1_in = nullptr) {
+  int create(az_ctx* c, az_net* net, az_net* net2, const az_mcts_params* mp_in, const az_sim_params* s, uint64_t seed, const az_mcts_params* mp1_in = nullptr,
+             const az_minmax_params* mm = nullptr) {
     if (!mp1_in) mp1_in = mp_in;
+    if (mm) {
+      // TwoPlayers(player, MinMax.Player) (Benchmark.Duel against Benchmark.MinMaxTS, src/benchmark.jl:178-196): the second
+      // tree of every worker is only a seat (root state, turn flags) -- no table entries, no oracle calls; net2 is a stand-in
+      if (!G::HAS_HEURISTIC) { c->err = "MinMax player: the game defines no heuristic_value for a two-player search"; return AZ_EUNSUPPORTED; }
+      if (mm->depth < 1 || mm->depth > AZ_MINMAX_MAX_DEPTH) { c->err = "MinMax player: 1 <= depth <= 8"; return AZ_EINVAL; }
+      if (!(mm->tau >= 0.0)) { c->err = "MinMax player: tau >= 0"; return AZ_EINVAL; }
+      sp.minmax1 = 1; sp.mm_depth = mm->depth; sp.mm_amplify = mm->amplify_rewards ? 1 : 0; sp.mm_tau = mm->tau; sp.mm_gamma = mm->gamma;
+    }
     // num_iters_per_turn == 0: NetworkPlayer under PlayerWithTemperature (Benchmark.NetworkOnly, src/benchmark.jl:166-176,
     // src/play.jl:226-235): the engine runs ONE simulation per turn -- on a root that is not in the table yet that is exactly
     // the oracle call think() makes -- and az_k_move reads the move distribution from the root's priors instead of the visit
@@ -599,7 +625,8 @@ struct SelfPlay : az_selfplay {
       if (q->num_iters_per_turn < 0) { c->err = "MctsPlayer: niters > 0 (src/play.jl:162); 0 selects NetworkPlayer"; return AZ_EINVAL; }
       if (q->num_iters_per_turn == 0) { q->num_iters_per_turn = 1; q->prior_temperature = 1.0; q->dirichlet_noise_eps = 0.0; }
     }
-    sp.netonly = mp_in->num_iters_per_turn == 0; sp.netonly1 = mp1_in->num_iters_per_turn == 0;
+    sp.netonly = mp_in->num_iters_per_turn == 0; sp.netonly1 = !mm && mp1_in->num_iters_per_turn == 0;
+    if (mm) mp1_l.gamma = mm->gamma;   // the z rows of a game in which the MinMax player held white
     if (mp1->temperature_n < 1 || mp1->temperature_n > AZ_MAX_SCHEDULE) { c->err = "temperature schedule: 1..8 points"; return AZ_EINVAL; }
     ctx = c; game = G::ID; simp = *s;
     if (s->num_workers <= 0) AZ_FAIL(ctx, AZ_EINVAL, "SimParams: num_workers must be positive");
@@ -663,6 +690,12 @@ struct SelfPlay : az_selfplay {
     games_cap = ng;
     return AZ_OK;
   }
+  // the per-move kernel, preceded by the MinMax player's search when the baseline is one (its trees move one tick after
+  // their turn began; the q-values travel in p.eta)
+  void launch_move(Mcts<G>& m, int grid1) {
+    if (sp.minmax1) az_k_minmax_think<G><<<(m.p.S * G::A + 127) / 128, 128, 0, ctx->stream>>>(m.p, sp);
+    az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 0);
+  }
   // WHILE graph whose body is one self-play tick: select -> oracle(s) -> expand + backup -> move -> assign -> loop condition
   int32_t* h_progress = nullptr;   // pinned, device-visible: [0] games finished
   int run_device_loop(Mcts<G>& m, int grid1) {
@@ -688,12 +721,12 @@ struct SelfPlay : az_selfplay {
     if (ok) ok = cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
       st = m.tick(false);
-      az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 0);
+      launch_move(m, grid1);
       az_k_assign<G><<<1, 1024, 0, ctx->stream>>>(m.p, sp);
       az_k_selfplay_cond<<<1, 1, 0, ctx->stream>>>(m.p, sp, h, h_progress);
       ok = cudaStreamEndCapture(ctx->stream, nullptr) == cudaSuccess && st == AZ_OK;
     }
-    const int64_t per_tick = ctx->launches - l0 + 3;
+    const int64_t per_tick = ctx->launches - l0 + 3 + (sp.minmax1 ? 1 : 0);
     ctx->launches = l0;
     if (ok) ok = cudaGraphInstantiate(&exec, g, 0) == cudaSuccess;
     if (g) cudaGraphDestroy(g);
@@ -737,9 +770,9 @@ struct SelfPlay : az_selfplay {
     }
     for (; !looped;) {
       AZ_TRY(ctx, m.tick_graphed([&] {
-        az_k_move<G><<<grid1, 128, 0, ctx->stream>>>(m.p, sp, 0);
+        launch_move(m, grid1);
         az_k_assign<G><<<1, 1024, 0, ctx->stream>>>(m.p, sp);
-        ctx->launches += 2;
+        ctx->launches += 2 + (sp.minmax1 ? 1 : 0);
       }));
       tick++;
       if (tick % 32 == 0) {
@@ -916,9 +949,9 @@ struct SelfPlay : az_selfplay {
 };
 template <class G>
 static int g_make_selfplay(az_ctx* ctx, az_net* net, az_net* net2, const az_mcts_params* mp, const az_sim_params* sp, uint64_t seed, az_selfplay** out,
-                           const az_mcts_params* mp1 = nullptr) {
+                           const az_mcts_params* mp1 = nullptr, const az_minmax_params* mm = nullptr) {
   auto* s = new SelfPlay<G>();
-  int st = s->create(ctx, net, net2, mp, sp, seed, mp1);
+  int st = s->create(ctx, net, net2, mp, sp, seed, mp1, mm);
   if (st != AZ_OK) { delete s; return st; }
   *out = s;
   return AZ_OK;
@@ -1048,6 +1081,11 @@ int32_t az_game_actions_mask(int32_t game, const uint8_t* s, uint8_t* m) { if (!
 int32_t az_game_play(int32_t game, const uint8_t* s, int32_t a, uint8_t* ns, int32_t* term, double* wr) {
   if (!s || !ns) return AZ_EINVAL;
   AZ_DISPATCH_GAME(game, g_play, s, a, ns, term, wr)
+}
+int32_t az_game_heuristic_value(int32_t game, const uint8_t* s, double* v) { if (!s || !v) return AZ_EINVAL; AZ_DISPATCH_GAME(game, g_heuristic, s, v) }
+int32_t az_game_minmax_think(int32_t game, const uint8_t* s, const az_minmax_params* mm, double* q, double* pi) {
+  if (!s || !mm) return AZ_EINVAL;
+  AZ_DISPATCH_GAME(game, g_minmax_think, s, mm, q, pi)
 }
 int32_t az_game_init_state(int32_t game, uint8_t* s) { if (!s) return AZ_EINVAL; AZ_DISPATCH_GAME(game, g_init_state, s) }
 int32_t az_game_random_positions(int32_t game, uint64_t seed, uint64_t first, int32_t n, int32_t max_plies, uint8_t* out) {
@@ -1212,6 +1250,15 @@ int32_t az_selfplay_create_duel_players(az_ctx* ctx, int32_t game, az_net* white
   cudaSetDevice(ctx->device);
   if (white->game != game || black->game != game) AZ_FAIL(ctx, AZ_EINVAL, "az_selfplay_create_duel_players: oracle was built for another game");
   AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, white, black, mp_white, sp, seed, out, mp_black)
+  AZ_GUARD_END(ctx)
+}
+int32_t az_selfplay_create_duel_minmax(az_ctx* ctx, int32_t game, az_net* oracle, const az_mcts_params* mp, const az_minmax_params* baseline,
+                                       const az_sim_params* sp, uint64_t seed, az_selfplay** out) {
+  if (!ctx || !oracle || !mp || !baseline || !sp || !out) return AZ_EINVAL;
+  AZ_GUARD_BEGIN
+  cudaSetDevice(ctx->device);
+  if (oracle->game != game) AZ_FAIL(ctx, AZ_EINVAL, "az_selfplay_create_duel_minmax: oracle was built for another game");
+  AZ_DISPATCH_GAME(game, g_make_selfplay, ctx, oracle, oracle, mp, sp, seed, out, mp, baseline)
   AZ_GUARD_END(ctx)
 }
 int32_t az_selfplay_export_samples(az_selfplay* s, az_samples** out) {

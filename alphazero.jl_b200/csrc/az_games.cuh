@@ -146,6 +146,36 @@ struct GameC4 {
       }
     s[42] = white_playing(e) ? 1 : 2;
   }
+  // GI.heuristic_value (game.jl:172-220), the leaf value of the MinMax baseline: every alignment of TO_CONNECT cells that
+  // holds none of the opponent's stones is worth 0.1 ^ (3 - N) with N own stones; the alignments are summed in the order of
+  // the ALIGNMENTS table (:192-196: directions (1,1), (1,-1), (0,1), (1,0); start cell x outer, y inner), own minus opponent.
+  // Bit (x, y) = 7 x + y, so an alignment is one 4-bit pattern shifted to its start cell.  0.1^2, 0.1^3 as products: the
+  // correctly rounded powers and the products are the same doubles for this base.
+  static constexpr bool HAS_HEURISTIC = true;
+  AZ_HD static double heuristic_for(uint64_t mine, uint64_t theirs) {
+    const double pw[5] = {0.1 * 0.1 * 0.1, 0.1 * 0.1, 0.1, 1.0, 1.0 / 0.1};
+    double sum = 0.0;
+    bool first = true;
+    for (int d = 0; d < 4; d++) {
+      const int dx = d == 2 ? 0 : 1, dy = d == 0 ? 1 : (d == 1 ? -1 : (d == 2 ? 1 : 0));
+      const int step = 7 * dx + dy;
+      const uint64_t pat = 1ull | (1ull << step) | (1ull << (2 * step)) | (1ull << (3 * step));
+      for (int x = 0; x < 7; x++)
+        for (int y = 0; y < 6; y++) {
+          const int xe = x + 3 * dx, ye = y + 3 * dy;
+          if (xe > 6 || ye < 0 || ye > 5) continue;
+          const uint64_t m = pat << (7 * x + y);   // all four steps (8, 6, 1, 7) are positive bit distances
+          const double v = (theirs & m) ? 0.0 : pw[az_popc64(mine & m)];
+          sum = first ? v : sum + v;
+          first = false;
+        }
+    }
+    return sum;
+  }
+  AZ_HD static double heuristic_value(const AzEnv& e) {
+    const uint64_t w = e.a, k = e.b & BOARD;
+    return white_playing(e) ? heuristic_for(w, k) - heuristic_for(k, w) : heuristic_for(k, w) - heuristic_for(w, k);
+  }
   // vectorize_state: x[col + 7*row + 42*c], c in {empty, current player, opponent}
   AZ_HD static float plane(const AzEnv& e, int col, int row, int c) {
     int bit = col * 7 + row;
@@ -213,6 +243,23 @@ struct GameTTT {
       n.a |= ((e.a >> (16 + src)) & 1ull) << (16 + p);
     }
     return n;
+  }
+  // GI.heuristic_value (game.jl:96-120): 0.3 ^ (2 - N) per alignment free of the opponent's marks, summed in the order of
+  // ALIGNMENTS (:43-51: x fixed, y fixed, diagonal, anti-diagonal), own minus opponent
+  static constexpr bool HAS_HEURISTIC = true;
+  AZ_HD static double heuristic_for(uint32_t mine, uint32_t theirs) {
+    const uint32_t al[8] = {0x049, 0x092, 0x124, 0x007, 0x038, 0x1C0, 0x111, 0x054};
+    const double pw[4] = {0.3 * 0.3, 0.3, 1.0, 1.0 / 0.3};
+    double sum = 0.0;
+    for (int i = 0; i < 8; i++) {
+      const double v = (theirs & al[i]) ? 0.0 : pw[az_popc64((uint64_t)(mine & al[i]))];
+      sum = i == 0 ? v : sum + v;
+    }
+    return sum;
+  }
+  AZ_HD static double heuristic_value(const AzEnv& e) {
+    const uint32_t w = wbits(e), k = kbits(e);
+    return white_playing(e) ? heuristic_for(w, k) - heuristic_for(k, w) : heuristic_for(k, w) - heuristic_for(w, k);
   }
   static AzEnv from_bytes(const uint8_t* s) {
     AzEnv e = {0, 0, 0};
@@ -350,6 +397,14 @@ struct GameMancala {
     unpack(e, s);
     s[14] = white_playing(e) ? 1 : 2;
   }
+  // GI.heuristic_value (game.jl:212-218): the store difference from the mover's side -- computed by the reference in UInt8
+  // arithmetic (stores are UInt8, :21), so a deficit wraps to 256 - d; reproduced as is
+  static constexpr bool HAS_HEURISTIC = true;
+  AZ_HD static double heuristic_value(const AzEnv& e) {
+    uint8_t v = (uint8_t)((uint8_t)(e.a & 0xFF) - (uint8_t)((e.a >> 8) & 0xFF));
+    if (!white_playing(e)) v = (uint8_t)(0u - v);
+    return (double)v;
+  }
   AZ_HD static void vectorize(const AzEnv& e, float* x) {  // incl. the flip_colors quirk (game.jl:224-229)
     uint8_t c[14];
     if (white_playing(e)) unpack(e, c);
@@ -412,6 +467,8 @@ struct GameGW {
     n.aux = (uint32_t)(time(e) + 1) | (1u << 16);
     return n;
   }
+  static constexpr bool HAS_HEURISTIC = false;   // GI.heuristic_value is 0 (game.jl:118); MinMax is a two-player baseline
+  AZ_HD static double heuristic_value(const AzEnv&) { return 0.0; }
   AZ_HD static AzEnv play(const AzEnv& e, int a) { AzNoise nz = {1.0, 0.0}; return play(e, a, nz); }  // noise-free step
   AZ_HD static AzEnv init() { AzEnv e = {1ull | (1ull << 8), 0, 0}; return e; }
   AZ_HD static AzEnv from_xy(int x, int y) { AzEnv e = {(uint64_t)x | ((uint64_t)y << 8), 0, 0}; return e; }
@@ -423,3 +480,79 @@ struct GameGW {
     x[(gx(e) - 1) + 10 * (gy(e) - 1)] = 1.0f;
   }
 };
+
+// =====================================================================================================
+// MinMax baseline player (src/minmax.jl; Benchmark.MinMaxTS, src/benchmark.jl:178-196), host + device.  qvalue (:29-43) of
+// one root action by an explicit stack of value() frames (:17-27: 0 on a terminal state, the heuristic at depth 0, else the
+// maximum of the q-values of the available actions).
+// =====================================================================================================
+constexpr int AZ_MINMAX_MAX_DEPTH = 8;
+template <class G>
+AZ_HD double az_minmax_qvalue(const AzEnv& root, int action, int depth, bool amplify, double gamma) {
+  AzEnv st[AZ_MINMAX_MAX_DEPTH];       // st[l]: the state value() is evaluated on at level l (l plies below root + 1)
+  uint32_t todo[AZ_MINMAX_MAX_DEPTH];  // actions of st[l] still to try
+  double best[AZ_MINMAX_MAX_DEPTH], er[AZ_MINMAX_MAX_DEPTH];
+  bool has[AZ_MINMAX_MAX_DEPTH], flip[AZ_MINMAX_MAX_DEPTH];
+  const double inf = az_bits_to_double(0x7FF0000000000000ull);
+  auto edge = [&](const AzEnv& from, int a, int l) {   // the part of qvalue before the recursive call
+    st[l] = G::play(from, a);
+    const double wr = G::white_reward(st[l]);
+    double r = G::white_playing(from) ? wr : -wr;
+    if (amplify && r != 0.0) r = r > 0.0 ? inf : -inf;   // amplify (:14)
+    er[l] = r;
+    flip[l] = G::white_playing(from) != G::white_playing(st[l]);
+    todo[l] = G::legal_mask(st[l]);
+    has[l] = false;
+    best[l] = 0.0;
+  };
+  edge(root, action, 0);
+  int l = 0;
+  for (;;) {
+    const int left = depth - 1 - l;   // the depth argument of value(st[l], .)
+    double v;
+    bool ret = true;
+    if (G::terminated(st[l])) v = 0.0;
+    else if (left == 0) v = G::heuristic_value(st[l]);
+    else if (todo[l] == 0) v = best[l];
+    else {
+      int a = 0;
+      while (!((todo[l] >> a) & 1u)) a++;   // available actions in ascending order
+      todo[l] &= todo[l] - 1;
+      edge(st[l], a, l + 1);
+      l++;
+      ret = false;
+    }
+    if (!ret) continue;
+    const double q = er[l] + gamma * (flip[l] ? -v : v);
+    if (l == 0) return q;
+    l--;
+    best[l] = has[l] ? (q > best[l] ? q : best[l]) : q;
+    has[l] = true;
+  }
+}
+
+// think(::MinMax.Player) after the q-values (src/minmax.jl:83-114): pi over the n available actions
+AZ_HD void az_minmax_policy(const double* qs, int n, double tau, double* pi) {
+  const double inf = az_bits_to_double(0x7FF0000000000000ull);
+  int nwin = 0, nnot = 0, best = 0;
+  for (int i = 0; i < n; i++) { nwin += qs[i] == inf; nnot += qs[i] > -inf; if (qs[i] > qs[best]) best = i; }
+  if (nwin > 0) { for (int i = 0; i < n; i++) pi[i] = qs[i] == inf ? 1.0 : 0.0; }
+  else if (nnot == 0) { for (int i = 0; i < n; i++) pi[i] = 1.0; }
+  else if (tau == 0.0) { for (int i = 0; i < n; i++) pi[i] = qs[i] == qs[best] ? 1.0 : 0.0; }
+  else {
+    const double qmax = qs[best];
+    double C = 0.0;
+    bool hc = false;
+    for (int i = 0; i < n; i++) if (qs[i] > -inf) { const double a = qs[i] < 0.0 ? -qs[i] : qs[i]; C = hc ? (a > C ? a : C) : a; hc = true; }
+    C = C + 2.220446049250313e-16;   // eps()
+    const double it = 1.0 / tau;
+    for (int i = 0; i < n; i++) {
+      const double x = (qs[i] - qmax) / C;
+      const double e = (x == -inf) ? 0.0 : az_det_exp(x);
+      pi[i] = (e > 0.0) ? az_det_exp(it * az_det_log(e)) : 0.0;   // pi .^= 1 / tau
+    }
+  }
+  double s = 0.0;
+  for (int i = 0; i < n; i++) s = (i == 0) ? pi[0] : s + pi[i];
+  for (int i = 0; i < n; i++) pi[i] = pi[i] / s;
+}

@@ -468,6 +468,11 @@ struct AzSelfPlay {
   int32_t nsims1;         // duel: of player 1
   int32_t netonly;        // player 0 is a NetworkPlayer (src/play.jl:226-235): nsims = 1 (the root evaluation), pi = the root's priors
   int32_t netonly1;       // duel: player 1 is a NetworkPlayer
+  int32_t minmax1;        // duel: player 1 is a MinMax.Player (src/minmax.jl:72-81): no tree, no oracle
+  int32_t mm_depth;       // MinMax.Player.depth
+  int32_t mm_amplify;     // MinMax.Player.amplify_rewards
+  double mm_tau;          // MinMax.Player.τ (inside think; the move temperature of such a player is 1, src/play.jl:37-39)
+  double mm_gamma;        // MinMax.Player.gamma
   int32_t reset_every;
   int32_t max_plies;
   int32_t sched_n;        // temperature schedule of player 0 (MctsPlayer.τ)
@@ -548,6 +553,7 @@ __device__ void az_begin_move(const AzPool& p, const AzSelfPlay& sp, int w, cons
   p.sims_target[slot] = (sp.duel && (slot & 1)) ? sp.nsims1 : sp.nsims;
   p.status[slot] = 1;
   p.pending[slot] = 0;
+  if (sp.duel && (slot & 1) && sp.minmax1) { p.sims_target[slot] = 0; return; }   // thinks in az_k_minmax_think of the next tick
   if (G::STOCHASTIC) { p.noise_game[slot] = game; p.noise_move[slot] = move; }
   double eta[A];
   int n = __popc(G::legal_mask(root));
@@ -566,7 +572,7 @@ __device__ void az_record_game_end(AzPool& p, AzSelfPlay& sp, int w, int g, int 
   sp.g_final[g] = last;
   int64_t nodes = 0, ts = 0, tn = 0;
   for (int k = 0; k < nt; k++) {
-    if (k ? sp.netonly1 : sp.netonly) continue;   // a NetworkPlayer has no MCTS.Env to measure (src/training.jl:269-273)
+    if (k ? (sp.netonly1 || sp.minmax1) : sp.netonly) continue;   // no MCTS.Env to measure (src/training.jl:269-273)
     nodes += p.node_count[t0 + k]; ts += p.total_sims[t0 + k]; tn += p.total_nodes[t0 + k];
   }
   sp.g_nodes[g] = nodes;
@@ -646,6 +652,24 @@ __global__ void __launch_bounds__(1024) az_k_assign(AzPool p, AzSelfPlay sp) {
   }
 }
 
+// =====================================================================================================
+// MinMax baseline player (src/minmax.jl; Benchmark.MinMaxTS, src/benchmark.jl:178-196): exhaustive depth-limited search
+// with GI.heuristic_value at the horizon.  The search itself (az_minmax_qvalue, az_minmax_policy) is host + device code in
+// az_games.cuh, next to the heuristics.
+// =====================================================================================================
+// one thread per (tree, action): the root q-values of the MinMax player's trees whose turn it is, into p.eta (the Dirichlet
+// buffer such a tree does not use); az_k_move turns them into the move distribution
+template <class G>
+__global__ void az_k_minmax_think(AzPool p, AzSelfPlay sp) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = t / G::A, a = t % G::A;
+  if (slot >= p.S || !(slot & 1)) return;
+  if (!(p.status[slot] && !p.pending[slot] && p.sims_done[slot] >= p.sims_target[slot])) return;
+  const AzEnv root = p.root[slot];
+  if (!((G::legal_mask(root) >> a) & 1u)) return;
+  p.eta[(size_t)slot * G::A + a] = az_minmax_qvalue<G>(root, a, sp.mm_depth, sp.mm_amplify != 0, sp.mm_gamma);
+}
+
 // one thread per slot (runs once per move: scalar code, not performance critical)
 template <class G>
 __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
@@ -677,41 +701,51 @@ __global__ void az_k_move(AzPool p, AzSelfPlay sp, int start_games) {
   const int64_t game = sp.first_game + g;
   const AzEnv root = p.root[slot];
   const uint32_t legal = G::legal_mask(root);
-  // MCTS.policy (src/mcts.jl:255-271): find the root line (single thread: read the L lanes one by one)
-  const uint4* tab = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
-  uint32_t h = az_hash(root.a, root.b) & p.cap_mask;
-  const uint32_t tag = p.tag[slot];
-  for (;;) {
-    AzLine16 k;
-    k.u = tab[(size_t)h * L];
-    if ((uint32_t)(k.key.b >> 57) == tag && k.key.a == root.a && (k.key.b & AZ_KEYB_MASK) == root.b) break;
-    if ((uint32_t)(k.key.b >> 57) != tag) { p.flags[3] = 1; break; }  // cannot happen after explore!
-    h = (h + 1) & p.cap_mask;
-  }
   int acts[A];
   double pi[A], pis[A];
   float pf[A];
   int n = 0;
-  int64_t ntot = 0;
-  // think(::NetworkPlayer) (src/play.jl:230-235): the oracle's policy over the available actions = the priors the root line
-  // holds since this turn's single simulation (or an earlier visit) evaluated it; prior_temperature is 1 for such a player
-  const bool netonly = (sp.duel && (slot & 1)) ? sp.netonly1 != 0 : sp.netonly != 0;
-  for (int i = 0; i < A; i++)
-    if ((legal >> i) & 1u) {
-      AzLine16 e;
-      e.u = tab[(size_t)h * L + 1 + i];
-      acts[n] = i;
-      pi[n] = netonly ? (double)e.e.P : (double)e.e.N;
-      ntot += e.e.N;
-      n++;
+  const bool minmax = sp.duel && (slot & 1) && sp.minmax1;
+  if (minmax) {
+    // think(::MinMax.Player): the q-values az_k_minmax_think left in p.eta
+    double qs[A];
+    for (int i = 0; i < A; i++)
+      if ((legal >> i) & 1u) { acts[n] = i; qs[n] = p.eta[(size_t)slot * A + i]; n++; }
+    az_minmax_policy(qs, n, sp.mm_tau, pi);
+  } else {
+    // MCTS.policy (src/mcts.jl:255-271): find the root line (single thread: read the L lanes one by one)
+    const uint4* tab = p.nodes + (size_t)slot * ((size_t)p.cap_mask + 1) * L;
+    uint32_t h = az_hash(root.a, root.b) & p.cap_mask;
+    const uint32_t tag = p.tag[slot];
+    for (;;) {
+      AzLine16 k;
+      k.u = tab[(size_t)h * L];
+      if ((uint32_t)(k.key.b >> 57) == tag && k.key.a == root.a && (k.key.b & AZ_KEYB_MASK) == root.b) break;
+      if ((uint32_t)(k.key.b >> 57) != tag) { p.flags[3] = 1; break; }  // cannot happen after explore!
+      h = (h + 1) & p.cap_mask;
     }
-  if (!netonly) {
-    double sum = 0.0;
-    for (int i = 0; i < n; i++) { pi[i] = pi[i] / (double)ntot; sum = (i == 0) ? pi[0] : sum + pi[i]; }
-    for (int i = 0; i < n; i++) pi[i] = pi[i] / sum;
+    int64_t ntot = 0;
+    // think(::NetworkPlayer) (src/play.jl:230-235): the oracle's policy over the available actions = the priors the root
+    // line holds since this turn's single simulation (or an earlier visit) evaluated it; prior_temperature is 1 for such a
+    // player
+    const bool netonly = (sp.duel && (slot & 1)) ? sp.netonly1 != 0 : sp.netonly != 0;
+    for (int i = 0; i < A; i++)
+      if ((legal >> i) & 1u) {
+        AzLine16 e;
+        e.u = tab[(size_t)h * L + 1 + i];
+        acts[n] = i;
+        pi[n] = netonly ? (double)e.e.P : (double)e.e.N;
+        ntot += e.e.N;
+        n++;
+      }
+    if (!netonly) {
+      double sum = 0.0;
+      for (int i = 0; i < n; i++) { pi[i] = pi[i] / (double)ntot; sum = (i == 0) ? pi[0] : sum + pi[i]; }
+      for (int i = 0; i < n; i++) pi[i] = pi[i] / sum;
+    }
   }
-  // temperature (src/play.jl:208-210,309-310; src/util.jl:98-110)
-  const double tau = az_schedule(sp, (sp.duel && (slot & 1)) ? 1 : 0, move);
+  // temperature (src/play.jl:208-210,309-310; src/util.jl:98-110); a MinMax.Player keeps the default of 1 (src/play.jl:37-39)
+  const double tau = minmax ? 1.0 : az_schedule(sp, (sp.duel && (slot & 1)) ? 1 : 0, move);
   if (tau == 1.0) { for (int i = 0; i < n; i++) pis[i] = pi[i]; }
   else if (tau == 0.0) {
     int k = 0;

@@ -9,15 +9,15 @@
 # (src/training.jl:137-139, 150-152).  Julia dispatches on the game-spec type, so loading this module ADDS the methods
 #     simulate_distributed(::Simulator, ::Examples.ConnectFour.GameSpec, ::SimParams; game_simulated)   (and simulate)
 # for the four games the library knows; no reference file changes and `Scripts.train("connect-four")` runs unchanged.
-# Everything the engine cannot express (players other than MctsPlayer, NetworkPlayer (bare or under PlayerWithTemperature)
-# and TwoPlayers of those -- MinMax, Human, EpsilonGreedy --, oracles other than ResNet / SimpleNet / RolloutOracle / RandomOracle, a timeout instead of an iteration budget)
+# Everything the engine cannot express (players other than MctsPlayer, NetworkPlayer (bare or under PlayerWithTemperature),
+# TwoPlayers of those and TwoPlayers(such a player, MinMax.Player) -- Human, EpsilonGreedy, RandomPlayer --, oracles other than ResNet / SimpleNet / RolloutOracle / RandomOracle, a timeout instead of an iteration budget)
 # falls back to the reference's own method through `invoke`.
 module AlphaZeroB200
 
 using AlphaZero
 using AlphaZero: GI, MCTS, Network, NetLib, Examples, Trace, Simulator, SimParams, MctsParams, SelfPlayParams,
-                 MctsPlayer, TwoPlayers, NetworkPlayer, PlayerWithTemperature, AbstractGameSpec, AbstractSchedule, PLSchedule,
-                 ConstSchedule
+                 MctsPlayer, TwoPlayers, NetworkPlayer, PlayerWithTemperature, MinMax, AbstractGameSpec, AbstractSchedule,
+                 PLSchedule, ConstSchedule
 import Flux
 import CUDA
 import JSON3
@@ -37,6 +37,12 @@ struct CMctsParams            # az_mcts_params (src/params.jl:49-57)
   prior_temperature::Cdouble
   temperature_xs::NTuple{8,Int32}
   temperature_ys::NTuple{8,Cdouble}
+end
+struct CMinMaxParams          # az_minmax_params (src/minmax.jl:72-81)
+  depth::Int32
+  amplify_rewards::Int32
+  tau::Cdouble
+  gamma::Cdouble
 end
 struct CSimParams             # az_sim_params (src/params.jl:92-101)
   num_games::Int32
@@ -296,26 +302,57 @@ function run_duel(gspec, nn_white, nn_black, mp::CMctsParams, mp_black::CMctsPar
   return out
 end
 
+function run_duel_minmax(gspec, nn_white, mp::CMctsParams, mm::CMinMaxParams, sp::CSimParams, first_game::Int; game_simulated, seed)
+  w = Engine(gspec, nn_white)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(w.ctx, ccall((:az_selfplay_create_duel_minmax, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ref{CMctsParams}, Ref{CMinMaxParams}, Ref{CSimParams}, UInt64, Ptr{Ptr{Cvoid}}),
+        w.ctx, w.game, w.net, mp, mm, sp, seed, h))
+  check(w.ctx, ccall((:az_selfplay_start, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), h[], sp.num_games, first_game))
+  poll_until_finished(w.ctx, h[], game_simulated)
+  out = fetch_traces(w.ctx, h[], gspec)
+  ccall((:az_selfplay_destroy, LIB), Int32, (Ptr{Cvoid},), h[])
+  close!(w)
+  return out
+end
+
 # ---- the seam ------------------------------------------------------------------------------------------------------------
 # What the engine can run: one MctsPlayer or NetworkPlayer, or TwoPlayers of two such players (each with its own parameters
 # and oracle: ResNet, SimpleNet, MCTS.RolloutOracle, MCTS.RandomOracle), measured by self_play_measurements (src/training.jl:269-273) or
 # record_trace (src/simulations.jl:195).
+# the oracle a constructed player consults: pit_networks hands make_player a tuple of two networks (src/training.jl:131-139),
+# Benchmark.run ONE network from which both players are instantiated (src/benchmark.jl:82-93: Benchmark.MctsRollouts ignores
+# it and brings a RolloutOracle) -- reading it off the player covers both
+player_oracle(pl::MctsPlayer) = pl.mcts.oracle
+player_oracle(pl::NetworkPlayer) = pl.network
+player_oracle(pl::PlayerWithTemperature) = player_oracle(pl.player)
+player_oracle(::Any) = nothing
 function plan(simulator::Simulator, gspec)
   isnothing(game_name(gspec)) && return nothing
   oracles = simulator.make_oracles()
   player = simulator.make_player(oracles)
-  if engine_player(player) && supported_network(oracles)
+  bpn = MCTS.memory_footprint_per_node(gspec)
+  if engine_player(player) && supported_network(player_oracle(player))
     mp = c_mcts_params(player)
     isnothing(mp) && return nothing
-    return (kind = :single, nets = (oracles,), mp = mp, mp_black = mp, bytes_per_node = MCTS.memory_footprint_per_node(gspec))
-  elseif player isa TwoPlayers && engine_player(player.white) && engine_player(player.black) &&
-         oracles isa Tuple && length(oracles) == 2 && all(supported_network, oracles)
-    mpw, mpb = c_mcts_params(player.white), c_mcts_params(player.black)
-    (isnothing(mpw) || isnothing(mpb)) && return nothing
-    return (kind = :duel, nets = oracles, mp = mpw, mp_black = mpb, bytes_per_node = MCTS.memory_footprint_per_node(gspec))
+    return (kind = :single, nets = (player_oracle(player),), mp = mp, mp_black = mp, mm = nothing, bytes_per_node = bpn)
+  elseif player isa TwoPlayers && engine_player(player.white) && supported_network(player_oracle(player.white))
+    mpw = c_mcts_params(player.white)
+    isnothing(mpw) && return nothing
+    b = player.black
+    if b isa MinMax.Player   # Benchmark.MinMaxTS (src/benchmark.jl:178-196): searched on the device, no oracle
+      (1 <= b.depth <= 8 && !isnothing(game_heuristic(gspec))) || return nothing
+      mm = CMinMaxParams(b.depth, b.amplify_rewards ? 1 : 0, b.τ, b.gamma)
+      return (kind = :minmax, nets = (player_oracle(player.white),), mp = mpw, mp_black = mpw, mm = mm, bytes_per_node = bpn)
+    elseif engine_player(b) && supported_network(player_oracle(b))
+      mpb = c_mcts_params(b)
+      isnothing(mpb) && return nothing
+      return (kind = :duel, nets = (player_oracle(player.white), player_oracle(b)), mp = mpw, mp_black = mpb, mm = nothing, bytes_per_node = bpn)
+    end
   end
   return nothing
 end
+game_heuristic(gspec) = game_name(gspec) == "grid-world" ? nothing : true   # GI.heuristic_value of grid-world is the constant 0
 
 function measure(simulator::Simulator, pl, trace, colors_flipped, edepth, nodes)
   if simulator.measure === AlphaZero.self_play_measurements
@@ -334,6 +371,8 @@ function simulate_on_gpu(simulator::Simulator, gspec, p::SimParams, pl, num_game
   traces, edepth, nodes, flipped =
     pl.kind == :single ?
       run_selfplay(gspec, pl.nets[1], pl.mp, sp, first_game; game_simulated = game_simulated, seed = seed) :
+    pl.kind == :minmax ?
+      run_duel_minmax(gspec, pl.nets[1], pl.mp, pl.mm, sp, first_game; game_simulated = game_simulated, seed = seed) :
       run_duel(gspec, pl.nets[1], pl.nets[2], pl.mp, pl.mp_black, sp, first_game; game_simulated = game_simulated, seed = seed)
   return [measure(simulator, pl, traces[g], flipped[g] != 0, edepth[g], nodes[g]) for g in 1:length(traces)]
 end

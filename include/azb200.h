@@ -84,6 +84,19 @@ typedef struct {
   double temperature_ys[AZ_MAX_SCHEDULE];
 } az_mcts_params;
 
+/* MinMax.Player (src/minmax.jl:72-81; Benchmark.MinMaxTS, src/benchmark.jl:178-196) */
+typedef struct {
+  int32_t depth;           /* 1..8 */
+  int32_t amplify_rewards; /* non-zero rewards become +-Inf (src/minmax.jl:14) */
+  double tau;              /* temperature inside think (src/minmax.jl:95-107) */
+  double gamma;            /* MinMax.Player's gamma (1 in Benchmark.MinMaxTS) */
+} az_minmax_params;
+/* GI.heuristic_value(GI.init(spec, s)) (games/<name>/game.jl) and think(::MinMax.Player, game) (src/minmax.jl:83-114) on host bytes,
+   evaluated by the same inline functions the kernels use: q[A] root q-values, pi[A] the move distribution (both zero on
+   unavailable actions; either may be NULL).  AZ_EUNSUPPORTED for grid-world. */
+int32_t az_game_heuristic_value(int32_t game, const uint8_t* state, double* value);
+int32_t az_game_minmax_think(int32_t game, const uint8_t* state, const az_minmax_params* player, double* q, double* pi);
+
 typedef struct {
   int32_t num_games;
   int32_t num_workers; /* concurrent game slots on this GPU (= worker tasks, src/simulations.jl:217) */
@@ -202,6 +215,14 @@ int32_t az_selfplay_create_duel(az_ctx* ctx, int32_t game, az_net* white_oracle,
 int32_t az_selfplay_create_duel_players(az_ctx* ctx, int32_t game, az_net* white_oracle, const az_mcts_params* white_params,
                                         az_net* black_oracle, const az_mcts_params* black_params, const az_sim_params* sp,
                                         uint64_t seed, az_selfplay** out);
+/* Benchmark.Duel(player, Benchmark.MinMaxTS(depth, amplify_rewards, tau)) (src/benchmark.jl:78-99, :178-196): the baseline
+   is a MinMax.Player (src/minmax.jl: exhaustive search `depth` plies deep with GI.heuristic_value at the horizon, rewards
+   optionally amplified to +-Inf, move distribution exp(q / (C tau)) over the non-losing moves, :83-114); it needs no oracle
+   and no tree, and its move temperature is the default 1 (src/play.jl:37-39).  `mp` / `oracle` describe the other player
+   (num_iters_per_turn = 0: a network-only player).  Games with a two-player heuristic only (connect-four, tictactoe,
+   mancala); 1 <= depth <= 8. */
+int32_t az_selfplay_create_duel_minmax(az_ctx* ctx, int32_t game, az_net* oracle, const az_mcts_params* mp,
+                                       const az_minmax_params* baseline, const az_sim_params* sp, uint64_t seed, az_selfplay** out);
 /* plays games first_game_index .. first_game_index + num_games - 1 (global indices key the RNG streams);
    returns immediately, the engine runs on its own host thread + CUDA stream */
 int32_t az_selfplay_start(az_selfplay* s, int32_t num_games, int64_t first_game_index);

@@ -776,6 +776,125 @@ void oz_apply_symmetry(int game_id, int sym, const uint8_t* in, uint8_t* out) {
   }
 }
 
+/* ------------------------------------------------------------------------- */
+/* MinMax baseline player (src/minmax.jl)                                      */
+/* ------------------------------------------------------------------------- */
+static double oz_powi(double x, int k) { /* x ^ k for the small integer exponents of the heuristics */
+  if (k < 0) return 1.0 / oz_powi(x, -k);
+  double r = 1.0;
+  for (int i = 0; i < k; i++) r = (i == 0) ? x : r * x;
+  return r;
+}
+static double c4_alignment_value_for(const oz_game* g, int player, int col, int row, int dc, int dr) { /* game.jl:198-210 */
+  int N = 0;
+  for (int i = 0; i < 4; i++) {
+    int cell = C4(g, col + i * dc, row + i * dr);
+    if (cell == player) N++;
+    else if (cell != 0) return 0.0;
+  }
+  return oz_powi(0.1, 4 - 1 - N);
+}
+static double c4_heuristic_value_for(const oz_game* g, int player) { /* :212-214 over ALIGNMENTS (:186-196) */
+  static const int DIRS[4][2] = {{1, 1}, {1, -1}, {0, 1}, {1, 0}};
+  double sum = 0.0;
+  int first = 1;
+  for (int d = 0; d < 4; d++)
+    for (int x = 0; x < C4_COLS; x++)
+      for (int y = 0; y < C4_ROWS; y++) {
+        if (!c4_valid(x + 3 * DIRS[d][0], y + 3 * DIRS[d][1])) continue; /* alignment_from returns nothing (:176-184) */
+        double v = c4_alignment_value_for(g, player, x, y, DIRS[d][0], DIRS[d][1]);
+        sum = first ? v : sum + v;
+        first = 0;
+      }
+  return sum;
+}
+static double ttt_heuristic_value_for(const oz_game* g, int player) { /* games/tictactoe/game.jl:98-114 */
+  double sum = 0.0;
+  for (int a = 0; a < 8; a++) {
+    int N = 0, blocked = 0;
+    for (int i = 0; i < 3 && !blocked; i++) {
+      int m = g->cells[TTT_AL[a][i]];
+      if (m == player) N++;
+      else if (m != 0) blocked = 1;
+    }
+    double v = blocked ? 0.0 : oz_powi(0.3, 3 - 1 - N);
+    sum = (a == 0) ? v : sum + v;
+  }
+  return sum;
+}
+double oz_heuristic_value(const oz_game* g) {
+  switch (g->game_id) {
+    case OZ_CONNECT_FOUR: return c4_heuristic_value_for(g, g->curplayer) - c4_heuristic_value_for(g, 3 - g->curplayer);
+    case OZ_TICTACTOE: return ttt_heuristic_value_for(g, g->curplayer) - ttt_heuristic_value_for(g, 3 - g->curplayer);
+    case OZ_MANCALA: { /* stores are UInt8 in the reference (game.jl:21): nw - nb and the negation wrap modulo 256 */
+      uint8_t v = (uint8_t)(MC_STORE(g, 1) - MC_STORE(g, 2));
+      if (g->curplayer == 2) v = (uint8_t)(0 - v);
+      return (double)v;
+    }
+    default: return 0.0;
+  }
+}
+typedef struct { int depth, amplify; double gamma; } oz_minmax;
+static double mm_qvalue(const oz_minmax* p, const oz_game* g, int action, int depth);
+static double mm_value(const oz_minmax* p, const oz_game* g, int depth) { /* src/minmax.jl:17-27 */
+  if (oz_game_terminated(g)) return 0.0;
+  if (depth == 0) return oz_heuristic_value(g);
+  int acts[OZ_MAX_ACTIONS];
+  int n = oz_legal_actions(g, acts);
+  double best = 0.0;
+  for (int i = 0; i < n; i++) {
+    double q = mm_qvalue(p, g, acts[i], depth);
+    best = (i == 0 || q > best) ? q : best;
+  }
+  return best;
+}
+static double mm_qvalue(const oz_minmax* p, const oz_game* g, int action, int depth) { /* :29-43 */
+  oz_game next = *g;
+  oz_game_play(&next, action, NULL);
+  double wr = oz_game_white_reward(&next);
+  double r = oz_game_white_playing(g) ? wr : -wr;
+  if (p->amplify && r != 0.0) r = (r > 0.0) ? INFINITY : -INFINITY; /* amplify :14 */
+  double nextv = mm_value(p, &next, depth - 1);
+  if (oz_game_white_playing(g) != oz_game_white_playing(&next)) nextv = -nextv;
+  return r + p->gamma * nextv;
+}
+int oz_minmax_think(const oz_game* g, int depth, int amplify, double tau, double gamma, int* acts, double* pi, double* qs_out) { /* :83-114 */
+  oz_minmax p = {depth, amplify, gamma};
+  double qs[OZ_MAX_ACTIONS];
+  int n = oz_legal_actions(g, acts);
+  int nwin = 0, nnot = 0, best = 0;
+  for (int i = 0; i < n; i++) qs[i] = mm_qvalue(&p, g, acts[i], depth);
+  for (int i = 0; i < n; i++) {
+    nwin += (qs[i] == INFINITY);
+    nnot += (qs[i] > -INFINITY);
+    if (qs[i] > qs[best]) best = i;
+  }
+  if (nwin > 0) {
+    for (int i = 0; i < n; i++) pi[i] = (qs[i] == INFINITY) ? 1.0 : 0.0;
+  } else if (nnot == 0) {
+    for (int i = 0; i < n; i++) pi[i] = 1.0;
+  } else if (tau == 0.0) {
+    for (int i = 0; i < n; i++) pi[i] = (qs[i] == qs[best]) ? 1.0 : 0.0;
+  } else {
+    double qmax = qs[best], Cn = 0.0;
+    int hc = 0;
+    for (int i = 0; i < n; i++)
+      if (qs[i] > -INFINITY) { double a = fabs(qs[i]); Cn = hc ? (a > Cn ? a : Cn) : a; hc = 1; }
+    Cn = Cn + 2.220446049250313e-16; /* eps() */
+    double it = 1.0 / tau;
+    for (int i = 0; i < n; i++) {
+      double x = (qs[i] - qmax) / Cn;
+      double e = (x == -INFINITY) ? 0.0 : oz_det_exp(x);
+      pi[i] = (e > 0.0) ? oz_det_exp(it * oz_det_log(e)) : 0.0; /* pi .^= 1 / tau */
+    }
+  }
+  double s = 0.0;
+  for (int i = 0; i < n; i++) s = (i == 0) ? pi[0] : s + pi[i];
+  for (int i = 0; i < n; i++) pi[i] = pi[i] / s;
+  if (qs_out) for (int i = 0; i < n; i++) qs_out[i] = qs[i];
+  return n;
+}
+
 void oz_play_game2(oz_env* white, oz_env* black, const oz_mcts_params* mp, double flip_p, uint64_t seed, uint64_t game_idx,
                    oz_trace* tr) {
   oz_play_game2p(white, mp, black, mp, flip_p, seed, game_idx, tr);
@@ -819,7 +938,9 @@ void oz_play_game2p(oz_env* white, const oz_mcts_params* mp_white, oz_env* black
     oz_env* env = oz_game_white_playing(&g) ? white : black;              /* think(::TwoPlayers): play.jl:258-264 */
     const oz_mcts_params* mp = oz_game_white_playing(&g) ? mp_white : mp_black;
     int nl = oz_legal_actions(&g, acts);
-    if (mp->num_iters_per_turn == 0) {
+    if (mp->player_kind == 1) { /* MinMax.Player */
+      oz_minmax_think(&g, mp->minmax_depth, mp->minmax_amplify, mp->minmax_tau, mp->gamma, acts, pi, NULL);
+    } else if (mp->num_iters_per_turn == 0) {
       /* NetworkPlayer under PlayerWithTemperature = Benchmark.NetworkOnly (src/play.jl:226-235, :112-127,
          src/benchmark.jl:166-176): think returns the oracle's policy over the available actions, no search */
       float P[OZ_MAX_ACTIONS], V = 0.0f;
@@ -831,7 +952,7 @@ void oz_play_game2p(oz_env* white, const oz_mcts_params* mp_white, oz_env* black
       oz_explore(env, &g, mp->num_iters_per_turn, eta);                      /* think: play.jl:196-206 */
       oz_policy(env, &g, acts, pi);
     }
-    double tau = oz_pl_schedule(mp->sched_n, mp->sched_xs, mp->sched_ys, n); /* schedule[length(trace)] */
+    double tau = mp->player_kind == 1 ? 1.0 : oz_pl_schedule(mp->sched_n, mp->sched_xs, mp->sched_ys, n); /* schedule[length(trace)] */
     oz_apply_temperature(pi, nl, tau, pis);
     oz_fix_probvec(pis, nl, pf);
     float u = oz_uniform_f32(seed, game_idx, (uint32_t)n, OZ_PURPOSE_CATEGORICAL, 0);

@@ -123,11 +123,24 @@ int oz_categorical(const float* p, int n, float u);
 /* ---- self-play ------------------------------------------------------------- */
 typedef struct {
   double gamma, cpuct, noise_eps, noise_alpha, prior_temperature;
-  int num_iters_per_turn;
+  int num_iters_per_turn; /* 0: NetworkPlayer under PlayerWithTemperature (Benchmark.NetworkOnly) */
   int sched_n;
   int sched_xs[8];
   double sched_ys[8];
+  /* player_kind 1: MinMax.Player (src/minmax.jl:72-81; Benchmark.MinMaxTS) with the four fields below and `gamma`; its
+     oracle env is never called and its move temperature is the AbstractPlayer default of 1 (src/play.jl:37-39) */
+  int player_kind;
+  int minmax_depth;
+  int minmax_amplify;
+  double minmax_tau;
 } oz_mcts_params;
+
+/* GI.heuristic_value (games/connect-four/game.jl:172-220, games/tictactoe/game.jl:96-120, games/mancala/game.jl:212-218
+   incl. its UInt8 wrap-around, games/grid-world/game.jl:118) */
+double oz_heuristic_value(const oz_game* g);
+/* think(::MinMax.Player, game) (src/minmax.jl:83-114): actions[n] (ascending) and pi[n]; returns n; qs (may be NULL)
+   receives the root q-values */
+int oz_minmax_think(const oz_game* g, int depth, int amplify_rewards, double tau, double gamma, int* actions, double* pi, double* qs);
 
 typedef struct {
   int n_moves;                                 /* length(trace) */

@@ -30,7 +30,15 @@ def build(force=False):
 class MctsParams(C.Structure):
     _fields_ = [("gamma", C.c_double), ("cpuct", C.c_double), ("noise_eps", C.c_double), ("noise_alpha", C.c_double),
                 ("prior_temperature", C.c_double), ("num_iters_per_turn", C.c_int), ("sched_n", C.c_int),
-                ("sched_xs", C.c_int * 8), ("sched_ys", C.c_double * 8)]
+                ("sched_xs", C.c_int * 8), ("sched_ys", C.c_double * 8),
+                ("player_kind", C.c_int), ("minmax_depth", C.c_int), ("minmax_amplify", C.c_int), ("minmax_tau", C.c_double)]
+
+
+def minmax_params(depth, amplify_rewards, tau=0.0, gamma=1.0):
+    """MinMax.Player (src/minmax.jl:72-81; Benchmark.MinMaxTS, src/benchmark.jl:178-196) as an oz_mcts_params block."""
+    p = mcts_params(gamma=gamma, num_iters_per_turn=0)
+    p.player_kind, p.minmax_depth, p.minmax_amplify, p.minmax_tau = 1, int(depth), int(bool(amplify_rewards)), float(tau)
+    return p
 
 
 def mcts_params(gamma=1.0, cpuct=1.0, noise_eps=0.0, noise_alpha=1.0, prior_temperature=1.0, num_iters_per_turn=50,
@@ -81,6 +89,9 @@ def lib():
         L.oz_root_stats.argtypes = [C.c_void_p, C.POINTER(Game)] + [C.c_void_p] * 4
         L.oz_policy.argtypes = [C.c_void_p, C.POINTER(Game), C.c_void_p, C.c_void_p]
         L.oz_game_white_reward.restype = C.c_double
+        L.oz_heuristic_value.restype = C.c_double
+        L.oz_heuristic_value.argtypes = [C.POINTER(Game)]
+        L.oz_minmax_think.argtypes = [C.POINTER(Game), C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oz_det_log.restype = C.c_double
         L.oz_det_log.argtypes = [C.c_double]
         L.oz_det_exp.restype = C.c_double

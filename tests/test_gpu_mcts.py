@@ -376,6 +376,56 @@ def test_duel_against_network_only_player_bit_exact(az, oz, ctx, game, tau):
     b_net.close()
 
 
+@pytest.mark.parametrize("game,depth,amplify,tau,flip", [("connect-four", 4, True, 0.2, 0.5), ("tictactoe", 5, True, 0.0, 0.5),
+                                                          ("mancala", 3, False, 0.5, 0.0), ("connect-four", 2, False, 1.0, 0.0)])
+def test_duel_against_minmax_player_bit_exact(az, oz, ctx, game, depth, amplify, tau, flip):
+    """Benchmark.Duel(Benchmark.Full(params), Benchmark.MinMaxTS(depth, amplify_rewards, τ)) (src/benchmark.jl:78-99,178-196;
+    the connect-four benchmark of the reference is this duel at depth 5, games/connect-four/params.jl): the baseline is a
+    MinMax.Player (src/minmax.jl) searched on the device, no oracle and no tree on its side."""
+    from tests import simref
+    gs, gid = az.GameSpec(game), oz.game_id(game)
+    S, NG, seed = 6, 18, 8086
+    mp_a = az.MctsParams(gamma=1.0, cpuct=2.0, num_iters_per_turn=20, temperature=az.ConstSchedule(0.5), dirichlet_noise_eps=0.2,
+                         dirichlet_noise_alpha=1.0)
+    a_net = az.SynthOracle(ctx, gs)
+    sim = az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=2, alternate_colors=True, flip_probability=flip)
+    out = az.simulate(ctx, gs, a_net, az.SelfPlayParams(mp_a, sim), seed=seed, baseline=az.MinMaxTS(depth, amplify, tau), gamma=1.0)
+    omp_a = oz.mcts_params(gamma=1.0, cpuct=2.0, noise_eps=0.2, noise_alpha=1.0, num_iters_per_turn=20, sched_xs=(0,), sched_ys=(0.5,))
+    omp_b = oz.minmax_params(depth, amplify, tau)
+    traces, _ = simref.oracle_simulate(oz, gid, "synth", omp_a, seed, S, NG, 2, baseline="uniform", alternate_colors=True,
+                                       flip_probability=flip, omp_baseline=omp_b)
+    simref.assert_same_samples(out, traces)
+    simref.assert_same_outcomes(out, traces)
+    a_net.close()
+
+
+def test_network_only_against_minmax_and_errors(az, oz, ctx):
+    """Benchmark.Duel(Benchmark.NetworkOnly(), Benchmark.MinMaxTS(...)): neither side searches a tree; plus the parameter
+    checks of the MinMax entry point."""
+    from tests import simref
+    gs, gid = az.GameSpec("connect-four"), oz.game_id("connect-four")
+    S, NG, seed = 4, 12, 99
+    net = az.SynthOracle(ctx, gs)
+    sim = az.SimParams(num_games=NG, num_workers=S, batch_size=S, reset_every=1, alternate_colors=True)
+    out = az.simulate(ctx, gs, net, az.SelfPlayParams(az.NetworkOnly(1.0), sim), seed=seed, baseline=az.MinMaxTS(3, True, 0.2), gamma=1.0)
+    traces, _ = simref.oracle_simulate(oz, gid, "synth", oz.mcts_params(num_iters_per_turn=0), seed, S, NG, 1, baseline="uniform",
+                                       alternate_colors=True, omp_baseline=oz.minmax_params(3, True, 0.2))
+    simref.assert_same_samples(out, traces)
+    simref.assert_same_outcomes(out, traces)
+    for bad in (az.MinMaxTS(0, True), az.MinMaxTS(9, True), az.MinMaxTS(2, True, -1.0)):
+        with pytest.raises(az.AzError) as e:
+            az.SelfPlay(ctx, gs, net, az.SelfPlayParams(az.NetworkOnly(1.0), sim), baseline=bad)
+        assert e.value.status == 1
+    gw = az.GameSpec("grid-world")
+    gnet = az.SynthOracle(ctx, gw)
+    with pytest.raises(az.AzError) as e:      # no two-player heuristic
+        az.SelfPlay(ctx, gw, gnet, az.SelfPlayParams(az.NetworkOnly(1.0), az.SimParams(num_games=4, num_workers=4, batch_size=4)),
+                    baseline=az.MinMaxTS(2, True))
+    assert e.value.status == 5
+    gnet.close()
+    net.close()
+
+
 @pytest.mark.parametrize("game", ["grid-world", "connect-four"])
 def test_network_only_player_alone_bit_exact(az, oz, ctx, game):
     """Benchmark.Single(Benchmark.NetworkOnly()) (src/benchmark.jl:101-110): simulate() with a NetworkPlayer on both sides /

@@ -19,7 +19,8 @@ UNITS = {
 
 
 def _deps():
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "azb200.h")]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]   # not the objects next to them
+    return srcs + [os.path.join(HERE, "..", "include", "azb200.h")]
 
 
 def build(force=False, verbose=False):

@@ -10,6 +10,8 @@ cp gpurun_out/launches_$T.csv profiles/${T}_launches.csv
 cp gpurun_out/bench_$T.json profiles/${T}_bench_1gpu.json
 cp gpurun_out/bench_${T}_reference.json profiles/${T}_bench_1gpu_reference_arm.json
 cp gpurun_out/other_configs_$T.json profiles/${T}_other_configs.json
+[ -s gpurun_out/benchmark_duels_$T.json ] && cp gpurun_out/benchmark_duels_$T.json profiles/${T}_benchmark_duels.json
+cp gpurun_out/pytest_$T.log profiles/${T}_pytest_gpu.log
 python - "$T" <<'P'
 import json, sys
 T = sys.argv[1]

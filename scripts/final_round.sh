@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 timeout 900 python bench.py > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err; tail -2 gpurun_out/bench_${tag}.err; cut -c1-300 gpurun_out/bench_${tag}.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${tag}_reference.json 2>/dev/null; cut -c1-200 gpurun_out/bench_${tag}_reference.json
 timeout 600 python scripts/run_other_configs.py > gpurun_out/other_configs_${tag}.json 2> gpurun_out/other_configs_${tag}.err; cat gpurun_out/other_configs_${tag}.json
+timeout 900 python scripts/run_benchmark_duels.py > gpurun_out/benchmark_duels_${tag}.json 2> gpurun_out/benchmark_duels_${tag}.err; cat gpurun_out/benchmark_duels_${tag}.json
 for T in 4096 16384 65536; do
   timeout 600 python bench.py --oracle-net uniform --trees $T --steps 2 --warmup 1 --no-selfplay --no-cpu-baseline > gpurun_out/tree_${T}_${tag}.json 2>/dev/null
 done

@@ -48,12 +48,52 @@ def selfplay_case(oz, game, orc, nsims, workers, games, seed, **kw):
                 games=out)
 
 
+def minmax_case(oz, game, depth, amplify, tau, n_pos, seed):
+    """think(::MinMax.Player) (src/minmax.jl:83-114): root q-values and move distribution, bit patterns."""
+    import ctypes as C
+    gid = oz.game_id(game)
+    out = []
+    for r in oz.random_positions(gid, seed, n_pos, 20 if game != "tictactoe" else 4):
+        g = oz.GameEnv(gid, r)
+        acts, pi, qs = (C.c_int * 16)(), (C.c_double * 16)(), (C.c_double * 16)()
+        n = oz.lib().oz_minmax_think(C.byref(g.g), depth, int(amplify), tau, 1.0, acts, pi, qs)
+        out.append(dict(root=bytes(r).hex(), actions=[int(a) for a in acts[:n]], q=[float(x).hex() for x in qs[:n]], pi=[float(x).hex() for x in pi[:n]],
+                        heuristic=float(oz.lib().oz_heuristic_value(C.byref(g.g))).hex()))
+    return dict(kind="minmax", game=game, depth=depth, amplify=bool(amplify), tau=tau, seed=seed, positions=out)
+
+
+def baseline_player_case(oz, game, baseline_kind, workers, games, seed, **kw):
+    """Duels against the non-MCTS baseline players of src/benchmark.jl: NetworkOnly(tau) and MinMaxTS(depth, amplify, tau)."""
+    from tests import simref
+    gid = oz.game_id(game)
+    mp = oz.mcts_params(gamma=1.0, cpuct=2.0, noise_eps=0.25, noise_alpha=1.0, num_iters_per_turn=16, sched_xs=(0,), sched_ys=(0.5,))
+    if baseline_kind == "network_only":
+        ob, borc = oz.mcts_params(num_iters_per_turn=0, sched_xs=(0,), sched_ys=(0.5,)), "synth"
+    else:
+        ob, borc = oz.minmax_params(3, True, 0.2), "uniform"
+    traces, slot_of = simref.oracle_simulate(oz, gid, "synth", mp, seed, workers, games, 2, baseline=borc, omp_baseline=ob, alternate_colors=True, **kw)
+    out = []
+    for g in sorted(traces):
+        t = traces[g]
+        h = hashlib.sha256()
+        for k in ("states", "pi64", "mask", "action", "rewards", "z", "t", "sym", "think_states"):
+            h.update(np.ascontiguousarray(t[k]).tobytes())
+        out.append(dict(game=g, worker=int(slot_of[g]), n_moves=int(t["n_moves"]), actions=[int(a) for a in t["action"]], sha256=h.hexdigest(),
+                        mem_nodes=int(t["mem_nodes"]), total_reward=float(t["total_reward"]).hex(), colors_flipped=bool(t["colors_flipped"])))
+    return dict(kind="baseline_player", game=game, baseline=baseline_kind, workers=workers, seed=seed, kw=kw, games=out)
+
+
 def build(oz):
     cases = [explore_case(oz, "connect-four", "synth", 200, 6, 11, 0.25), explore_case(oz, "connect-four", "uniform", 120, 4, 12, 0.0),
              explore_case(oz, "tictactoe", "synth", 50, 4, 13, 0.25), explore_case(oz, "mancala", "synth", 100, 4, 14, 0.25),
              selfplay_case(oz, "connect-four", "synth", 32, 3, 6, 21), selfplay_case(oz, "tictactoe", "synth", 24, 2, 5, 22, flip_probability=0.5),
              selfplay_case(oz, "connect-four", "synth", 24, 2, 5, 23, baseline="uniform", alternate_colors=True, flip_probability=0.5),
-             selfplay_case(oz, "grid-world", "synth", 20, 3, 6, 24)]
+             selfplay_case(oz, "grid-world", "synth", 20, 3, 6, 24),
+             minmax_case(oz, "connect-four", 4, True, 0.2, 6, 31), minmax_case(oz, "tictactoe", 5, False, 0.0, 4, 32),
+             minmax_case(oz, "mancala", 3, True, 0.5, 4, 33),
+             baseline_player_case(oz, "connect-four", "network_only", 3, 6, 41, flip_probability=0.5),
+             baseline_player_case(oz, "connect-four", "minmax", 3, 6, 42, flip_probability=0.5),
+             baseline_player_case(oz, "mancala", "minmax", 2, 4, 43)]
     return dict(format=1, note="oracle self-consistency vectors (not reference-pinned); see make_oracle_kats.py", cases=cases)
 
 

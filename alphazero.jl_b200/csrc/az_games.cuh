@@ -222,7 +222,7 @@ struct GameTTT {
   AZ_HD static AzEnv init() { AzEnv e = {0, 0, 0}; return e; }
   static constexpr bool STOCHASTIC = false;
   static constexpr bool HAS_PLANE = false;  // plane(e, col, row, c) gives one element of vectorize_state directly
-  static constexpr long long MAX_STATES = 1ll << 40;  // no useful bound on distinct states
+  static constexpr long long MAX_STATES = 5478;  // reachable tic-tac-toe positions: a tree never holds more nodes
   AZ_HD static AzEnv play(const AzEnv& e, int a, const AzNoise&) { return play(e, a); }
   AZ_HD static AzEnv init_game(uint64_t, uint64_t) { return init(); }
   // GI.symmetries (game.jl:149-168): rot, rot2, rot3, flip, flip.rot, flip.rot2, flip.rot3 with rot(x,y) = (y, N-x+1),

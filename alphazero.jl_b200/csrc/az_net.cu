@@ -979,9 +979,12 @@ az_k_conv_yrow(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //     warps x 1 per layer, monotonic over launches: the base is read at kernel start) and a producer spins only on
 //     its lower neighbour (start of the layer) and its upper neighbour (just before the top halo row).  All CTAs are
 //     co-resident (one per SM), so spinning cannot deadlock.  The same waits order the in-place reuse of T / X.
-//   * inside a CTA the producer waits on `ldone` (its own 8 epilogue warps have completed the layer's TMA stores).
-//   * the weights of the next layer are (re)loaded into the resident 144 KB as soon as the last MMA of the layer has
-//     retired (`wfree`, multicast tcgen05.commit), in parallel with the epilogue drain and the first A loads.
+//   * a pair's first and last segments (the only rows neighbours read) are processed FIRST in every layer and published as
+//     soon as they are stored; the middle groups follow.  Inside a CTA the 8 epilogue warps count the units whose TMA
+//     stores have completed (`stored[]`); the producer loads a segment of layer l+1 when the same segment of layer l
+//     is in memory, so at a layer boundary the ring already holds the next layer's first stages.
+//   * the weights of the next layer are (re)loaded into the resident 144 KB by warp 1 of both CTAs as soon as the last
+//     MMA of the layer has retired (`wfree`, multicast tcgen05.commit); the A producer never waits for them.
 //   * the TMEM accumulator ring, the A-stage ring and all barrier phases simply continue across layers.
 // Weights of all layers live in ONE [L*128][1152] fp16 tensor (one tensor map), biases in one [L][128] array.
 // ------------------------------------------------------------------------------------------------
@@ -993,9 +996,35 @@ struct Smem {
   uint8_t epi[yr::EPI_BYTES];
   uint8_t ident[256];
   uint8_t ident8[512];   // lo8 mode: this CTA's 16 x 32 slice of 2^-14 * I32 in e5m2 (B operand of the fp8 residual MMAs)
-  uint64_t full[yr::ASTAGES], empty[yr::ASTAGES], tfull[yr::NACC], tempty[yr::NACC], bfull[tc2::NCHUNK], wfree, ldone;
+  uint64_t full[yr::ASTAGES], empty[yr::ASTAGES], tfull[yr::NACC], tempty[yr::NACC], bfull[tc2::NCHUNK], wfree;
   uint32_t tmem_base;
+  int stored[8];         // per epilogue warp: units (all layers, processing order) whose TMA stores have completed
 };
+// A pair's unit range [u0, u1) is a run of SEGMENTS = maximal runs of output rows inside one 32-board group.  Other pairs read
+// exactly two of its rows as halo: the LAST row u1-1 (pair above: bottom halo of its first segment) and the FIRST row u0
+// (pair below: top halo of its last segment).  Every layer therefore processes the last segment first, then the first one,
+// then the middle groups (k = processing order), and publishes the two rows separately the moment they are stored
+// (`done[128 + pair]`: row u1-1, `done[pair]`: row u0): when a layer ends, everything the neighbours and this pair's own
+// first segments of the next layer need has been in memory for about half a layer, the producer has already put the next
+// layer's first A stages into the ring, and the only wait left at the boundary is the first weight chunk.
+struct Seg { int g, j_lo, j_hi; };
+__device__ __forceinline__ Seg segment(int k, int nseg, int u0, int u1, bool natural) {
+  int i = k;
+  if (!natural && nseg >= 2) i = (k == 0) ? nseg - 1 : k - 1;
+  Seg sg;
+  sg.g = u0 / 6 + i;
+  sg.j_lo = (i == 0) ? u0 - sg.g * 6 : 0;
+  sg.j_hi = min(u1 - sg.g * 6, 6);
+  return sg;
+}
+__device__ __forceinline__ int ld_acquire_shared_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_shared_s32(int* p, int v) {
+  asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -1059,7 +1088,8 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     for (int i = 0; i < ASTAGES; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     for (int i = 0; i < yr::NACC; i++) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 16); }
     for (int i = 0; i < NCHUNK; i++) mbar_init(&s.bfull[i], 1);
-    mbar_init(&s.wfree, 1); mbar_init(&s.ldone, 8);
+    mbar_init(&s.wfree, 1);
+    for (int i = 0; i < 8; i++) s.stored[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 64) {
@@ -1099,8 +1129,9 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   int u0, u1;
   yr::unit_range(*ga.n_boards, pair, npairs, u0, u1);
   const bool has_work = u0 < u1;
-  // flag protocol: every pair adds 16 per layer (one per epilogue warp); counters are never reset, the value a pair
-  // finds in its own counter at kernel start is the base of this launch (identical for all pairs)
+  // flag protocol: every pair adds 16 per layer (one per epilogue warp) to each of its two counters (first row stored /
+  // last row stored); counters are never reset, the value a pair finds in its own counter at kernel start is the base of
+  // this launch (identical for all pairs and for both counters)
   const unsigned long long base = done[pair];
   // neighbours whose rows this pair reads as halo (only when the range boundary falls inside a 32-board group)
   int q_lo = -1, q_hi = -1;
@@ -1108,13 +1139,20 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (u0 % H != 0) { q_lo = pair - 1; for (;;) { int a, b; yr::unit_range(*ga.n_boards, q_lo, npairs, a, b); if (a < b) break; q_lo--; } }
     if (u1 % H != 0) { q_hi = pair + 1; for (;;) { int a, b; yr::unit_range(*ga.n_boards, q_hi, npairs, a, b); if (a < b) break; q_hi++; } }
   }
+  const int Up = u1 - u0;                                         // units per layer
+  const int nseg = has_work ? (u1 - 1) / H - u0 / H + 1 : 0;
+  const bool natural = (ga.debug & 16) != 0;                      // AZ_TOWER_DEBUG=16 (A/B runs): segments in range order
+  unsigned long long* const done_up = done + 128;                 // row u1-1 of a layer stored (read by the pair above); `done`: row u0
   cluster_sync_all();  // `base` is read by both CTAs before any warp of the pair can add to the counter
 
   if (!has_work) {
     // idle pair (fewer units than pairs): keep the counter in step so that its base stays equal to everybody else's
-    if (threadIdx.x == 0 && leader) tw::red_release_add_u64(done + pair, 16ull * (unsigned long long)num_layers);
+    if (threadIdx.x == 0 && leader) {
+      tw::red_release_add_u64(done + pair, 16ull * (unsigned long long)num_layers);
+      tw::red_release_add_u64(done + 128 + pair, 16ull * (unsigned long long)num_layers);
+    }
   } else if (warp == 0) {
-    // ===== TMA producer (both CTAs) =====
+    // ===== TMA producer (both CTAs): A stages only (the weights are loaded by warp 1), so it runs ahead across layer boundaries =====
     int stage = 0;
     uint32_t phase = 0;
     // (Tried and removed: starting pair p p*skew cycles late so that half the pairs are in an L2-hungry conv2 layer while the
@@ -1123,36 +1161,33 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     for (int l = 0; l < num_layers; l++) {
       const bool conv2 = (l & 1) != 0;
       const CUtensorMap* mA = conv2 ? &tmT : &tmX;
-      if (l > 0) {
-        mbar_wait(&s.wfree, (uint32_t)(l - 1) & 1u);   // every MMA of layer l-1 (reads both CTAs' weights) has retired
-      }
-      if (elect_one()) {
-        // one barrier per 8 KB weight chunk, loaded in the order the layer's first MMAs use them (K half 0 first; vertical
-        // taps ky = 2, 1, 0), so the tensor pipe restarts when the first taps have landed, not after all 144 KB
-        for (int half = 0; half < 2; half++)
-          for (int ky = 2; ky >= 0; ky--)
-            for (int kx = 0; kx < 3; kx++) {
-              const int ch = (ky * 3 + kx) * 2 + half;
-              if (leader) mbar_expect_tx(&s.bfull[ch], 2 * B_CHUNK);
-              tma_load_2d_2sm(s.b[ch], &tmW, &s.bfull[ch], ch * BK, l * 128 + (int)rank * BNH);
-            }
-      }
-      __syncwarp();
-      if (l > 0) {
-        mbar_wait(&s.ldone, (uint32_t)(l - 1) & 1u);   // this CTA's stores of layer l-1 are complete
-        if (q_lo >= 0) {
-          if (lane == 0) { while (tw::ld_acquire_u64(done + q_lo) < base + 16ull * (unsigned long long)l) {} }
-          __syncwarp();
+      int cum = 0;   // units of this layer's segments up to and including the current one (processing order)
+      for (int k = 0; k < nseg; k++) {
+        const tw::Seg sg = tw::segment(k, nseg, u0, u1, natural);
+        const int g = sg.g, j_lo = sg.j_lo, j_hi = sg.j_hi;
+        cum += j_hi - j_lo;
+        const bool lo_halo = q_lo >= 0 && g * H + j_lo == u0;   // bottom halo row: produced by the pair below in layer l-1
+        bool hi_ok = (l == 0) || !(q_hi >= 0 && g * H + j_hi == u1);
+        if (l > 0) {
+          // the rows of layer l-1 this segment reads: the same segment of this CTA (its 8 epilogue warps count the units whose
+          // stores have completed, same processing order in every layer) ...
+          const int need = (l - 1) * Up + cum;
+          for (;;) {
+            const int v = tw::ld_acquire_shared_s32(&s.stored[lane & 7]);
+            if (__all_sync(0xFFFFFFFFu, v >= need)) break;
+            __nanosleep(64);
+          }
+          // ... plus the halo row below = the LAST row of the lower neighbour in layer l-1
+          if (lo_halo) {
+            if (lane == 0) { while (tw::ld_acquire_u64(done_up + q_lo) < base + 16ull * (unsigned long long)l) {} }
+            __syncwarp();
+          }
+          fence_proxy_async();
         }
-        fence_proxy_async();
-      }
-      bool hi_ok = (l == 0) || q_hi < 0;
-      for (int u = u0; u < u1;) {
-        const int g = u / H, j_lo = u - g * H, j_hi = min(u1 - g * H, H);
         const int y_lo = max(0, j_lo - 1), y_hi = min(H - 1, j_hi);
         const int b0 = g * 2 * NB + (int)rank * NB;
         for (int y = y_lo; y <= y_hi; y++) {
-          if (!hi_ok && y == j_hi && g * H + j_hi == u1) {  // top halo row: produced by the next pair in layer l-1
+          if (!hi_ok && y == j_hi) {  // top halo row = the FIRST row of the next pair in layer l-1
             if (lane == 0) { while (tw::ld_acquire_u64(done + q_hi) < base + 16ull * (unsigned long long)l) {} }
             __syncwarp();
             fence_proxy_async();
@@ -1172,11 +1207,31 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
           }
         }
-        u = g * H + j_hi;
       }
     }
   } else if (warp == 1) {
-    if (leader) {  // ===== MMA issuer (leader CTA only) =====
+    // this CTA's half of layer l's weights: one barrier per 8 KB chunk, requested in the order the layer's first MMAs use them
+    // (K half 0 first; vertical taps ky = 2, 1, 0), so the tensor pipe restarts when the first taps have landed, not after all
+    // 144 KB.  Issued by warp 1 of BOTH CTAs as soon as every MMA of the previous layer has retired (`wfree`, multicast commit)
+    auto load_weights = [&](int l) {
+      if (elect_one()) {
+        for (int half = 0; half < 2; half++)
+          for (int ky = 2; ky >= 0; ky--)
+            for (int kx = 0; kx < 3; kx++) {
+              const int ch = (ky * 3 + kx) * 2 + half;
+              if (leader) mbar_expect_tx(&s.bfull[ch], 2 * B_CHUNK);
+              tma_load_2d_2sm(s.b[ch], &tmW, &s.bfull[ch], ch * BK, l * 128 + (int)rank * BNH);
+            }
+      }
+      __syncwarp();
+    };
+    load_weights(0);
+    if (!leader) {
+      for (int l = 1; l < num_layers; l++) {
+        mbar_wait(&s.wfree, (uint32_t)(l - 1) & 1u);   // every MMA of layer l-1 (reads both CTAs' weights) has retired
+        load_weights(l);
+      }
+    } else {  // ===== MMA issuer (leader CTA only) =====
       constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);    // M = 256, N = 128
       constexpr uint32_t IDESC_R = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256, N = 16
       const uint64_t idsc = umma_desc_interleave(smem_u32(s.ident), 128u, 256u);
@@ -1189,8 +1244,9 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int l = 0; l < num_layers; l++) {
         const bool conv2 = (l & 1) != 0;
         uint32_t wready = 0;   // bit ch: this layer's weight chunk ch has been waited for
-        for (int u = u0; u < u1;) {
-          const int g = u / H, j_lo = u - g * H, j_hi = min(u1 - g * H, H);
+        for (int k = 0; k < nseg; k++) {
+          const tw::Seg sg = tw::segment(k, nseg, u0, u1, natural);
+          const int j_lo = sg.j_lo, j_hi = sg.j_hi;
           const int y_lo = max(0, j_lo - 1), y_hi = min(H - 1, j_hi);
           for (int y = y_lo; y <= y_hi; y++) {
             for (int j = (y == 0 ? 0 : y + 1); j <= y + 1; j++) {
@@ -1263,10 +1319,13 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             __syncwarp();
           }
           nbase += j_hi - j_lo;
-          u = g * H + j_hi;
         }
         if (elect_one()) umma_commit_2sm(&s.wfree);  // the resident weights may be replaced
         __syncwarp();
+        if (l + 1 < num_layers) {
+          mbar_wait(&s.wfree, (uint32_t)l & 1u);
+          load_weights(l + 1);
+        }
       }
     }
   } else {  // ===== epilogue warps 2..9 (both CTAs) =====
@@ -1280,72 +1339,77 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const bool want_lo = conv2 && l != num_layers - 1 && use_lo;   // nobody reads the low-order part of the last block's output
       const float* __restrict__ bias_g = ga.bias + (size_t)l * 128 + colhalf * 64;
       const CUtensorMap* mO = conv2 ? &tmXo : &tmTo;
-      for (int u = u0; u < u1; u++, n++) {
-        const int g = u / H, j = u - g * H;
-        const int bq = g * 2 * NB + (int)rank * NB + quarter * 4;
-        const int slot = n & 3;
-        mbar_wait(&s.tfull[slot], (uint32_t)(n >> 2) & 1u);
-        tcgen05_fence_after();
-        uint4 l8[4];   // lo8 mode: this row's 64 low-order bytes of the OUTPUT, filled over the two 32-column steps
-        uint32_t* l8w = reinterpret_cast<uint32_t*>(l8);
-#pragma unroll
-        for (int sc = 0; sc < 2; sc++) {
-          const int col = colhalf * 64 + sc * 32;
-          uint32_t v[32];
-          tmem_ld32(tmem_base + slot * BN + col + ((uint32_t)(quarter * 32) << 16), v);
-          uint4 oh4[4], ol4[4];
-          __half2* oh = reinterpret_cast<__half2*>(oh4);
-          __half2* ol = reinterpret_cast<__half2*>(ol4);
-#pragma unroll
-          for (int jj = 0; jj < 16; jj++) {
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_g + sc * 32) + jj);
-            const float x0 = fmaxf(__uint_as_float(v[2 * jj]) + bb.x, 0.f);
-            const float x1 = fmaxf(__uint_as_float(v[2 * jj + 1]) + bb.y, 0.f);
-            const __half2 h = __floats2half2_rn(x0, x1);
-            oh[jj] = h;
-            if (want_lo) {  // lo = y - hi: hi + lo carries ~22 (fp16 lo) / ~15 (e4m3 lo) significant bits of the skip path
-              const float2 hf = __half22float2(h);
-              if (lo8) {
-                const uint32_t b2 = tw::cvt_e4m3x2((x0 - hf.x) * tw::LO8_SCALE, (x1 - hf.y) * tw::LO8_SCALE);
-                if (jj & 1) l8w[sc * 8 + (jj >> 1)] |= b2 << 16; else l8w[sc * 8 + (jj >> 1)] = b2;
-              } else {
-                ol[jj] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+      for (int k = 0; k < nseg; k++) {
+        const tw::Seg sg = tw::segment(k, nseg, u0, u1, natural);
+        const int g = sg.g;
+        for (int j = sg.j_lo; j < sg.j_hi; j++, n++) {
+          const int bq = g * 2 * NB + (int)rank * NB + quarter * 4;
+          const int slot = n & 3;
+          mbar_wait(&s.tfull[slot], (uint32_t)(n >> 2) & 1u);
+          tcgen05_fence_after();
+          uint4 l8[4];   // lo8 mode: this row's 64 low-order bytes of the OUTPUT, filled over the two 32-column steps
+          uint32_t* l8w = reinterpret_cast<uint32_t*>(l8);
+  #pragma unroll
+          for (int sc = 0; sc < 2; sc++) {
+            const int col = colhalf * 64 + sc * 32;
+            uint32_t v[32];
+            tmem_ld32(tmem_base + slot * BN + col + ((uint32_t)(quarter * 32) << 16), v);
+            uint4 oh4[4], ol4[4];
+            __half2* oh = reinterpret_cast<__half2*>(oh4);
+            __half2* ol = reinterpret_cast<__half2*>(ol4);
+  #pragma unroll
+            for (int jj = 0; jj < 16; jj++) {
+              const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_g + sc * 32) + jj);
+              const float x0 = fmaxf(__uint_as_float(v[2 * jj]) + bb.x, 0.f);
+              const float x1 = fmaxf(__uint_as_float(v[2 * jj + 1]) + bb.y, 0.f);
+              const __half2 h = __floats2half2_rn(x0, x1);
+              oh[jj] = h;
+              if (want_lo) {  // lo = y - hi: hi + lo carries ~22 (fp16 lo) / ~15 (e4m3 lo) significant bits of the skip path
+                const float2 hf = __half22float2(h);
+                if (lo8) {
+                  const uint32_t b2 = tw::cvt_e4m3x2((x0 - hf.x) * tw::LO8_SCALE, (x1 - hf.y) * tw::LO8_SCALE);
+                  if (jj & 1) l8w[sc * 8 + (jj >> 1)] |= b2 << 16; else l8w[sc * 8 + (jj >> 1)] = b2;
+                } else {
+                  ol[jj] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                }
               }
             }
+            const int nparts = (want_lo && !lo8) ? 2 : 1;
+            for (int part = 0; part < nparts; part++) {
+              if (lane == 0) tma_store_wait_read<0>();  // the previous store has finished reading the tile
+              __syncwarp();
+              const uint4* o = part ? ol4 : oh4;
+  #pragma unroll
+              for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(tile + lane * 64 + ((c ^ sw) << 4)) = o[c];
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0 && !(ga.debug & 4)) { tma_store_4d(part ? &tmXLo : mO, tile, col, 0, j, bq); tma_store_commit(); }
+            }
           }
-          const int nparts = (want_lo && !lo8) ? 2 : 1;
-          for (int part = 0; part < nparts; part++) {
-            if (lane == 0) tma_store_wait_read<0>();  // the previous store has finished reading the tile
+          if (want_lo && lo8) {  // one 32-row x 64-byte tile of e4m3 bytes (channels colhalf*64 .. +63)
+            if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
-            const uint4* o = part ? ol4 : oh4;
-#pragma unroll
-            for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(tile + lane * 64 + ((c ^ sw) << 4)) = o[c];
+  #pragma unroll
+            for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(tile + lane * 64 + ((c ^ sw) << 4)) = l8[c];
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && !(ga.debug & 4)) { tma_store_4d(part ? &tmXLo : mO, tile, col, 0, j, bq); tma_store_commit(); }
+            if (lane == 0 && !(ga.debug & 4)) { tma_store_4d(&tmXL8o, tile, colhalf * 64, 0, j, bq); tma_store_commit(); }
           }
-        }
-        if (want_lo && lo8) {  // one 32-row x 64-byte tile of e4m3 bytes (channels colhalf*64 .. +63)
-          if (lane == 0) tma_store_wait_read<0>();
+          tcgen05_fence_before();
           __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(tile + lane * 64 + ((c ^ sw) << 4)) = l8[c];
-          fence_proxy_async();
+          if (lane == 0) mbar_arrive_cluster(&s.tempty[slot], 0);
+          // this unit's rows are in memory once the warp's stores have completed: count it for this CTA's producer, and tell
+          // the neighbouring pairs when it is one of the two rows they read
+          if (lane == 0) {
+            tma_store_wait_all();
+            fence_proxy_async();
+            tw::st_release_shared_s32(&s.stored[warp - 2], n + 1);
+            if (g * H + j == u0) tw::red_release_add_u64(done + pair, 1ull);
+            if (g * H + j == u1 - 1) tw::red_release_add_u64(done_up + pair, 1ull);
+          }
           __syncwarp();
-          if (lane == 0 && !(ga.debug & 4)) { tma_store_4d(&tmXL8o, tile, colhalf * 64, 0, j, bq); tma_store_commit(); }
         }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&s.tempty[slot], 0);
       }
-      // layer l of this warp's rows is in memory: tell this CTA's producer and the neighbouring pairs
-      if (lane == 0) {
-        tma_store_wait_all();
-        fence_proxy_async();
-        mbar_arrive(&s.ldone);
-        tw::red_release_add_u64(done + pair, 1ull);
-      }
-      __syncwarp();
     }
   }
   tcgen05_fence_before();

@@ -1225,6 +1225,9 @@ az_k_tower_yrow(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       __syncwarp();
     };
+    // (Tried and removed: the six ky = 2 chunks are free one input row before a layer ends and are what the next layer's first
+    // input row needs; requesting them from the producer's wait loops on an extra `wearly` commit gave 27.93 vs 27.88 us per
+    // layer -- the first weight chunk's latency is not what is left of the layer boundary.)
     load_weights(0);
     if (!leader) {
       for (int l = 1; l < num_layers; l++) {

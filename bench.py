@@ -34,7 +34,7 @@ CONV_MFLOP_PER_LEAF = 2 * 42 * 128 * 1152 / 1e6     # one 3x3 conv layer, valid 
 NET_MFLOP_PER_LEAF = 174.7                           # whole 7-block network
 METRIC = "mcts_node_expansions_per_s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (ncu --set full, cold caches)
-NCU_TRAFFIC_BYTES = 399.1e6  # profiles/r02final_tower_ncu_summary.txt: 51.4 MB read + 347.7 MB written per launch of az_k_tower_yrow (ONE launch = all 14 layers; ncu, cold caches, ~3000 leaves)
+NCU_TRAFFIC_BYTES = 401.4e6  # profiles/r02final_tower_ncu_summary.txt: 50.3 MB read + 351.1 MB written per launch of az_k_tower_yrow (ONE launch = all 14 layers; ncu, cold caches, ~3000 leaves)
 
 
 def resnet_blob(dim, num_actions, hp, seed=1):

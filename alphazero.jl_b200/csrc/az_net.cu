@@ -1002,15 +1002,16 @@ struct Smem {
 };
 // A pair's unit range [u0, u1) is a run of SEGMENTS = maximal runs of output rows inside one 32-board group.  Other pairs read
 // exactly two of its rows as halo: the LAST row u1-1 (pair above: bottom halo of its first segment) and the FIRST row u0
-// (pair below: top halo of its last segment).  Every layer therefore processes the last segment first, then the first one,
-// then the middle groups (k = processing order), and publishes the two rows separately the moment they are stored
+// (pair below: top halo of its last segment).  Every layer therefore processes the last segment first (when the range ends
+// inside a group), then the first one, then the middle groups (k = processing order), and publishes the two rows separately
 // (`done[128 + pair]`: row u1-1, `done[pair]`: row u0): when a layer ends, everything the neighbours and this pair's own
 // first segments of the next layer need has been in memory for about half a layer, the producer has already put the next
 // layer's first A stages into the ring, and the only wait left at the boundary is the first weight chunk.
 struct Seg { int g, j_lo, j_hi; };
 __device__ __forceinline__ Seg segment(int k, int nseg, int u0, int u1, bool natural) {
   int i = k;
-  if (!natural && nseg >= 2) i = (k == 0) ? nseg - 1 : k - 1;
+  if (!natural && nseg >= 2 && u1 % 6 != 0) i = (k == 0) ? nseg - 1 : k - 1;   // (a range that ends on a group boundary has no
+                                                                              // reader above: its first segment goes first)
   Seg sg;
   sg.g = u0 / 6 + i;
   sg.j_lo = (i == 0) ? u0 - sg.g * 6 : 0;

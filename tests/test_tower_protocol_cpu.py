@@ -84,7 +84,7 @@ class Graph:
         return anc
 
 
-def build(n_boards, num_layers, natural=False, resources=True):
+def build(n_boards, num_layers, natural=False, resources=True, drop=()):
     """Events: ('L', p, l, g, y) input row y of group g requested by the producer; ('C', p, l, g, y) its stages consumed by the MMAs;
     ('A', p, l, u) accumulator of output row u complete; ('E', p, l, u) epilogue of u (the TMA stores are issued: the WRITE);
     ('S', p, l, u) stores complete and published (stored[] += 1, and the pair's counters if u is its first / last row);
@@ -105,7 +105,7 @@ def build(n_boards, num_layers, natural=False, resources=True):
             segs = segments(u0, u1, natural)
             units = [g * H + j for (g, j_lo, j_hi) in segs for j in range(j_lo, j_hi)]
             order_check.append((p, l, units))
-            if l > 0:
+            if l > 0 and "wfree" not in drop:
                 G.edge(('F', p, l - 1), ('W', p, l))            # warp 1: wfree, then the weight loads
             for (g, j_lo, j_hi) in segs:
                 y_lo, y_hi = max(0, j_lo - 1), min(H - 1, j_hi)
@@ -118,10 +118,11 @@ def build(n_boards, num_layers, natural=False, resources=True):
                         G.edge(prev_load, L)                     # producer program order
                     if l > 0 and first:
                         for j in range(j_lo, j_hi):              # stored[] >= units through this segment of layer l-1
-                            G.edge(('S', p, l - 1, g * H + j), L)
-                        if lo_halo:
+                            if "own" not in drop:
+                                G.edge(('S', p, l - 1, g * H + j), L)
+                        if lo_halo and "lo" not in drop:
                             G.edge(('S', q_lo, l - 1, rng[q_lo][1] - 1), L)     # done_up[q_lo]
-                    if l > 0 and hi_halo and y == j_hi:
+                    if l > 0 and hi_halo and y == j_hi and "hi" not in drop:
                         G.edge(('S', q_hi, l - 1, rng[q_hi][0]), L)             # done[q_hi]
                     first = False
                     G.edge(L, C)                                 # full barrier
@@ -151,15 +152,15 @@ def build(n_boards, num_layers, natural=False, resources=True):
     return G, pairs, rng, reads, order_check
 
 
-def check(n_boards, num_layers=4, natural=False):
+def check(n_boards, num_layers=4, natural=False, drop=()):
     # 1. no deadlock under the tightest resource limits
-    G, pairs, rng, reads, order_check = build(n_boards, num_layers, natural, resources=True)
+    G, pairs, rng, reads, order_check = build(n_boards, num_layers, natural, resources=True, drop=drop)
     assert G.topo() is not None, "cyclic wait graph (deadlock) at %d boards" % n_boards
     # 2. every unit exactly once, all roles in the same order (the three device loops share tw::segment)
     for p, l, units in order_check:
         assert sorted(units) == list(range(*rng[p])), (p, l)
     # 3. hazards, from protocol edges only
-    G, pairs, rng, reads, _ = build(n_boards, num_layers, natural, resources=False)
+    G, pairs, rng, reads, _ = build(n_boards, num_layers, natural, resources=False, drop=drop)
     anc = G.ancestors()
     owner = {}
     for p in pairs:
@@ -168,6 +169,9 @@ def check(n_boards, num_layers=4, natural=False):
     def before(a, b):
         return (anc[G.ids[b]] >> G.ids[a]) & 1
     n_raw = n_war = 0
+    for p in pairs:                                               # the resident weights are overwritten in place, too
+        for l in range(1, num_layers):
+            assert before(('F', p, l - 1), ('W', p, l)), ("weights", n_boards, p, l)
     for (l, row), consumers in reads.items():
         q = owner[row]
         for c in consumers:
@@ -217,3 +221,12 @@ def test_boundary_rows_are_processed_early():
                 assert units.index(u0) == 0
             if u0 % H != 0:      # the layer goes on for at least one more unit (~4 us) after the row the pair below waits for
                 assert units.index(u0) + 1 <= len(units) - 1
+
+
+@pytest.mark.parametrize("drop", ["hi", "lo", "own", "wfree"])
+def test_the_model_notices_a_missing_wait(drop):
+    """Sensitivity of the check: without the wait on the upper neighbour's first row, on the lower neighbour's last row, on
+    the CTA's own store counter, or on `wfree`, some read / overwrite is no longer ordered."""
+    with pytest.raises(AssertionError):
+        for n in (2750, 4096, 100):
+            check(n, drop=(drop,))

@@ -331,6 +331,63 @@ class SimpleNetHP:  # src/networks/architectures/simplenet.jl:15-22
         self.use_batch_norm, self.batch_norm_momentum = use_batch_norm, batch_norm_momentum
 
 
+def fresh_resnet_blob(gspec, hp, seed=1):
+    """Parameters of a freshly constructed Flux ResNet (`ResNet(gspec, hp)`, src/networks/architectures/resnet.jl:65-92:
+    Glorot-uniform conv / dense weights, zero biases, BatchNorm gamma 1, beta 0, mu 0, sigma2 1) as the float32 blob
+    `Network.load` takes (order: include/azb200.h).  No checkpoints travel with the repository: benches and scripts start here."""
+    W, H, C = gspec.state_dim
+    nf, nb, npf, nvf = hp.num_filters, hp.num_blocks, hp.num_policy_head_filters, hp.num_value_head_filters
+    kw, kh = hp.conv_kernel_size
+    rng = np.random.default_rng(seed)
+    parts = []
+
+    def conv(kw_, kh_, ci, co):
+        s = np.sqrt(6.0 / (kw_ * kh_ * ci + kw_ * kh_ * co))
+        parts.extend([rng.uniform(-s, s, kw_ * kh_ * ci * co), np.zeros(co)])
+
+    def bn(n):
+        parts.extend([np.ones(n), np.zeros(n), np.zeros(n), np.ones(n)])
+
+    def dense(out, inn):
+        s = np.sqrt(6.0 / (inn + out))
+        parts.extend([rng.uniform(-s, s, out * inn), np.zeros(out)])
+    conv(kw, kh, C, nf); bn(nf)
+    for _ in range(nb):
+        conv(kw, kh, nf, nf); bn(nf); conv(kw, kh, nf, nf); bn(nf)
+    conv(1, 1, nf, nvf); bn(nvf); dense(nf, W * H * nvf); dense(1, nf)
+    conv(1, 1, nf, npf); bn(npf); dense(gspec.num_actions, W * H * npf)
+    return np.concatenate(parts).astype(np.float32)
+
+
+def fresh_simplenet_blob(gspec, hp, seed=1):
+    """The same for `SimpleNet(gspec, hp)` (src/networks/architectures/simplenet.jl:24-49): common = Dense(indim, width) + depth_common
+    hidden layers, vhead = depth_vhead hidden layers + Dense(width, 1), phead = depth_phead hidden layers + Dense(width, A); a
+    hidden layer is Dense [+ BatchNorm] with zero bias."""
+    W, H, C = gspec.state_dim
+    w = hp.width
+    rng = np.random.default_rng(seed)
+    parts = []
+
+    def dense(out, inn):
+        s = np.sqrt(6.0 / (inn + out))
+        parts.extend([rng.uniform(-s, s, out * inn), np.zeros(out)])
+
+    def hidden(inn, out):
+        dense(out, inn)
+        if hp.use_batch_norm:
+            parts.extend([np.ones(out), np.zeros(out), np.zeros(out), np.ones(out)])
+    hidden(W * H * C, w)
+    for _ in range(hp.depth_common):
+        hidden(w, w)
+    for _ in range(hp.depth_vhead):
+        hidden(w, w)
+    dense(1, w)
+    for _ in range(hp.depth_phead):
+        hidden(w, w)
+    dense(gspec.num_actions, w)
+    return np.concatenate(parts).astype(np.float32)
+
+
 class Network:
     """An MCTS oracle living on the GPU (az_net): RandomOracle, the synthetic hash oracle, ResNet or SimpleNet."""
 

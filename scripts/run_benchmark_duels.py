@@ -13,13 +13,12 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import _pkg  # noqa: E402
-from oracle import netref  # noqa: E402  (blob construction only)
 
 az = _pkg.load()
 ctx = az.Context(0)
 gs = az.GameSpec("connect-four")
-hp = dict(num_blocks=5, num_filters=128, conv_kernel_size=(3, 3), num_policy_head_filters=32, num_value_head_filters=32)
-net = az.ResNet(ctx, gs, az.ResNetHP(5, 128, (3, 3), 32, 32)).load(netref.make_blob(gs.state_dim, 7, hp, seed=1, randomize=False))
+hp = az.ResNetHP(5, 128, (3, 3), 32, 32)
+net = az.ResNet(ctx, gs, hp).load(az.fresh_resnet_blob(gs, hp, seed=1))
 arena_mcts = az.MctsParams(num_iters_per_turn=600, cpuct=2.0, temperature=az.ConstSchedule(0.2), dirichlet_noise_eps=0.05, dirichlet_noise_alpha=1.0)
 rollout_mcts = az.MctsParams(num_iters_per_turn=1000, cpuct=1.0, temperature=az.ConstSchedule(0.2), dirichlet_noise_eps=0.05, dirichlet_noise_alpha=1.0)
 sim = az.SimParams(num_games=256, num_workers=256, batch_size=256, reset_every=2, flip_probability=0.5, alternate_colors=False)

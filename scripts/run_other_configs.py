@@ -12,7 +12,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import _pkg  # noqa: E402
-from oracle import netref  # noqa: E402  (blob construction only)
 
 az = _pkg.load()
 ctx = az.Context(0)
@@ -20,8 +19,8 @@ out = {}
 
 # ---- config[3]: mancala, ResNet (5 blocks x 128 as shipped in games/mancala/params.jl), 4096 trees x 400 sims ----
 gs = az.GameSpec("mancala")
-hp = dict(num_blocks=5, num_filters=128, conv_kernel_size=(3, 3), num_policy_head_filters=32, num_value_head_filters=32)
-net = az.ResNet(ctx, gs, az.ResNetHP(5, 128, (3, 3), 32, 32)).load(netref.make_blob(gs.state_dim, 6, hp, seed=1, randomize=False))
+hp = az.ResNetHP(5, 128, (3, 3), 32, 32)
+net = az.ResNet(ctx, gs, hp).load(az.fresh_resnet_blob(gs, hp, seed=1))
 S, nsims = 4096, 400
 roots = gs.random_positions(11, S, 30)
 rng = np.random.default_rng(0)
@@ -48,8 +47,8 @@ net.close()
 
 # ---- config[4]: grid-world, SimpleNet(100, 4) (games/grid-world/params.jl), 8192 envs x 200 sims, eps = 0 ----
 gs = az.GameSpec("grid-world")
-hp = dict(width=100, depth_common=4, use_batch_norm=False)
-net = az.SimpleNet(ctx, gs, az.SimpleNetHP(100, 4)).load(netref.simplenet_make_blob(gs.state_dim, 4, hp, seed=1))
+hp = az.SimpleNetHP(100, 4)
+net = az.SimpleNet(ctx, gs, hp).load(az.fresh_simplenet_blob(gs, hp, seed=1))
 S, nsims = 8192, 200
 roots = gs.random_positions(5, S)
 mp = az.MctsParams(gamma=1.0, cpuct=1.0, num_iters_per_turn=nsims, dirichlet_noise_eps=0.0, dirichlet_noise_alpha=1.0)

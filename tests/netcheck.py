@@ -7,7 +7,7 @@ Tolerances (BASELINE.json north_star: "value/policy logits within 1e-3"):
         statistics are randomised: logits there reach |2|, and tensor-core operands carry 11 significand bits (fp16, the
         same as the TF32 math cuDNN's default mode gives the reference's own fp32 convs on Ampere+; the reference never
         sets a pedantic math mode), i.e. a unit round-off of 4.9e-4 per operand per layer.  The measured distribution over
-        7-block networks is RMS 3e-4..6e-4, max 1.9e-3 (scripts/probes/precision_emul.py reproduces it on the CPU and shows
+        7-block networks is RMS 3e-4..6e-4, max 1.9e-3 (tests/probes/precision_emul.py reproduces it on the CPU and shows
         the 14 tower layers, not the heads, set it); closing it needs two-term operands = 3x the tower's MMA work."""
 import numpy as np
 

@@ -1,5 +1,5 @@
 """CPU emulation of the rounding points of the tcgen05 network path (which ones dominate the logit error).
-Not part of the product or the tests: a design probe (DESIGN.md "precision")."""
+A design probe kept with the test infrastructure because it leans on the oracle's network restatement (DESIGN.md "precision"); not collected by pytest."""
 import sys, os
 import numpy as np, torch
 import torch.nn.functional as F

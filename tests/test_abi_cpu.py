@@ -130,3 +130,22 @@ def test_evaluation_helpers_host_logic(az, monkeypatch):
     ev = az.compare_networks(None, None, "new", "old", P, two_players=False)
     assert [c[:2] for c in calls] == [("new", None), ("old", None)] and ev.avgr == 0.25 - 0.0 and ev.redundancy == 0.5
     assert (ev.baseline_rewards == [0.0, 0.0, -1.0, 1.0]).all()
+
+
+def test_fresh_network_initialisers_match_the_restatement(az):
+    """`fresh_resnet_blob` / `fresh_simplenet_blob` (what scripts and benches load, no oracle import on the product side) build
+    the blob of a freshly constructed Flux model in the order `az_net_load` expects: same length and same values as the
+    oracle-side builder with the same seed."""
+    from oracle import netref
+    for game, hp, hd in [("connect-four", az.ResNetHP(5, 128, (3, 3), 32, 32),
+                          dict(num_blocks=5, num_filters=128, conv_kernel_size=(3, 3), num_policy_head_filters=32, num_value_head_filters=32)),
+                         ("mancala", az.ResNetHP(2, 64, (3, 3), 2, 1),
+                          dict(num_blocks=2, num_filters=64, conv_kernel_size=(3, 3), num_policy_head_filters=2, num_value_head_filters=1))]:
+        gs = az.GameSpec(game)
+        b = az.fresh_resnet_blob(gs, hp, seed=3)
+        assert len(b) == netref.num_params(gs.state_dim, gs.num_actions, hd)
+        assert np.array_equal(b, netref.make_blob(gs.state_dim, gs.num_actions, hd, seed=3, randomize=False))
+    gs = az.GameSpec("grid-world")
+    for hp, hd in [(az.SimpleNetHP(100, 4), dict(width=100, depth_common=4, use_batch_norm=False)),
+                   (az.SimpleNetHP(64, 2, 2, 0, True), dict(width=64, depth_common=2, depth_phead=2, depth_vhead=0, use_batch_norm=True))]:
+        assert np.array_equal(az.fresh_simplenet_blob(gs, hp, seed=2), netref.simplenet_make_blob(gs.state_dim, 4, hd, seed=2, randomize=False))

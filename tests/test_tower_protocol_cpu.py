@@ -186,9 +186,10 @@ def check(n_boards, num_layers=4, natural=False, drop=()):
 
 @pytest.mark.parametrize("natural", [False, True])
 def test_tower_protocol_small_and_odd_sizes(natural):
-    """Every board count up to 20 groups (one unit per pair, neighbours without work, ranges inside one group, ...)."""
+    """Every board count up to 20 groups = 640 boards (one unit per pair, neighbours without work, ranges inside one group, ...);
+    the range-order variant of the A/B switch (AZ_TOWER_DEBUG=16) on every 7th."""
     seen_pairs = set()
-    for n in list(range(1, 32 * 20 + 1, 7)) + [1, 31, 32, 33, 63, 64, 65, 395, 396, 397]:
+    for n in list(range(1, 32 * 20 + 1, 1 if not natural else 7)) + [1, 31, 32, 33, 63, 64, 65, 395, 396, 397]:
         npairs, n_raw, n_war = check(n, natural=natural)
         seen_pairs.add(npairs)
         assert n_raw > 0

@@ -204,6 +204,12 @@ def test_tower_protocol_bench_sizes():
     check(2750, num_layers=14)   # the real layer count once
 
 
+def test_tower_protocol_sweep_of_tick_sizes():
+    """The leaf count changes every tick (anything from a few hundred to 4096): every 29th size up to one group past 4096."""
+    for n in range(641, 4129, 29):
+        check(n, num_layers=3)
+
+
 def test_boundary_rows_are_processed_early():
     """What the reordering is for: with >= 2 segments the row the pair above waits for (last row) is published after at most
     the first segment, and the row the pair below waits for (first row) right after the first row of the second segment."""

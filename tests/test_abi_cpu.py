@@ -149,3 +149,37 @@ def test_fresh_network_initialisers_match_the_restatement(az):
     for hp, hd in [(az.SimpleNetHP(100, 4), dict(width=100, depth_common=4, use_batch_norm=False)),
                    (az.SimpleNetHP(64, 2, 2, 0, True), dict(width=64, depth_common=2, depth_phead=2, depth_vhead=0, use_batch_norm=True))]:
         assert np.array_equal(az.fresh_simplenet_blob(gs, hp, seed=2), netref.simplenet_make_blob(gs.state_dim, 4, hd, seed=2, randomize=False))
+
+
+def test_struct_layouts_of_header_and_ctypes_mirror_agree(az, tmp_path):
+    """sizeof / offsetof of every parameter struct in include/azb200.h, as gcc lays them out, against the ctypes mirrors of the
+    host package (field names taken from the header: a renamed, reordered or retyped field shows up here without a GPU)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc")
+    if cc is None:
+        pytest.skip("gcc not available")
+    hdr = open(os.path.join(ROOT, "include", "azb200.h")).read()
+    mirrors = {"az_mcts_params": az._MctsParams, "az_minmax_params": az._MinMaxParams, "az_sim_params": az._SimParams,
+               "az_resnet_hp": az._ResNetHP, "az_simplenet_hp": az._SimpleNetHP}
+    structs = {}
+    for body, name in re.findall(r"typedef struct \{(.*?)\} (az_\w+);", hdr, flags=re.S):
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        structs[name] = [re.sub(r"\[.*", "", d.strip().split()[-1]) for d in body.split(";") if d.strip()]
+    assert set(structs) == set(mirrors), set(structs) ^ set(mirrors)
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "azb200.h"', "int main(void) {"]
+    for name, fields in structs.items():
+        src.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f in fields:
+            src.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    src.append("return 0; }")
+    cfile, exe = tmp_path / "layout.c", tmp_path / "layout"
+    cfile.write_text("\n".join(src))
+    subprocess.check_call([cc, "-std=c99", "-I" + os.path.join(ROOT, "include"), str(cfile), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, fields in structs.items():
+        m = mirrors[name]
+        assert [f for f, _ in m._fields_] == fields, name
+        assert int(got[name]) == C.sizeof(m), name
+        for f in fields:
+            assert int(got[name + "." + f]) == getattr(m, f).offset, (name, f)

@@ -150,3 +150,38 @@ def test_grid_world_rules(oz):
     assert g.terminated() and g.state() == bytes([1, 1])
     x = oz.vectorize_state(gid, bytes([3, 7]))
     assert x.shape == (10, 10, 1) and x[2, 6, 0] == 1 and x.sum() == 1
+
+
+def test_oracle_struct_layouts_match_the_ctypes_mirrors(oz, tmp_path):
+    """The checker's own boundary: oz_game / oz_mcts_params / oz_trace / oz_rollout_ctx as gcc lays them out against the
+    ctypes mirrors of oracle/oracle.py (every field offset and the sizes)."""
+    import ctypes as C
+    import os
+    import re
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc")
+    if cc is None:
+        pytest.skip("gcc not available")
+    here = os.path.dirname(os.path.abspath(oz.__file__))
+    mirrors = {"oz_game": oz.Game, "oz_mcts_params": oz.MctsParams, "oz_trace": oz.Trace, "oz_rollout_ctx": oz.RolloutCtx}
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "az_oracle.h"', "int main(void) {"]
+    for name, m in mirrors.items():
+        src.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f, _ in m._fields_:
+            src.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    src.append("return 0; }")
+    cfile, exe = tmp_path / "ozlayout.c", tmp_path / "ozlayout"
+    cfile.write_text("\n".join(src))
+    subprocess.check_call([cc, "-std=c11", "-I" + here, str(cfile), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, m in mirrors.items():
+        assert int(got[name]) == C.sizeof(m), name
+        for f, _ in m._fields_:
+            assert int(got[name + "." + f]) == getattr(m, f).offset, (name, f)
+    # and the mirrors name every field of the C structs (count of declarators in the header)
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(here, "az_oracle.h")).read(), flags=re.S)
+    for name, m in mirrors.items():
+        body = re.search(r"typedef struct \{([^}]*)\} %s;" % name, hdr, flags=re.S).group(1)
+        n_decl = sum(len(d.split(",")) for d in body.split(";") if d.strip())
+        assert n_decl == len(m._fields_), (name, n_decl, len(m._fields_))

@@ -45,6 +45,7 @@ def test_game_queries_match_oracle(az, oz):
                 m = g.actions_mask()
                 assert (gs.actions_mask(s) == m).all()
                 assert (gs.vectorize_state(s) == oz.vectorize_state(gid, g.state())).all()
+                assert gs.heuristic_value(s) == oz.lib().oz_heuristic_value(C.byref(g.g))      # GI.heuristic_value
                 a = int(rng.choice(np.flatnonzero(m)))
                 g.play(a)
                 s, term, wr = gs.play(s, a)
